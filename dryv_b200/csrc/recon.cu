@@ -1,0 +1,652 @@
+// recon.cu — kernels' entry points and the extern "C" ABI of include/dryv_recon.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+//             recon.cu recon_tables.cpp -o libdryv_recon.so        (see __graft_entry__.build)
+// There is no CPU implementation behind this ABI: without a usable CUDA device every reconstructing
+// entry point returns DRYV_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <string>
+
+#include "recon_kernels.cuh"
+
+namespace dryv {
+
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct MbHeader {
+  int mbt, t8, cm, qp, mbcls;
+};
+
+// lanes 0..3 fetch mb_type / transform_size_8x8_flag / intra_chroma_pred_mode / qp of macroblock `mb`
+__device__ __forceinline__ uint32_t load_header_lane(const KernelArgs& a, int lane, size_t mb) {
+  const uint8_t* p = lane == 0 ? a.mb_type : (lane == 1 ? a.t8x8 : (lane == 2 ? a.chroma_mode : a.qp));
+  return lane < 4 ? (uint32_t)__ldg(p + mb) : 0u;
+}
+__device__ __forceinline__ MbHeader decode_header(uint32_t hdr_lane, int* status) {
+  MbHeader h;
+  h.mbt = __shfl_sync(0xffffffffu, hdr_lane, 0);
+  h.t8 = __shfl_sync(0xffffffffu, hdr_lane, 1);
+  h.cm = __shfl_sync(0xffffffffu, hdr_lane, 2);
+  h.qp = __shfl_sync(0xffffffffu, hdr_lane, 3);
+  if (h.mbt > 24 || h.cm > 3 || h.qp > 51) {  // I_PCM / inter / out-of-range syntax: flagged, never decoded
+    *status = STATUS_UNSUPPORTED;
+    h.mbt = min(h.mbt, 24);
+    h.cm &= 3;
+    h.qp = min(h.qp, 51);
+  }
+  h.mbcls = h.mbt == 0 ? (h.t8 ? 1 : 0) : 2;  // slice/macroblock.rs:682-716
+  return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full reconstruction: persistent row walkers over an x+2y macroblock wavefront.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(const KernelArgs a) {
+  __shared__ alignas(16) CtaSmem cs;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.tables);
+    uint4* dst = reinterpret_cast<uint4*>(&cs.tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceTables) / 16); i += kThreadsPerCta) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  WarpSmem& ws = cs.warp[threadIdx.x >> 5];
+  const LaneConst lc = make_lane_const(lane, cs.tab);
+
+  const int W = a.W, H = a.H;
+  const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
+  const size_t n_mb = (size_t)W * H;
+  const int strideY = W * 16, strideC = W * 8;
+  // raster-grid cell of this lane and the pred_syntax entry that covers it
+  const int g = lane & 15, gx = g & 3, gy = g >> 2;
+  const int syn_idx4 = 8 * (gy >> 1) + 4 * (gx >> 1) + 2 * (gy & 1) + (gx & 1);  // spec 4x4 block index of the cell
+  const int syn_src8 = ((gy >> 1) ? 4 : 0) + (gx >> 1);  // lane that loaded pred_syntax[blk8] (cells 0,1,4,5)
+
+  int local_status = STATUS_OK;
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= total_rows) break;
+    // tickets are dealt row-major over pictures so that a row only ever waits on a lower ticket
+    const int row = (int)(t / (unsigned)a.n_frames), frame = (int)(t % (unsigned)a.n_frames);
+    const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
+    uint8_t* const Y = a.out + (size_t)frame * n_mb * 384;
+    uint8_t* const Cb = Y + n_mb * 256;
+    uint8_t* const Cr = Cb + n_mb * 64;
+    const int* const prog_above = a.progress + (size_t)frame * H + row - 1;
+    int* const prog_mine = a.progress + (size_t)frame * H + row;
+    const bool availB = row > 0;
+
+    // per-lane pieces of the top-strip fetch: lanes 0..6 luma words, 8..10 Cb, 12..14 Cr, 16 mode word
+    const uint8_t* strip_base = nullptr;
+    int strip_w = 0, strip_dst = 0;
+    if (availB) {
+      if (lane < 7) {
+        strip_base = Y + (size_t)(16 * row - 1) * strideY;
+        strip_w = lane;
+        strip_dst = 12 + 4 * lane;  // luma tile row 0, x = -4 + 4*lane
+      } else if (lane >= 8 && lane < 11) {
+        strip_base = Cb + (size_t)(8 * row - 1) * strideC;
+        strip_w = lane - 8;
+        strip_dst = 4 + 4 * (lane - 8);
+      } else if (lane >= 12 && lane < 15) {
+        strip_base = Cr + (size_t)(8 * row - 1) * strideC;
+        strip_w = lane - 12;
+        strip_dst = 4 + 4 * (lane - 12);
+      }
+    }
+    // per-lane store address pieces
+    uint8_t* st_base;
+    int st_stride;
+    if (lane < 16) { st_base = Y + (size_t)(16 * row + lane) * strideY; st_stride = 16; }
+    else if (lane < 24) { st_base = Cb + (size_t)(8 * row + (lane - 16)) * strideC; st_stride = 8; }
+    else { st_base = Cr + (size_t)(8 * row + (lane - 24)) * strideC; st_stride = 8; }
+
+    // prefetch macroblock 0
+    uint32_t hdr_n = load_header_lane(a, lane, mb_row0);
+    uint32_t syn_n = lane < 16 ? (uint32_t)__ldg(a.pred_syntax + mb_row0 * 16 + syn_idx4) : 0u;
+    uint4 c0_n = make_uint4(0, 0, 0, 0), c1_n = make_uint4(0, 0, 0, 0);
+    if (lane < 24) {
+      const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 2;
+      c0_n = __ldg(cp);
+      c1_n = __ldg(cp + 1);
+    }
+    int seen = 0;   // last observed progress of the row above
+    int a_col = 2;  // resolved mode of the cell left of grid column 0 (previous MB of this row)
+
+    for (int x = 0; x < W; x++) {
+      const uint32_t hdr_c = hdr_n, syn_c = syn_n;
+      const uint4 c0 = c0_n, c1 = c1_n;
+      if (x + 1 < W) {
+        const size_t mbn = mb_row0 + x + 1;
+        hdr_n = load_header_lane(a, lane, mbn);
+        if (lane < 16) syn_n = (uint32_t)__ldg(a.pred_syntax + mbn * 16 + syn_idx4);
+        if (lane < 24) {
+          const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mbn * DRYV_COEFFS_PER_MB) + lane * 2;
+          c0_n = __ldg(cp);
+          c1_n = __ldg(cp + 1);
+        }
+      }
+      const MbHeader h = decode_header(hdr_c, &local_status);
+
+      // 1. residual (independent of every other macroblock)
+      residual_stage(cs, ws, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
+
+      // 2. wavefront wait: the row above must have finished MB min(x+1, W-1)
+      const bool availA = x > 0, availC = availB && x < W - 1, availD = availA && availB;
+      int b_row = 2;
+      if (availB) {
+        const int need = min(x + 2, W);
+        if (seen < need) {
+          unsigned spins = 0;
+          while ((seen = ld_acquire_gpu(prog_above)) < need) {
+            if (++spins > 16u) __nanosleep(spins > 256u ? 400u : 40u);
+            if ((spins & 0xfffu) == 0u) {
+              if (spins > (1u << 24) || ld_acquire_gpu(a.status) == STATUS_WATCHDOG) {
+                local_status = STATUS_WATCHDOG;
+                atomicExch(a.status, STATUS_WATCHDOG);
+                return;
+              }
+            }
+          }
+        }
+        // 3a. top strip (28 luma + 2 x 12 chroma bytes) and the bottom-row modes of the MB above
+        uint32_t wv = 0;
+        bool have = false;
+        if (strip_base) {
+          const int col = (lane < 7 ? 16 : 8) * x - 4 + 4 * strip_w;
+          const int lim = lane < 7 ? strideY : strideC;
+          have = col >= 0 && col < lim;
+          if (have) wv = ld_relaxed_gpu_u32(strip_base + col);
+        }
+        uint32_t mw = 0;
+        if (lane == 16) mw = ld_relaxed_gpu_u32(a.mode_line + mb_row0 - W + x);
+        if (have) {
+          if (lane < 7) *reinterpret_cast<uint32_t*>(&ws.luma[strip_dst]) = wv;
+          else *reinterpret_cast<uint32_t*>(&ws.chroma[lane >= 12 ? 1 : 0][strip_dst]) = wv;
+        }
+        mw = __shfl_sync(0xffffffffu, mw, 16);
+        b_row = (mw >> (8 * gx)) & 0xff;
+        __syncwarp();
+      }
+
+      // 3b. prediction modes
+      int syn = (int)syn_c;
+      if (h.mbcls == 1) syn = __shfl_sync(0xffffffffu, syn, syn_src8);
+      const int m = resolve_modes(lane, h.mbcls, syn, a_col, b_row, availA, availB);
+
+      // 3c. prediction + residual + clip into the pixel tiles
+      if (h.mbcls == 0) predict_i4x4(cs, ws, lane, m, availA, availB, availC, availD);
+      else if (h.mbcls == 1) predict_i8x8(cs, ws, lane, m, availA, availB, availC, availD);
+      else predict_i16x16(ws, lane, (h.mbt - 1) & 3, availA, availB);
+      predict_chroma(ws, lane, h.cm, availA, availB, availD);
+
+      // 4. store the macroblock (16 x 16 B luma rows, 2 x 8 x 8 B chroma rows), publish modes + progress
+      if (lane < 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(&ws.luma[luma_at(0, lane)]);
+        *reinterpret_cast<uint4*>(st_base + (size_t)x * 16) = v;
+      } else {
+        const uint2 v = *reinterpret_cast<const uint2*>(&ws.chroma[lane >= 24 ? 1 : 0][chroma_at(0, lane & 7)]);
+        *reinterpret_cast<uint2*>(st_base + (size_t)x * 8) = v;
+      }
+      {
+        uint32_t mv = (lane >= 12 && lane < 16) ? ((uint32_t)m << (8 * (lane & 3))) : 0u;
+        mv |= __shfl_xor_sync(0xffffffffu, mv, 1);
+        mv |= __shfl_xor_sync(0xffffffffu, mv, 2);
+        if (lane == 12) a.mode_line[mb_row0 + x] = mv;
+      }
+      a_col = __shfl_sync(0xffffffffu, m, gy * 4 + 3);
+      __syncwarp();
+      if (lane == 0) st_release_gpu(prog_mine, x + 1);
+      // carry the right-most column into the left-neighbour column of the next macroblock
+      if (lane < 16) ws.luma[luma_at(-1, lane)] = ws.luma[luma_at(15, lane)];
+      else {
+        uint8_t* tile = ws.chroma[lane >= 24 ? 1 : 0];
+        tile[chroma_at(-1, lane & 7)] = tile[chroma_at(7, lane & 7)];
+      }
+      __syncwarp();
+    }
+  }
+  if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Residual only (BASELINE config "dequant + IDCT + residual add"): out = clip(pred_in + residual).
+// One warp per macroblock, grid-stride; no dependencies between macroblocks.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsPerCta, 8) recon_residual_add_kernel(const KernelArgs a) {
+  __shared__ alignas(16) CtaSmem cs;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.tables);
+    uint4* dst = reinterpret_cast<uint4*>(&cs.tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceTables) / 16); i += kThreadsPerCta) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  WarpSmem& ws = cs.warp[threadIdx.x >> 5];
+  const LaneConst lc = make_lane_const(lane, cs.tab);
+  const int W = a.W, H = a.H;
+  const size_t n_mb = (size_t)W * H, total = n_mb * a.n_frames;
+  const int strideY = W * 16, strideC = W * 8;
+  const size_t warps = (size_t)gridDim.x * kWarpsPerCta;
+  int local_status = STATUS_OK;
+  for (size_t mb = (size_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); mb < total; mb += warps) {
+    const size_t frame = mb / n_mb, addr = mb % n_mb;
+    const int x = (int)(addr % W), row = (int)(addr / W);
+    const uint32_t hdr = load_header_lane(a, lane, mb);
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
+    if (lane < 24) {
+      const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb * DRYV_COEFFS_PER_MB) + lane * 2;
+      c0 = __ldg(cp);
+      c1 = __ldg(cp + 1);
+    }
+    const MbHeader h = decode_header(hdr, &local_status);
+    residual_stage(cs, ws, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
+    const size_t fo = frame * n_mb * 384;
+    {  // luma: lane = (row r, half h): 8 pixels
+      const int r = lane >> 1, hf = lane & 1;
+      const size_t o = fo + (size_t)(16 * row + r) * strideY + 16 * x + 8 * hf;
+      const uint2 pv = __ldg(reinterpret_cast<const uint2*>(a.pred_in + o));
+      const uint4 rv = *reinterpret_cast<const uint4*>(&ws.res[r * 16 + 8 * hf]);
+      const int o0 = clip255((int)(pv.x & 0xff) + lo16(rv.x)), o1 = clip255((int)((pv.x >> 8) & 0xff) + hi16(rv.x));
+      const int o2 = clip255((int)((pv.x >> 16) & 0xff) + lo16(rv.y)), o3 = clip255((int)(pv.x >> 24) + hi16(rv.y));
+      const int o4 = clip255((int)(pv.y & 0xff) + lo16(rv.z)), o5 = clip255((int)((pv.y >> 8) & 0xff) + hi16(rv.z));
+      const int o6 = clip255((int)((pv.y >> 16) & 0xff) + lo16(rv.w)), o7 = clip255((int)(pv.y >> 24) + hi16(rv.w));
+      *reinterpret_cast<uint2*>(a.out + o) = make_uint2(pack4(o0, o1, o2, o3), pack4(o4, o5, o6, o7));
+    }
+    {  // chroma: lane = (plane, row r, half): 4 pixels
+      const int pl = lane >> 4, r = (lane >> 1) & 7, hf = lane & 1;
+      const size_t o = fo + n_mb * 256 + (size_t)pl * n_mb * 64 + (size_t)(8 * row + r) * strideC + 8 * x + 4 * hf;
+      const uint32_t pv = __ldg(reinterpret_cast<const uint32_t*>(a.pred_in + o));
+      const uint2 rv = *reinterpret_cast<const uint2*>(&ws.res[256 + pl * 64 + r * 8 + 4 * hf]);
+      const int o0 = clip255((int)(pv & 0xff) + lo16(rv.x)), o1 = clip255((int)((pv >> 8) & 0xff) + hi16(rv.x));
+      const int o2 = clip255((int)((pv >> 16) & 0xff) + lo16(rv.y)), o3 = clip255((int)(pv >> 24) + hi16(rv.y));
+      *reinterpret_cast<uint32_t*>(a.out + o) = pack4(o0, o1, o2, o3);
+    }
+    __syncwarp();
+  }
+  if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
+}
+
+}  // namespace dryv
+
+// ================================================================================================
+// Host side: the C ABI
+// ================================================================================================
+using dryv::DeviceTables;
+using dryv::KernelArgs;
+
+struct dryv_recon_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int wave_ctas_per_sm = 0, resid_ctas_per_sm = 0;
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_kernel[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
+  // tables
+  DeviceTables* d_tables = nullptr;
+  DeviceTables* h_tables = nullptr;  // pinned
+  dryv_pic_params tables_pp;
+  bool tables_valid = false;
+  // wavefront control block
+  int* d_progress = nullptr;
+  uint32_t* d_mode_line = nullptr;
+  size_t progress_cap = 0, mode_cap = 0;
+  unsigned int* d_ticket = nullptr;  // [0] ticket, [1] status
+  int* h_status = nullptr;           // pinned
+  // staging for dryv_recon_submit (two slots)
+  uint8_t* d_in[2] = {nullptr, nullptr};
+  uint8_t* d_out[2] = {nullptr, nullptr};
+  size_t in_cap = 0, out_cap = 0;
+  cudaStream_t pending_user = nullptr;
+  bool pending_user_valid = false;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(dryv_recon_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(ctx, DRYV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+bool pp_ok(const dryv_pic_params* pp) {
+  return pp && pp->pic_width_in_mbs >= 1 && pp->pic_width_in_mbs <= 1024 && pp->pic_height_in_mbs >= 1 &&
+         pp->pic_height_in_mbs <= 1024 && pp->flags == 0 && pp->chroma_qp_index_offset >= -12 &&
+         pp->chroma_qp_index_offset <= 12 && pp->second_chroma_qp_index_offset >= -12 &&
+         pp->second_chroma_qp_index_offset <= 12;
+}
+
+int ensure_tables(dryv_recon_ctx* ctx, const dryv_pic_params* pp, cudaStream_t s) {
+  if (ctx->tables_valid && memcmp(&ctx->tables_pp, pp, sizeof *pp) == 0) return DRYV_OK;
+  // the pinned host copy may still be in flight from a previous upload on another stream
+  CU(cudaStreamSynchronize(ctx->s_compute));
+  if (ctx->pending_user_valid) CU(cudaStreamSynchronize(ctx->pending_user));
+  dryv::build_device_tables(*pp, ctx->h_tables);
+  CU(cudaMemcpyAsync(ctx->d_tables, ctx->h_tables, sizeof(DeviceTables), cudaMemcpyHostToDevice, s));
+  CU(cudaStreamSynchronize(s));
+  ctx->tables_pp = *pp;
+  ctx->tables_valid = true;
+  return DRYV_OK;
+}
+
+int ensure_control(dryv_recon_ctx* ctx, size_t rows, size_t mbs) {
+  if (rows > ctx->progress_cap) {
+    CU(cudaDeviceSynchronize());
+    if (ctx->d_progress) cudaFree(ctx->d_progress);
+    ctx->d_progress = nullptr;
+    CU(cudaMalloc(&ctx->d_progress, rows * sizeof(int)));
+    ctx->progress_cap = rows;
+  }
+  if (mbs > ctx->mode_cap) {
+    CU(cudaDeviceSynchronize());
+    if (ctx->d_mode_line) cudaFree(ctx->d_mode_line);
+    ctx->d_mode_line = nullptr;
+    CU(cudaMalloc(&ctx->d_mode_line, mbs * sizeof(uint32_t)));
+    ctx->mode_cap = mbs;
+  }
+  return DRYV_OK;
+}
+
+KernelArgs make_args(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa, uint32_t n_frames,
+                     uint8_t* out) {
+  KernelArgs a;
+  memset(&a, 0, sizeof a);
+  a.mb_type = soa->mb_type;
+  a.t8x8 = soa->transform_size_8x8_flag;
+  a.chroma_mode = soa->intra_chroma_pred_mode;
+  a.qp = soa->qp;
+  a.pred_syntax = soa->pred_syntax;
+  a.coeff = soa->coeff;
+  a.out = out;
+  a.tables = ctx->d_tables;
+  a.progress = ctx->d_progress;
+  a.mode_line = ctx->d_mode_line;
+  a.ticket = ctx->d_ticket;
+  a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
+  a.W = pp->pic_width_in_mbs;
+  a.H = pp->pic_height_in_mbs;
+  a.n_frames = (int)n_frames;
+  a.cb_off = pp->chroma_qp_index_offset;
+  a.cr_off = pp->second_chroma_qp_index_offset;
+  return a;
+}
+
+bool soa_ok(const dryv_mb_soa* s) {
+  return s && s->mb_type && s->transform_size_8x8_flag && s->intra_chroma_pred_mode && s->qp && s->pred_syntax &&
+         s->coeff && (reinterpret_cast<uintptr_t>(s->coeff) % 16 == 0);
+}
+
+// enqueue the wavefront kernel for device-resident buffers on stream s
+int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa, uint32_t n_frames,
+                     uint8_t* d_out, cudaStream_t s) {
+  const size_t rows = (size_t)n_frames * pp->pic_height_in_mbs;
+  const size_t mbs = rows * pp->pic_width_in_mbs;
+  int rc = ensure_control(ctx, rows, mbs);
+  if (rc != DRYV_OK) return rc;
+  CU(cudaMemsetAsync(ctx->d_progress, 0, rows * sizeof(int), s));
+  CU(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
+  KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out);
+  size_t want = (rows + dryv::kWarpsPerCta - 1) / dryv::kWarpsPerCta;
+  size_t cap = (size_t)ctx->sm_count * ctx->wave_ctas_per_sm;
+  int grid = (int)(want < cap ? want : cap);
+  dryv::recon_wavefront_kernel<<<grid, dryv::kThreadsPerCta, 0, s>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  return DRYV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dryv_recon_abi_version(void) { return DRYV_RECON_ABI_VERSION; }
+
+size_t dryv_recon_frame_bytes(const dryv_pic_params* pp) {
+  if (!pp) return 0;
+  return (size_t)pp->pic_width_in_mbs * pp->pic_height_in_mbs * 384;
+}
+
+int dryv_recon_create(int device, dryv_recon_ctx** out) {
+  if (!out) return DRYV_ERR_ARG;
+  *out = nullptr;
+  dryv_recon_ctx* ctx = new dryv_recon_ctx();
+  ctx->device = device;
+  auto bail = [&](int code) {
+    delete ctx;
+    return code;
+  };
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return bail(DRYV_ERR_CUDA);
+  if (cudaSetDevice(device) != cudaSuccess) return bail(DRYV_ERR_CUDA);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(DRYV_ERR_CUDA);
+  if (prop.major != 10) {  // sm_100a SASS only: no PTX fallback, no other architecture
+    fprintf(stderr, "dryv_recon: device %d is sm_%d%d, this library is built for sm_100a only\n", device, prop.major,
+            prop.minor);
+    return bail(DRYV_ERR_CUDA);
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; i++)
+    ok = cudaEventCreateWithFlags(&ctx->e_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->e_kernel[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->e_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_tables, sizeof(DeviceTables)) == cudaSuccess &&
+       cudaMallocHost(&ctx->h_tables, sizeof(DeviceTables)) == cudaSuccess &&
+       cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)) == cudaSuccess &&
+       cudaMallocHost(&ctx->h_status, sizeof(int)) == cudaSuccess &&
+       cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wave_ctas_per_sm, dryv::recon_wavefront_kernel,
+                                                           dryv::kThreadsPerCta, 0) == cudaSuccess &&
+       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resid_ctas_per_sm, dryv::recon_residual_add_kernel,
+                                                     dryv::kThreadsPerCta, 0) == cudaSuccess;
+  if (!ok || ctx->wave_ctas_per_sm < 1 || ctx->resid_ctas_per_sm < 1) {
+    dryv_recon_destroy(ctx);
+    return DRYV_ERR_CUDA;
+  }
+  *out = ctx;
+  return DRYV_OK;
+}
+
+void dryv_recon_destroy(dryv_recon_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; i++) {
+    if (ctx->e_h2d[i]) cudaEventDestroy(ctx->e_h2d[i]);
+    if (ctx->e_kernel[i]) cudaEventDestroy(ctx->e_kernel[i]);
+    if (ctx->e_d2h[i]) cudaEventDestroy(ctx->e_d2h[i]);
+    if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+    if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+  }
+  if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+  if (ctx->d_progress) cudaFree(ctx->d_progress);
+  if (ctx->d_mode_line) cudaFree(ctx->d_mode_line);
+  if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  delete ctx;
+}
+
+const char* dryv_recon_last_error(dryv_recon_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dryv_recon_alloc_pinned(size_t bytes, void** out) {
+  if (!out || bytes == 0) return DRYV_ERR_ARG;
+  *out = nullptr;
+  return cudaMallocHost(out, bytes) == cudaSuccess ? DRYV_OK : DRYV_ERR_CUDA;
+}
+void dryv_recon_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int dryv_recon_reconstruct_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa,
+                                  uint32_t n_frames, uint8_t* d_out_yuv, void* cuda_stream) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!pp_ok(pp) || !soa_ok(d_soa) || !d_out_yuv || n_frames == 0) return fail(ctx, DRYV_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute;
+  int rc = ensure_tables(ctx, pp, s);
+  if (rc != DRYV_OK) return rc;
+  rc = launch_wavefront(ctx, pp, d_soa, n_frames, d_out_yuv, s);
+  if (rc != DRYV_OK) return rc;
+  if (cuda_stream) {
+    ctx->pending_user = s;
+    ctx->pending_user_valid = true;
+  }
+  return DRYV_OK;
+}
+
+int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa,
+                                   uint32_t n_frames, const uint8_t* d_pred_yuv, uint8_t* d_out_yuv,
+                                   void* cuda_stream) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!pp_ok(pp) || !soa_ok(d_soa) || !d_out_yuv || !d_pred_yuv || n_frames == 0)
+    return fail(ctx, DRYV_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute;
+  int rc = ensure_tables(ctx, pp, s);
+  if (rc != DRYV_OK) return rc;
+  KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out_yuv);
+  a.pred_in = d_pred_yuv;
+  const size_t mbs = (size_t)n_frames * pp->pic_width_in_mbs * pp->pic_height_in_mbs;
+  size_t want = (mbs + dryv::kWarpsPerCta - 1) / dryv::kWarpsPerCta;
+  size_t cap = (size_t)ctx->sm_count * ctx->resid_ctas_per_sm;
+  int grid = (int)(want < cap ? want : cap);
+  dryv::recon_residual_add_kernel<<<grid, dryv::kThreadsPerCta, 0, s>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  if (cuda_stream) {
+    ctx->pending_user = s;
+    ctx->pending_user_valid = true;
+  }
+  return DRYV_OK;
+}
+
+int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa, uint32_t n_frames,
+                      uint8_t* out_yuv) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!pp_ok(pp) || !soa_ok(soa) || !out_yuv || n_frames == 0) return fail(ctx, DRYV_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_tables(ctx, pp, ctx->s_compute);
+  if (rc != DRYV_OK) return rc;
+  const size_t n_mb = (size_t)pp->pic_width_in_mbs * pp->pic_height_in_mbs;
+  const size_t in_per_frame = n_mb * (4 + 16 + 768);
+  const size_t out_per_frame = n_mb * 384;
+  // chunk = pictures per pipeline stage: ~48 MB of input per stage, at least 1 picture
+  uint32_t chunk = (uint32_t)((48u << 20) / in_per_frame);
+  if (chunk < 1) chunk = 1;
+  if (chunk > n_frames) chunk = n_frames;
+  const size_t need_in = in_per_frame * chunk, need_out = out_per_frame * chunk;
+  if (need_in > ctx->in_cap || need_out > ctx->out_cap) {
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; i++) {
+      if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+      if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+      ctx->d_in[i] = ctx->d_out[i] = nullptr;
+    }
+    ctx->in_cap = ctx->out_cap = 0;
+    for (int i = 0; i < 2; i++) {
+      CU(cudaMalloc(&ctx->d_in[i], need_in));
+      CU(cudaMalloc(&ctx->d_out[i], need_out));
+    }
+    ctx->in_cap = need_in;
+    ctx->out_cap = need_out;
+  }
+  uint32_t done = 0;
+  for (uint32_t i = 0; done < n_frames; i++) {
+    const int slot = (int)(i & 1);
+    const uint32_t nf = (n_frames - done) < chunk ? (n_frames - done) : chunk;
+    const size_t mb0 = (size_t)done * n_mb, cnt = (size_t)nf * n_mb;
+    uint8_t* base = ctx->d_in[slot];
+    dryv_mb_soa d;
+    d.coeff = reinterpret_cast<const int16_t*>(base);
+    d.pred_syntax = base + cnt * 768;
+    d.mb_type = base + cnt * (768 + 16);
+    d.transform_size_8x8_flag = base + cnt * (768 + 17);
+    d.intra_chroma_pred_mode = base + cnt * (768 + 18);
+    d.qp = base + cnt * (768 + 19);
+    // H2D: the slot's previous kernel must have consumed its inputs
+    if (i >= 2) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->e_kernel[slot], 0));
+    CU(cudaMemcpyAsync(const_cast<int16_t*>(d.coeff), soa->coeff + mb0 * 384, cnt * 768, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.pred_syntax), soa->pred_syntax + mb0 * 16, cnt * 16, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.mb_type), soa->mb_type + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.transform_size_8x8_flag), soa->transform_size_8x8_flag + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.intra_chroma_pred_mode), soa->intra_chroma_pred_mode + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.qp), soa->qp + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(cudaEventRecord(ctx->e_h2d[slot], ctx->s_h2d));
+    // kernel: inputs landed, the slot's previous output has been copied out
+    CU(cudaStreamWaitEvent(ctx->s_compute, ctx->e_h2d[slot], 0));
+    if (i >= 2) CU(cudaStreamWaitEvent(ctx->s_compute, ctx->e_d2h[slot], 0));
+    rc = launch_wavefront(ctx, pp, &d, nf, ctx->d_out[slot], ctx->s_compute);
+    if (rc != DRYV_OK) return rc;
+    CU(cudaEventRecord(ctx->e_kernel[slot], ctx->s_compute));
+    // D2H
+    CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->e_kernel[slot], 0));
+    CU(cudaMemcpyAsync(out_yuv + (size_t)done * out_per_frame, ctx->d_out[slot], (size_t)nf * out_per_frame,
+                       cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU(cudaEventRecord(ctx->e_d2h[slot], ctx->s_d2h));
+    done += nf;
+  }
+  return DRYV_OK;
+}
+
+int dryv_recon_wait(dryv_recon_ctx* ctx) {
+  if (!ctx) return DRYV_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->s_h2d));
+  CU(cudaStreamSynchronize(ctx->s_compute));
+  CU(cudaStreamSynchronize(ctx->s_d2h));
+  if (ctx->pending_user_valid) {
+    CU(cudaStreamSynchronize(ctx->pending_user));
+    ctx->pending_user_valid = false;
+  }
+  CU(cudaMemcpy(ctx->h_status, ctx->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  const int st = *ctx->h_status;
+  if (st != dryv::STATUS_OK) {
+    CU(cudaMemset(ctx->d_ticket + 1, 0, sizeof(int)));
+    if (st == dryv::STATUS_WATCHDOG) return fail(ctx, DRYV_ERR_WATCHDOG, "wavefront watchdog fired");
+    return fail(ctx, DRYV_ERR_UNSUPPORTED, "unsupported macroblock syntax (mb_type > 24, chroma mode > 3 or qp > 51)");
+  }
+  return DRYV_OK;
+}
+
+int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char* path) {
+  if (!frame_yuv || !path || bytes == 0) return DRYV_ERR_ARG;
+  std::string p(path);
+  size_t slash = p.find_last_of('/');
+  if (slash != std::string::npos && slash > 0) {
+    std::string dir = p.substr(0, slash);
+    if (mkdir(dir.c_str(), 0777) != 0 && errno != EEXIST) return DRYV_ERR_ARG;
+  }
+  FILE* f = fopen(path, "wb");
+  if (!f) return DRYV_ERR_ARG;
+  size_t w = fwrite(frame_yuv, 1, bytes, f);
+  fclose(f);
+  return w == bytes ? DRYV_OK : DRYV_ERR_ARG;
+}
+
+uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""ctypes binding of libdryv_recon.so — the C ABI declared in include/dryv_recon.h.
+
+The shared library holds the hand-written sm_100a CUDA kernels (dryv_b200/csrc). There is no CPU
+fallback: if the library is missing or no B200 is present, construction raises.
+PyTorch is used only as the owner of device memory / streams for the device-pointer entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .abi import FIELDS, MbSoa, PicParams, SyntaxBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libdryv_recon.so")
+
+OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WATCHDOG = 0, -1, -2, -3, -4
+
+EXPORTS = [
+    "dryv_recon_abi_version", "dryv_recon_frame_bytes", "dryv_recon_create", "dryv_recon_destroy",
+    "dryv_recon_last_error", "dryv_recon_alloc_pinned", "dryv_recon_free_pinned", "dryv_recon_submit",
+    "dryv_recon_wait", "dryv_recon_reconstruct_device", "dryv_recon_residual_add_device",
+    "dryv_recon_write_yuv_file", "dryv_recon_launch_count",
+]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "recon_tables.h")] + [
+        os.path.join(_HERE, "..", "include", "dryv_recon.h")]
+    if not force and os.path.exists(LIB_PATH) and all(
+            os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB_PATH]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class ReconError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dryv_recon error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libdryv_recon.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ReconError(ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                   "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, sz = C.c_void_p, C.c_uint32, C.c_size_t
+    lib.dryv_recon_abi_version.restype = C.c_int
+    lib.dryv_recon_frame_bytes.restype = sz
+    lib.dryv_recon_frame_bytes.argtypes = [C.POINTER(PicParams)]
+    lib.dryv_recon_create.restype = C.c_int
+    lib.dryv_recon_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.dryv_recon_destroy.restype = None
+    lib.dryv_recon_destroy.argtypes = [vp]
+    lib.dryv_recon_last_error.restype = C.c_char_p
+    lib.dryv_recon_last_error.argtypes = [vp]
+    lib.dryv_recon_alloc_pinned.restype = C.c_int
+    lib.dryv_recon_alloc_pinned.argtypes = [sz, C.POINTER(vp)]
+    lib.dryv_recon_free_pinned.restype = None
+    lib.dryv_recon_free_pinned.argtypes = [vp]
+    lib.dryv_recon_submit.restype = C.c_int
+    lib.dryv_recon_submit.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, vp]
+    lib.dryv_recon_wait.restype = C.c_int
+    lib.dryv_recon_wait.argtypes = [vp]
+    lib.dryv_recon_reconstruct_device.restype = C.c_int
+    lib.dryv_recon_reconstruct_device.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, vp, vp]
+    lib.dryv_recon_residual_add_device.restype = C.c_int
+    lib.dryv_recon_residual_add_device.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, vp, vp, vp]
+    lib.dryv_recon_write_yuv_file.restype = C.c_int
+    lib.dryv_recon_write_yuv_file.argtypes = [vp, sz, C.c_char_p]
+    lib.dryv_recon_launch_count.restype = C.c_uint64
+    lib.dryv_recon_launch_count.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from dryv_recon_alloc_pinned."""
+
+    def __init__(self, shape, dtype):
+        lib = load_library()
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
+        p = C.c_void_p()
+        rc = lib.dryv_recon_alloc_pinned(nbytes, C.byref(p))
+        if rc != OK:
+            raise ReconError(rc, "pinned allocation failed")
+        self._ptr = p
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            load_library().dryv_recon_free_pinned(self._ptr)
+            self._ptr = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pinned_batch(pp: PicParams, n_frames: int):
+    """A SyntaxBatch whose arrays live in pinned memory (+ the PinnedArray owners to keep alive)."""
+    n = pp.n_mb * n_frames
+    owners = [PinnedArray(n, np.uint8), PinnedArray(n, np.uint8), PinnedArray(n, np.uint8), PinnedArray(n, np.uint8),
+              PinnedArray((n, 16), np.uint8), PinnedArray((n, 384), np.int16)]
+    b = SyntaxBatch(pp, n_frames, *[o.array for o in owners])
+    return b, owners
+
+
+class DeviceSoa:
+    """SoA syntax buffers resident in HBM (torch owns the memory)."""
+
+    def __init__(self, batch: SyntaxBatch, device="cuda:0"):
+        import torch
+        self.pp = batch.pp
+        self.n_frames = batch.n_frames
+        self.tensors = {f: torch.from_numpy(np.ascontiguousarray(getattr(batch, f))).to(device) for f in FIELDS}
+
+    def as_soa(self) -> MbSoa:
+        soa = MbSoa()
+        for f in FIELDS:
+            setattr(soa, f, self.tensors[f].data_ptr())
+        return soa
+
+    @property
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.tensors.values())
+
+
+class ReconContext:
+    """One dryv_recon_ctx (one CUDA device). Not thread-safe; create one per device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.device = device
+        h = C.c_void_p()
+        rc = self.lib.dryv_recon_create(device, C.byref(h))
+        if rc != OK:
+            raise ReconError(rc, f"dryv_recon_create(device={device}) failed: no usable sm_100 GPU "
+                                 "(this path has no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.dryv_recon_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != OK:
+            raise ReconError(rc, (self.lib.dryv_recon_last_error(self.h) or b"").decode())
+
+    # -- host-buffer path (what a decoder host calls): H2D + kernels + D2H inside --------------------
+    def submit(self, batch: SyntaxBatch, out: np.ndarray):
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= batch.n_frames * batch.pp.frame_bytes
+        soa = batch.as_soa()
+        self._keep = (batch, soa, out)
+        self._check(self.lib.dryv_recon_submit(self.h, C.byref(batch.pp), C.byref(soa), batch.n_frames,
+                                               out.ctypes.data))
+
+    def wait(self):
+        self._check(self.lib.dryv_recon_wait(self.h))
+
+    def reconstruct(self, batch: SyntaxBatch, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((batch.n_frames, batch.pp.frame_bytes), np.uint8)
+        self.submit(batch, out)
+        self.wait()
+        return out
+
+    # -- device-pointer path ------------------------------------------------------------------------
+    def reconstruct_device(self, dsoa: DeviceSoa, d_out, stream_ptr: int = 0):
+        soa = dsoa.as_soa()
+        self._check(self.lib.dryv_recon_reconstruct_device(self.h, C.byref(dsoa.pp), C.byref(soa), dsoa.n_frames,
+                                                           d_out.data_ptr(), stream_ptr or None))
+
+    def residual_add_device(self, dsoa: DeviceSoa, d_pred, d_out, stream_ptr: int = 0):
+        soa = dsoa.as_soa()
+        self._check(self.lib.dryv_recon_residual_add_device(self.h, C.byref(dsoa.pp), C.byref(soa), dsoa.n_frames,
+                                                            d_pred.data_ptr(), d_out.data_ptr(), stream_ptr or None))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.dryv_recon_launch_count(self.h))
+
+
+def write_yuv_file(frame: np.ndarray, path: str):
+    """Frame::write_to_yuv_file (reference src/video/frame/mod.rs:48-70) for one reconstructed picture."""
+    lib = load_library()
+    frame = np.ascontiguousarray(frame, np.uint8)
+    rc = lib.dryv_recon_write_yuv_file(frame.ctypes.data, frame.nbytes, path.encode())
+    if rc != OK:
+        raise OSError(f"cannot write {path}")

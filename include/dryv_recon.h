@@ -1,0 +1,147 @@
+/*
+ * dryv_recon.h — C ABI of the B200 (sm_100a) AVC intra macroblock reconstruction path.
+ *
+ * This library replaces ONE path of the dryv H.264 decoder (reference = Stuff7/dryv, Rust):
+ * everything under src/video/frame/ — inverse quantisation, the 4x4/8x8 inverse integer transforms,
+ * Intra4x4/8x8/16x16/chroma prediction, residual add + clip, picture construction and the planar YUV
+ * frame the decoder writes to ./temp/yuv_frame.
+ *
+ * The reference has no FFI; the seam is three Rust call sites (file:line relative to the reference):
+ *   Frame::new(&slice)                       src/video/decoder.rs:124   (frame/mod.rs:29-46)
+ *   frame.decode(slice)   once per MB        src/video/cabac/mod.rs:208 (frame/mod.rs:72-90)
+ *   frame.write_to_yuv_file("temp/yuv_frame") src/video/decoder.rs:141-143 (frame/mod.rs:48-70)
+ * A host that keeps CABAC/slice/atom parsing on the CPU appends each macroblock's parsed syntax to the
+ * structure-of-arrays buffers below (instead of calling Frame::decode), then calls dryv_recon_submit
+ * once per batch of independent IDR pictures. INTEGRATION.md shows the Rust binding.
+ *
+ * No CPU fallback exists behind this ABI: every entry point that reconstructs runs CUDA kernels and
+ * fails with DRYV_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef DRYV_RECON_H
+#define DRYV_RECON_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRYV_RECON_ABI_VERSION 1
+
+/* Return codes (the reference's hot path returns () and panics/todo!()s on unsupported input:
+ * frame/mod.rs:85-88, pred8x8.rs:693-695; here nothing aborts across the ABI). */
+enum {
+  DRYV_OK = 0,
+  DRYV_ERR_ARG = -1,         /* null pointer, zero size, geometry out of range */
+  DRYV_ERR_UNSUPPORTED = -2, /* mb_type > 24 (I_PCM / inter), chroma mode > 3 ... */
+  DRYV_ERR_CUDA = -3,        /* CUDA runtime error, no device */
+  DRYV_ERR_WATCHDOG = -4     /* wavefront spin exceeded its bound (never expected) */
+};
+
+/* Coefficients per macroblock: 16 luma 4x4 blocks (or 4 luma 8x8 blocks) + 4 Cb + 4 Cr blocks of 16. */
+#define DRYV_COEFFS_PER_MB 384
+#define DRYV_MB_TYPE_I_NXN 0  /* slice/consts.rs:8  */
+#define DRYV_MB_TYPE_I_PCM 25 /* rejected */
+
+/* Per-batch picture parameters: every picture of a batch shares them.
+ * Sources in the reference: pic_width_in_mbs / pic_height_in_mbs  slice/mod.rs:125-138;
+ * chroma_qp_index_offset / second_chroma_qp_index_offset  atom/avcc/pps.rs:22,65 (the second one
+ * equals the first when the PPS has no extension, frame/transform.rs:194-204);
+ * scaling_list4x4[0] / scaling_list8x8[0]  slice/header.rs:317-332 (flat 16 when no matrix).
+ * Only list 0 (Intra-Y) is consumed: chroma re-uses the luma LevelScale4x4 in the reference
+ * (trans_chroma.rs never calls Frame::scaling) and so does this library.
+ * 8-bit 4:2:0, frame macroblocks, one slice per picture (first_mb_in_slice == 0). */
+typedef struct dryv_pic_params {
+  uint16_t pic_width_in_mbs;             /* 1..1024 */
+  uint16_t pic_height_in_mbs;            /* 1..1024 */
+  int8_t chroma_qp_index_offset;         /* -12..12 (Cb) */
+  int8_t second_chroma_qp_index_offset;  /* -12..12 (Cr) */
+  uint8_t reserved0[2];
+  uint32_t flags;                        /* must be 0 */
+  uint8_t scaling_list4x4[16];           /* zig-zag order, list 0 */
+  uint8_t scaling_list8x8[64];           /* zig-zag order, list 0 */
+} dryv_pic_params;
+
+/* Per-macroblock syntax, structure of arrays, macroblock raster order (= mbaddr) inside a picture,
+ * picture f at element offset f * n_mb where n_mb = pic_width_in_mbs * pic_height_in_mbs.
+ * Field sources: struct Macroblock, slice/macroblock.rs:21-129.
+ *
+ *  mb_type      dryv/H.264 I-slice code: 0 = I_NxN, 1..24 = I_16x16_<pred>_<cbpC>_<cbpL>
+ *               (slice/consts.rs:8-113; pred16 = (code-1)%4, slice/macroblock.rs:682-716)
+ *  transform_size_8x8_flag   0/1; with mb_type 0 selects Intra4x4 vs Intra8x8
+ *  intra_chroma_pred_mode    0 DC, 1 Horizontal, 2 Vertical, 3 Plane
+ *  qp           QP'Y = qp1y (cabac/mod.rs:186-191), 0..51
+ *  pred_syntax  [16] per MB: bit 3 = prev_intra{4x4,8x8}_pred_mode_flag, bits 0..2 =
+ *               rem_intra{4x4,8x8}_pred_mode; Intra8x8 uses entries 0..3; ignored for Intra16x16
+ *  coeff        [24][16] int16 per MB, every block in coefficient (zig-zag) order as CABAC stores it:
+ *                 Intra4x4 : block b (0..15, spec 4x4 block order) = block_luma_4x4[0][b][0..16]
+ *                 Intra8x8 : the 256 luma slots = block_luma_8x8[0][b8][0..64], b8 = 0..3
+ *                 Intra16x16: slot [b][0] = block_luma_dc[0][b] (the b-th entry of the DC list),
+ *                             slots [b][1..16] = block_luma_ac[0][b][0..15]
+ *                 chroma   : block 16+b (Cb) / 20+b (Cr), b = 0..3: slot [0] = block_chroma_dc[iCbCr][b],
+ *                             slots [1..16] = block_chroma_ac[iCbCr][b][0..15]
+ *               768 bytes per MB, 16-byte aligned.
+ * Reconstruction never reads coded_block_pattern: absent blocks are all-zero arrays (cabac/mod.rs:669-673).
+ */
+typedef struct dryv_mb_soa {
+  const uint8_t* mb_type;
+  const uint8_t* transform_size_8x8_flag;
+  const uint8_t* intra_chroma_pred_mode;
+  const uint8_t* qp;
+  const uint8_t* pred_syntax; /* 16 bytes per MB */
+  const int16_t* coeff;       /* DRYV_COEFFS_PER_MB int16 per MB */
+} dryv_mb_soa;
+
+/* Bytes of one reconstructed picture: Y (W*H) then Cb (W/2*H/2) then Cr, row-major, macroblock
+ * aligned, no cropping — byte-identical to what Frame::write_to_yuv_file emits (frame/mod.rs:48-70). */
+size_t dryv_recon_frame_bytes(const dryv_pic_params* pp);
+
+typedef struct dryv_recon_ctx dryv_recon_ctx;
+
+int dryv_recon_abi_version(void);
+
+/* One context per CUDA device (owns device buffers, streams, wavefront progress counters).
+ * Not thread-safe: one submitting thread per context; distinct contexts are independent. */
+int dryv_recon_create(int device, dryv_recon_ctx** out);
+void dryv_recon_destroy(dryv_recon_ctx* ctx);
+const char* dryv_recon_last_error(dryv_recon_ctx* ctx);
+
+/* Pinned (page-locked) host memory for the SoA buffers and the output frames. */
+int dryv_recon_alloc_pinned(size_t bytes, void** out);
+void dryv_recon_free_pinned(void* p);
+
+/* Replaces Frame::new + n_mb x Frame::decode (+ the planes write_to_yuv_file serialises) for
+ * n_frames independent IDR pictures. HOST pointers in `soa` / `out_yuv` (pinned for full speed).
+ * Asynchronous on the context's streams: H2D copy, kernels, D2H copy are pipelined in chunks of
+ * pictures; call dryv_recon_wait before reading out_yuv or reusing the inputs. */
+int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa,
+                      uint32_t n_frames, uint8_t* out_yuv);
+int dryv_recon_wait(dryv_recon_ctx* ctx);
+
+/* Same computation with DEVICE pointers (inputs already resident in HBM, output left in HBM),
+ * enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream). Completion and
+ * device-side status are collected by dryv_recon_wait (which synchronises that stream). */
+int dryv_recon_reconstruct_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp,
+                                  const dryv_mb_soa* d_soa, uint32_t n_frames, uint8_t* d_out_yuv,
+                                  void* cuda_stream);
+
+/* BASELINE config "dequant + 4x4/8x8 IDCT + residual add only": no intra prediction, no wavefront.
+ * out = clip(pred + residual) where `d_pred_yuv` is a caller-supplied prediction picture in the output
+ * layout. Covers frame/transform.rs:116-191, pred8x8.rs:51-150, pred16x16.rs:428-482,
+ * trans_chroma.rs:369-456 and the clip/picture-construction of frame/mod.rs:93-165. DEVICE pointers. */
+int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp,
+                                   const dryv_mb_soa* d_soa, uint32_t n_frames,
+                                   const uint8_t* d_pred_yuv, uint8_t* d_out_yuv, void* cuda_stream);
+
+/* Frame::write_to_yuv_file (frame/mod.rs:48-70): writes one reconstructed picture (host memory, the
+ * layout above) to `path`, creating the parent directory of "temp/yuv_frame"-style paths if needed. */
+int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char* path);
+
+/* Number of kernel launches issued by this context so far (bench bookkeeping). */
+uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRYV_RECON_H */

@@ -1,0 +1,6 @@
+"""CPU oracle of dryv's reconstruction path — TEST INFRASTRUCTURE ONLY (see dryv_oracle.c header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+PARITY UNPINNED by the reference (no tests/fixtures there; Rust toolchain absent here).
+"""
+from .oracle import *  # noqa: F401,F403

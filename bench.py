@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — IDR reconstruct Mpixels/s on N B200s (one process per GPU, frame-sharded, no collective).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on for one GPU): 1080p
+(120x68 MB) full intra reconstruction, mixed Intra4x4/8x8/16x16 + chroma, batch of 64 IDR pictures per
+GPU, seeded synthetic spec-legal syntax buffers (dryv_b200/synth). Weak scaling: every rank gets its
+own 64 pictures.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # CPU path (oracle port of the Rust reference) on host cores
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+_ROOT = os.path.dirname(os.path.abspath(__file__))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "idr_reconstruct_mpixels_per_s"
+UNIT = "Mpixels/s"
+BYTES_PER_MB_FULL = 1172   # 768 levels + 20 syntax + 384 pixels out (SURVEY.md §8d / BASELINE.md §3)
+BYTES_PER_MB_RESID = 1540  # 768 + 4 + 384 prediction in + 384 out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="IDR pictures per GPU per step")
+    ap.add_argument("--width-mbs", type=int, default=120)
+    ap.add_argument("--height-mbs", type=int, default=68)
+    ap.add_argument("--qp", type=int, default=26)
+    ap.add_argument("--seed", type=int, default=3000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the residual-only (configs[1]) side measurement")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = os.path.join(_ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def workload_name(args):
+    return (f"{args.width_mbs * 16}x{args.height_mbs * 16} full intra reconstruct (mixed Intra4x4/8x8/16x16 + chroma, "
+            f"MB wavefront), batch of {args.frames} IDR frames per GPU (BASELINE.json configs[2])")
+
+
+def config_dict(args, n_gpus):
+    return {
+        "workload": workload_name(args),
+        "pic_width_in_mbs": args.width_mbs, "pic_height_in_mbs": args.height_mbs,
+        "frames_per_gpu": args.frames, "qp_base": args.qp, "seed": args.seed,
+        "mb_mix": "40% Intra4x4 / 25% Intra8x8 / 35% Intra16x16, 10% stress MBs",
+        "sharding": f"frames x{n_gpus} (independent IDR pictures per GPU, no collective)",
+        "l2": "per-step working set (levels+syntax in, pictures out) is larger than the 126 MB L2, no flush needed",
+    }
+
+
+def cpu_oracle_run(batch, threads):
+    import oracle
+    t0 = time.perf_counter()
+    oracle.reconstruct(batch, threads=threads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path. dryv is Rust and cannot be built in
+    this image (no cargo/rustc), so this times the C oracle port (oracle/) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from dryv_b200 import synth
+    from dryv_b200.abi import PicParams
+    cores = os.cpu_count() or 1
+    pp = PicParams.make(args.width_mbs, args.height_mbs)
+    n = args.frames if cores >= 8 else max(1, min(args.frames, 2 * cores))
+    batch = synth.generate(pp, n, args.seed, qp_base=args.qp)
+    for _ in range(args.warmup):
+        cpu_oracle_run(batch, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_oracle_run(batch, cores)
+    per_step = t / max(1, args.steps)
+    value = n * pp.luma_pixels / per_step / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "i64 (oracle port, isize in the reference)",
+        "data": "synthetic", "config": config_dict(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} of {args.frames} pictures per step, one picture per host thread, "
+                                   f"{cores} threads (C oracle port of dryv's Rust frame/ path; the Rust reference "
+                                   "itself cannot be built here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from dryv_b200 import recon, synth
+    from dryv_b200.abi import PicParams
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the reconstruction path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pp = PicParams.make(args.width_mbs, args.height_mbs)
+    n_frames = args.frames
+    # pinned host buffers (the e2e path copies from these every step)
+    hbatch, owners = recon.pinned_batch(pp, n_frames)
+    synth.generate(pp, n_frames, args.seed + rank * n_frames, qp_base=args.qp, out=hbatch)
+    hout = recon.PinnedArray((n_frames, pp.frame_bytes), np.uint8)
+
+    ctx = recon.ReconContext(local_rank)
+    dsoa = recon.DeviceSoa(hbatch, device=dev)
+    d_out = torch.zeros((n_frames, pp.frame_bytes), dtype=torch.uint8, device=dev)
+    # a dedicated (non-default) torch stream: kernels are launched on it through the C ABI and the
+    # torch.cuda.Event pair below is recorded on the same stream
+    stream = torch.cuda.Stream(dev)
+    sptr = stream.cuda_stream
+    assert sptr != 0
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        ctx.reconstruct_device(dsoa, d_out, sptr)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    ctx.wait()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ctx.wait()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+
+    # ---- e2e through the host-buffer C ABI call: pinned H2D + kernels + D2H inside the timed region
+    e2e_ms = None
+    if not args.no_e2e:
+        for _ in range(2):
+            ctx.submit(hbatch, hout.array)
+            ctx.wait()
+        barrier()
+        tot = 0.0
+        for _ in range(args.steps):
+            ctx.submit(hbatch, hout.array)
+            ctx.wait()
+            tot += ctx.last_submit_ms
+        barrier()
+        e2e_ms = tot / args.steps
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_total, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_max = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    total_px = world * n_frames * pp.luma_pixels
+    value = total_px / (ms_per_step * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # parity spot check outside the timed region: first picture against the oracle
+    import oracle
+    got0 = d_out[0].cpu().numpy()
+    ref0 = oracle.reconstruct(hbatch.frames(0, 1))[0]
+    parity = bool(np.array_equal(got0, ref0))
+
+    peak, peak_src = measured_peak_gbs()
+    n_mb_step = n_frames * pp.n_mb
+    kernel_s = ms_per_step * 1e-3  # one wavefront kernel (+ two tiny memsets) per step on the timed stream
+    achieved = n_mb_step * BYTES_PER_MB_FULL / kernel_s / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32 (int16 levels -> int32 arithmetic -> u8 pixels)", "data": "synthetic",
+        "config": config_dict(args, world),
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "parity_vs_oracle_first_picture": parity,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "dryv::recon_wavefront_kernel",
+                     "algorithmic_bytes_per_mb": BYTES_PER_MB_FULL, "mbs_per_launch": n_mb_step},
+    }
+    if e2e_ms is not None:
+        line["e2e"] = {"value": total_px / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
+                       "h2d_bytes_per_step": int(hbatch.input_bytes), "d2h_bytes_per_step": int(hout.array.nbytes),
+                       "ms_per_step": e2e_ms_max,
+                       "how": "dryv_recon_submit + dryv_recon_wait on pinned host buffers, CUDA-event timed"}
+
+    if not args.no_extra:
+        # side measurement, BASELINE.json configs[1]: dequant + IDCT + residual add only
+        g = torch.Generator(device="cpu").manual_seed(1080)
+        d_pred = torch.randint(0, 256, d_out.shape, dtype=torch.uint8, generator=g).to(dev)
+        for _ in range(3):
+            ctx.residual_add_device(dsoa, d_pred, d_out, sptr)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a0.record(stream)
+        for _ in range(args.steps):
+            ctx.residual_add_device(dsoa, d_pred, d_out, sptr)
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        ctx.wait()
+        rms = a0.elapsed_time(a1) / args.steps
+        rach = n_mb_step * BYTES_PER_MB_RESID / (rms * 1e-3) / 1e9
+        line["residual_only"] = {"workload": "dequant + 4x4/8x8 IDCT + residual add only (BASELINE.json configs[1] "
+                                             f"kernel, same {n_frames}-picture buffers so it streams from HBM)",
+                                 "value": n_frames * pp.luma_pixels / (rms * 1e-3) / 1e6, "unit": UNIT,
+                                 "ms_per_step": rms,
+                                 "roofline": {"bound": "hbm", "achieved": rach, "peak": peak, "unit": "GB/s",
+                                              "frac": rach / peak, "algorithmic_bytes_per_mb": BYTES_PER_MB_RESID}}
+
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = n_frames if cores >= 8 else max(1, min(n_frames, 2 * cores))
+        sample = hbatch.frames(0, n)
+        cpu_oracle_run(sample.frames(0, min(n, cores)), cores)  # warm
+        reps = 3
+        best = min(cpu_oracle_run(sample, cores) for _ in range(reps))
+        one = cpu_oracle_run(sample.frames(0, min(4, n)), 1)
+        line["cpu_baseline"] = {
+            "value": n * pp.luma_pixels / best / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "single_thread_value": min(4, n) * pp.luma_pixels / one / 1e6,
+            "sample": f"{n} of the {n_frames} pictures of rank 0's batch, best of {reps}, one picture per host thread "
+                      f"({cores} threads); C oracle port of dryv's Rust frame/ path (the Rust binary cannot be built here)"}
+
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -107,10 +107,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(cons
     }
     // per-lane store address pieces
     uint8_t* st_base;
-    int st_stride;
-    if (lane < 16) { st_base = Y + (size_t)(16 * row + lane) * strideY; st_stride = 16; }
-    else if (lane < 24) { st_base = Cb + (size_t)(8 * row + (lane - 16)) * strideC; st_stride = 8; }
-    else { st_base = Cr + (size_t)(8 * row + (lane - 24)) * strideC; st_stride = 8; }
+    if (lane < 16) { st_base = Y + (size_t)(16 * row + lane) * strideY; }
+    else if (lane < 24) { st_base = Cb + (size_t)(8 * row + (lane - 16)) * strideC; }
+    else { st_base = Cr + (size_t)(8 * row + (lane - 24)) * strideC; }
 
     // prefetch macroblock 0
     uint32_t hdr_n = load_header_lane(a, lane, mb_row0);
@@ -292,6 +291,8 @@ struct dryv_recon_ctx {
   int wave_ctas_per_sm = 0, resid_ctas_per_sm = 0;
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_kernel[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t e_sub_begin = nullptr, e_sub_end = nullptr;
+  bool sub_timed = false;
   // tables
   DeviceTables* d_tables = nullptr;
   DeviceTables* h_tables = nullptr;  // pinned
@@ -450,6 +451,7 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
     ok = cudaEventCreateWithFlags(&ctx->e_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->e_kernel[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->e_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->e_sub_begin) == cudaSuccess && cudaEventCreate(&ctx->e_sub_end) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_tables, sizeof(DeviceTables)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_tables, sizeof(DeviceTables)) == cudaSuccess &&
        cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)) == cudaSuccess &&
@@ -478,6 +480,8 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
     if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
     if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
   }
+  if (ctx->e_sub_begin) cudaEventDestroy(ctx->e_sub_begin);
+  if (ctx->e_sub_end) cudaEventDestroy(ctx->e_sub_end);
   if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -575,6 +579,8 @@ int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv
     ctx->out_cap = need_out;
   }
   uint32_t done = 0;
+  ctx->sub_timed = false;
+  CU(cudaEventRecord(ctx->e_sub_begin, ctx->s_h2d));
   for (uint32_t i = 0; done < n_frames; i++) {
     const int slot = (int)(i & 1);
     const uint32_t nf = (n_frames - done) < chunk ? (n_frames - done) : chunk;
@@ -609,7 +615,16 @@ int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv
     CU(cudaEventRecord(ctx->e_d2h[slot], ctx->s_d2h));
     done += nf;
   }
+  CU(cudaEventRecord(ctx->e_sub_end, ctx->s_d2h));
+  ctx->sub_timed = true;
   return DRYV_OK;
+}
+
+double dryv_recon_last_submit_ms(dryv_recon_ctx* ctx) {
+  if (!ctx || !ctx->sub_timed) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->e_sub_begin, ctx->e_sub_end) != cudaSuccess) return -1.0;
+  return (double)ms;
 }
 
 int dryv_recon_wait(dryv_recon_ctx* ctx) {

@@ -24,7 +24,7 @@ EXPORTS = [
     "dryv_recon_abi_version", "dryv_recon_frame_bytes", "dryv_recon_create", "dryv_recon_destroy",
     "dryv_recon_last_error", "dryv_recon_alloc_pinned", "dryv_recon_free_pinned", "dryv_recon_submit",
     "dryv_recon_wait", "dryv_recon_reconstruct_device", "dryv_recon_residual_add_device",
-    "dryv_recon_write_yuv_file", "dryv_recon_launch_count",
+    "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -87,6 +87,8 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_residual_add_device.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, vp, vp, vp]
     lib.dryv_recon_write_yuv_file.restype = C.c_int
     lib.dryv_recon_write_yuv_file.argtypes = [vp, sz, C.c_char_p]
+    lib.dryv_recon_last_submit_ms.restype = C.c_double
+    lib.dryv_recon_last_submit_ms.argtypes = [vp]
     lib.dryv_recon_launch_count.restype = C.c_uint64
     lib.dryv_recon_launch_count.argtypes = [vp]
     _lib = lib
@@ -207,6 +209,10 @@ class ReconContext:
         soa = dsoa.as_soa()
         self._check(self.lib.dryv_recon_residual_add_device(self.h, C.byref(dsoa.pp), C.byref(soa), dsoa.n_frames,
                                                             d_pred.data_ptr(), d_out.data_ptr(), stream_ptr or None))
+
+    @property
+    def last_submit_ms(self) -> float:
+        return float(self.lib.dryv_recon_last_submit_ms(self.h))
 
     @property
     def launch_count(self) -> int:

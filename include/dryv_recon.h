@@ -138,6 +138,10 @@ int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* p
  * layout above) to `path`, creating the parent directory of "temp/yuv_frame"-style paths if needed. */
 int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char* path);
 
+/* Device-measured duration (CUDA events: first H2D enqueue -> last D2H complete) of the most recent
+ * dryv_recon_submit, in milliseconds; valid after dryv_recon_wait. Returns < 0 if unavailable. */
+double dryv_recon_last_submit_ms(dryv_recon_ctx* ctx);
+
 /* Number of kernel launches issued by this context so far (bench bookkeeping). */
 uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx);
 

@@ -49,6 +49,13 @@ __device__ __forceinline__ MbHeader decode_header(uint32_t hdr_lane, int* status
 
 // ------------------------------------------------------------------------------------------------
 // Full reconstruction: persistent row walkers over an x+2y macroblock wavefront.
+//
+// Row-to-row hand-off: the walker of row y never reads the picture. After finishing MB x it writes
+// that MB's bottom line (kLineWords 64-bit words = payload | launch tag) to the line buffer; the
+// walker of row y+1 needs line x+1 before it can predict MB x (top-right neighbour), fetches it with
+// one relaxed 64-bit load per lane issued BEFORE its residual stage, and only checks the tags after
+// the residual stage and the mode derivation, so the L2 round trip hides behind independent work.
+// Picture stores are fire-and-forget (nobody on the GPU reads them back).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(const KernelArgs a) {
   __shared__ alignas(16) CtaSmem cs;
@@ -66,10 +73,31 @@ __global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(cons
   const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
   const size_t n_mb = (size_t)W * H;
   const int strideY = W * 16, strideC = W * 8;
+  const uint32_t tag = a.tag;
   // raster-grid cell of this lane and the pred_syntax entry that covers it
   const int g = lane & 15, gx = g & 3, gy = g >> 2;
   const int syn_idx4 = 8 * (gy >> 1) + 4 * (gx >> 1) + 2 * (gy & 1) + (gx & 1);  // spec 4x4 block index of the cell
   const int syn_src8 = ((gy >> 1) ? 4 : 0) + (gx >> 1);  // lane that loaded pred_syntax[blk8] (cells 0,1,4,5)
+
+  // Top-row slots of the pixel tiles. Luma row -1 holds 9 words: [x-1].w3 | [x].w0..3 | [x+1].w0..3 at byte
+  // 12 + 4k; each chroma row -1 holds 5 words: [x-1].w1 | [x].w0..1 | [x+1].w0..1 at byte 4 + 4k.
+  // line word of this lane (lanes 0..8): 0..3 luma, 4..5 Cb, 6..7 Cr, 8 modes
+  uint8_t* fresh_dst = nullptr;   // where this lane's freshly fetched word of line x+1 goes
+  const uint8_t* pub_src = nullptr;  // where this lane's word of the line it publishes comes from
+  if (lane < 4) {
+    fresh_dst = &ws.luma[12 + 4 * (5 + lane)];
+    pub_src = &ws.luma[luma_at(4 * lane, 15)];
+  } else if (lane < 8) {
+    const int pl = (lane - 4) >> 1, k = (lane - 4) & 1;
+    fresh_dst = &ws.chroma[pl][4 + 4 * (3 + k)];
+    pub_src = &ws.chroma[pl][chroma_at(4 * k, 7)];
+  }
+  // shift of the top-row slots when the walker advances one macroblock: lanes 0..4 luma, 8..10 Cb, 12..14 Cr
+  uint8_t* shift_dst = nullptr;
+  int shift_by = 0;
+  if (lane < 5) { shift_dst = &ws.luma[12 + 4 * lane]; shift_by = 16; }
+  else if (lane >= 8 && lane < 11) { shift_dst = &ws.chroma[0][4 + 4 * (lane - 8)]; shift_by = 8; }
+  else if (lane >= 12 && lane < 15) { shift_dst = &ws.chroma[1][4 + 4 * (lane - 12)]; shift_by = 8; }
 
   int local_status = STATUS_OK;
   for (;;) {
@@ -83,28 +111,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(cons
     uint8_t* const Y = a.out + (size_t)frame * n_mb * 384;
     uint8_t* const Cb = Y + n_mb * 256;
     uint8_t* const Cr = Cb + n_mb * 64;
-    const int* const prog_above = a.progress + (size_t)frame * H + row - 1;
-    int* const prog_mine = a.progress + (size_t)frame * H + row;
-    const bool availB = row > 0;
+    const bool availB = row > 0, publish = row + 1 < H;
+    const unsigned long long* const line_above = a.line + (mb_row0 - W) * kLineWords + lane;  // valid if availB, lane < 9
+    unsigned long long* const line_mine = a.line + mb_row0 * kLineWords + lane;
 
-    // per-lane pieces of the top-strip fetch: lanes 0..6 luma words, 8..10 Cb, 12..14 Cr, 16 mode word
-    const uint8_t* strip_base = nullptr;
-    int strip_w = 0, strip_dst = 0;
-    if (availB) {
-      if (lane < 7) {
-        strip_base = Y + (size_t)(16 * row - 1) * strideY;
-        strip_w = lane;
-        strip_dst = 12 + 4 * lane;  // luma tile row 0, x = -4 + 4*lane
-      } else if (lane >= 8 && lane < 11) {
-        strip_base = Cb + (size_t)(8 * row - 1) * strideC;
-        strip_w = lane - 8;
-        strip_dst = 4 + 4 * (lane - 8);
-      } else if (lane >= 12 && lane < 15) {
-        strip_base = Cr + (size_t)(8 * row - 1) * strideC;
-        strip_w = lane - 12;
-        strip_dst = 4 + 4 * (lane - 12);
-      }
-    }
     // per-lane store address pieces
     uint8_t* st_base;
     if (lane < 16) { st_base = Y + (size_t)(16 * row + lane) * strideY; }
@@ -120,12 +130,52 @@ __global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(cons
       c0_n = __ldg(cp);
       c1_n = __ldg(cp + 1);
     }
-    int seen = 0;   // last observed progress of the row above
-    int a_col = 2;  // resolved mode of the cell left of grid column 0 (previous MB of this row)
+    int a_col = 2;          // resolved mode of the cell left of grid column 0 (previous MB of this row)
+    uint32_t mw_cur = 0x02020202u;  // bottom-row modes of the MB above the current one
+
+    // Waits for line `xl` of the row above (all kLineWords tags), returns this lane's payload.
+    // `long_wait`: the row above may not even have started (row start): back off in microseconds.
+    auto wait_line = [&](int xl, unsigned long long first, bool long_wait, bool& dead) -> uint32_t {
+      unsigned long long v = first;
+      unsigned spins = 0;
+      while (!__all_sync(0xffffffffu, lane >= kLineWords || (uint32_t)(v >> 32) == tag)) {
+        ++spins;
+        if (long_wait) __nanosleep(spins < 4u ? 200u : 2000u);
+        else if (spins > 2u) __nanosleep(spins > 64u ? 1000u : 100u);
+        if ((spins & 0x3ffu) == 0u) {
+          if (spins > (1u << 22) || ld_relaxed_gpu_s32(a.status) == STATUS_WATCHDOG) {
+            if (lane == 0) atomicExch(a.status, STATUS_WATCHDOG);
+            dead = true;
+            return 0u;
+          }
+        }
+        if (lane < kLineWords) v = ld_relaxed_gpu_u64(line_above + (size_t)xl * kLineWords);
+      }
+      return (uint32_t)v;
+    };
+
+    bool dead = false;
+    if (availB) {
+      // row start: line 0 of the row above becomes "line x" of macroblock 0
+      unsigned long long v0 = 0;
+      if (lane < kLineWords) v0 = ld_relaxed_gpu_u64(line_above);
+      const uint32_t w = wait_line(0, v0, true, dead);
+      if (dead) break;
+      if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+      mw_cur = __shfl_sync(0xffffffffu, w, 8);
+      __syncwarp();
+      uint32_t sv = 0;
+      if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + shift_by);
+      __syncwarp();
+      if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
+    }
 
     for (int x = 0; x < W; x++) {
       const uint32_t hdr_c = hdr_n, syn_c = syn_n;
       const uint4 c0 = c0_n, c1 = c1_n;
+      const bool need_line = availB && x + 1 < W;
+      unsigned long long lv = 0;
+      if (need_line && lane < kLineWords) lv = ld_relaxed_gpu_u64(line_above + (size_t)(x + 1) * kLineWords);
       if (x + 1 < W) {
         const size_t mbn = mb_row0 + x + 1;
         hdr_n = load_header_lane(a, lane, mbn);
@@ -141,80 +191,60 @@ __global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(cons
       // 1. residual (independent of every other macroblock)
       residual_stage(cs, ws, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
 
-      // 2. wavefront wait: the row above must have finished MB min(x+1, W-1)
+      // 2. prediction modes: need only the modes of the MB above (line x, already here) and of the previous MB
       const bool availA = x > 0, availC = availB && x < W - 1, availD = availA && availB;
-      int b_row = 2;
-      if (availB) {
-        const int need = min(x + 2, W);
-        if (seen < need) {
-          unsigned spins = 0;
-          while ((seen = ld_acquire_gpu(prog_above)) < need) {
-            if (++spins > 16u) __nanosleep(spins > 256u ? 400u : 40u);
-            if ((spins & 0xfffu) == 0u) {
-              if (spins > (1u << 24) || ld_acquire_gpu(a.status) == STATUS_WATCHDOG) {
-                local_status = STATUS_WATCHDOG;
-                atomicExch(a.status, STATUS_WATCHDOG);
-                return;
-              }
-            }
-          }
-        }
-        // 3a. top strip (28 luma + 2 x 12 chroma bytes) and the bottom-row modes of the MB above
-        uint32_t wv = 0;
-        bool have = false;
-        if (strip_base) {
-          const int col = (lane < 7 ? 16 : 8) * x - 4 + 4 * strip_w;
-          const int lim = lane < 7 ? strideY : strideC;
-          have = col >= 0 && col < lim;
-          if (have) wv = ld_relaxed_gpu_u32(strip_base + col);
-        }
-        uint32_t mw = 0;
-        if (lane == 16) mw = ld_relaxed_gpu_u32(a.mode_line + mb_row0 - W + x);
-        if (have) {
-          if (lane < 7) *reinterpret_cast<uint32_t*>(&ws.luma[strip_dst]) = wv;
-          else *reinterpret_cast<uint32_t*>(&ws.chroma[lane >= 12 ? 1 : 0][strip_dst]) = wv;
-        }
-        mw = __shfl_sync(0xffffffffu, mw, 16);
-        b_row = (mw >> (8 * gx)) & 0xff;
-        __syncwarp();
-      }
-
-      // 3b. prediction modes
+      const int b_row = (mw_cur >> (8 * gx)) & 0xff;
       int syn = (int)syn_c;
       if (h.mbcls == 1) syn = __shfl_sync(0xffffffffu, syn, syn_src8);
       const int m = resolve_modes(lane, h.mbcls, syn, a_col, b_row, availA, availB);
 
-      // 3c. prediction + residual + clip into the pixel tiles
+      // 3. wavefront wait: line x+1 of the row above (top-right neighbour), fetched before the residual stage
+      uint32_t mw_next = 0x02020202u;
+      if (need_line) {
+        const uint32_t w = wait_line(x + 1, lv, false, dead);
+        if (dead) break;
+        if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+        mw_next = __shfl_sync(0xffffffffu, w, 8);
+        __syncwarp();
+      }
+
+      // 4. prediction + residual + clip into the pixel tiles
       if (h.mbcls == 0) predict_i4x4(cs, ws, lane, m, availA, availB, availC, availD);
       else if (h.mbcls == 1) predict_i8x8(cs, ws, lane, m, availA, availB, availC, availD);
       else predict_i16x16(ws, lane, (h.mbt - 1) & 3, availA, availB);
       predict_chroma(ws, lane, h.cm, availA, availB, availD);
 
-      // 4. store the macroblock (16 x 16 B luma rows, 2 x 8 x 8 B chroma rows), publish modes + progress
+      // 5. store the macroblock (16 x 16 B luma rows, 2 x 8 x 8 B chroma rows) and publish its bottom line
       if (lane < 16) {
         const uint4 v = *reinterpret_cast<const uint4*>(&ws.luma[luma_at(0, lane)]);
-        *reinterpret_cast<uint4*>(st_base + (size_t)x * 16) = v;
+        __stcs(reinterpret_cast<uint4*>(st_base + (size_t)x * 16), v);
       } else {
         const uint2 v = *reinterpret_cast<const uint2*>(&ws.chroma[lane >= 24 ? 1 : 0][chroma_at(0, lane & 7)]);
-        *reinterpret_cast<uint2*>(st_base + (size_t)x * 8) = v;
+        __stcs(reinterpret_cast<uint2*>(st_base + (size_t)x * 8), v);
       }
-      {
-        uint32_t mv = (lane >= 12 && lane < 16) ? ((uint32_t)m << (8 * (lane & 3))) : 0u;
-        mv |= __shfl_xor_sync(0xffffffffu, mv, 1);
-        mv |= __shfl_xor_sync(0xffffffffu, mv, 2);
-        if (lane == 12) a.mode_line[mb_row0 + x] = mv;
+      uint32_t mv = (lane >= 12 && lane < 16) ? ((uint32_t)m << (8 * (lane & 3))) : 0u;
+      mv |= __shfl_xor_sync(0xffffffffu, mv, 1);
+      mv |= __shfl_xor_sync(0xffffffffu, mv, 2);
+      mv = __shfl_sync(0xffffffffu, mv, 12);
+      if (publish && lane < kLineWords) {
+        const uint32_t payload = pub_src ? *reinterpret_cast<const uint32_t*>(pub_src) : mv;
+        st_relaxed_gpu_u64(line_mine + (size_t)x * kLineWords, ((unsigned long long)tag << 32) | payload);
       }
       a_col = __shfl_sync(0xffffffffu, m, gy * 4 + 3);
+      mw_cur = mw_next;
+      // carry: right-most column -> left-neighbour column, top-row slots shift by one macroblock
+      uint32_t sv = 0;
+      int cv;
+      if (lane < 16) cv = ws.luma[luma_at(15, lane)];
+      else cv = ws.chroma[lane >= 24 ? 1 : 0][chroma_at(7, lane & 7)];
+      if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + shift_by);
       __syncwarp();
-      if (lane == 0) st_release_gpu(prog_mine, x + 1);
-      // carry the right-most column into the left-neighbour column of the next macroblock
-      if (lane < 16) ws.luma[luma_at(-1, lane)] = ws.luma[luma_at(15, lane)];
-      else {
-        uint8_t* tile = ws.chroma[lane >= 24 ? 1 : 0];
-        tile[chroma_at(-1, lane & 7)] = tile[chroma_at(7, lane & 7)];
-      }
+      if (lane < 16) ws.luma[luma_at(-1, lane)] = (uint8_t)cv;
+      else ws.chroma[lane >= 24 ? 1 : 0][chroma_at(-1, lane & 7)] = (uint8_t)cv;
+      if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
       __syncwarp();
     }
+    if (dead) break;
   }
   if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
 }
@@ -299,9 +329,9 @@ struct dryv_recon_ctx {
   dryv_pic_params tables_pp;
   bool tables_valid = false;
   // wavefront control block
-  int* d_progress = nullptr;
-  uint32_t* d_mode_line = nullptr;
-  size_t progress_cap = 0, mode_cap = 0;
+  unsigned long long* d_line = nullptr;  // bottom-line hand-off buffer, kLineWords words per macroblock
+  size_t line_cap = 0;                   // in macroblocks
+  uint32_t tag = 0;                      // launch tag, incremented per wavefront launch (0 = never written)
   unsigned int* d_ticket = nullptr;  // [0] ticket, [1] status
   int* h_status = nullptr;           // pinned
   // staging for dryv_recon_submit (two slots)
@@ -347,20 +377,16 @@ int ensure_tables(dryv_recon_ctx* ctx, const dryv_pic_params* pp, cudaStream_t s
   return DRYV_OK;
 }
 
-int ensure_control(dryv_recon_ctx* ctx, size_t rows, size_t mbs) {
-  if (rows > ctx->progress_cap) {
+int ensure_control(dryv_recon_ctx* ctx, size_t mbs) {
+  if (mbs > ctx->line_cap) {
     CU(cudaDeviceSynchronize());
-    if (ctx->d_progress) cudaFree(ctx->d_progress);
-    ctx->d_progress = nullptr;
-    CU(cudaMalloc(&ctx->d_progress, rows * sizeof(int)));
-    ctx->progress_cap = rows;
-  }
-  if (mbs > ctx->mode_cap) {
-    CU(cudaDeviceSynchronize());
-    if (ctx->d_mode_line) cudaFree(ctx->d_mode_line);
-    ctx->d_mode_line = nullptr;
-    CU(cudaMalloc(&ctx->d_mode_line, mbs * sizeof(uint32_t)));
-    ctx->mode_cap = mbs;
+    if (ctx->d_line) cudaFree(ctx->d_line);
+    ctx->d_line = nullptr;
+    ctx->line_cap = 0;
+    const size_t bytes = mbs * dryv::kLineWords * sizeof(unsigned long long);
+    CU(cudaMalloc(&ctx->d_line, bytes));
+    CU(cudaMemset(ctx->d_line, 0, bytes));  // tag 0 is never used by a launch
+    ctx->line_cap = mbs;
   }
   return DRYV_OK;
 }
@@ -377,8 +403,8 @@ KernelArgs make_args(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   a.coeff = soa->coeff;
   a.out = out;
   a.tables = ctx->d_tables;
-  a.progress = ctx->d_progress;
-  a.mode_line = ctx->d_mode_line;
+  a.line = ctx->d_line;
+  a.tag = ctx->tag;
   a.ticket = ctx->d_ticket;
   a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
   a.W = pp->pic_width_in_mbs;
@@ -399,9 +425,9 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
                      uint8_t* d_out, cudaStream_t s) {
   const size_t rows = (size_t)n_frames * pp->pic_height_in_mbs;
   const size_t mbs = rows * pp->pic_width_in_mbs;
-  int rc = ensure_control(ctx, rows, mbs);
+  int rc = ensure_control(ctx, mbs);
   if (rc != DRYV_OK) return rc;
-  CU(cudaMemsetAsync(ctx->d_progress, 0, rows * sizeof(int), s));
+  if (++ctx->tag == 0) ctx->tag = 1;  // every launch validates line words with its own tag: no per-launch clearing
   CU(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
   KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out);
   size_t want = (rows + dryv::kWarpsPerCta - 1) / dryv::kWarpsPerCta;
@@ -487,8 +513,7 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
-  if (ctx->d_progress) cudaFree(ctx->d_progress);
-  if (ctx->d_mode_line) cudaFree(ctx->d_mode_line);
+  if (ctx->d_line) cudaFree(ctx->d_line);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   delete ctx;

@@ -30,9 +30,9 @@ constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 
 // Per-warp shared memory (bytes): residual tile, luma/chroma pixel tiles, transform scratch.
 constexpr int kResBytes = 768;           // int16 luma[16][16] + cb[8][8] + cr[8][8]
-constexpr int kLumaStride = 48;          // pixel (x, y) at (y + 1) * 48 + 16 + x, x in -4..23, y in -1..15
+constexpr int kLumaStride = 48;          // pixel (x, y) at (y + 1) * 48 + 16 + x, x in -4..31 (row -1), y in -1..15
 constexpr int kLumaTileBytes = 17 * kLumaStride;
-constexpr int kChromaStride = 16;        // pixel (x, y) at (y + 1) * 16 + 8 + x, x in -4..7, y in -1..7
+constexpr int kChromaStride = 24;        // pixel (x, y) at (y + 1) * 24 + 8 + x, x in -4..15 (row -1), y in -1..7
 constexpr int kChromaTileBytes = 9 * kChromaStride;
 constexpr int kScratchBytes = 1152;      // 8x8 coefficient slab (4 * 144 B) aliased with the transpose buffer (4 * 72 words)
 constexpr int kWarpSmemBytes = kResBytes + kLumaTileBytes + 2 * kChromaTileBytes + kScratchBytes;
@@ -53,6 +53,12 @@ struct CtaSmem {
 
 enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
 
+// Bottom line a macroblock hands to the row below: 4 luma words (16 px), 2 Cb, 2 Cr words (8 px each)
+// and one word with the resolved prediction modes of its bottom 4x4 blocks. Every 32-bit payload
+// travels with the launch tag in one 64-bit word, so a single relaxed 64-bit load both fetches the
+// data and proves it is there: no fence, no separate flag, no second round trip.
+constexpr int kLineWords = 9;
+
 struct KernelArgs {
   const uint8_t* mb_type;
   const uint8_t* t8x8;
@@ -63,8 +69,8 @@ struct KernelArgs {
   uint8_t* out;             // n_frames pictures, Y | Cb | Cr each
   const uint8_t* pred_in;   // residual-add kernel only
   const DeviceTables* tables;
-  int* progress;            // [n_frames * H] finished MBs per row
-  uint32_t* mode_line;      // [n_frames * H * W] bottom-row prediction modes of each MB
+  unsigned long long* line; // [n_frames * H * W][kLineWords] bottom line of each MB: payload | tag << 32
+  uint32_t tag;             // launch tag: a line word is valid when its upper half equals it
   unsigned int* ticket;     // row ticket counter
   int* status;
   int W, H, n_frames;
@@ -74,13 +80,18 @@ struct KernelArgs {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_gpu_s32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
   int d;
@@ -315,65 +326,80 @@ __device__ __forceinline__ uint32_t legal_mask(bool t, bool l, bool c) {
 
 // Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110. Ten dependency steps, two blocks per step
 // where the decode-order availability rules allow it; one pixel per lane, 16 lanes per block.
-__device__ __forceinline__ void predict_i4x4(const CtaSmem& cs, WarpSmem& ws, int lane, int my_mode_grid,
-                                             bool availA, bool availB, bool availC, bool availD) {
-  const int half = lane >> 4, p = lane & 15, px = p & 3, py = p >> 2;
-  // step -> block handled by half 0 / half 1 (0xf = none); nibble tables
-  // step -> block: half 0 runs 0,1,2,3,6,7,10,11,14,15; half 1 runs 4,5,8,9,12,13 in steps 2..7 (nibble tables)
-  const unsigned long long blk_tab = half ? 0x00DC985400ull : 0xFEBA763210ull;
-#pragma unroll 1
-  for (int s = 0; s < 10; s++) {
-    const bool active = !half || (s >= 2 && s <= 7);
-    const int b = (int)((blk_tab >> (4 * s)) & 15ull);
-    const int bx = ((b >> 2) & 1) * 8 + (b & 1) * 4;
-    const int by = (b >> 3) * 8 + ((b >> 1) & 1) * 4;
-    const int gl = (by >> 2) * 4 + (bx >> 2);  // lane holding this block's resolved mode (raster grid)
-    const int mode = __shfl_sync(0xffffffffu, my_mode_grid, gl);
-    const bool aL = bx > 0 || availA;
-    const bool aT = by > 0 || availB;
-    const bool aTL = (bx > 0 && by > 0) ? true : (bx > 0 ? availB : (by > 0 ? availA : availD));
-    // top-right availability, pred4x4.rs:39-43 + MbPosition::from_coords (slice/macroblock.rs:448-462)
-    bool aTR;
-    if (b == 3 || b == 11 || b == 7 || b == 13 || b == 15) aTR = false;
-    else if (b == 5) aTR = availC;
-    else if (b == 0 || b == 1 || b == 4) aTR = availB;
-    else aTR = true;
-    // edge sample of this lane: 0..7 top (4..7 replicated from 3 when top-right is missing), 8..11 left, 12 corner
-    int ex, ey;
-    if (p < 8) { ex = bx + ((p >= 4 && !aTR) ? 3 : p); ey = by - 1; }
-    else if (p < 12) { ex = bx - 1; ey = by + (p - 8); }
-    else { ex = bx - 1; ey = by - 1; }
-    int ev = ws.luma[luma_at(ex, ey)];
-    // DC value (pred4x4.rs:116-167): sums over lanes 0..3 (top) and 8..11 (left) of this half
-    int sum = ev + __shfl_xor_sync(0xffffffffu, ev, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    const int sumT = __shfl_sync(0xffffffffu, sum, 0, 16);
-    const int sumL = __shfl_sync(0xffffffffu, sum, 8, 16);
-    int dc;
-    if (aT && aL) dc = (sumT + sumL + 4) >> 3;
-    else if (aL) dc = (sumL + 2) >> 2;
-    else if (aT) dc = (sumT + 2) >> 2;
-    else dc = 128;
-    if (p == E4_DC) ev = dc;
-    const uint32_t taps = cs.tab.lut4[mode > 8 ? 2 : mode][p];
-    const int e0 = __shfl_sync(0xffffffffu, ev, taps & 15, 16);
-    const int e1 = __shfl_sync(0xffffffffu, ev, (taps >> 4) & 15, 16);
-    const int e2 = __shfl_sync(0xffffffffu, ev, (taps >> 8) & 15, 16);
-    int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
-    const bool ok = mode <= 8 && ((legal_mask(aT, aL, aTL) >> mode) & 1u);
-    if (!ok) pred = 0;
-    if (active) {
-      const int r = ws.res[(by + py) * 16 + bx + px];
-      ws.luma[luma_at(bx + px, by + py)] = (uint8_t)clip255(pred + r);
+// BA / BB = block handled by lanes 0..15 / 16..31 in this step (BB < 0: upper half idle).
+template <int BA, int BB>
+__device__ __forceinline__ void i4x4_step(const CtaSmem& cs, WarpSmem& ws, int lane, int my_mode_grid, bool availA,
+                                          bool availB, bool availC, bool availD) {
+  constexpr int BBe = BB < 0 ? BA : BB;
+  constexpr int bxA = ((BA >> 2) & 1) * 8 + (BA & 1) * 4, byA = (BA >> 3) * 8 + ((BA >> 1) & 1) * 4;
+  constexpr int bxB = ((BBe >> 2) & 1) * 8 + (BBe & 1) * 4, byB = (BBe >> 3) * 8 + ((BBe >> 1) & 1) * 4;
+  const bool half = lane >= 16;
+  const int p = lane & 15, px = p & 3, py = p >> 2;
+  const bool active = !half || BB >= 0;
+  const int b = half ? BBe : BA;
+  const int bx = half ? bxB : bxA, by = half ? byB : byA;
+  const int mode = __shfl_sync(0xffffffffu, my_mode_grid, half ? ((byB >> 2) * 4 + (bxB >> 2)) : ((byA >> 2) * 4 + (bxA >> 2)));
+  const bool aL = bx > 0 || availA;
+  const bool aT = by > 0 || availB;
+  const bool aTL = (bx > 0 && by > 0) ? true : (bx > 0 ? availB : (by > 0 ? availA : availD));
+  // top-right availability, pred4x4.rs:39-43 + MbPosition::from_coords (slice/macroblock.rs:448-462)
+  bool aTR;
+  if (b == 3 || b == 11 || b == 7 || b == 13 || b == 15) aTR = false;
+  else if (b == 5) aTR = availC;
+  else if (b == 0 || b == 1 || b == 4) aTR = availB;
+  else aTR = true;
+  const int org = luma_at(bx, by);
+  int ev;
+  if (p == E4_DC) {
+    // DC value (pred4x4.rs:116-167), computed by this lane alone and only when the block's mode is DC
+    ev = 128;
+    if (mode == 2) {
+      const uint32_t tw = *reinterpret_cast<const uint32_t*>(&ws.luma[org - kLumaStride]);
+      const int sumT = dp4a_us(tw, 0x01010101, 0);
+      const int sumL = ws.luma[org - 1] + ws.luma[org + kLumaStride - 1] + ws.luma[org + 2 * kLumaStride - 1] +
+                       ws.luma[org + 3 * kLumaStride - 1];
+      if (aT && aL) ev = (sumT + sumL + 4) >> 3;
+      else if (aL) ev = (sumL + 2) >> 2;
+      else if (aT) ev = (sumT + 2) >> 2;
     }
-    __syncwarp();
+  } else {
+    // edge sample of this lane: 0..7 top (4..7 replicated from 3 when top-right is missing), 8..11 left, 12 corner
+    int off;
+    if (p < 8) off = -kLumaStride + ((p >= 4 && !aTR) ? 3 : p);
+    else if (p < 12) off = (p - 8) * kLumaStride - 1;
+    else off = -kLumaStride - 1;
+    ev = ws.luma[org + off];
   }
+  const int res = ws.res[(by + py) * 16 + bx + px];
+  const uint32_t taps = cs.tab.lut4[mode > 8 ? 2 : mode][p];
+  const int e0 = __shfl_sync(0xffffffffu, ev, taps & 15, 16);
+  const int e1 = __shfl_sync(0xffffffffu, ev, (taps >> 4) & 15, 16);
+  const int e2 = __shfl_sync(0xffffffffu, ev, (taps >> 8) & 15, 16);
+  int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
+  const bool ok = mode <= 8 && ((legal_mask(aT, aL, aTL) >> mode) & 1u);
+  if (!ok) pred = 0;
+  if (active) ws.luma[org + py * kLumaStride + px] = (uint8_t)clip255(pred + res);
+  __syncwarp();
+}
+
+__device__ __forceinline__ void predict_i4x4(const CtaSmem& cs, WarpSmem& ws, int lane, int m, bool availA,
+                                             bool availB, bool availC, bool availD) {
+  i4x4_step<0, -1>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<1, -1>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<2, 4>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<3, 5>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<6, 8>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<7, 9>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<10, 12>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<11, 13>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<14, -1>(cs, ws, lane, m, availA, availB, availC, availD);
+  i4x4_step<15, -1>(cs, ws, lane, m, availA, availB, availC, availD);
 }
 
 // Intra8x8 luma, pred8x8.rs:152-696 + pred8x8.rs:34-46. Four sequential blocks, two pixels per lane.
 __device__ __forceinline__ void predict_i8x8(const CtaSmem& cs, WarpSmem& ws, int lane, int my_mode_grid,
                                              bool availA, bool availB, bool availC, bool availD) {
-#pragma unroll 1
+#pragma unroll
   for (int b = 0; b < 4; b++) {
     const int bx = (b & 1) * 8, by = (b >> 1) * 8;
     const int mode = __shfl_sync(0xffffffffu, my_mode_grid, (by >> 2) * 4 + (bx >> 2));
@@ -397,17 +423,19 @@ __device__ __forceinline__ void predict_i8x8(const CtaSmem& cs, WarpSmem& ws, in
     if (lane == 0 && !aTL) pv = -1;  // Q2: raw p[-1,-1] sentinel enters the filter
     int ev = (pv + 2 * raw + nv + 2) >> 2;
     // DC, pred8x8.rs:326-425: sums of the filtered top 0..7 (lanes 0..7) and left (lanes 16..23)
-    int sum = ev + __shfl_xor_sync(0xffffffffu, ev, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-    const int sumT = __shfl_sync(0xffffffffu, sum, 0);
-    const int sumL = __shfl_sync(0xffffffffu, sum, 16);
-    int dc;
-    if (aT && aL) dc = (sumT + sumL + 8) >> 4;
-    else if (aL) dc = (sumL + 4) >> 3;
-    else if (aT) dc = (sumT + 4) >> 3;
-    else dc = 128;
-    if (lane == E8_DC) ev = dc;
+    if (mode == 2) {  // warp-uniform
+      int sum = ev + __shfl_xor_sync(0xffffffffu, ev, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const int sumT = __shfl_sync(0xffffffffu, sum, 0);
+      const int sumL = __shfl_sync(0xffffffffu, sum, 16);
+      int dc;
+      if (aT && aL) dc = (sumT + sumL + 8) >> 4;
+      else if (aL) dc = (sumL + 4) >> 3;
+      else if (aT) dc = (sumT + 4) >> 3;
+      else dc = 128;
+      if (lane == E8_DC) ev = dc;
+    }
     const int m = mode > 8 ? 2 : mode;
     const int py = lane >> 2, px = (lane & 3) * 2;
     const uint32_t tw = *reinterpret_cast<const uint32_t*>(&cs.tab.lut8[m][py * 8 + px]);

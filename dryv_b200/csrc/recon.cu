@@ -47,206 +47,357 @@ __device__ __forceinline__ MbHeader decode_header(uint32_t hdr_lane, int* status
   return h;
 }
 
+// Stage clocks (development builds only: -DDRYV_STAGE_CLOCKS): per-role cycle sums per stage.
+#ifdef DRYV_STAGE_CLOCKS
+#define CLK_DECL long long clk_t0 = clock64(), clk_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define CLK_MARK(i)                    \
+  do {                                 \
+    long long t_ = clock64();          \
+    clk_acc[i] += t_ - clk_t0;         \
+    clk_t0 = t_;                       \
+  } while (0)
+#define CLK_FLUSH(base)                                                                         \
+  do {                                                                                          \
+    if (lane == 0 && a.prof)                                                                    \
+      for (int i_ = 0; i_ < 8; i_++) atomicAdd(a.prof + (base) + i_, (unsigned long long)clk_acc[i_]); \
+  } while (0)
+#else
+#define CLK_DECL
+#define CLK_MARK(i)
+#define CLK_FLUSH(base)
+#endif
+
 // ------------------------------------------------------------------------------------------------
-// Full reconstruction: persistent row walkers over an x+2y macroblock wavefront.
+// mbarrier helpers (CTA-scope producer/consumer hand-off between the two warps of a row team)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+
+// Waits until the line words of lanes [lo, hi) carry this launch's tag; returns the lane's payload.
+// `first` is the value of a load issued earlier (so its latency overlapped with other work).
+// On a watchdog trip `dead` is set and every later wait returns immediately (the kernel drains with
+// garbage and the host reports DRYV_ERR_WATCHDOG).
+__device__ __forceinline__ uint32_t wait_line_words(const unsigned long long* p, unsigned long long first, int lane,
+                                                    int lo, int hi, uint32_t tag, bool long_wait, int* status,
+                                                    bool& dead) {
+  unsigned long long v = first;
+  const bool mine = lane >= lo && lane < hi;
+  unsigned spins = 0;
+  while (!dead && !__all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) {
+    ++spins;
+    if (long_wait || spins > 4u) __nanosleep(long_wait ? 1000u : 64u);
+    if ((spins & 0x3ffu) == 0u) {
+      if (spins > (1u << 21) || ld_relaxed_gpu_s32(status) == STATUS_WATCHDOG) {
+        if (lane == 0) atomicExch(status, STATUS_WATCHDOG);
+        dead = true;
+      }
+    }
+    if (mine) v = ld_relaxed_gpu_u64(p);
+  }
+  return (uint32_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full reconstruction: persistent row teams over an x+2y macroblock wavefront.
 //
-// Row-to-row hand-off: the walker of row y never reads the picture. After finishing MB x it writes
-// that MB's bottom line (kLineWords 64-bit words = payload | launch tag) to the line buffer; the
-// walker of row y+1 needs line x+1 before it can predict MB x (top-right neighbour), fetches it with
-// one relaxed 64-bit load per lane issued BEFORE its residual stage, and only checks the tags after
-// the residual stage and the mode derivation, so the L2 round trip hides behind independent work.
-// Picture stores are fire-and-forget (nobody on the GPU reads them back).
+// A row team (one CTA, two warps) walks one macroblock row of one picture left to right:
+//   front warp  - 128-bit coefficient loads, dequant + Hadamard + 4x4/8x8 inverse transforms (residual
+//                 tile -> ring slot), Intra4x4/8x8 mode derivation, chroma prediction + stores
+//   luma warp   - Intra4x4/8x8/16x16 prediction + residual add + clip, 16 x 128-bit luma row stores
+// Rows hand data down through the line buffer: after a macroblock the team writes its bottom line
+// (4 luma words, 2+2 chroma words, 1 word of bottom-block modes), each as payload | launch tag in one
+// 64-bit word. The row below fetches a line with one relaxed 64-bit load per lane, issued before the
+// work it can overlap with, and checks the tags later: no fences, no flags, and nobody reads the
+// picture back. Luma needs line x+1 of the row above (top-right neighbour: x+2y wavefront); chroma
+// and the mode derivation only need line x.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(const KernelArgs a) {
-  __shared__ alignas(16) CtaSmem cs;
+__global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const KernelArgs a) {
+  __shared__ alignas(16) TeamSmem ts;
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.tables);
-    uint4* dst = reinterpret_cast<uint4*>(&cs.tab);
-    for (int i = threadIdx.x; i < (int)(sizeof(DeviceTables) / 16); i += kThreadsPerCta) dst[i] = src[i];
+    uint4* dst = reinterpret_cast<uint4*>(&ts.tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceTables) / 16); i += kTeamThreads) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kSlots; i++) {
+        mbar_init(&ts.full[i], 1);
+        mbar_init(&ts.empty[i], 1);
+      }
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  WarpSmem& ws = cs.warp[threadIdx.x >> 5];
-  const LaneConst lc = make_lane_const(lane, cs.tab);
-
+  const bool is_front = threadIdx.x < 32;
+  const DeviceTables& tab = ts.tab;
   const int W = a.W, H = a.H;
-  const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
   const size_t n_mb = (size_t)W * H;
   const int strideY = W * 16, strideC = W * 8;
   const uint32_t tag = a.tag;
-  // raster-grid cell of this lane and the pred_syntax entry that covers it
-  const int g = lane & 15, gx = g & 3, gy = g >> 2;
-  const int syn_idx4 = 8 * (gy >> 1) + 4 * (gx >> 1) + 2 * (gy & 1) + (gx & 1);  // spec 4x4 block index of the cell
-  const int syn_src8 = ((gy >> 1) ? 4 : 0) + (gx >> 1);  // lane that loaded pred_syntax[blk8] (cells 0,1,4,5)
+  const int g = lane & 15, gx = g & 3, gy = g >> 2;  // raster-grid cell of this lane
+  bool dead = false;
 
-  // Top-row slots of the pixel tiles. Luma row -1 holds 9 words: [x-1].w3 | [x].w0..3 | [x+1].w0..3 at byte
-  // 12 + 4k; each chroma row -1 holds 5 words: [x-1].w1 | [x].w0..1 | [x+1].w0..1 at byte 4 + 4k.
-  // line word of this lane (lanes 0..8): 0..3 luma, 4..5 Cb, 6..7 Cr, 8 modes
-  uint8_t* fresh_dst = nullptr;   // where this lane's freshly fetched word of line x+1 goes
-  const uint8_t* pub_src = nullptr;  // where this lane's word of the line it publishes comes from
-  if (lane < 4) {
-    fresh_dst = &ws.luma[12 + 4 * (5 + lane)];
-    pub_src = &ws.luma[luma_at(4 * lane, 15)];
-  } else if (lane < 8) {
-    const int pl = (lane - 4) >> 1, k = (lane - 4) & 1;
-    fresh_dst = &ws.chroma[pl][4 + 4 * (3 + k)];
-    pub_src = &ws.chroma[pl][chroma_at(4 * k, 7)];
-  }
-  // shift of the top-row slots when the walker advances one macroblock: lanes 0..4 luma, 8..10 Cb, 12..14 Cr
-  uint8_t* shift_dst = nullptr;
-  int shift_by = 0;
-  if (lane < 5) { shift_dst = &ws.luma[12 + 4 * lane]; shift_by = 16; }
-  else if (lane >= 8 && lane < 11) { shift_dst = &ws.chroma[0][4 + 4 * (lane - 8)]; shift_by = 8; }
-  else if (lane >= 12 && lane < 15) { shift_dst = &ws.chroma[1][4 + 4 * (lane - 12)]; shift_by = 8; }
-
-  int local_status = STATUS_OK;
-  for (;;) {
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(a.ticket, 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= total_rows) break;
-    // tickets are dealt row-major over pictures so that a row only ever waits on a lower ticket
-    const int row = (int)(t / (unsigned)a.n_frames), frame = (int)(t % (unsigned)a.n_frames);
-    const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
-    uint8_t* const Y = a.out + (size_t)frame * n_mb * 384;
-    uint8_t* const Cb = Y + n_mb * 256;
-    uint8_t* const Cr = Cb + n_mb * 64;
-    const bool availB = row > 0, publish = row + 1 < H;
-    const unsigned long long* const line_above = a.line + (mb_row0 - W) * kLineWords + lane;  // valid if availB, lane < 9
-    unsigned long long* const line_mine = a.line + mb_row0 * kLineWords + lane;
-
-    // per-lane store address pieces
-    uint8_t* st_base;
-    if (lane < 16) { st_base = Y + (size_t)(16 * row + lane) * strideY; }
-    else if (lane < 24) { st_base = Cb + (size_t)(8 * row + (lane - 16)) * strideC; }
-    else { st_base = Cr + (size_t)(8 * row + (lane - 24)) * strideC; }
-
-    // prefetch macroblock 0
-    uint32_t hdr_n = load_header_lane(a, lane, mb_row0);
-    uint32_t syn_n = lane < 16 ? (uint32_t)__ldg(a.pred_syntax + mb_row0 * 16 + syn_idx4) : 0u;
-    uint4 c0_n = make_uint4(0, 0, 0, 0), c1_n = make_uint4(0, 0, 0, 0);
-    if (lane < 24) {
-      const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 2;
-      c0_n = __ldg(cp);
-      c1_n = __ldg(cp + 1);
+  if (is_front) {
+    // =========================================== front warp ===========================================
+    const LaneConst lc = make_lane_const(lane, tab);
+    const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
+    const int syn_idx4 = 8 * (gy >> 1) + 4 * (gx >> 1) + 2 * (gy & 1) + (gx & 1);  // spec 4x4 block index of the cell
+    const int syn_src8 = ((gy >> 1) ? 4 : 0) + (gx >> 1);  // lane that loaded pred_syntax[blk8] (cells 0,1,4,5)
+    // chroma top-row slots per plane: [x-1].w1 | [x].w0 | [x].w1 at byte 4 + 4k of tile row -1
+    // line words handled by this warp: lanes 4..5 Cb, 6..7 Cr, 8 modes
+    uint8_t* fresh_dst = nullptr;
+    const uint8_t* pub_src = nullptr;
+    if (lane >= 4 && lane < 8) {
+      const int pl = (lane - 4) >> 1, k = (lane - 4) & 1;
+      fresh_dst = &ts.chroma[pl * kChromaTileBytes + 4 + 4 * (1 + k)];
+      pub_src = &ts.chroma[pl * kChromaTileBytes + chroma_at(4 * k, 7)];
     }
-    int a_col = 2;          // resolved mode of the cell left of grid column 0 (previous MB of this row)
-    uint32_t mw_cur = 0x02020202u;  // bottom-row modes of the MB above the current one
+    // chroma row this lane stores / carries (lanes 0..15: plane = lane >> 3, row = lane & 7)
+    uint8_t* const my_ct = &ts.chroma[((lane >> 3) & 1) * kChromaTileBytes];
+    int local_status = STATUS_OK;
+    unsigned n = 0;  // macroblocks handed to the luma warp so far
+    CLK_DECL;
+    for (;;) {
+      unsigned t = 0;
+      if (lane == 0) t = atomicAdd(a.ticket, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= total_rows) break;
+      // tickets are dealt row-major over pictures so that a row only ever waits on a lower ticket
+      const int row = (int)(t / (unsigned)a.n_frames), frame = (int)(t % (unsigned)a.n_frames);
+      const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
+      uint8_t* const Cb = a.out + (size_t)frame * n_mb * 384 + n_mb * 256;
+      const bool availB = row > 0, publish = row + 1 < H;
+      const unsigned long long* const line_above = a.line + (mb_row0 - W) * kLineWords + lane;
+      unsigned long long* const line_mine = a.line + mb_row0 * kLineWords + lane;
+      uint8_t* st_base = nullptr;
+      if (lane < 16) st_base = Cb + (size_t)(lane >> 3) * n_mb * 64 + (size_t)(8 * row + (lane & 7)) * strideC;
 
-    // Waits for line `xl` of the row above (all kLineWords tags), returns this lane's payload.
-    // `long_wait`: the row above may not even have started (row start): back off in microseconds.
-    auto wait_line = [&](int xl, unsigned long long first, bool long_wait, bool& dead) -> uint32_t {
-      unsigned long long v = first;
-      unsigned spins = 0;
-      while (!__all_sync(0xffffffffu, lane >= kLineWords || (uint32_t)(v >> 32) == tag)) {
-        ++spins;
-        if (long_wait) __nanosleep(spins < 4u ? 200u : 2000u);
-        else if (spins > 2u) __nanosleep(spins > 64u ? 1000u : 100u);
-        if ((spins & 0x3ffu) == 0u) {
-          if (spins > (1u << 22) || ld_relaxed_gpu_s32(a.status) == STATUS_WATCHDOG) {
-            if (lane == 0) atomicExch(a.status, STATUS_WATCHDOG);
-            dead = true;
-            return 0u;
+      // prefetch macroblock 0
+      uint32_t hdr_n = load_header_lane(a, lane, mb_row0);
+      uint32_t syn_n = lane < 16 ? (uint32_t)__ldg(a.pred_syntax + mb_row0 * 16 + syn_idx4) : 0u;
+      uint4 c0_n = make_uint4(0, 0, 0, 0), c1_n = make_uint4(0, 0, 0, 0);
+      if (lane < 24) {
+        const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 2;
+        c0_n = __ldg(cp);
+        c1_n = __ldg(cp + 1);
+      }
+      int a_col = 2;  // resolved mode of the cell left of grid column 0 (previous MB of this row)
+
+      for (int x = 0; x < W; x++) {
+        const uint32_t hdr_c = hdr_n, syn_c = syn_n;
+        const uint4 c0 = c0_n, c1 = c1_n;
+        // line x of the row above (chroma words + modes word): fetch now, check after the residual stage
+        unsigned long long lv = 0;
+        const bool my_word = lane >= 4 && lane < kLineWords;
+        if (availB && my_word) lv = ld_relaxed_gpu_u64(line_above + (size_t)x * kLineWords);
+        if (x + 1 < W) {
+          const size_t mbn = mb_row0 + x + 1;
+          hdr_n = load_header_lane(a, lane, mbn);
+          if (lane < 16) syn_n = (uint32_t)__ldg(a.pred_syntax + mbn * 16 + syn_idx4);
+          if (lane < 24) {
+            const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mbn * DRYV_COEFFS_PER_MB) + lane * 2;
+            c0_n = __ldg(cp);
+            c1_n = __ldg(cp + 1);
           }
         }
-        if (lane < kLineWords) v = ld_relaxed_gpu_u64(line_above + (size_t)xl * kLineWords);
+        const MbHeader h = decode_header(hdr_c, &local_status);
+        const bool availA = x > 0, availD = availA && availB;
+
+        // ring slot: wait until the luma warp has released its previous use
+        const unsigned si = n % kSlots, use = n / kSlots;
+        Slot& slot = ts.slot[si];
+        CLK_MARK(0);  // prefetch + header
+        if (use > 0) mbar_wait(&ts.empty[si], (use - 1) & 1);
+        CLK_MARK(1);  // wait for a free slot
+
+        // 1. residual (independent of every other macroblock)
+        residual_stage(tab, ts.scratch, slot.res, ts.cres, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
+
+        CLK_MARK(2);  // residual stage
+        // 2. line x of the row above: chroma top row + the modes of the MB above
+        uint32_t mw = 0x02020202u;
+        if (availB) {
+          const uint32_t w = wait_line_words(line_above + (size_t)x * kLineWords, lv, lane, 4, kLineWords, tag, x == 0,
+                                             a.status, dead);
+          if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+          mw = __shfl_sync(0xffffffffu, w, 8);
+        }
+
+        CLK_MARK(3);  // wait for line x of the row above
+        // 3. prediction modes -> slot, bottom-row modes -> line buffer, hand the slot to the luma warp
+        const int b_row = (mw >> (8 * gx)) & 0xff;
+        int syn = (int)syn_c;
+        if (h.mbcls == 1) syn = __shfl_sync(0xffffffffu, syn, syn_src8);
+        const int m = resolve_modes(lane, h.mbcls, syn, a_col, b_row, availA, availB);
+        // 4-bit modes of cells 0..7 -> lanes 0..7 (lo word), cells 8..15 -> lanes 8..15 (hi word)
+        uint32_t mp = lane < 16 ? ((uint32_t)m << (4 * (lane & 7))) : 0u;
+        mp |= __shfl_xor_sync(0xffffffffu, mp, 1);
+        mp |= __shfl_xor_sync(0xffffffffu, mp, 2);
+        mp |= __shfl_xor_sync(0xffffffffu, mp, 4);
+        if (lane == 8) slot.modes_hi = mp;
+        if (lane == 0) {
+          slot.modes_lo = mp;
+          slot.frame = frame;
+          slot.row = row;
+          slot.x = x;
+          slot.mbcls = h.mbcls;
+          slot.mode16 = (h.mbt - 1) & 3;
+        }
+        if (publish && lane == 8) {
+          // bottom-row modes (cells 12..15 = nibbles 4..7 of the hi word), one byte each, for the row below
+          const uint32_t mv = ((mp >> 16) & 15u) | (((mp >> 20) & 15u) << 8) | (((mp >> 24) & 15u) << 16) |
+                              (((mp >> 28) & 15u) << 24);
+          st_relaxed_gpu_u64(line_mine + (size_t)x * kLineWords, ((unsigned long long)tag << 32) | mv);
+        }
+        a_col = __shfl_sync(0xffffffffu, m, gy * 4 + 3);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ts.full[si]);
+        n++;
+        CLK_MARK(4);  // mode derivation + hand-off
+
+        // 4. chroma prediction + residual + clip, stores, bottom line, carry
+        predict_chroma(ts.chroma, ts.cres, lane, h.cm, availA, availB, availD);
+        CLK_MARK(5);  // chroma prediction
+        if (lane < 16) {
+          const uint2 v = *reinterpret_cast<const uint2*>(&my_ct[chroma_at(0, lane & 7)]);
+          __stcs(reinterpret_cast<uint2*>(st_base + (size_t)x * 8), v);
+        }
+        if (publish && pub_src)
+          st_relaxed_gpu_u64(line_mine + (size_t)x * kLineWords,
+                             ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
+        // carry: right-most column -> left-neighbour column; top-row corner slot <- [x].w1
+        int cv = 0;
+        uint32_t sv = 0;
+        if (lane < 16) cv = my_ct[chroma_at(7, lane & 7)];
+        else if (lane < 18) sv = *reinterpret_cast<const uint32_t*>(&ts.chroma[(lane - 16) * kChromaTileBytes + 4 + 8]);
+        __syncwarp();
+        if (lane < 16) my_ct[chroma_at(-1, lane & 7)] = (uint8_t)cv;
+        else if (lane < 18) *reinterpret_cast<uint32_t*>(&ts.chroma[(lane - 16) * kChromaTileBytes + 4]) = sv;
+        __syncwarp();
+        CLK_MARK(6);  // chroma stores + publish + carry
       }
-      return (uint32_t)v;
-    };
-
-    bool dead = false;
-    if (availB) {
-      // row start: line 0 of the row above becomes "line x" of macroblock 0
-      unsigned long long v0 = 0;
-      if (lane < kLineWords) v0 = ld_relaxed_gpu_u64(line_above);
-      const uint32_t w = wait_line(0, v0, true, dead);
-      if (dead) break;
-      if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
-      mw_cur = __shfl_sync(0xffffffffu, w, 8);
-      __syncwarp();
-      uint32_t sv = 0;
-      if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + shift_by);
-      __syncwarp();
-      if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
+      CLK_MARK(7);  // row change
     }
-
-    for (int x = 0; x < W; x++) {
-      const uint32_t hdr_c = hdr_n, syn_c = syn_n;
-      const uint4 c0 = c0_n, c1 = c1_n;
-      const bool need_line = availB && x + 1 < W;
-      unsigned long long lv = 0;
-      if (need_line && lane < kLineWords) lv = ld_relaxed_gpu_u64(line_above + (size_t)(x + 1) * kLineWords);
-      if (x + 1 < W) {
-        const size_t mbn = mb_row0 + x + 1;
-        hdr_n = load_header_lane(a, lane, mbn);
-        if (lane < 16) syn_n = (uint32_t)__ldg(a.pred_syntax + mbn * 16 + syn_idx4);
-        if (lane < 24) {
-          const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mbn * DRYV_COEFFS_PER_MB) + lane * 2;
-          c0_n = __ldg(cp);
-          c1_n = __ldg(cp + 1);
+    CLK_FLUSH(0);
+    // no more rows: tell the luma warp
+    {
+      const unsigned si = n % kSlots, use = n / kSlots;
+      if (use > 0) mbar_wait(&ts.empty[si], (use - 1) & 1);
+      if (lane == 0) ts.slot[si].row = -1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ts.full[si]);
+    }
+    if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
+  } else {
+    // =========================================== luma warp ============================================
+    // luma top-row slots (tile row -1): 9 words [x-1].w3 | [x].w0..3 | [x+1].w0..3 at byte 12 + 4k
+    uint8_t* fresh_dst = lane < 4 ? &ts.luma[12 + 4 * (5 + lane)] : nullptr;
+    const uint8_t* pub_src = lane < 4 ? &ts.luma[luma_at(4 * lane, 15)] : nullptr;
+    uint8_t* shift_dst = lane < 5 ? &ts.luma[12 + 4 * lane] : nullptr;
+    unsigned n = 0;
+    int W1 = W - 1;
+    const unsigned long long* line_above = nullptr;
+    unsigned long long* line_mine = nullptr;
+    uint8_t* st_base = nullptr;
+    bool availB = false, publish = false;
+    unsigned long long lv = 0;  // in-flight fetch of line x+1 of the row above
+    CLK_DECL;
+    for (;;) {
+      const unsigned si = n % kSlots, use = n / kSlots;
+      Slot& slot = ts.slot[si];
+      mbar_wait(&ts.full[si], use & 1);
+      CLK_MARK(0);  // wait for a filled slot
+      const int row = slot.row;
+      if (row < 0) break;
+      const int x = slot.x;
+      if (x == 0) {
+        // row start
+        const int frame = slot.frame;
+        const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
+        uint8_t* const Y = a.out + (size_t)frame * n_mb * 384;
+        availB = row > 0;
+        publish = row + 1 < H;
+        line_above = a.line + (mb_row0 - W) * kLineWords + lane;
+        line_mine = a.line + mb_row0 * kLineWords + lane;
+        st_base = lane < 16 ? Y + (size_t)(16 * row + lane) * strideY : nullptr;
+        if (availB) {
+          // line 0 of the row above becomes "line x" of macroblock 0 (long wait: that row may not have started)
+          unsigned long long v0 = 0;
+          if (lane < 4) v0 = ld_relaxed_gpu_u64(line_above);
+          const uint32_t w = wait_line_words(line_above, v0, lane, 0, 4, tag, true, a.status, dead);
+          if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+          __syncwarp();
+          uint32_t sv = 0;
+          if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
+          __syncwarp();
+          if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
+          if (W1 > 0 && lane < 4) lv = ld_relaxed_gpu_u64(line_above + kLineWords);
         }
       }
-      const MbHeader h = decode_header(hdr_c, &local_status);
-
-      // 1. residual (independent of every other macroblock)
-      residual_stage(cs, ws, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
-
-      // 2. prediction modes: need only the modes of the MB above (line x, already here) and of the previous MB
-      const bool availA = x > 0, availC = availB && x < W - 1, availD = availA && availB;
-      const int b_row = (mw_cur >> (8 * gx)) & 0xff;
-      int syn = (int)syn_c;
-      if (h.mbcls == 1) syn = __shfl_sync(0xffffffffu, syn, syn_src8);
-      const int m = resolve_modes(lane, h.mbcls, syn, a_col, b_row, availA, availB);
-
-      // 3. wavefront wait: line x+1 of the row above (top-right neighbour), fetched before the residual stage
-      uint32_t mw_next = 0x02020202u;
-      if (need_line) {
-        const uint32_t w = wait_line(x + 1, lv, false, dead);
-        if (dead) break;
+      CLK_MARK(1);  // row start (incl. long wait for line 0)
+      const int mbcls = slot.mbcls, mode16 = slot.mode16;
+      const uint32_t modes_lo = slot.modes_lo, modes_hi = slot.modes_hi;
+      const bool availA = x > 0, availC = availB && x < W1, availD = availA && availB;
+      if (availC) {
+        const uint32_t w = wait_line_words(line_above + (size_t)(x + 1) * kLineWords, lv, lane, 0, 4, tag, false,
+                                           a.status, dead);
         if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
-        mw_next = __shfl_sync(0xffffffffu, w, 8);
-        __syncwarp();
       }
+      // fetch for the next macroblock of this row (line x+2), overlapped with this macroblock's prediction
+      if (availB && x + 2 <= W1 && lane < 4) lv = ld_relaxed_gpu_u64(line_above + (size_t)(x + 2) * kLineWords);
+      __syncwarp();
+      CLK_MARK(2);  // wait for line x+1 of the row above
 
-      // 4. prediction + residual + clip into the pixel tiles
-      if (h.mbcls == 0) predict_i4x4(cs, ws, lane, m, availA, availB, availC, availD);
-      else if (h.mbcls == 1) predict_i8x8(cs, ws, lane, m, availA, availB, availC, availD);
-      else predict_i16x16(ws, lane, (h.mbt - 1) & 3, availA, availB);
-      predict_chroma(ws, lane, h.cm, availA, availB, availD);
-
-      // 5. store the macroblock (16 x 16 B luma rows, 2 x 8 x 8 B chroma rows) and publish its bottom line
-      if (lane < 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&ws.luma[luma_at(0, lane)]);
-        __stcs(reinterpret_cast<uint4*>(st_base + (size_t)x * 16), v);
+      if (mbcls == 0) {
+        predict_i4x4(tab, ts.luma, slot.res, lane, modes_lo, modes_hi,
+                     1u | (availA ? 2u : 0u) | (availB ? 4u : 0u) | (availC ? 8u : 0u) | (availD ? 16u : 0u));
+        CLK_MARK(3);
+      } else if (mbcls == 1) {
+        predict_i8x8(tab, ts.luma, slot.res, lane, modes_lo, modes_hi, availA, availB, availC, availD);
+        CLK_MARK(4);
       } else {
-        const uint2 v = *reinterpret_cast<const uint2*>(&ws.chroma[lane >= 24 ? 1 : 0][chroma_at(0, lane & 7)]);
-        __stcs(reinterpret_cast<uint2*>(st_base + (size_t)x * 8), v);
+        predict_i16x16(ts.luma, slot.res, lane, mode16, availA, availB);
+        CLK_MARK(5);
       }
-      uint32_t mv = (lane >= 12 && lane < 16) ? ((uint32_t)m << (8 * (lane & 3))) : 0u;
-      mv |= __shfl_xor_sync(0xffffffffu, mv, 1);
-      mv |= __shfl_xor_sync(0xffffffffu, mv, 2);
-      mv = __shfl_sync(0xffffffffu, mv, 12);
-      if (publish && lane < kLineWords) {
-        const uint32_t payload = pub_src ? *reinterpret_cast<const uint32_t*>(pub_src) : mv;
-        st_relaxed_gpu_u64(line_mine + (size_t)x * kLineWords, ((unsigned long long)tag << 32) | payload);
+
+      if (lane < 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(&ts.luma[luma_at(0, lane)]);
+        __stcs(reinterpret_cast<uint4*>(st_base + (size_t)x * 16), v);
       }
-      a_col = __shfl_sync(0xffffffffu, m, gy * 4 + 3);
-      mw_cur = mw_next;
+      if (publish && pub_src)
+        st_relaxed_gpu_u64(line_mine + (size_t)x * kLineWords,
+                           ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
       // carry: right-most column -> left-neighbour column, top-row slots shift by one macroblock
+      int cv = 0;
       uint32_t sv = 0;
-      int cv;
-      if (lane < 16) cv = ws.luma[luma_at(15, lane)];
-      else cv = ws.chroma[lane >= 24 ? 1 : 0][chroma_at(7, lane & 7)];
-      if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + shift_by);
+      if (lane < 16) cv = ts.luma[luma_at(15, lane)];
+      else if (lane < 21) sv = *reinterpret_cast<const uint32_t*>(&ts.luma[12 + 4 * (lane - 16) + 16]);
       __syncwarp();
-      if (lane < 16) ws.luma[luma_at(-1, lane)] = (uint8_t)cv;
-      else ws.chroma[lane >= 24 ? 1 : 0][chroma_at(-1, lane & 7)] = (uint8_t)cv;
-      if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
+      if (lane < 16) ts.luma[luma_at(-1, lane)] = (uint8_t)cv;
+      else if (lane < 21) *reinterpret_cast<uint32_t*>(&ts.luma[12 + 4 * (lane - 16)]) = sv;
       __syncwarp();
+      if (lane == 0) mbar_arrive(&ts.empty[si]);
+      n++;
+      CLK_MARK(6);  // stores + publish + carry
     }
-    if (dead) break;
+    CLK_FLUSH(8);
   }
-  if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -254,7 +405,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 6) recon_wavefront_kernel(cons
 // One warp per macroblock, grid-stride; no dependencies between macroblocks.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsPerCta, 8) recon_residual_add_kernel(const KernelArgs a) {
-  __shared__ alignas(16) CtaSmem cs;
+  __shared__ alignas(16) ResidCtaSmem cs;
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.tables);
     uint4* dst = reinterpret_cast<uint4*>(&cs.tab);
@@ -262,7 +413,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 8) recon_residual_add_kernel(c
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  WarpSmem& ws = cs.warp[threadIdx.x >> 5];
+  ResidWarpSmem& ws = cs.warp[threadIdx.x >> 5];
   const LaneConst lc = make_lane_const(lane, cs.tab);
   const int W = a.W, H = a.H;
   const size_t n_mb = (size_t)W * H, total = n_mb * a.n_frames;
@@ -280,7 +431,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 8) recon_residual_add_kernel(c
       c1 = __ldg(cp + 1);
     }
     const MbHeader h = decode_header(hdr, &local_status);
-    residual_stage(cs, ws, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
+    residual_stage(cs.tab, ws.scratch, ws.res, ws.res + 256, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
     const size_t fo = frame * n_mb * 384;
     {  // luma: lane = (row r, half h): 8 pixels
       const int r = lane >> 1, hf = lane & 1;
@@ -333,6 +484,7 @@ struct dryv_recon_ctx {
   size_t line_cap = 0;                   // in macroblocks
   uint32_t tag = 0;                      // launch tag, incremented per wavefront launch (0 = never written)
   unsigned int* d_ticket = nullptr;  // [0] ticket, [1] status
+  unsigned long long* d_prof = nullptr;  // stage clocks (development builds)
   int* h_status = nullptr;           // pinned
   // staging for dryv_recon_submit (two slots)
   uint8_t* d_in[2] = {nullptr, nullptr};
@@ -407,6 +559,9 @@ KernelArgs make_args(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   a.tag = ctx->tag;
   a.ticket = ctx->d_ticket;
   a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
+#ifdef DRYV_STAGE_CLOCKS
+  a.prof = ctx->d_prof;
+#endif
   a.W = pp->pic_width_in_mbs;
   a.H = pp->pic_height_in_mbs;
   a.n_frames = (int)n_frames;
@@ -430,10 +585,10 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   if (++ctx->tag == 0) ctx->tag = 1;  // every launch validates line words with its own tag: no per-launch clearing
   CU(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
   KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out);
-  size_t want = (rows + dryv::kWarpsPerCta - 1) / dryv::kWarpsPerCta;
+  size_t want = rows;  // one row team (CTA) per macroblock row at most
   size_t cap = (size_t)ctx->sm_count * ctx->wave_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
-  dryv::recon_wavefront_kernel<<<grid, dryv::kThreadsPerCta, 0, s>>>(a);
+  dryv::recon_wavefront_kernel<<<grid, dryv::kTeamThreads, 0, s>>>(a);
   CU(cudaGetLastError());
   ctx->launches++;
   return DRYV_OK;
@@ -481,10 +636,12 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
   ok = ok && cudaMalloc(&ctx->d_tables, sizeof(DeviceTables)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_tables, sizeof(DeviceTables)) == cudaSuccess &&
        cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)) == cudaSuccess &&
+       cudaMalloc(&ctx->d_prof, 16 * sizeof(unsigned long long)) == cudaSuccess &&
+       cudaMemset(ctx->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_status, sizeof(int)) == cudaSuccess &&
        cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wave_ctas_per_sm, dryv::recon_wavefront_kernel,
-                                                           dryv::kThreadsPerCta, 0) == cudaSuccess &&
+                                                           dryv::kTeamThreads, 0) == cudaSuccess &&
        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resid_ctas_per_sm, dryv::recon_residual_add_kernel,
                                                      dryv::kThreadsPerCta, 0) == cudaSuccess;
   if (!ok || ctx->wave_ctas_per_sm < 1 || ctx->resid_ctas_per_sm < 1) {
@@ -515,6 +672,7 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
   if (ctx->d_line) cudaFree(ctx->d_line);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   delete ctx;
 }
@@ -688,5 +846,15 @@ int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char
 }
 
 uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+#ifdef DRYV_STAGE_CLOCKS
+// development builds only (not part of include/dryv_recon.h): read and reset the stage clocks
+int dryv_recon_debug_clocks(dryv_recon_ctx* ctx, unsigned long long out[16]) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (cudaMemcpy(out, ctx->d_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return DRYV_ERR_CUDA;
+  cudaMemset(ctx->d_prof, 0, 16 * sizeof(unsigned long long));
+  return DRYV_OK;
+}
+#endif
 
 }  // extern "C"

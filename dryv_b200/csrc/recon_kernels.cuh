@@ -28,27 +28,45 @@ namespace dryv {
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 
-// Per-warp shared memory (bytes): residual tile, luma/chroma pixel tiles, transform scratch.
-constexpr int kResBytes = 768;           // int16 luma[16][16] + cb[8][8] + cr[8][8]
 constexpr int kLumaStride = 48;          // pixel (x, y) at (y + 1) * 48 + 16 + x, x in -4..31 (row -1), y in -1..15
 constexpr int kLumaTileBytes = 17 * kLumaStride;
 constexpr int kChromaStride = 24;        // pixel (x, y) at (y + 1) * 24 + 8 + x, x in -4..15 (row -1), y in -1..7
 constexpr int kChromaTileBytes = 9 * kChromaStride;
 constexpr int kScratchBytes = 1152;      // 8x8 coefficient slab (4 * 144 B) aliased with the transpose buffer (4 * 72 words)
-constexpr int kWarpSmemBytes = kResBytes + kLumaTileBytes + 2 * kChromaTileBytes + kScratchBytes;
 
-struct WarpSmem {
-  int16_t res[384];
-  uint8_t luma[kLumaTileBytes];
-  uint8_t chroma[2][kChromaTileBytes];
+// residual-only kernel: one warp per macroblock
+struct ResidWarpSmem {
+  alignas(16) int16_t res[384];  // luma [16][16] | cb [8][8] | cr [8][8]
   alignas(16) uint8_t scratch[kScratchBytes];
 };
-static_assert(sizeof(WarpSmem) == kWarpSmemBytes, "smem layout");
-static_assert(sizeof(WarpSmem) % 16 == 0, "smem alignment");
-
-struct CtaSmem {
+struct ResidCtaSmem {
   DeviceTables tab;
-  WarpSmem warp[kWarpsPerCta];
+  ResidWarpSmem warp[kWarpsPerCta];
+};
+
+// wavefront kernel: a "row team" = one CTA of two warps walking one macroblock row.
+//   front warp: residual (luma + chroma), prediction-mode derivation, chroma prediction/stores
+//   luma warp : luma prediction/stores
+// The front warp hands each macroblock to the luma warp through a ring of kSlots slots.
+constexpr int kSlots = 4;
+constexpr int kTeamThreads = 64;
+struct Slot {
+  alignas(16) int16_t res[256];  // luma residual [16][16]
+  uint32_t modes_lo, modes_hi;   // resolved Intra4x4/8x8 modes of the raster 4x4 grid cells 0..7 / 8..15, 4 bits each
+  int32_t frame, row, x;         // row < 0: no more work
+  int32_t mbcls, mode16;         // 0/1/2 = Intra4x4/8x8/16x16, Intra16x16 prediction mode
+  int32_t pad[1];
+};
+static_assert(sizeof(Slot) % 16 == 0, "slot alignment");
+struct TeamSmem {
+  DeviceTables tab;
+  Slot slot[kSlots];
+  alignas(16) int16_t cres[128];                    // chroma residual of the macroblock in flight (front warp)
+  alignas(16) uint8_t luma[kLumaTileBytes];         // luma pixel tile (luma warp)
+  alignas(16) uint8_t chroma[2 * kChromaTileBytes]; // chroma pixel tiles (front warp)
+  alignas(16) uint8_t scratch[kScratchBytes];
+  alignas(8) unsigned long long full[kSlots];       // mbarriers: slot filled by the front warp
+  alignas(8) unsigned long long empty[kSlots];      // mbarriers: slot released by the luma warp
 };
 
 enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
@@ -72,6 +90,7 @@ struct KernelArgs {
   unsigned long long* line; // [n_frames * H * W][kLineWords] bottom line of each MB: payload | tag << 32
   uint32_t tag;             // launch tag: a line word is valid when its upper half equals it
   unsigned int* ticket;     // row ticket counter
+  unsigned long long* prof; // stage clocks (development builds), may be null
   int* status;
   int W, H, n_frames;
   int cb_off, cr_off;
@@ -138,7 +157,7 @@ __device__ __forceinline__ void idct8(int* d) {
 
 // Per-lane constants that do not change over the kernel.
 struct LaneConst {
-  int res_off;      // int16 offset of this lane's 4x4 block inside WarpSmem::res (lanes 0..23)
+  int res_off;      // int16 offset of this lane's 4x4 block inside the luma (lanes 0..15) / chroma (16..23) residual tile
   int res_stride;   // 16 (luma) or 8 (chroma)
   // Intra16x16 luma-DC Hadamard: partner lanes / signs of the four butterfly stages + final routing
   uint32_t dc_partners;  // 5 x 5 bits: stage0..3 partner lane, then routing source lane
@@ -156,7 +175,7 @@ __device__ __forceinline__ LaneConst make_lane_const(int lane, const DeviceTable
     lc.res_stride = 16;
   } else {
     int b = lane & 3, pl = (lane >> 2) & 1;
-    lc.res_off = 256 + pl * 64 + (b >> 1) * 32 + (b & 1) * 4;
+    lc.res_off = pl * 64 + (b >> 1) * 32 + (b & 1) * 4;
     lc.res_stride = 8;
   }
   // luma DC: lane L (< 16) holds c[i][j] with (i, j) = zig-zag position of L.
@@ -199,19 +218,20 @@ __device__ __forceinline__ LaneConst make_lane_const(int lane, const DeviceTable
 // Residual stage: levels (registers c0, c1 of lanes 0..23) -> int16 residual tile.
 //   mbcls: 0 Intra4x4, 1 Intra8x8, 2 Intra16x16.  qp: QP'Y of the MB.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void residual_stage(const CtaSmem& cs, WarpSmem& ws, const LaneConst& lc, int lane,
-                                               uint4 c0, uint4 c1, int mbcls, int qp, int cb_off, int cr_off) {
-  const DeviceTables& tab = cs.tab;
+//   res_luma: int16 [16][16]; res_chroma: int16 [2][8][8]; scratch: kScratchBytes, 16-byte aligned.
+__device__ __forceinline__ void residual_stage(const DeviceTables& tab, uint8_t* scratch, int16_t* res_luma,
+                                               int16_t* res_chroma, const LaneConst& lc, int lane, uint4 c0, uint4 c1,
+                                               int mbcls, int qp, int cb_off, int cr_off) {
   // ---- Intra8x8 luma: 8 lanes per block -----------------------------------------------------
   if (mbcls == 1) {
     if (lane < 16) {
-      uint8_t* dst = ws.scratch + (lane >> 2) * 144 + (lane & 3) * 32;
+      uint8_t* dst = scratch + (lane >> 2) * 144 + (lane & 3) * 32;
       *reinterpret_cast<uint4*>(dst) = c0;
       *reinterpret_cast<uint4*>(dst + 16) = c1;
     }
     __syncwarp();
     const int blk = lane >> 3, i = lane & 7;
-    const uint8_t* slab = ws.scratch + blk * 144;
+    const uint8_t* slab = scratch + blk * 144;
     const int qpm = qp % 6, qpd = qp / 6;
     const uint4 lsv = *reinterpret_cast<const uint4*>(&tab.ls8[qpm][i * 8]);
     const uint32_t lsw[4] = {lsv.x, lsv.y, lsv.z, lsv.w};
@@ -228,14 +248,14 @@ __device__ __forceinline__ void residual_stage(const CtaSmem& cs, WarpSmem& ws, 
     if (i == 0) d[0] += 32;  // folds the final (m + 32) >> 6 rounding: d00 reaches every output with weight 1
     idct8(d);
     __syncwarp();
-    int* tb = reinterpret_cast<int*>(ws.scratch) + blk * 72;
+    int* tb = reinterpret_cast<int*>(scratch) + blk * 72;
     *reinterpret_cast<int4*>(tb + i * 8) = make_int4(d[0], d[1], d[2], d[3]);
     *reinterpret_cast<int4*>(tb + i * 8 + 4) = make_int4(d[4], d[5], d[6], d[7]);
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < 8; r++) d[r] = tb[r * 8 + i];
     idct8(d);
-    int16_t* rl = ws.res + ((blk >> 1) * 8) * 16 + (blk & 1) * 8 + i;
+    int16_t* rl = res_luma + ((blk >> 1) * 8) * 16 + (blk & 1) * 8 + i;
 #pragma unroll
     for (int r = 0; r < 8; r++) rl[r * 16] = (int16_t)(d[r] >> 6);
   }
@@ -302,7 +322,7 @@ __device__ __forceinline__ void residual_stage(const CtaSmem& cs, WarpSmem& ws, 
     idct4(v[1], v[4], v[8], v[10]);
     idct4(v[5], v[7], v[11], v[14]);
     idct4(v[6], v[12], v[13], v[15]);
-    int16_t* r = ws.res + lc.res_off;
+    int16_t* r = (is_chroma_lane ? res_chroma : res_luma) + lc.res_off;
     const int st = lc.res_stride;
     *reinterpret_cast<uint2*>(r) = make_uint2(pack2(v[0] >> 6, v[1] >> 6), pack2(v[5] >> 6, v[6] >> 6));
     *reinterpret_cast<uint2*>(r + st) = make_uint2(pack2(v[2] >> 6, v[4] >> 6), pack2(v[7] >> 6, v[12] >> 6));
@@ -324,95 +344,74 @@ __device__ __forceinline__ uint32_t legal_mask(bool t, bool l, bool c) {
   return 0x004u | (t ? 0x089u : 0u) | (l ? 0x102u : 0u) | ((t && l && c) ? 0x070u : 0u);
 }
 
-// Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110. Ten dependency steps, two blocks per step
-// where the decode-order availability rules allow it; one pixel per lane, 16 lanes per block.
-// BA / BB = block handled by lanes 0..15 / 16..31 in this step (BB < 0: upper half idle).
-template <int BA, int BB>
-__device__ __forceinline__ void i4x4_step(const CtaSmem& cs, WarpSmem& ws, int lane, int my_mode_grid, bool availA,
-                                          bool availB, bool availC, bool availD) {
-  constexpr int BBe = BB < 0 ? BA : BB;
-  constexpr int bxA = ((BA >> 2) & 1) * 8 + (BA & 1) * 4, byA = (BA >> 3) * 8 + ((BA >> 1) & 1) * 4;
-  constexpr int bxB = ((BBe >> 2) & 1) * 8 + (BBe & 1) * 4, byB = (BBe >> 3) * 8 + ((BBe >> 1) & 1) * 4;
-  const bool half = lane >= 16;
-  const int p = lane & 15, px = p & 3, py = p >> 2;
-  const bool active = !half || BB >= 0;
-  const int b = half ? BBe : BA;
-  const int bx = half ? bxB : bxA, by = half ? byB : byA;
-  const int mode = __shfl_sync(0xffffffffu, my_mode_grid, half ? ((byB >> 2) * 4 + (bxB >> 2)) : ((byA >> 2) * 4 + (bxA >> 2)));
-  const bool aL = bx > 0 || availA;
-  const bool aT = by > 0 || availB;
-  const bool aTL = (bx > 0 && by > 0) ? true : (bx > 0 ? availB : (by > 0 ? availA : availD));
-  // top-right availability, pred4x4.rs:39-43 + MbPosition::from_coords (slice/macroblock.rs:448-462)
-  bool aTR;
-  if (b == 3 || b == 11 || b == 7 || b == 13 || b == 15) aTR = false;
-  else if (b == 5) aTR = availC;
-  else if (b == 0 || b == 1 || b == 4) aTR = availB;
-  else aTR = true;
-  const int org = luma_at(bx, by);
-  int ev;
-  if (p == E4_DC) {
-    // DC value (pred4x4.rs:116-167), computed by this lane alone and only when the block's mode is DC
-    ev = 128;
-    if (mode == 2) {
-      const uint32_t tw = *reinterpret_cast<const uint32_t*>(&ws.luma[org - kLumaStride]);
-      const int sumT = dp4a_us(tw, 0x01010101, 0);
-      const int sumL = ws.luma[org - 1] + ws.luma[org + kLumaStride - 1] + ws.luma[org + 2 * kLumaStride - 1] +
-                       ws.luma[org + 3 * kLumaStride - 1];
-      if (aT && aL) ev = (sumT + sumL + 4) >> 3;
-      else if (aL) ev = (sumL + 2) >> 2;
-      else if (aT) ev = (sumT + 2) >> 2;
+// Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110. Ten dependency steps (DeviceTables::i4step),
+// two blocks per step where the decode-order availability rules allow it; one pixel per lane, 16 lanes
+// per block. Kept as a rolled loop: the kernel is instruction-fetch sensitive.
+//   avm = 1 | A<<1 | B<<2 | C<<3 | D<<4 (macroblock availability), modes_lo/hi = 4-bit modes per cell.
+__device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma, int lane,
+                                             uint32_t modes_lo, uint32_t modes_hi, uint32_t avm) {
+  const int half = lane >> 4, p = lane & 15, px = p & 3, py = p >> 2;
+  // edge sample fetched by this lane, relative to the block origin: 0..7 top / top-right (4..7 fall back to
+  // sample 3 when top-right is missing), 8..11 left, 12 corner, 13..15 contribute 0
+  const int edge_off = p < 8 ? (p - kLumaStride) : (p < 12 ? (p - 8) * kLumaStride - 1 : -kLumaStride - 1);
+  const int edge_off_notr = (p >= 4 && p < 8) ? (3 - kLumaStride) : edge_off;
+  const int edge_sel_shift = p < 8 ? 17 : (p < 12 ? 14 : 20);  // which availability selector guards the sample
+  const int pix_off = py * kLumaStride + px, res_off = py * 16 + px;
+  uint32_t nxt = tab.i4step[0][half];
+#pragma unroll 1
+  for (int s = 0; s < 10; s++) {
+    const uint32_t cur = nxt;
+    nxt = tab.i4step[s < 9 ? s + 1 : 9][half];
+    const int org = cur & 1023, cell = (cur >> 10) & 15;
+    const bool aL = (avm >> ((cur >> 14) & 7)) & 1, aT = (avm >> ((cur >> 17) & 7)) & 1;
+    const bool aTL = (avm >> ((cur >> 20) & 7)) & 1, aTR = (avm >> ((cur >> 23) & 7)) & 1;
+    const uint32_t mw = (cell & 8) ? modes_hi : modes_lo;
+    const int mode = (mw >> ((cell & 7) * 4)) & 15;
+    int ev = lt[org + (aTR ? edge_off : edge_off_notr)];
+    if (p > 12 || !((avm >> ((cur >> edge_sel_shift) & 7)) & 1)) ev = 0;  // unavailable samples count as 0
+    const uint32_t taps = tab.lut4[mode > 8 ? 2 : mode][p];
+    const int res = res_luma[(cell >> 2) * 64 + (cell & 3) * 4 + res_off];
+    const int e0 = __shfl_sync(0xffffffffu, ev, taps & 15, 16);
+    const int e1 = __shfl_sync(0xffffffffu, ev, (taps >> 4) & 15, 16);
+    const int e2 = __shfl_sync(0xffffffffu, ev, (taps >> 8) & 15, 16);
+    const int t3 = e0 + e1 + e2;
+    int pred = (t3 + e1 + 2) >> 2;
+    if (__any_sync(0xffffffffu, mode == 2)) {
+      // DC (pred4x4.rs:116-167): second summation round over the three partial sums held by lanes 0..2
+      const int q = __shfl_sync(0xffffffffu, t3, 0, 16) + __shfl_sync(0xffffffffu, t3, 1, 16) +
+                    __shfl_sync(0xffffffffu, t3, 2, 16);
+      const int dcv = (aT && aL) ? ((q + 4) >> 3) : ((aT || aL) ? ((q + 2) >> 2) : 128);
+      if (mode == 2) pred = dcv;
     }
-  } else {
-    // edge sample of this lane: 0..7 top (4..7 replicated from 3 when top-right is missing), 8..11 left, 12 corner
-    int off;
-    if (p < 8) off = -kLumaStride + ((p >= 4 && !aTR) ? 3 : p);
-    else if (p < 12) off = (p - 8) * kLumaStride - 1;
-    else off = -kLumaStride - 1;
-    ev = ws.luma[org + off];
+    const bool ok = mode <= 8 && ((legal_mask(aT, aL, aTL) >> mode) & 1u);
+    if (!ok) pred = 0;
+    if ((cur >> 26) & 1) lt[org + pix_off] = (uint8_t)clip255(pred + res);
+    __syncwarp();
   }
-  const int res = ws.res[(by + py) * 16 + bx + px];
-  const uint32_t taps = cs.tab.lut4[mode > 8 ? 2 : mode][p];
-  const int e0 = __shfl_sync(0xffffffffu, ev, taps & 15, 16);
-  const int e1 = __shfl_sync(0xffffffffu, ev, (taps >> 4) & 15, 16);
-  const int e2 = __shfl_sync(0xffffffffu, ev, (taps >> 8) & 15, 16);
-  int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
-  const bool ok = mode <= 8 && ((legal_mask(aT, aL, aTL) >> mode) & 1u);
-  if (!ok) pred = 0;
-  if (active) ws.luma[org + py * kLumaStride + px] = (uint8_t)clip255(pred + res);
-  __syncwarp();
-}
-
-__device__ __forceinline__ void predict_i4x4(const CtaSmem& cs, WarpSmem& ws, int lane, int m, bool availA,
-                                             bool availB, bool availC, bool availD) {
-  i4x4_step<0, -1>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<1, -1>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<2, 4>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<3, 5>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<6, 8>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<7, 9>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<10, 12>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<11, 13>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<14, -1>(cs, ws, lane, m, availA, availB, availC, availD);
-  i4x4_step<15, -1>(cs, ws, lane, m, availA, availB, availC, availD);
 }
 
 // Intra8x8 luma, pred8x8.rs:152-696 + pred8x8.rs:34-46. Four sequential blocks, two pixels per lane.
-__device__ __forceinline__ void predict_i8x8(const CtaSmem& cs, WarpSmem& ws, int lane, int my_mode_grid,
-                                             bool availA, bool availB, bool availC, bool availD) {
-#pragma unroll
+__device__ __forceinline__ void predict_i8x8(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma, int lane,
+                                             uint32_t modes_lo, uint32_t modes_hi, bool availA, bool availB,
+                                             bool availC, bool availD) {
+  const int py = lane >> 2, px = (lane & 3) * 2;
+#pragma unroll 1
   for (int b = 0; b < 4; b++) {
     const int bx = (b & 1) * 8, by = (b >> 1) * 8;
-    const int mode = __shfl_sync(0xffffffffu, my_mode_grid, (by >> 2) * 4 + (bx >> 2));
+    const int mode = (((b & 2) ? modes_hi : modes_lo) >> ((b & 1) * 8)) & 15;  // cells 0, 2, 8, 10
     const bool aL = bx > 0 || availA;
     const bool aT = by > 0 || availB;
     const bool aTL = b == 0 ? availD : (b == 1 ? availB : (b == 2 ? availA : true));
     const bool aTR = b == 0 ? availB : (b == 1 ? availC : (b == 2));
+    const int m = mode > 8 ? 2 : mode;
+    const uint32_t tw = *reinterpret_cast<const uint32_t*>(&tab.lut8[m][py * 8 + px]);
+    const uint32_t rw = *reinterpret_cast<const uint32_t*>(&res_luma[(by + py) * 16 + bx + px]);
     // raw edge sample of this lane: 0..15 top, 16..23 left, 24 corner
     int ex, ey;
     if (lane < 16) { ex = bx + ((lane >= 8 && !aTR) ? 7 : lane); ey = by - 1; }
     else if (lane < 24) { ex = bx - 1; ey = by + (lane - 16); }
     else { ex = bx - 1; ey = by - 1; }
-    const int raw = ws.luma[luma_at(ex, ey)];
+    const int raw = lt[luma_at(ex, ey)];
     // reference sample filter, pred8x8.rs:222-288 (with the x = 0 overwrite of quirk Q2)
     int srcp, srcn;  // lanes supplying the previous / next sample of the 3-tap filter
     if (lane < 16) { srcp = lane == 0 ? E8_CORNER : lane - 1; srcn = lane == 15 ? 15 : lane + 1; }
@@ -422,8 +421,7 @@ __device__ __forceinline__ void predict_i8x8(const CtaSmem& cs, WarpSmem& ws, in
     const int nv = __shfl_sync(0xffffffffu, raw, srcn & 31);
     if (lane == 0 && !aTL) pv = -1;  // Q2: raw p[-1,-1] sentinel enters the filter
     int ev = (pv + 2 * raw + nv + 2) >> 2;
-    // DC, pred8x8.rs:326-425: sums of the filtered top 0..7 (lanes 0..7) and left (lanes 16..23)
-    if (mode == 2) {  // warp-uniform
+    if (mode == 2) {  // DC, pred8x8.rs:326-425 (warp-uniform): sums of the filtered top 0..7 and left 0..7
       int sum = ev + __shfl_xor_sync(0xffffffffu, ev, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       sum += __shfl_xor_sync(0xffffffffu, sum, 4);
@@ -436,9 +434,6 @@ __device__ __forceinline__ void predict_i8x8(const CtaSmem& cs, WarpSmem& ws, in
       else dc = 128;
       if (lane == E8_DC) ev = dc;
     }
-    const int m = mode > 8 ? 2 : mode;
-    const int py = lane >> 2, px = (lane & 3) * 2;
-    const uint32_t tw = *reinterpret_cast<const uint32_t*>(&cs.tab.lut8[m][py * 8 + px]);
     const bool ok = mode <= 8 && ((legal_mask(aT, aL, aTL) >> mode) & 1u);
     int pr[2];
 #pragma unroll
@@ -449,19 +444,19 @@ __device__ __forceinline__ void predict_i8x8(const CtaSmem& cs, WarpSmem& ws, in
       const int e2 = __shfl_sync(0xffffffffu, ev, (taps >> 10) & 31);
       pr[q] = ok ? ((e0 + 2 * e1 + e2 + 2) >> 2) : 0;
     }
-    const uint32_t rw = *reinterpret_cast<const uint32_t*>(&ws.res[(by + py) * 16 + bx + px]);
     const int o0 = clip255(pr[0] + lo16(rw)), o1 = clip255(pr[1] + hi16(rw));
-    *reinterpret_cast<uint16_t*>(&ws.luma[luma_at(bx + px, by + py)]) = (uint16_t)(o0 | (o1 << 8));
+    *reinterpret_cast<uint16_t*>(&lt[luma_at(bx + px, by + py)]) = (uint16_t)(o0 | (o1 << 8));
     __syncwarp();
   }
 }
 
 // Intra16x16 luma, pred16x16.rs:79-425 + pred16x16.rs:64-75. Lane = (row, half): 8 pixels.
-__device__ __forceinline__ void predict_i16x16(WarpSmem& ws, int lane, int mode, bool availA, bool availB) {
+__device__ __forceinline__ void predict_i16x16(uint8_t* lt, const int16_t* res_luma, int lane, int mode, bool availA,
+                                               bool availB) {
   const int row = lane >> 1, h = lane & 1;
-  const uint32_t t0 = *reinterpret_cast<const uint32_t*>(&ws.luma[luma_at(8 * h, -1)]);
-  const uint32_t t1 = *reinterpret_cast<const uint32_t*>(&ws.luma[luma_at(8 * h + 4, -1)]);
-  const int left = ws.luma[luma_at(-1, row)];
+  const uint32_t t0 = *reinterpret_cast<const uint32_t*>(&lt[luma_at(8 * h, -1)]);
+  const uint32_t t1 = *reinterpret_cast<const uint32_t*>(&lt[luma_at(8 * h + 4, -1)]);
+  const int left = lt[luma_at(-1, row)];
   int pr[8];
   if (mode == 0) {  // vertical
 #pragma unroll
@@ -490,7 +485,7 @@ __device__ __forceinline__ void predict_i16x16(WarpSmem& ws, int lane, int mode,
 #pragma unroll
     for (int k = 0; k < 8; k++) pr[k] = dc;
   } else {  // plane (needs A and B; the corner is read unchecked like pred16x16.rs:404, quirk Q5)
-    const int corner = ws.luma[luma_at(-1, -1)];
+    const int corner = lt[luma_at(-1, -1)];
     // H = sum_{x'=0..7} (x'+1) * (p[8+x',-1] - p[6-x',-1]),  p[-1,-1] = corner
     int hp;
     if (h) hp = dp4a_us(t1, 0x08070605, dp4a_us(t0, 0x04030201, 0));
@@ -513,21 +508,22 @@ __device__ __forceinline__ void predict_i16x16(WarpSmem& ws, int lane, int mode,
 #pragma unroll
     for (int k = 0; k < 8; k++) pr[k] = ok ? clip255((base + bb * k) >> 5) : 0;
   }
-  const uint4 rv = *reinterpret_cast<const uint4*>(&ws.res[row * 16 + 8 * h]);
+  const uint4 rv = *reinterpret_cast<const uint4*>(&res_luma[row * 16 + 8 * h]);
   const int o0 = clip255(pr[0] + lo16(rv.x)), o1 = clip255(pr[1] + hi16(rv.x));
   const int o2 = clip255(pr[2] + lo16(rv.y)), o3 = clip255(pr[3] + hi16(rv.y));
   const int o4 = clip255(pr[4] + lo16(rv.z)), o5 = clip255(pr[5] + hi16(rv.z));
   const int o6 = clip255(pr[6] + lo16(rv.w)), o7 = clip255(pr[7] + hi16(rv.w));
   __syncwarp();  // every lane has read the neighbours it needs before the tile is overwritten
-  *reinterpret_cast<uint2*>(&ws.luma[luma_at(8 * h, row)]) = make_uint2(pack4(o0, o1, o2, o3), pack4(o4, o5, o6, o7));
+  *reinterpret_cast<uint2*>(&lt[luma_at(8 * h, row)]) = make_uint2(pack4(o0, o1, o2, o3), pack4(o4, o5, o6, o7));
   __syncwarp();
 }
 
 // Chroma Cb + Cr, trans_chroma.rs:96-366 + trans_chroma.rs:81-92. Lane = (plane, row, half): 4 pixels.
-__device__ __forceinline__ void predict_chroma(WarpSmem& ws, int lane, int mode, bool availA, bool availB,
-                                               bool availD) {
+//   ct: two chroma tiles of kChromaTileBytes each; res_chroma: int16 [2][8][8]
+__device__ __forceinline__ void predict_chroma(uint8_t* ct, const int16_t* res_chroma, int lane, int mode, bool availA,
+                                               bool availB, bool availD) {
   const int pl = lane >> 4, row = (lane >> 1) & 7, h = lane & 1;
-  uint8_t* tile = ws.chroma[pl];
+  uint8_t* tile = ct + pl * kChromaTileBytes;
   const uint32_t tw = *reinterpret_cast<const uint32_t*>(&tile[chroma_at(4 * h, -1)]);
   const int left = tile[chroma_at(-1, row)];
   int pr[4];
@@ -588,7 +584,7 @@ __device__ __forceinline__ void predict_chroma(WarpSmem& ws, int lane, int mode,
 #pragma unroll
     for (int k = 0; k < 4; k++) pr[k] = ok ? clip255((base + bb * k) >> 5) : 0;
   }
-  const uint2 rv = *reinterpret_cast<const uint2*>(&ws.res[256 + pl * 64 + row * 8 + 4 * h]);
+  const uint2 rv = *reinterpret_cast<const uint2*>(&res_chroma[pl * 64 + row * 8 + 4 * h]);
   const int o0 = clip255(pr[0] + lo16(rv.x)), o1 = clip255(pr[1] + hi16(rv.x));
   const int o2 = clip255(pr[2] + lo16(rv.y)), o3 = clip255(pr[3] + hi16(rv.y));
   __syncwarp();

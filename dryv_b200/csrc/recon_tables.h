@@ -13,11 +13,12 @@
 namespace dryv {
 
 // Edge-sample numbering used by the tap tables.
-//   4x4: 0..7 = p[0..7,-1] (top, top-right), 8..11 = p[-1,0..3] (left), 12 = p[-1,-1], 13 = DC value
+//   4x4: 0..7 = p[0..7,-1] (top, top-right), 8..11 = p[-1,0..3] (left), 12 = p[-1,-1], 13 = always 0;
+//        mode 2 (DC) holds the first of two summation rounds: lanes 0..2 add three edge samples each
 //   8x8: 0..15 = p'[0..15,-1], 16..23 = p'[-1,0..7], 24 = p'[-1,-1], 25 = DC value
 // Every predicted sample of every mode is (E[i0] + 2*E[i1] + E[i2] + 2) >> 2 for a triple of edge
 // indices: a 2-tap average (a + b + 1) >> 1 is the triple (a, b, a), a copy is (a, a, a).
-enum { E4_LEFT = 8, E4_CORNER = 12, E4_DC = 13, E8_LEFT = 16, E8_CORNER = 24, E8_DC = 25 };
+enum { E4_LEFT = 8, E4_CORNER = 12, E4_ZERO = 13, E8_LEFT = 16, E8_CORNER = 24, E8_DC = 25 };
 
 struct DeviceTables {
   int32_t t4[52][16];      // [qP][zig-zag k] = LevelScale4x4[qP%6][pos(k)] << max(qP/6 - 4, 0)
@@ -27,6 +28,11 @@ struct DeviceTables {
   uint8_t zz8inv[8][8];    // [i][j] -> zig-zag index
   uint8_t qpc[52];         // qPI -> QPC
   uint8_t pad[12];
+  // Intra4x4 dependency schedule: [step][half] -> tile origin (10 bits) | raster cell << 10 |
+  // availability selectors (3 bits each: left, top, corner, top-right) << 14 | active << 26.
+  // A selector indexes the mask 1 | A<<1 | B<<2 | C<<3 | D<<4 (5 = never available).
+  uint32_t i4step[10][2];
+  uint32_t pad2[12];
 };
 
 void build_device_tables(const dryv_pic_params& pp, DeviceTables* t);

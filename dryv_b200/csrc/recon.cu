@@ -26,10 +26,17 @@ struct MbHeader {
   int mbt, t8, cm, qp, mbcls;
 };
 
-// lanes 0..3 fetch mb_type / transform_size_8x8_flag / intra_chroma_pred_mode / qp of macroblock `mb`
-__device__ __forceinline__ uint32_t load_header_lane(const KernelArgs& a, int lane, size_t mb) {
-  const uint8_t* p = lane == 0 ? a.mb_type : (lane == 1 ? a.t8x8 : (lane == 2 ? a.chroma_mode : a.qp));
-  return lane < 4 ? (uint32_t)__ldg(p + mb) : 0u;
+// lanes 0..3 fetch mb_type / transform_size_8x8_flag / intra_chroma_pred_mode / qp of macroblock `mb`;
+// `base` is the lane's array (header_base), selected once per kernel
+__device__ __forceinline__ const uint8_t* header_base(const KernelArgs& a, int lane) {
+  const uint8_t* p = a.qp;
+  if (lane == 0) p = a.mb_type;
+  if (lane == 1) p = a.t8x8;
+  if (lane == 2) p = a.chroma_mode;
+  return p;
+}
+__device__ __forceinline__ uint32_t load_header_lane(const uint8_t* base, int lane, size_t mb) {
+  return lane < 4 ? (uint32_t)__ldg(base + mb) : 0u;
 }
 __device__ __forceinline__ MbHeader decode_header(uint32_t hdr_lane, int* status) {
   MbHeader h;
@@ -78,16 +85,17 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+  const uint32_t addr = smem_u32(b);
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(smem_u32(b)),
-      "r"(parity)
+      "}" ::"r"(addr),
+      "r"(parity), "r"(20000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
 }
 
@@ -100,17 +108,20 @@ __device__ __forceinline__ uint32_t wait_line_words(const unsigned long long* p,
                                                     bool& dead) {
   unsigned long long v = first;
   const bool mine = lane >= lo && lane < hi;
+  if (dead || __all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) return (uint32_t)v;
+  const unsigned ns = long_wait ? 4000u : 200u;
   unsigned spins = 0;
-  while (!dead && !__all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) {
-    ++spins;
-    if (long_wait || spins > 4u) __nanosleep(long_wait ? 1000u : 64u);
-    if ((spins & 0x3ffu) == 0u) {
-      if (spins > (1u << 21) || ld_relaxed_gpu_s32(status) == STATUS_WATCHDOG) {
+  for (;;) {
+    __nanosleep(ns);
+    if (mine) v = ld_relaxed_gpu_u64(p);
+    if (__all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) break;
+    if ((++spins & 0x3ffu) == 0u) {
+      if (spins > (1u << 20) || ld_relaxed_gpu_s32(status) == STATUS_WATCHDOG) {
         if (lane == 0) atomicExch(status, STATUS_WATCHDOG);
         dead = true;
+        break;
       }
     }
-    if (mine) v = ld_relaxed_gpu_u64(p);
   }
   return (uint32_t)v;
 }
@@ -120,16 +131,20 @@ __device__ __forceinline__ uint32_t wait_line_words(const unsigned long long* p,
 //
 // A row team (one CTA, two warps) walks one macroblock row of one picture left to right:
 //   front warp  - 128-bit coefficient loads, dequant + Hadamard + 4x4/8x8 inverse transforms (residual
-//                 tile -> ring slot), Intra4x4/8x8 mode derivation, chroma prediction + stores
-//   luma warp   - Intra4x4/8x8/16x16 prediction + residual add + clip, 16 x 128-bit luma row stores
+//                 tiles -> ring slot) and the Intra4x4/8x8 prediction-mode derivation. It depends on the
+//                 row above only through that row's modes, so it runs ahead of the pixels.
+//   pixel warp  - Intra4x4/8x8/16x16 + chroma prediction, residual add + clip, 128-bit row stores.
 // Rows hand data down through the line buffer: after a macroblock the team writes its bottom line
 // (4 luma words, 2+2 chroma words, 1 word of bottom-block modes), each as payload | launch tag in one
-// 64-bit word. The row below fetches a line with one relaxed 64-bit load per lane, issued before the
-// work it can overlap with, and checks the tags later: no fences, no flags, and nobody reads the
-// picture back. Luma needs line x+1 of the row above (top-right neighbour: x+2y wavefront); chroma
-// and the mode derivation only need line x.
+// 64-bit word. The row below fetches a line with one relaxed 64-bit load per lane, issued a whole
+// macroblock before it is needed, and only checks the tags later: no fences, no flags, and nobody
+// reads the picture back. Luma needs line x+1 of the row above (top-right neighbour: x+2y wavefront);
+// chroma and the mode derivation only need line x.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const KernelArgs a) {
+#ifndef DRYV_TEAMS_PER_SM
+#define DRYV_TEAMS_PER_SM 12
+#endif
+__global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefront_kernel(const KernelArgs a) {
   __shared__ alignas(16) TeamSmem ts;
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.tables);
@@ -150,28 +165,18 @@ __global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const
   const size_t n_mb = (size_t)W * H;
   const int strideY = W * 16, strideC = W * 8;
   const uint32_t tag = a.tag;
-  const int g = lane & 15, gx = g & 3, gy = g >> 2;  // raster-grid cell of this lane
   bool dead = false;
 
   if (is_front) {
     // =========================================== front warp ===========================================
     const LaneConst lc = make_lane_const(lane, tab);
+    const uint8_t* const hdr_base = header_base(a, lane);
     const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
+    const int g = lane & 15, gx = g & 3, gy = g >> 2;  // raster-grid cell of this lane
     const int syn_idx4 = 8 * (gy >> 1) + 4 * (gx >> 1) + 2 * (gy & 1) + (gx & 1);  // spec 4x4 block index of the cell
     const int syn_src8 = ((gy >> 1) ? 4 : 0) + (gx >> 1);  // lane that loaded pred_syntax[blk8] (cells 0,1,4,5)
-    // chroma top-row slots per plane: [x-1].w1 | [x].w0 | [x].w1 at byte 4 + 4k of tile row -1
-    // line words handled by this warp: lanes 4..5 Cb, 6..7 Cr, 8 modes
-    uint8_t* fresh_dst = nullptr;
-    const uint8_t* pub_src = nullptr;
-    if (lane >= 4 && lane < 8) {
-      const int pl = (lane - 4) >> 1, k = (lane - 4) & 1;
-      fresh_dst = &ts.chroma[pl * kChromaTileBytes + 4 + 4 * (1 + k)];
-      pub_src = &ts.chroma[pl * kChromaTileBytes + chroma_at(4 * k, 7)];
-    }
-    // chroma row this lane stores / carries (lanes 0..15: plane = lane >> 3, row = lane & 7)
-    uint8_t* const my_ct = &ts.chroma[((lane >> 3) & 1) * kChromaTileBytes];
     int local_status = STATUS_OK;
-    unsigned n = 0;  // macroblocks handed to the luma warp so far
+    unsigned n = 0;  // macroblocks handed to the pixel warp so far
     CLK_DECL;
     for (;;) {
       unsigned t = 0;
@@ -181,19 +186,19 @@ __global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const
       // tickets are dealt row-major over pictures so that a row only ever waits on a lower ticket
       const int row = (int)(t / (unsigned)a.n_frames), frame = (int)(t % (unsigned)a.n_frames);
       const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
-      uint8_t* const Cb = a.out + (size_t)frame * n_mb * 384 + n_mb * 256;
       const bool availB = row > 0, publish = row + 1 < H;
-      const unsigned long long* const line_above = a.line + (mb_row0 - W) * kLineWords + lane;
-      unsigned long long* const line_mine = a.line + mb_row0 * kLineWords + lane;
-      uint8_t* st_base = nullptr;
-      if (lane < 16) st_base = Cb + (size_t)(lane >> 3) * n_mb * 64 + (size_t)(8 * row + (lane & 7)) * strideC;
+      // modes word (line word 8) of the row above / of this row
+      const unsigned long long* modes_above = a.line + (mb_row0 - W) * kLineWords + 8;
+      unsigned long long* modes_mine = a.line + mb_row0 * kLineWords + 8;
 
       // prefetch macroblock 0
-      uint32_t hdr_n = load_header_lane(a, lane, mb_row0);
-      uint32_t syn_n = lane < 16 ? (uint32_t)__ldg(a.pred_syntax + mb_row0 * 16 + syn_idx4) : 0u;
+      const uint8_t* hp = hdr_base + mb_row0;
+      const uint8_t* sp = a.pred_syntax + mb_row0 * 16 + syn_idx4;
+      const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 2;
+      uint32_t hdr_n = lane < 4 ? (uint32_t)__ldg(hp) : 0u;
+      uint32_t syn_n = lane < 16 ? (uint32_t)__ldg(sp) : 0u;
       uint4 c0_n = make_uint4(0, 0, 0, 0), c1_n = make_uint4(0, 0, 0, 0);
       if (lane < 24) {
-        const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 2;
         c0_n = __ldg(cp);
         c1_n = __ldg(cp + 1);
       }
@@ -202,24 +207,24 @@ __global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const
       for (int x = 0; x < W; x++) {
         const uint32_t hdr_c = hdr_n, syn_c = syn_n;
         const uint4 c0 = c0_n, c1 = c1_n;
-        // line x of the row above (chroma words + modes word): fetch now, check after the residual stage
+        // modes of the MB above: fetch now, check after the residual stage
         unsigned long long lv = 0;
-        const bool my_word = lane >= 4 && lane < kLineWords;
-        if (availB && my_word) lv = ld_relaxed_gpu_u64(line_above + (size_t)x * kLineWords);
+        if (availB && lane == 8) lv = ld_relaxed_gpu_u64(modes_above);
         if (x + 1 < W) {
-          const size_t mbn = mb_row0 + x + 1;
-          hdr_n = load_header_lane(a, lane, mbn);
-          if (lane < 16) syn_n = (uint32_t)__ldg(a.pred_syntax + mbn * 16 + syn_idx4);
+          hp += 1;
+          sp += 16;
+          cp += DRYV_COEFFS_PER_MB / 8;
+          if (lane < 4) hdr_n = (uint32_t)__ldg(hp);
+          if (lane < 16) syn_n = (uint32_t)__ldg(sp);
           if (lane < 24) {
-            const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mbn * DRYV_COEFFS_PER_MB) + lane * 2;
             c0_n = __ldg(cp);
             c1_n = __ldg(cp + 1);
           }
         }
         const MbHeader h = decode_header(hdr_c, &local_status);
-        const bool availA = x > 0, availD = availA && availB;
+        const bool availA = x > 0;
 
-        // ring slot: wait until the luma warp has released its previous use
+        // ring slot: wait until the pixel warp has released its previous use
         const unsigned si = n % kSlots, use = n / kSlots;
         Slot& slot = ts.slot[si];
         CLK_MARK(0);  // prefetch + header
@@ -227,20 +232,18 @@ __global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const
         CLK_MARK(1);  // wait for a free slot
 
         // 1. residual (independent of every other macroblock)
-        residual_stage(tab, ts.scratch, slot.res, ts.cres, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
-
+        residual_stage(tab, ts.scratch, slot.res, slot.cres, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
         CLK_MARK(2);  // residual stage
-        // 2. line x of the row above: chroma top row + the modes of the MB above
+
+        // 2. modes of the MB above
         uint32_t mw = 0x02020202u;
         if (availB) {
-          const uint32_t w = wait_line_words(line_above + (size_t)x * kLineWords, lv, lane, 4, kLineWords, tag, x == 0,
-                                             a.status, dead);
-          if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+          const uint32_t w = wait_line_words(modes_above, lv, lane, 8, 9, tag, x == 0, a.status, dead);
           mw = __shfl_sync(0xffffffffu, w, 8);
         }
+        CLK_MARK(3);  // wait for the modes of the row above
 
-        CLK_MARK(3);  // wait for line x of the row above
-        // 3. prediction modes -> slot, bottom-row modes -> line buffer, hand the slot to the luma warp
+        // 3. prediction modes -> slot, bottom-row modes -> line buffer, hand the slot to the pixel warp
         const int b_row = (mw >> (8 * gx)) & 0xff;
         int syn = (int)syn_c;
         if (h.mbcls == 1) syn = __shfl_sync(0xffffffffu, syn, syn_src8);
@@ -250,52 +253,35 @@ __global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const
         mp |= __shfl_xor_sync(0xffffffffu, mp, 1);
         mp |= __shfl_xor_sync(0xffffffffu, mp, 2);
         mp |= __shfl_xor_sync(0xffffffffu, mp, 4);
-        if (lane == 8) slot.modes_hi = mp;
+        if (lane == 8) {
+          slot.modes_hi = mp;
+          if (publish) {
+            // bottom-row modes (cells 12..15 = nibbles 4..7 of the hi word), one byte each, for the row below
+            const uint32_t mv = ((mp >> 16) & 15u) | (((mp >> 20) & 15u) << 8) | (((mp >> 24) & 15u) << 16) |
+                                (((mp >> 28) & 15u) << 24);
+            st_relaxed_gpu_u64(modes_mine, ((unsigned long long)tag << 32) | mv);
+          }
+        }
         if (lane == 0) {
           slot.modes_lo = mp;
           slot.frame = frame;
           slot.row = row;
           slot.x = x;
           slot.mbcls = h.mbcls;
-          slot.mode16 = (h.mbt - 1) & 3;
-        }
-        if (publish && lane == 8) {
-          // bottom-row modes (cells 12..15 = nibbles 4..7 of the hi word), one byte each, for the row below
-          const uint32_t mv = ((mp >> 16) & 15u) | (((mp >> 20) & 15u) << 8) | (((mp >> 24) & 15u) << 16) |
-                              (((mp >> 28) & 15u) << 24);
-          st_relaxed_gpu_u64(line_mine + (size_t)x * kLineWords, ((unsigned long long)tag << 32) | mv);
+          slot.mode16 = ((h.mbt - 1) & 3) | (h.cm << 8);
         }
         a_col = __shfl_sync(0xffffffffu, m, gy * 4 + 3);
+        modes_above += kLineWords;
+        modes_mine += kLineWords;
         __syncwarp();
         if (lane == 0) mbar_arrive(&ts.full[si]);
         n++;
         CLK_MARK(4);  // mode derivation + hand-off
-
-        // 4. chroma prediction + residual + clip, stores, bottom line, carry
-        predict_chroma(ts.chroma, ts.cres, lane, h.cm, availA, availB, availD);
-        CLK_MARK(5);  // chroma prediction
-        if (lane < 16) {
-          const uint2 v = *reinterpret_cast<const uint2*>(&my_ct[chroma_at(0, lane & 7)]);
-          __stcs(reinterpret_cast<uint2*>(st_base + (size_t)x * 8), v);
-        }
-        if (publish && pub_src)
-          st_relaxed_gpu_u64(line_mine + (size_t)x * kLineWords,
-                             ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
-        // carry: right-most column -> left-neighbour column; top-row corner slot <- [x].w1
-        int cv = 0;
-        uint32_t sv = 0;
-        if (lane < 16) cv = my_ct[chroma_at(7, lane & 7)];
-        else if (lane < 18) sv = *reinterpret_cast<const uint32_t*>(&ts.chroma[(lane - 16) * kChromaTileBytes + 4 + 8]);
-        __syncwarp();
-        if (lane < 16) my_ct[chroma_at(-1, lane & 7)] = (uint8_t)cv;
-        else if (lane < 18) *reinterpret_cast<uint32_t*>(&ts.chroma[(lane - 16) * kChromaTileBytes + 4]) = sv;
-        __syncwarp();
-        CLK_MARK(6);  // chroma stores + publish + carry
       }
       CLK_MARK(7);  // row change
     }
     CLK_FLUSH(0);
-    // no more rows: tell the luma warp
+    // no more rows: tell the pixel warp
     {
       const unsigned si = n % kSlots, use = n / kSlots;
       if (use > 0) mbar_wait(&ts.empty[si], (use - 1) & 1);
@@ -305,18 +291,38 @@ __global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const
     }
     if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
   } else {
-    // =========================================== luma warp ============================================
-    // luma top-row slots (tile row -1): 9 words [x-1].w3 | [x].w0..3 | [x+1].w0..3 at byte 12 + 4k
-    uint8_t* fresh_dst = lane < 4 ? &ts.luma[12 + 4 * (5 + lane)] : nullptr;
-    const uint8_t* pub_src = lane < 4 ? &ts.luma[luma_at(4 * lane, 15)] : nullptr;
-    uint8_t* shift_dst = lane < 5 ? &ts.luma[12 + 4 * lane] : nullptr;
+    // =========================================== pixel warp ===========================================
+    // Top-row slots of the pixel tiles (tile row -1):
+    //   luma  : 9 words [x-1].w3 | [x].w0..3 | [x+1].w0..3 at byte 12 + 4k
+    //   chroma: 3 words per plane [x-1].w1 | [x].w0..1 at byte 4 + 4k
+    // Line words handled by lane: 0..3 luma (of line x+1), 4..5 Cb, 6..7 Cr (of line x).
+    uint8_t* fresh_dst = nullptr;      // where this lane's fetched line word goes
+    const uint8_t* pub_src = nullptr;  // where this lane's word of the published line comes from
+    if (lane < 4) {
+      fresh_dst = &ts.luma[12 + 4 * (5 + lane)];
+      pub_src = &ts.luma[luma_at(4 * lane, 15)];
+    } else if (lane < 8) {
+      const int pl = (lane - 4) >> 1, k = (lane - 4) & 1;
+      fresh_dst = &ts.chroma[pl * kChromaTileBytes + 4 + 4 * (1 + k)];
+      pub_src = &ts.chroma[pl * kChromaTileBytes + chroma_at(4 * k, 7)];
+    }
+    // top-row shift when the walker advances: lanes 0..4 luma slots k+4 -> k, lanes 8..9 chroma slot 2 -> 0
+    uint8_t* shift_dst = nullptr;
+    int shift_by = 0;
+    if (lane < 5) { shift_dst = &ts.luma[12 + 4 * lane]; shift_by = 16; }
+    else if (lane == 8 || lane == 9) { shift_dst = &ts.chroma[(lane - 8) * kChromaTileBytes + 4]; shift_by = 8; }
+    // pixel column / row this lane carries and stores: lanes 0..15 luma row, 16..23 Cb row, 24..31 Cr row
+    uint8_t* const my_tile = lane < 16 ? ts.luma : &ts.chroma[((lane >> 3) & 1) * kChromaTileBytes];
+    const int my_first = lane < 16 ? luma_at(0, lane) : chroma_at(0, lane & 7);  // first pixel of my row
+    const int my_last = lane < 16 ? luma_at(15, lane) : chroma_at(7, lane & 7);
+    const int my_left = lane < 16 ? luma_at(-1, lane) : chroma_at(-1, lane & 7);
     unsigned n = 0;
-    int W1 = W - 1;
-    const unsigned long long* line_above = nullptr;
+    const int W1 = W - 1;
+    const unsigned long long* line_above = nullptr;  // + lane; line x+1 for luma lanes, line x for chroma lanes
     unsigned long long* line_mine = nullptr;
-    uint8_t* st_base = nullptr;
+    uint8_t* st_ptr = nullptr;
     bool availB = false, publish = false;
-    unsigned long long lv = 0;  // in-flight fetch of line x+1 of the row above
+    unsigned long long lv = 0;  // in-flight fetch of this lane's line word for the current macroblock
     CLK_DECL;
     for (;;) {
       const unsigned si = n % kSlots, use = n / kSlots;
@@ -335,38 +341,43 @@ __global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const
         publish = row + 1 < H;
         line_above = a.line + (mb_row0 - W) * kLineWords + lane;
         line_mine = a.line + mb_row0 * kLineWords + lane;
-        st_base = lane < 16 ? Y + (size_t)(16 * row + lane) * strideY : nullptr;
+        if (lane < 16) st_ptr = Y + (size_t)(16 * row + lane) * strideY;
+        else st_ptr = Y + n_mb * 256 + (size_t)((lane >> 3) & 1) * n_mb * 64 + (size_t)(8 * row + (lane & 7)) * strideC;
         if (availB) {
-          // line 0 of the row above becomes "line x" of macroblock 0 (long wait: that row may not have started)
+          // luma line 0 of the row above becomes "line x" of macroblock 0 (long wait: that row may not have started)
           unsigned long long v0 = 0;
           if (lane < 4) v0 = ld_relaxed_gpu_u64(line_above);
           const uint32_t w = wait_line_words(line_above, v0, lane, 0, 4, tag, true, a.status, dead);
-          if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+          if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
           __syncwarp();
           uint32_t sv = 0;
-          if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
+          if (lane < 5) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
           __syncwarp();
-          if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
-          if (W1 > 0 && lane < 4) lv = ld_relaxed_gpu_u64(line_above + kLineWords);
+          if (lane < 5) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
+          // luma lanes look one line ahead from here on
+          if (lane < 4) line_above += kLineWords;
+          if ((lane < 4 && W1 > 0) || (lane >= 4 && lane < 8)) lv = ld_relaxed_gpu_u64(line_above);
         }
       }
       CLK_MARK(1);  // row start (incl. long wait for line 0)
-      const int mbcls = slot.mbcls, mode16 = slot.mode16;
+      const int mbcls = slot.mbcls, mode16 = slot.mode16 & 3, cm = slot.mode16 >> 8;
       const uint32_t modes_lo = slot.modes_lo, modes_hi = slot.modes_hi;
       const bool availA = x > 0, availC = availB && x < W1, availD = availA && availB;
-      if (availC) {
-        const uint32_t w = wait_line_words(line_above + (size_t)(x + 1) * kLineWords, lv, lane, 0, 4, tag, false,
-                                           a.status, dead);
-        if (fresh_dst) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+      if (availB) {
+        // luma lanes: line x+1 (only if it exists); chroma lanes: line x
+        const int lo = availC ? 0 : 4;
+        const uint32_t w = wait_line_words(line_above, lv, lane, lo, 8, tag, false, a.status, dead);
+        if (lane >= lo && lane < 8) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+        // fetch for the next macroblock of this row, overlapped with this macroblock's prediction
+        line_above += kLineWords;
+        if ((lane < 4 && x + 2 <= W1) || (lane >= 4 && lane < 8 && x + 1 <= W1)) lv = ld_relaxed_gpu_u64(line_above);
       }
-      // fetch for the next macroblock of this row (line x+2), overlapped with this macroblock's prediction
-      if (availB && x + 2 <= W1 && lane < 4) lv = ld_relaxed_gpu_u64(line_above + (size_t)(x + 2) * kLineWords);
       __syncwarp();
-      CLK_MARK(2);  // wait for line x+1 of the row above
+      CLK_MARK(2);  // wait for the lines of the row above
 
       if (mbcls == 0) {
         predict_i4x4(tab, ts.luma, slot.res, lane, modes_lo, modes_hi,
-                     1u | (availA ? 2u : 0u) | (availB ? 4u : 0u) | (availC ? 8u : 0u) | (availD ? 16u : 0u));
+                     (availA ? 1 : 0) | (availB ? 2 : 0) | (availC ? 4 : 0) | (availD ? 8 : 0));
         CLK_MARK(3);
       } else if (mbcls == 1) {
         predict_i8x8(tab, ts.luma, slot.res, lane, modes_lo, modes_hi, availA, availB, availC, availD);
@@ -375,26 +386,33 @@ __global__ void __launch_bounds__(kTeamThreads, 12) recon_wavefront_kernel(const
         predict_i16x16(ts.luma, slot.res, lane, mode16, availA, availB);
         CLK_MARK(5);
       }
+      predict_chroma(ts.chroma, slot.cres, lane, cm, availA, availB, availD);
+      CLK_MARK(6);  // chroma prediction
 
+      // store the macroblock (16 x 16 B luma rows, 2 x 8 x 8 B chroma rows) and publish its bottom line
       if (lane < 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&ts.luma[luma_at(0, lane)]);
-        __stcs(reinterpret_cast<uint4*>(st_base + (size_t)x * 16), v);
+        const uint4 v = *reinterpret_cast<const uint4*>(&my_tile[my_first]);
+        __stcs(reinterpret_cast<uint4*>(st_ptr), v);
+        st_ptr += 16;
+      } else {
+        const uint2 v = *reinterpret_cast<const uint2*>(&my_tile[my_first]);
+        __stcs(reinterpret_cast<uint2*>(st_ptr), v);
+        st_ptr += 8;
       }
-      if (publish && pub_src)
-        st_relaxed_gpu_u64(line_mine + (size_t)x * kLineWords,
-                           ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
+      if (publish && lane < 8)
+        st_relaxed_gpu_u64(line_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
+      line_mine += kLineWords;
       // carry: right-most column -> left-neighbour column, top-row slots shift by one macroblock
-      int cv = 0;
+      const int cv = my_tile[my_last];
       uint32_t sv = 0;
-      if (lane < 16) cv = ts.luma[luma_at(15, lane)];
-      else if (lane < 21) sv = *reinterpret_cast<const uint32_t*>(&ts.luma[12 + 4 * (lane - 16) + 16]);
+      if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + shift_by);
       __syncwarp();
-      if (lane < 16) ts.luma[luma_at(-1, lane)] = (uint8_t)cv;
-      else if (lane < 21) *reinterpret_cast<uint32_t*>(&ts.luma[12 + 4 * (lane - 16)]) = sv;
+      my_tile[my_left] = (uint8_t)cv;
+      if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
       __syncwarp();
       if (lane == 0) mbar_arrive(&ts.empty[si]);
       n++;
-      CLK_MARK(6);  // stores + publish + carry
+      CLK_MARK(7);  // stores + publish + carry
     }
     CLK_FLUSH(8);
   }
@@ -415,6 +433,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 8) recon_residual_add_kernel(c
   const int lane = threadIdx.x & 31;
   ResidWarpSmem& ws = cs.warp[threadIdx.x >> 5];
   const LaneConst lc = make_lane_const(lane, cs.tab);
+  const uint8_t* const hdr_base = header_base(a, lane);
   const int W = a.W, H = a.H;
   const size_t n_mb = (size_t)W * H, total = n_mb * a.n_frames;
   const int strideY = W * 16, strideC = W * 8;
@@ -423,7 +442,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 8) recon_residual_add_kernel(c
   for (size_t mb = (size_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); mb < total; mb += warps) {
     const size_t frame = mb / n_mb, addr = mb % n_mb;
     const int x = (int)(addr % W), row = (int)(addr / W);
-    const uint32_t hdr = load_header_lane(a, lane, mb);
+    const uint32_t hdr = load_header_lane(hdr_base, lane, mb);
     uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
     if (lane < 24) {
       const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb * DRYV_COEFFS_PER_MB) + lane * 2;

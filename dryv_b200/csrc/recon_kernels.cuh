@@ -45,28 +45,28 @@ struct ResidCtaSmem {
 };
 
 // wavefront kernel: a "row team" = one CTA of two warps walking one macroblock row.
-//   front warp: residual (luma + chroma), prediction-mode derivation, chroma prediction/stores
-//   luma warp : luma prediction/stores
+//   front warp: residual (luma + chroma) and prediction-mode derivation
+//   pixel warp: luma + chroma prediction, stores
 // The front warp hands each macroblock to the luma warp through a ring of kSlots slots.
 constexpr int kSlots = 4;
 constexpr int kTeamThreads = 64;
 struct Slot {
   alignas(16) int16_t res[256];  // luma residual [16][16]
+  alignas(16) int16_t cres[128]; // chroma residual [2][8][8]
   uint32_t modes_lo, modes_hi;   // resolved Intra4x4/8x8 modes of the raster 4x4 grid cells 0..7 / 8..15, 4 bits each
   int32_t frame, row, x;         // row < 0: no more work
-  int32_t mbcls, mode16;         // 0/1/2 = Intra4x4/8x8/16x16, Intra16x16 prediction mode
+  int32_t mbcls, mode16;         // 0/1/2 = Intra4x4/8x8/16x16; Intra16x16 prediction mode | intra_chroma_pred_mode << 8
   int32_t pad[1];
 };
 static_assert(sizeof(Slot) % 16 == 0, "slot alignment");
 struct TeamSmem {
   DeviceTables tab;
   Slot slot[kSlots];
-  alignas(16) int16_t cres[128];                    // chroma residual of the macroblock in flight (front warp)
-  alignas(16) uint8_t luma[kLumaTileBytes];         // luma pixel tile (luma warp)
-  alignas(16) uint8_t chroma[2 * kChromaTileBytes]; // chroma pixel tiles (front warp)
+  alignas(16) uint8_t luma[kLumaTileBytes];         // luma pixel tile (pixel warp)
+  alignas(16) uint8_t chroma[2 * kChromaTileBytes]; // chroma pixel tiles (pixel warp)
   alignas(16) uint8_t scratch[kScratchBytes];
   alignas(8) unsigned long long full[kSlots];       // mbarriers: slot filled by the front warp
-  alignas(8) unsigned long long empty[kSlots];      // mbarriers: slot released by the luma warp
+  alignas(8) unsigned long long empty[kSlots];      // mbarriers: slot released by the pixel warp
 };
 
 enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
@@ -347,45 +347,48 @@ __device__ __forceinline__ uint32_t legal_mask(bool t, bool l, bool c) {
 // Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110. Ten dependency steps (DeviceTables::i4step),
 // two blocks per step where the decode-order availability rules allow it; one pixel per lane, 16 lanes
 // per block. Kept as a rolled loop: the kernel is instruction-fetch sensitive.
-//   avm = 1 | A<<1 | B<<2 | C<<3 | D<<4 (macroblock availability), modes_lo/hi = 4-bit modes per cell.
+//   av = A | B<<1 | C<<2 | D<<3 (macroblock availability), modes_lo/hi = 4-bit modes per raster cell.
 __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma, int lane,
-                                             uint32_t modes_lo, uint32_t modes_hi, uint32_t avm) {
+                                             uint32_t modes_lo, uint32_t modes_hi, int av) {
   const int half = lane >> 4, p = lane & 15, px = p & 3, py = p >> 2;
   // edge sample fetched by this lane, relative to the block origin: 0..7 top / top-right (4..7 fall back to
   // sample 3 when top-right is missing), 8..11 left, 12 corner, 13..15 contribute 0
   const int edge_off = p < 8 ? (p - kLumaStride) : (p < 12 ? (p - 8) * kLumaStride - 1 : -kLumaStride - 1);
   const int edge_off_notr = (p >= 4 && p < 8) ? (3 - kLumaStride) : edge_off;
-  const int edge_sel_shift = p < 8 ? 17 : (p < 12 ? 14 : 20);  // which availability selector guards the sample
-  const int pix_off = py * kLumaStride + px, res_off = py * 16 + px;
-  uint32_t nxt = tab.i4step[0][half];
+  const int guard_bit = p < 8 ? 25 : (p < 12 ? 26 : (p == 12 ? 27 : 31));  // availability bit guarding the sample
+  const int pix_off = py * kLumaStride + px;
+  const int res_lane = py * 16 + px;
+  const uint32_t* steps = &tab.i4step[av][0][half];
+  uint32_t nxt = steps[0];
 #pragma unroll 1
   for (int s = 0; s < 10; s++) {
     const uint32_t cur = nxt;
-    nxt = tab.i4step[s < 9 ? s + 1 : 9][half];
-    const int org = cur & 1023, cell = (cur >> 10) & 15;
-    const bool aL = (avm >> ((cur >> 14) & 7)) & 1, aT = (avm >> ((cur >> 17) & 7)) & 1;
-    const bool aTL = (avm >> ((cur >> 20) & 7)) & 1, aTR = (avm >> ((cur >> 23) & 7)) & 1;
-    const uint32_t mw = (cell & 8) ? modes_hi : modes_lo;
-    const int mode = (mw >> ((cell & 7) * 4)) & 15;
-    int ev = lt[org + (aTR ? edge_off : edge_off_notr)];
-    if (p > 12 || !((avm >> ((cur >> edge_sel_shift) & 7)) & 1)) ev = 0;  // unavailable samples count as 0
+    nxt = steps[s < 9 ? 2 * s + 2 : 18];
+    const int org = cur & 1023;
+    const int msh = (cur >> 10) & 31;
+    const int mode = (((cur & 0x8000u) ? modes_hi : modes_lo) >> msh) & 15;
+    int ev = lt[org + ((cur & (1u << 28)) ? edge_off : edge_off_notr)];
+    if (!((cur >> guard_bit) & 1u)) ev = 0;  // unavailable samples (and lanes 13..15) count as 0
     const uint32_t taps = tab.lut4[mode > 8 ? 2 : mode][p];
-    const int res = res_luma[(cell >> 2) * 64 + (cell & 3) * 4 + res_off];
-    const int e0 = __shfl_sync(0xffffffffu, ev, taps & 15, 16);
-    const int e1 = __shfl_sync(0xffffffffu, ev, (taps >> 4) & 15, 16);
-    const int e2 = __shfl_sync(0xffffffffu, ev, (taps >> 8) & 15, 16);
+    // residual of this lane's pixel: cell -> (cell >> 2) * 64 + (cell & 3) * 4 = msh-derived
+    const int cell = (msh >> 2) | ((cur >> 12) & 8);
+    const int res = res_luma[(cell >> 2) * 64 + (cell & 3) * 4 + res_lane];
+    // __shfl_sync with width 16 takes the source lane modulo 16: no masking of the tap fields needed
+    const int e0 = __shfl_sync(0xffffffffu, ev, taps, 16);
+    const int e1 = __shfl_sync(0xffffffffu, ev, taps >> 4, 16);
+    const int e2 = __shfl_sync(0xffffffffu, ev, taps >> 8, 16);
     const int t3 = e0 + e1 + e2;
     int pred = (t3 + e1 + 2) >> 2;
     if (__any_sync(0xffffffffu, mode == 2)) {
       // DC (pred4x4.rs:116-167): second summation round over the three partial sums held by lanes 0..2
       const int q = __shfl_sync(0xffffffffu, t3, 0, 16) + __shfl_sync(0xffffffffu, t3, 1, 16) +
                     __shfl_sync(0xffffffffu, t3, 2, 16);
-      const int dcv = (aT && aL) ? ((q + 4) >> 3) : ((aT || aL) ? ((q + 2) >> 2) : 128);
+      const int nav = ((cur >> 25) & 1) + ((cur >> 26) & 1);  // available sides: top, left
+      const int dcv = nav == 2 ? ((q + 4) >> 3) : (nav == 1 ? ((q + 2) >> 2) : 128);
       if (mode == 2) pred = dcv;
     }
-    const bool ok = mode <= 8 && ((legal_mask(aT, aL, aTL) >> mode) & 1u);
-    if (!ok) pred = 0;
-    if ((cur >> 26) & 1) lt[org + pix_off] = (uint8_t)clip255(pred + res);
+    if (!((cur >> (16 + mode)) & 1u) || mode > 8) pred = 0;  // mode needs a missing neighbour: prediction stays 0 (Q4)
+    if (cur & (1u << 29)) lt[org + pix_off] = (uint8_t)clip255(pred + res);
     __syncwarp();
   }
 }
@@ -603,6 +606,7 @@ __device__ __forceinline__ int resolve_modes(int lane, int mbcls, int syn, int a
                                              bool availB) {
   const int g = lane & 15, gx = g & 3, gy = g >> 2;
   int m = 2;
+  if (mbcls == 2) return 2;  // warp-uniform
   const int step = mbcls == 1 ? 2 : 1;  // Intra8x8: cells move in 2x2 groups
   const int ox = gx & ~(step - 1), oy = gy & ~(step - 1);  // origin cell of the block covering this cell
   const bool haveA = ox > 0 || availA, haveB = oy > 0 || availB;
@@ -618,13 +622,11 @@ __device__ __forceinline__ int resolve_modes(int lane, int mbcls, int syn, int a
     int b = __shfl_sync(0xffffffffu, m, (max(oy - 1, 0) * 4 + ox) | (lane & 16));
     if (ox == 0) a = a_col;
     if (oy == 0) b = b_row;
-    const int mine = (ox + oy) / step;
-    if (mine == d) {
-      const int pred = (haveA && haveB) ? min(a, b) : 2;
-      m = prev ? pred : (rem < pred ? rem : rem + 1);
-    }
+    const int pred = (haveA && haveB) ? min(a, b) : 2;
+    const int cand = prev ? pred : (rem < pred ? rem : rem + 1);
+    m = (((ox + oy) >> (step - 1)) == d) ? cand : m;
   }
-  return mbcls == 2 ? 2 : m;
+  return m;
 }
 
 }  // namespace dryv

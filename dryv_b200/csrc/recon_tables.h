@@ -28,11 +28,10 @@ struct DeviceTables {
   uint8_t zz8inv[8][8];    // [i][j] -> zig-zag index
   uint8_t qpc[52];         // qPI -> QPC
   uint8_t pad[12];
-  // Intra4x4 dependency schedule: [step][half] -> tile origin (10 bits) | raster cell << 10 |
-  // availability selectors (3 bits each: left, top, corner, top-right) << 14 | active << 26.
-  // A selector indexes the mask 1 | A<<1 | B<<2 | C<<3 | D<<4 (5 = never available).
-  uint32_t i4step[10][2];
-  uint32_t pad2[12];
+  // Intra4x4 dependency schedule, specialised per macroblock availability av = A | B<<1 | C<<2 | D<<3:
+  // [av][step][half] -> tile origin (10 bits) | mode nibble shift (0..28) << 10 | modes-hi-word flag << 15 |
+  // legal-mode mask (9 bits) << 16 | top << 25 | left << 26 | corner << 27 | top-right << 28 | active << 29
+  uint32_t i4step[16][10][2];
 };
 
 void build_device_tables(const dryv_pic_params& pp, DeviceTables* t);

@@ -16,7 +16,7 @@ from .abi import FIELDS, MbSoa, PicParams, SyntaxBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libdryv_recon.so")
+LIB_PATH = os.environ.get("DRYV_RECON_LIB") or os.path.join(CSRC, "libdryv_recon.so")  # override: dev variants only
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WATCHDOG = 0, -1, -2, -3, -4
 

@@ -40,10 +40,9 @@ nmb = frames * pp.n_mb
 cls = np.where(b.mb_type != 0, 2, b.transform_size_8x8_flag)
 n4, n8, n16 = [(cls == k).sum() for k in (0, 1, 2)]
 print(f"frames {frames}, {nmb} MBs ({n4} I4x4, {n8} I8x8, {n16} I16x16)")
-fn = ["prefetch+header", "wait free slot", "residual", "wait line x (above)", "modes+handoff", "chroma pred",
-      "chroma store/publish/carry", "row change"]
-ln = ["wait filled slot", "row start", "wait line x+1 (above)", "I4x4 pred (per I4x4 MB)", "I8x8 pred (per I8x8 MB)",
-      "I16x16 pred (per I16 MB)", "store/publish/carry", "-"]
+fn = ["prefetch+header", "wait free slot", "residual", "wait modes (above)", "modes+handoff", "-", "-", "row change"]
+ln = ["wait filled slot", "row start", "wait lines (above)", "I4x4 pred (per I4x4 MB)", "I8x8 pred (per I8x8 MB)",
+      "I16x16 pred (per I16 MB)", "chroma pred", "store/publish/carry"]
 tot_f = sum(clk[:8]) / nmb
 tot_l = sum(clk[8:]) / nmb
 print("front warp: cycles per MB")

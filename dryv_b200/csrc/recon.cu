@@ -866,6 +866,15 @@ int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char
 
 uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+size_t dryv_recon_device_tables(const dryv_pic_params* pp, void* out, size_t cap) {
+  if (!pp) return 0;
+  DeviceTables* t = new DeviceTables();
+  dryv::build_device_tables(*pp, t);
+  if (out) memcpy(out, t, cap < sizeof(DeviceTables) ? cap : sizeof(DeviceTables));
+  delete t;
+  return sizeof(DeviceTables);
+}
+
 #ifdef DRYV_STAGE_CLOCKS
 // development builds only (not part of include/dryv_recon.h): read and reset the stage clocks
 int dryv_recon_debug_clocks(dryv_recon_ctx* ctx, unsigned long long out[16]) {

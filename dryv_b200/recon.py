@@ -24,7 +24,7 @@ EXPORTS = [
     "dryv_recon_abi_version", "dryv_recon_frame_bytes", "dryv_recon_create", "dryv_recon_destroy",
     "dryv_recon_last_error", "dryv_recon_alloc_pinned", "dryv_recon_free_pinned", "dryv_recon_submit",
     "dryv_recon_wait", "dryv_recon_reconstruct_device", "dryv_recon_residual_add_device",
-    "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms",
+    "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms", "dryv_recon_device_tables",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -89,6 +89,8 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_write_yuv_file.argtypes = [vp, sz, C.c_char_p]
     lib.dryv_recon_last_submit_ms.restype = C.c_double
     lib.dryv_recon_last_submit_ms.argtypes = [vp]
+    lib.dryv_recon_device_tables.restype = sz
+    lib.dryv_recon_device_tables.argtypes = [C.POINTER(PicParams), vp, sz]
     lib.dryv_recon_launch_count.restype = C.c_uint64
     lib.dryv_recon_launch_count.argtypes = [vp]
     _lib = lib

@@ -142,6 +142,11 @@ int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char
  * dryv_recon_submit, in milliseconds; valid after dryv_recon_wait. Returns < 0 if unavailable. */
 double dryv_recon_last_submit_ms(dryv_recon_ctx* ctx);
 
+/* Diagnostic: the host-built lookup tables the kernels consume for `pp` (LevelScale, zig-zag, tap and
+ * schedule tables; layout = struct dryv::DeviceTables, dryv_b200/csrc/recon_tables.h). Copies up to `cap`
+ * bytes into `out` and returns the table size in bytes. Needs no GPU. */
+size_t dryv_recon_device_tables(const dryv_pic_params* pp, void* out, size_t cap);
+
 /* Number of kernel launches issued by this context so far (bench bookkeeping). */
 uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx);
 

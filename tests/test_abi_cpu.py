@@ -1,0 +1,137 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol the header declares, agrees
+with the ctypes mirror on struct layout, builds its host-side tables correctly and fails loudly (never
+falls back) without a GPU. No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dryv_b200 import recon
+from dryv_b200.abi import MbSoa, PicParams
+from oracle import spec_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "dryv_recon.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dryv_recon_\w+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(recon_lib):
+    names = header_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(recon_lib, n), f"{n} declared in include/dryv_recon.h but not exported"
+    assert sorted(recon.EXPORTS) == names
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(PicParams) == 2 + 2 + 1 + 1 + 2 + 4 + 16 + 64
+    assert PicParams.scaling_list4x4.offset == 12 and PicParams.scaling_list8x8.offset == 28
+    assert C.sizeof(MbSoa) == 6 * C.sizeof(C.c_void_p)
+
+
+def test_abi_version_and_frame_bytes(recon_lib):
+    assert recon_lib.dryv_recon_abi_version() == 1
+    pp = PicParams.make(120, 68)
+    assert recon_lib.dryv_recon_frame_bytes(C.byref(pp)) == 1920 * 1088 * 3 // 2 == pp.frame_bytes
+
+
+def test_no_gpu_means_error_not_fallback(recon_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert recon_lib.dryv_recon_create(0, C.byref(h)) == recon.ERR_CUDA
+    assert not h.value
+    with pytest.raises(recon.ReconError):
+        recon.ReconContext(0)
+
+
+def test_null_arguments_are_rejected(recon_lib):
+    assert recon_lib.dryv_recon_create(0, None) == recon.ERR_ARG
+    assert recon_lib.dryv_recon_wait(None) == recon.ERR_ARG
+    assert recon_lib.dryv_recon_submit(None, None, None, 1, None) == recon.ERR_ARG
+    assert recon_lib.dryv_recon_write_yuv_file(None, 0, b"x") == recon.ERR_ARG
+
+
+def test_write_yuv_file_creates_temp_dir(recon_lib, tmp_path):
+    frame = np.arange(384, dtype=np.uint8)
+    path = tmp_path / "temp" / "yuv_frame"
+    recon.write_yuv_file(frame, str(path))
+    assert np.array_equal(np.fromfile(path, np.uint8), frame)
+
+
+class Tables(C.Structure):
+    _fields_ = [("t4", (C.c_int32 * 16) * 52), ("ls8", (C.c_uint16 * 64) * 6), ("lut4", (C.c_uint16 * 16) * 9),
+                ("lut8", (C.c_uint16 * 64) * 9), ("zz8inv", (C.c_uint8 * 8) * 8), ("qpc", C.c_uint8 * 52),
+                ("pad", C.c_uint8 * 12), ("i4step", ((C.c_uint32 * 2) * 10) * 16)]
+
+
+def get_tables(lib, pp):
+    t = Tables()
+    n = lib.dryv_recon_device_tables(C.byref(pp), C.byref(t), C.sizeof(t))
+    assert n == C.sizeof(t)
+    return t
+
+
+@pytest.mark.parametrize("custom", [False, True])
+def test_level_scale_tables(recon_lib, custom):
+    l4 = list(range(6, 38, 2)) if custom else [16] * 16
+    l8 = [8 + (k * 3) % 40 for k in range(64)] if custom else [16] * 64
+    t = get_tables(recon_lib, PicParams.make(2, 2, 0, 0, l4, l8))
+    for qp in range(52):
+        ls = spec_model.level_scale4(l4, qp % 6)
+        for k, (i, j) in enumerate(spec_model.ZZ4):
+            assert t.t4[qp][k] == int(ls[i, j]) << max(qp // 6 - 4, 0)
+    for m in range(6):
+        assert np.array_equal(np.array(t.ls8[m]).reshape(8, 8), spec_model.level_scale8(l8, m))
+    assert [int(v) for v in t.qpc] == spec_model.QPC
+
+
+def test_zigzag_and_tap_tables(recon_lib):
+    t = get_tables(recon_lib, PicParams.make(1, 1))
+    for k, (i, j) in enumerate(spec_model.ZZ8):
+        assert t.zz8inv[i][j] == k
+    # the reference's own table starts 0,1 / 1,0 / 2,0 / 1,1 (frame/mod.rs:215-219) and ends ... 7,6 / 7,7
+    assert spec_model.ZZ8[:5] == [(0, 0), (0, 1), (1, 0), (2, 0), (1, 1)] and spec_model.ZZ8[-2:] == [(7, 6), (7, 7)]
+
+    # every tap triple reproduces the closed-form predictor on random edges (4x4: modes other than DC)
+    rng = np.random.default_rng(1)
+    for n, lut, bits, left0, corner in ((4, t.lut4, 4, 8, 12), (8, t.lut8, 5, 16, 24)):
+        T = rng.integers(0, 256, 2 * n).tolist()
+        L = rng.integers(0, 256, n).tolist()
+        TL = int(rng.integers(0, 256))
+        E = T + L + [TL]
+        for mode in (0, 1, 3, 4, 5, 6, 7, 8):
+            want = spec_model.pred_nxn(n, mode, T, L, TL)
+            for y in range(n):
+                for x in range(n):
+                    w = lut[mode][y * n + x]
+                    i0, i1, i2 = w & (2 ** bits - 1), (w >> bits) & (2 ** bits - 1), (w >> (2 * bits)) & (2 ** bits - 1)
+                    assert (E[i0] + 2 * E[i1] + E[i2] + 2) >> 2 == want[y, x], (n, mode, x, y)
+
+
+def test_intra4x4_schedule_respects_decode_order(recon_lib):
+    """A block may only be scheduled after every neighbour it can read (left, top, top-left, and top-right
+    unless the reference treats it as unavailable) — the availability rules of pred4x4.rs:39-43."""
+    t = get_tables(recon_lib, PicParams.make(1, 1))
+    step_of = {}
+    for s in range(10):
+        for h in range(2):
+            w = t.i4step[15][s][h]
+            if (w >> 29) & 1:
+                org = w & 1023
+                by, bx = (org - 16) // 48 - 1, (org - 16) % 48
+                step_of[(bx // 4, by // 4)] = (s, w)
+    assert len(step_of) == 16
+    for (gx, gy), (s, w) in step_of.items():
+        tr = (w >> 28) & 1
+        for dx, dy, needed in ((-1, 0, True), (0, -1, True), (-1, -1, True), (1, -1, bool(tr))):
+            nx, ny = gx + dx, gy + dy
+            if needed and 0 <= nx < 4 and 0 <= ny < 4:
+                assert step_of[(nx, ny)][0] < s

@@ -118,7 +118,14 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
   return d;
 }
 __device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
-__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+// two residuals -> one s16x2 word, saturating: the final sample is clip(pred + r, 0, 255) with pred in 0..255,
+// so any r beyond +-255 already pins the result and saturating at +-32767 keeps every input exact
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) {
+  uint32_t d;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+  return d;
+}
+__device__ __forceinline__ int16_t sat16(int v) { return (int16_t)min(max(v, -32768), 32767); }
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
   return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
 }
@@ -257,7 +264,7 @@ __device__ __forceinline__ void residual_stage(const DeviceTables& tab, uint8_t*
     idct8(d);
     int16_t* rl = res_luma + ((blk >> 1) * 8) * 16 + (blk & 1) * 8 + i;
 #pragma unroll
-    for (int r = 0; r < 8; r++) rl[r * 16] = (int16_t)(d[r] >> 6);
+    for (int r = 0; r < 8; r++) rl[r * 16] = sat16(d[r] >> 6);
   }
 
   // ---- 4x4 path: one block per lane (luma lanes 0..15 unless Intra8x8, chroma lanes 16..23) --

@@ -99,17 +99,47 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
       : "memory");
 }
 
+// Long waits (the front warp runs kSlots macroblocks ahead and then blocks on the pixel warp for a whole
+// macroblock time): the hinted try_wait above is woken by every mbarrier event of the SM and re-issues ~100
+// times per wait, so poll with a plain timed sleep instead — nothing on the critical path depends on how
+// quickly a freed slot is noticed.
+#ifndef DRYV_FRONT_SLEEP_NS
+#define DRYV_FRONT_SLEEP_NS 500
+#endif
+__device__ __forceinline__ bool mbar_test(unsigned long long* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* b, uint32_t parity) {
+  while (!mbar_test(b, parity)) __nanosleep(DRYV_FRONT_SLEEP_NS);
+}
+
 // Waits until the line words of lanes [lo, hi) carry this launch's tag; returns the lane's payload.
 // `first` is the value of a load issued earlier (so its latency overlapped with other work).
 // On a watchdog trip `dead` is set and every later wait returns immediately (the kernel drains with
 // garbage and the host reports DRYV_ERR_WATCHDOG).
+#ifndef DRYV_LINE_SLEEP_NS
+#define DRYV_LINE_SLEEP_NS 200u
+#endif
+#ifndef DRYV_LINE_LONG_NS
+#define DRYV_LINE_LONG_NS 4000u
+#endif
 __device__ __forceinline__ uint32_t wait_line_words(const unsigned long long* p, unsigned long long first, int lane,
                                                     int lo, int hi, uint32_t tag, bool long_wait, int* status,
                                                     bool& dead) {
   unsigned long long v = first;
   const bool mine = lane >= lo && lane < hi;
   if (dead || __all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) return (uint32_t)v;
-  const unsigned ns = long_wait ? 4000u : 200u;
+  const unsigned ns = long_wait ? DRYV_LINE_LONG_NS : DRYV_LINE_SLEEP_NS;
   unsigned spins = 0;
   for (;;) {
     __nanosleep(ns);
@@ -228,7 +258,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         const unsigned si = n % kSlots, use = n / kSlots;
         Slot& slot = ts.slot[si];
         CLK_MARK(0);  // prefetch + header
-        if (use > 0) mbar_wait(&ts.empty[si], (use - 1) & 1);
+        if (use > 0) mbar_wait_backoff(&ts.empty[si], (use - 1) & 1);
         CLK_MARK(1);  // wait for a free slot
 
         // 1. residual (independent of every other macroblock)
@@ -284,7 +314,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     // no more rows: tell the pixel warp
     {
       const unsigned si = n % kSlots, use = n / kSlots;
-      if (use > 0) mbar_wait(&ts.empty[si], (use - 1) & 1);
+      if (use > 0) mbar_wait_backoff(&ts.empty[si], (use - 1) & 1);
       if (lane == 0) ts.slot[si].row = -1;
       __syncwarp();
       if (lane == 0) mbar_arrive(&ts.full[si]);

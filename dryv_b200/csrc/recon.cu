@@ -22,6 +22,23 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const void* p) {
   return v;
 }
 
+#ifndef DRYV_PREFETCH_MBS
+#define DRYV_PREFETCH_MBS 6
+#endif
+constexpr int kPrefetchMbs = DRYV_PREFETCH_MBS;
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+constexpr int kCoefAhead = 3;                 // macroblocks of look-ahead on the level fetch
+constexpr int kCoefStages = kCoefAhead + 1;   // ring depth
+__device__ __forceinline__ void cp_async_32(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(reinterpret_cast<const uint8_t*>(gmem_src) + 16) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct MbHeader {
   int mbt, t8, cm, qp, mbcls;
 };
@@ -53,6 +70,22 @@ __device__ __forceinline__ MbHeader decode_header(uint32_t hdr_lane, int* status
   h.mbcls = h.mbt == 0 ? (h.t8 ? 1 : 0) : 2;  // slice/macroblock.rs:682-716
   return h;
 }
+
+// Timeline trace (development builds only: -DDRYV_TRACE): the pixel warp records, for picture 0, the global
+// timer at four points of every macroblock (slot ready, lines ready, prediction done, macroblock done).
+#ifdef DRYV_TRACE
+__device__ __forceinline__ unsigned int gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return (unsigned int)t;
+}
+#define TRACE_MARK(k)                                                                                  \
+  do {                                                                                                 \
+    if (a.trace && lane == 0 && slot.frame == 0) a.trace[((size_t)row * W + x) * 4 + (k)] = gtimer_ns(); \
+  } while (0)
+#else
+#define TRACE_MARK(k)
+#endif
 
 // Stage clocks (development builds only: -DDRYV_STAGE_CLOCKS): per-role cycle sums per stage.
 #ifdef DRYV_STAGE_CLOCKS
@@ -99,6 +132,33 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
       : "memory");
 }
 
+// Hand-off between the two warps of a team:
+//   full[i]  (front -> pixel)  an mbarrier. The front warp normally runs ahead, so the pixel warp's
+//            try_wait succeeds on its first issue.
+//   empty[i] (pixel -> front)  a named barrier (ids 1..kSlots): the pixel warp announces with bar.arrive, the
+//            front warp parks in bar.sync. The front warp's waits are long (a whole macroblock time); a warp
+//            parked in bar.sync issues nothing, whereas an mbarrier try_wait / nanosleep loop was measured
+//            re-issuing hundreds of times per macroblock in this kernel (sleepers are woken far earlier than
+//            their time-out). Ids are compile-time constants: the SM has 64 barriers, a CTA that indexes them
+//            with a register is charged all 16 and caps residency at 4 teams per SM.
+__device__ __forceinline__ void bar_sync_empty(unsigned si) {
+  switch (si) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ void bar_arrive_empty(unsigned si) {
+  switch (si) {
+    case 0: asm volatile("bar.arrive 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.arrive 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.arrive 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
+  }
+}
+static_assert(kSlots == 4, "named-barrier ids above assume four ring slots");
+
 // Long waits (the front warp runs kSlots macroblocks ahead and then blocks on the pixel warp for a whole
 // macroblock time): the hinted try_wait above is woken by every mbarrier event of the SM and re-issues ~100
 // times per wait, so poll with a plain timed sleep instead — nothing on the critical path depends on how
@@ -128,10 +188,10 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned long long* b, uint32_
 // On a watchdog trip `dead` is set and every later wait returns immediately (the kernel drains with
 // garbage and the host reports DRYV_ERR_WATCHDOG).
 #ifndef DRYV_LINE_SLEEP_NS
-#define DRYV_LINE_SLEEP_NS 200u
+#define DRYV_LINE_SLEEP_NS 0u
 #endif
 #ifndef DRYV_LINE_LONG_NS
-#define DRYV_LINE_LONG_NS 4000u
+#define DRYV_LINE_LONG_NS 500u
 #endif
 __device__ __forceinline__ uint32_t wait_line_words(const unsigned long long* p, unsigned long long first, int lane,
                                                     int lo, int hi, uint32_t tag, bool long_wait, int* status,
@@ -142,7 +202,7 @@ __device__ __forceinline__ uint32_t wait_line_words(const unsigned long long* p,
   const unsigned ns = long_wait ? DRYV_LINE_LONG_NS : DRYV_LINE_SLEEP_NS;
   unsigned spins = 0;
   for (;;) {
-    __nanosleep(ns);
+    if (ns) __nanosleep(ns);  // short waits poll back to back: one L2 round trip per iteration is pause enough
     if (mine) v = ld_relaxed_gpu_u64(p);
     if (__all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) break;
     if ((++spins & 0x3ffu) == 0u) {
@@ -157,20 +217,153 @@ __device__ __forceinline__ uint32_t wait_line_words(const unsigned long long* p,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Prediction-mode derivation for Intra4x4 / Intra8x8 macroblocks, pred4x4.rs:363-427 / pred8x8.rs:698-764.
+//
+// Pixel-independent, so it runs as a pre-pass. A macroblock is a 4x4 grid of cells; a cell's mode needs the
+// cell to its left and the cell above. An Intra8x8 macroblock stores each block's mode in the four cells it
+// covers, which makes "A is Intra8x8 -> its 8x8 mode" and "A is Intra4x4 -> block 4*blk8+1" (and the B
+// rules) plain cell look-ups; cells of Intra16x16 macroblocks hold 2 (DC), which is what the reference
+// substitutes for a non-NxN neighbour.
+//
+// One CTA per picture, one lane per macroblock row, one warp per band of 32 rows. At its step s a lane
+// resolves all sixteen cells of macroblock s - lane in registers (left column carried over from its previous
+// macroblock), taking the bottom cell row of the macroblock above from the lane below it in index, which
+// resolved it one step earlier (__shfl_up). Lane 0 reads it from the last row of the band above through
+// shared memory, behind a progress counter. No block-wide barrier inside the walk.
+// ------------------------------------------------------------------------------------------------
+constexpr int kModeThreadsMax = 1024;  // 32 bands of 32 macroblock rows: pic_height_in_mbs <= 1024
+__global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const KernelArgs a) {
+  __shared__ uint16_t bandline[2][1024];  // bottom cell row of the last MB row of the even / odd bands, per MB column
+  __shared__ int bandprog[32];            // columns finished by that row
+  const int W = a.W, H = a.H;
+  const size_t n_mb = (size_t)W * H;
+  const size_t frame_mb0 = (size_t)blockIdx.x * n_mb;
+  const int lane = threadIdx.x & 31, band = threadIdx.x >> 5;
+  if (threadIdx.x < 32) bandprog[threadIdx.x] = 0;
+  // pull the picture's syntax (16 + 2 bytes per macroblock) into L2 up front: the walk below is a latency
+  // chain with two macroblocks of register look-ahead, which covers an L2 hit but not a DRAM miss
+  {
+    const uint8_t* ps = a.pred_syntax + frame_mb0 * 16;
+    for (size_t o = (size_t)threadIdx.x * 128; o < n_mb * 16; o += (size_t)blockDim.x * 128) prefetch_l2(ps + o);
+    for (size_t o = (size_t)threadIdx.x * 128; o < n_mb; o += (size_t)blockDim.x * 128) {
+      prefetch_l2(a.mb_type + frame_mb0 + o);
+      prefetch_l2(a.t8x8 + frame_mb0 + o);
+    }
+  }
+  __syncthreads();
+  const int y = 32 * band + lane;  // macroblock row
+  const bool row_ok = y < H;
+  const size_t mb_row0 = frame_mb0 + (size_t)(row_ok ? y : 0) * W;
+  const int rows_here = min(32, H - 32 * band);
+  if (rows_here <= 0) return;
+  const bool last_row = lane == rows_here - 1 && 32 * (band + 1) < H;
+  volatile int* prog_above = &bandprog[band > 0 ? band - 1 : 0];
+  const volatile uint16_t* line_above = bandline[(band + 1) & 1];
+  // two macroblocks of look-ahead on the syntax loads (raw loaded values are only combined when consumed)
+  uint4 syn_n1 = make_uint4(0, 0, 0, 0), syn_n2 = syn_n1;
+  uint8_t mbt_n1 = 0, mbt_n2 = 0, t8_n1 = 0, t8_n2 = 0;
+  auto load_mb = [&](int x, uint4& syn, uint8_t& mbt, uint8_t& t8) {
+    if (row_ok && x >= 0 && x < W) {
+      const size_t mb = mb_row0 + x;
+      syn = __ldg(reinterpret_cast<const uint4*>(a.pred_syntax + mb * 16));
+      mbt = __ldg(a.mb_type + mb);
+      t8 = __ldg(a.t8x8 + mb);
+    }
+  };
+  uint32_t leftcol = 0x2222u;  // modes of cells (3, 0..3) of this lane's previous macroblock, one nibble each
+  uint32_t bottom = 0x2222u;   // modes of cells (0..3, 3) of the macroblock this lane resolved in the previous step
+  const bool haveB0 = y > 0;
+  const int steps = W + rows_here - 1;
+  for (int s = -2; s < steps; s++) {
+    const int x = s - lane;
+    const uint4 syn_c = syn_n1;
+    const int mbt = mbt_n1, t8 = t8_n1;
+    syn_n1 = syn_n2;
+    mbt_n1 = mbt_n2;
+    t8_n1 = t8_n2;
+    load_mb(x + 2, syn_n2, mbt_n2, t8_n2);
+    if (s < 0) continue;
+    uint32_t top4 = __shfl_up_sync(0xffffffffu, bottom, 1);
+    if (lane == 0) {
+      top4 = 0x2222u;
+      if (band > 0 && x < W) {
+        while (*prog_above <= x) __nanosleep(64);
+        top4 = line_above[x];
+      }
+    }
+    if (row_ok && x >= 0 && x < W) {
+      const int cls = mbt == 0 ? (t8 ? 1 : 0) : 2;  // slice/macroblock.rs:682-716
+      const bool haveA0 = x > 0;
+      uint32_t c[4][4];  // resolved modes, [gy][gx]
+      if (cls == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) c[i >> 2][i & 3] = 2;
+      } else if (cls == 0) {
+        const uint32_t sw[4] = {syn_c.x, syn_c.y, syn_c.z, syn_c.w};
+#pragma unroll
+        for (int gy = 0; gy < 4; gy++)
+#pragma unroll
+          for (int gx = 0; gx < 4; gx++) {
+            const int blk = 8 * (gy >> 1) + 4 * (gx >> 1) + 2 * (gy & 1) + (gx & 1);  // pred4x4.rs:14-17
+            const uint32_t syn = (sw[blk >> 2] >> (8 * (blk & 3))) & 0xffu;
+            const uint32_t prev = (syn >> 3) & 1u, rem = syn & 7u;
+            const uint32_t am = gx > 0 ? c[gy][gx - 1] : ((leftcol >> (4 * gy)) & 15u);
+            const uint32_t bm = gy > 0 ? c[gy - 1][gx] : ((top4 >> (4 * gx)) & 15u);
+            const bool haveA = gx > 0 || haveA0, haveB = gy > 0 || haveB0;
+            const uint32_t pred = (haveA && haveB) ? min(am, bm) : 2u;  // pred4x4.rs:386-414
+            c[gy][gx] = prev ? pred : (rem < pred ? rem : rem + 1);     // pred4x4.rs:416-426
+          }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int bx = b & 1, by = b >> 1;
+          const uint32_t syn = (syn_c.x >> (8 * b)) & 0xffu;
+          const uint32_t prev = (syn >> 3) & 1u, rem = syn & 7u;
+          const uint32_t am = bx > 0 ? c[2 * by][1] : ((leftcol >> (8 * by)) & 15u);
+          const uint32_t bm = by > 0 ? c[1][2 * bx] : ((top4 >> (8 * bx)) & 15u);
+          const bool haveA = bx > 0 || haveA0, haveB = by > 0 || haveB0;
+          const uint32_t pred = (haveA && haveB) ? min(am, bm) : 2u;  // pred8x8.rs:723-763
+          const uint32_t m = prev ? pred : (rem < pred ? rem : rem + 1);
+          c[2 * by][2 * bx] = c[2 * by][2 * bx + 1] = c[2 * by + 1][2 * bx] = c[2 * by + 1][2 * bx + 1] = m;
+        }
+      }
+      leftcol = c[0][3] | (c[1][3] << 4) | (c[2][3] << 8) | (c[3][3] << 12);
+      bottom = c[3][0] | (c[3][1] << 4) | (c[3][2] << 8) | (c[3][3] << 12);
+      if (cls != 2) {
+        // record layout: see kModeBytes (recon_kernels.cuh)
+        uint32_t lo = 0, hi = c[3][2] | (c[3][3] << 4);
+#pragma unroll
+        for (int gy = 0; gy < 4; gy++) lo |= (c[gy][0] | (c[gy][1] << 4)) << (8 * gy);
+#pragma unroll
+        for (int gy = 0; gy < 3; gy++) hi |= (c[gy][2] | (c[gy][3] << 4)) << (8 * (gy + 1));
+        *reinterpret_cast<uint2*>(a.modes + (mb_row0 + x) * kModeBytes) = make_uint2(lo, hi);
+      }
+      if (last_row) {
+        bandline[band & 1][x] = (uint16_t)bottom;
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&bandprog[band]) = x + 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Full reconstruction: persistent row teams over an x+2y macroblock wavefront.
 //
 // A row team (one CTA, two warps) walks one macroblock row of one picture left to right:
-//   front warp  - 128-bit coefficient loads, dequant + Hadamard + 4x4/8x8 inverse transforms (residual
-//                 tiles -> ring slot) and the Intra4x4/8x8 prediction-mode derivation. It depends on the
-//                 row above only through that row's modes, so it runs ahead of the pixels.
+//   front warp  - 128-bit coefficient loads, dequant + Hadamard + 4x4/8x8 inverse transforms into a ring
+//                 slot. Depends on nothing but its own macroblock, so it runs ahead of the pixels.
 //   pixel warp  - Intra4x4/8x8/16x16 + chroma prediction, residual add + clip, 128-bit row stores.
 // Rows hand data down through the line buffer: after a macroblock the team writes its bottom line
-// (4 luma words, 2+2 chroma words, 1 word of bottom-block modes), each as payload | launch tag in one
-// 64-bit word. The row below fetches a line with one relaxed 64-bit load per lane, issued a whole
-// macroblock before it is needed, and only checks the tags later: no fences, no flags, and nobody
-// reads the picture back. Luma needs line x+1 of the row above (top-right neighbour: x+2y wavefront);
-// chroma and the mode derivation only need line x.
+// (4 luma words, 2+2 chroma words), each as payload | launch tag in one 64-bit word. The row below
+// fetches a line with one relaxed 64-bit load per lane, issued a whole macroblock before it is needed,
+// and only checks the tags later: no fences, no flags, and nobody reads the picture back. Luma needs
+// line x+1 of the row above (top-right neighbour: x+2y wavefront); chroma only needs line x.
 // ------------------------------------------------------------------------------------------------
+#ifndef DRYV_START_LAG
+#define DRYV_START_LAG 4
+#endif
+constexpr int kStartLag = DRYV_START_LAG;
 #ifndef DRYV_TEAMS_PER_SM
 #define DRYV_TEAMS_PER_SM 12
 #endif
@@ -180,12 +373,8 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     const uint4* src = reinterpret_cast<const uint4*>(a.tables);
     uint4* dst = reinterpret_cast<uint4*>(&ts.tab);
     for (int i = threadIdx.x; i < (int)(sizeof(DeviceTables) / 16); i += kTeamThreads) dst[i] = src[i];
-    if (threadIdx.x == 0) {
-      for (int i = 0; i < kSlots; i++) {
-        mbar_init(&ts.full[i], 1);
-        mbar_init(&ts.empty[i], 1);
-      }
-    }
+    if (threadIdx.x == 0)
+      for (int i = 0; i < kSlots; i++) mbar_init(&ts.full[i], 1);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -193,20 +382,31 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
   const DeviceTables& tab = ts.tab;
   const int W = a.W, H = a.H;
   const size_t n_mb = (size_t)W * H;
-  const int strideY = W * 16, strideC = W * 8;
+  const int strideY = W * 16;
   const uint32_t tag = a.tag;
-  bool dead = false;
 
   if (is_front) {
     // =========================================== front warp ===========================================
     const LaneConst lc = make_lane_const(lane, tab);
     const uint8_t* const hdr_base = header_base(a, lane);
     const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
-    const int g = lane & 15, gx = g & 3, gy = g >> 2;  // raster-grid cell of this lane
-    const int syn_idx4 = 8 * (gy >> 1) + 4 * (gx >> 1) + 2 * (gy & 1) + (gx & 1);  // spec 4x4 block index of the cell
-    const int syn_src8 = ((gy >> 1) ? 4 : 0) + (gx >> 1);  // lane that loaded pred_syntax[blk8] (cells 0,1,4,5)
     int local_status = STATUS_OK;
     unsigned n = 0;  // macroblocks handed to the pixel warp so far
+    // chroma lane roles: lanes 4..5 / 6..7 fetch and publish the two Cb / Cr words of a bottom line,
+    // lanes 8..9 shift the top-row slots [x-1].w1 | [x].w0..1 (byte 4 + 4k of tile row -1) when the walker
+    // advances, lanes 16..23 / 24..31 store and carry one Cb / Cr pixel row each
+    uint8_t* c_fresh = nullptr;
+    const uint8_t* c_pub = nullptr;
+    if (lane >= 4 && lane < 8) {
+      const int pln = (lane - 4) >> 1, k = (lane - 4) & 1;
+      c_fresh = &ts.chroma[pln * kChromaTileBytes + 4 + 4 * (1 + k)];
+      c_pub = &ts.chroma[pln * kChromaTileBytes + chroma_at(4 * k, 7)];
+    }
+    uint8_t* const c_shift = (lane == 8 || lane == 9) ? &ts.chroma[(lane - 8) * kChromaTileBytes + 4] : nullptr;
+    uint8_t* const c_tile = &ts.chroma[((lane >> 3) & 1) * kChromaTileBytes];
+    const int c_first = chroma_at(0, lane & 7), c_last = chroma_at(7, lane & 7), c_left = chroma_at(-1, lane & 7);
+    const int strideC = W * 8;
+    bool dead = false;
     CLK_DECL;
     for (;;) {
       unsigned t = 0;
@@ -217,96 +417,118 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
       const int row = (int)(t / (unsigned)a.n_frames), frame = (int)(t % (unsigned)a.n_frames);
       const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
       const bool availB = row > 0, publish = row + 1 < H;
-      // modes word (line word 8) of the row above / of this row
-      const unsigned long long* modes_above = a.line + (mb_row0 - W) * kLineWords + 8;
-      unsigned long long* modes_mine = a.line + mb_row0 * kLineWords + 8;
+      const unsigned long long* c_above = a.line + (mb_row0 - W) * kLineWords + lane;  // chroma words of line x above
+      unsigned long long* c_mine = a.line + mb_row0 * kLineWords + lane;
+      uint8_t* c_st = a.out + (size_t)frame * n_mb * 384 + n_mb * 256 + (size_t)((lane >> 3) & 1) * n_mb * 64 +
+                      (size_t)(8 * row + (lane & 7)) * strideC;
+      unsigned long long lvc = 0;
+      if (availB && lane >= 4 && lane < 8) lvc = ld_relaxed_gpu_u64(c_above);
 
-      // prefetch macroblock 0
+      // Level fetch: cp.async (LDGSTS) copies of the macroblock's 768 B into a ring in shared memory, kCoefAhead
+      // macroblocks ahead of their use. No staging registers and no scoreboard: under load the front warp used to
+      // stall on a one-macroblock-ahead register prefetch (DRAM latency > one macroblock time).
+      // Lanes 0..23 copy (and later read back) the 32 bytes of their own 4x4 block.
       const uint8_t* hp = hdr_base + mb_row0;
-      const uint8_t* sp = a.pred_syntax + mb_row0 * 16 + syn_idx4;
-      const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 2;
-      uint32_t hdr_n = lane < 4 ? (uint32_t)__ldg(hp) : 0u;
-      uint32_t syn_n = lane < 16 ? (uint32_t)__ldg(sp) : 0u;
-      uint4 c0_n = make_uint4(0, 0, 0, 0), c1_n = make_uint4(0, 0, 0, 0);
-      if (lane < 24) {
-        c0_n = __ldg(cp);
-        c1_n = __ldg(cp + 1);
+      const uint8_t* cp = reinterpret_cast<const uint8_t*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 32;
+      const uint2* mp = reinterpret_cast<const uint2*>(a.modes + mb_row0 * kModeBytes);
+      for (int k = 0; k < kCoefAhead; k++) {
+        if (lane < 24 && k < W) cp_async_32(&ts.coef[k % kCoefStages][lane * 16], cp + (size_t)k * (DRYV_COEFFS_PER_MB * 2));
+        cp_async_commit();
       }
-      int a_col = 2;  // resolved mode of the cell left of grid column 0 (previous MB of this row)
+      uint32_t hdr_n = lane < 4 ? (uint32_t)__ldg(hp) : 0u;
+      uint2 mv_n = make_uint2(0, 0);
+      if (lane == 24) mv_n = __ldg(mp);
 
       for (int x = 0; x < W; x++) {
-        const uint32_t hdr_c = hdr_n, syn_c = syn_n;
-        const uint4 c0 = c0_n, c1 = c1_n;
-        // modes of the MB above: fetch now, check after the residual stage
-        unsigned long long lv = 0;
-        if (availB && lane == 8) lv = ld_relaxed_gpu_u64(modes_above);
+        const uint32_t hdr_c = hdr_n;
+        const uint2 mv_c = mv_n;
+        {
+          const int k = x + kCoefAhead;
+          if (lane < 24 && k < W) cp_async_32(&ts.coef[k % kCoefStages][lane * 16], cp + (size_t)k * (DRYV_COEFFS_PER_MB * 2));
+          cp_async_commit();
+        }
+        if ((x & 15) == 0 && x + 24 < W) {
+          // the byte-per-MB arrays and the modes: L2 prefetch now and then
+          if (lane >= 8 && lane < 12) prefetch_l2(header_base(a, lane - 8) + mb_row0 + x + 24);
+          if (lane == 12) prefetch_l2(a.modes + (mb_row0 + x + 8) * kModeBytes);
+          if (lane == 13) prefetch_l2(a.modes + (mb_row0 + x + 16) * kModeBytes);
+        }
         if (x + 1 < W) {
           hp += 1;
-          sp += 16;
-          cp += DRYV_COEFFS_PER_MB / 8;
+          mp += 1;
           if (lane < 4) hdr_n = (uint32_t)__ldg(hp);
-          if (lane < 16) syn_n = (uint32_t)__ldg(sp);
-          if (lane < 24) {
-            c0_n = __ldg(cp);
-            c1_n = __ldg(cp + 1);
-          }
+          if (lane == 24) mv_n = __ldg(mp);
+        }
+        cp_async_wait<kCoefAhead>();  // this macroblock's copy has landed (each lane reads what it copied itself)
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+        if (lane < 24) {
+          const uint4* src = reinterpret_cast<const uint4*>(&ts.coef[x % kCoefStages][lane * 16]);
+          c0 = src[0];
+          c1 = src[1];
         }
         const MbHeader h = decode_header(hdr_c, &local_status);
-        const bool availA = x > 0;
 
         // ring slot: wait until the pixel warp has released its previous use
         const unsigned si = n % kSlots, use = n / kSlots;
         Slot& slot = ts.slot[si];
         CLK_MARK(0);  // prefetch + header
-        if (use > 0) mbar_wait_backoff(&ts.empty[si], (use - 1) & 1);
+        if (use > 0) bar_sync_empty(si);
         CLK_MARK(1);  // wait for a free slot
 
-        // 1. residual (independent of every other macroblock)
-        residual_stage(tab, ts.scratch, slot.res, slot.cres, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
+        residual_stage(tab, ts.scratch, slot.res, ts.cres, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
         CLK_MARK(2);  // residual stage
 
-        // 2. modes of the MB above
-        uint32_t mw = 0x02020202u;
-        if (availB) {
-          const uint32_t w = wait_line_words(modes_above, lv, lane, 8, 9, tag, x == 0, a.status, dead);
-          mw = __shfl_sync(0xffffffffu, w, 8);
-        }
-        CLK_MARK(3);  // wait for the modes of the row above
-
-        // 3. prediction modes -> slot, bottom-row modes -> line buffer, hand the slot to the pixel warp
-        const int b_row = (mw >> (8 * gx)) & 0xff;
-        int syn = (int)syn_c;
-        if (h.mbcls == 1) syn = __shfl_sync(0xffffffffu, syn, syn_src8);
-        const int m = resolve_modes(lane, h.mbcls, syn, a_col, b_row, availA, availB);
-        // 4-bit modes of cells 0..7 -> lanes 0..7 (lo word), cells 8..15 -> lanes 8..15 (hi word)
-        uint32_t mp = lane < 16 ? ((uint32_t)m << (4 * (lane & 7))) : 0u;
-        mp |= __shfl_xor_sync(0xffffffffu, mp, 1);
-        mp |= __shfl_xor_sync(0xffffffffu, mp, 2);
-        mp |= __shfl_xor_sync(0xffffffffu, mp, 4);
-        if (lane == 8) {
-          slot.modes_hi = mp;
-          if (publish) {
-            // bottom-row modes (cells 12..15 = nibbles 4..7 of the hi word), one byte each, for the row below
-            const uint32_t mv = ((mp >> 16) & 15u) | (((mp >> 20) & 15u) << 8) | (((mp >> 24) & 15u) << 16) |
-                                (((mp >> 28) & 15u) << 24);
-            st_relaxed_gpu_u64(modes_mine, ((unsigned long long)tag << 32) | mv);
-          }
+        if (lane == 24) {
+          slot.modes_lo = mv_c.x;
+          slot.modes_hi = mv_c.y;
         }
         if (lane == 0) {
-          slot.modes_lo = mp;
           slot.frame = frame;
           slot.row = row;
           slot.x = x;
           slot.mbcls = h.mbcls;
           slot.mode16 = ((h.mbt - 1) & 3) | (h.cm << 8);
         }
-        a_col = __shfl_sync(0xffffffffu, m, gy * 4 + 3);
-        modes_above += kLineWords;
-        modes_mine += kLineWords;
         __syncwarp();
         if (lane == 0) mbar_arrive(&ts.full[si]);
         n++;
-        CLK_MARK(4);  // mode derivation + hand-off
+        CLK_MARK(4);  // hand-off
+
+        // ---- chroma of this macroblock: prediction needs line x of the row above (no top-right), so the chroma
+        // walk of a row depends only on the chroma walk of the row above and stays off the luma critical path
+        const bool availA = x > 0;
+        if (availB) {
+          const uint32_t w = wait_line_words(c_above, lvc, lane, 4, 8, tag, x == 0, a.status, dead);
+          if (lane >= 4 && lane < 8) {
+            *reinterpret_cast<uint32_t*>(c_fresh) = w;
+            c_above += kLineWords;
+            if (x + 1 < W) lvc = ld_relaxed_gpu_u64(c_above);
+          }
+          __syncwarp();
+        }
+        CLK_MARK(3);  // wait for the chroma line of the row above
+        predict_chroma(ts.chroma, ts.ccol, ts.cres, lane, h.cm, availA, availB, availA && availB);
+        if (publish && lane >= 4 && lane < 8)
+          st_relaxed_gpu_u64(c_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(c_pub));
+        c_mine += kLineWords;
+        if (lane >= 16) {
+          const uint2 v = *reinterpret_cast<const uint2*>(&c_tile[c_first]);
+          __stcs(reinterpret_cast<uint2*>(c_st), v);
+          c_st += 8;
+        }
+        {  // carry: right-most column -> left-neighbour column (tile column -1 and its contiguous copy), top-row shift
+          const int cv = c_tile[c_last];
+          uint32_t sv = 0;
+          if (c_shift) sv = *reinterpret_cast<const uint32_t*>(c_shift + 8);
+          __syncwarp();
+          if (lane >= 16) {
+            c_tile[c_left] = (uint8_t)cv;
+            ts.ccol[lane - 16] = (uint8_t)cv;
+          }
+          if (c_shift) *reinterpret_cast<uint32_t*>(c_shift) = sv;
+          __syncwarp();
+        }
+        CLK_MARK(5);  // chroma prediction + store + carry
       }
       CLK_MARK(7);  // row change
     }
@@ -314,7 +536,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     // no more rows: tell the pixel warp
     {
       const unsigned si = n % kSlots, use = n / kSlots;
-      if (use > 0) mbar_wait_backoff(&ts.empty[si], (use - 1) & 1);
+      if (use > 0) bar_sync_empty(si);
       if (lane == 0) ts.slot[si].row = -1;
       __syncwarp();
       if (lane == 0) mbar_arrive(&ts.full[si]);
@@ -322,33 +544,19 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
   } else {
     // =========================================== pixel warp ===========================================
-    // Top-row slots of the pixel tiles (tile row -1):
-    //   luma  : 9 words [x-1].w3 | [x].w0..3 | [x+1].w0..3 at byte 12 + 4k
-    //   chroma: 3 words per plane [x-1].w1 | [x].w0..1 at byte 4 + 4k
-    // Line words handled by lane: 0..3 luma (of line x+1), 4..5 Cb, 6..7 Cr (of line x).
-    uint8_t* fresh_dst = nullptr;      // where this lane's fetched line word goes
-    const uint8_t* pub_src = nullptr;  // where this lane's word of the published line comes from
-    if (lane < 4) {
-      fresh_dst = &ts.luma[12 + 4 * (5 + lane)];
-      pub_src = &ts.luma[luma_at(4 * lane, 15)];
-    } else if (lane < 8) {
-      const int pl = (lane - 4) >> 1, k = (lane - 4) & 1;
-      fresh_dst = &ts.chroma[pl * kChromaTileBytes + 4 + 4 * (1 + k)];
-      pub_src = &ts.chroma[pl * kChromaTileBytes + chroma_at(4 * k, 7)];
-    }
-    // top-row shift when the walker advances: lanes 0..4 luma slots k+4 -> k, lanes 8..9 chroma slot 2 -> 0
-    uint8_t* shift_dst = nullptr;
-    int shift_by = 0;
-    if (lane < 5) { shift_dst = &ts.luma[12 + 4 * lane]; shift_by = 16; }
-    else if (lane == 8 || lane == 9) { shift_dst = &ts.chroma[(lane - 8) * kChromaTileBytes + 4]; shift_by = 8; }
-    // pixel column / row this lane carries and stores: lanes 0..15 luma row, 16..23 Cb row, 24..31 Cr row
-    uint8_t* const my_tile = lane < 16 ? ts.luma : &ts.chroma[((lane >> 3) & 1) * kChromaTileBytes];
-    const int my_first = lane < 16 ? luma_at(0, lane) : chroma_at(0, lane & 7);  // first pixel of my row
-    const int my_last = lane < 16 ? luma_at(15, lane) : chroma_at(7, lane & 7);
-    const int my_left = lane < 16 ? luma_at(-1, lane) : chroma_at(-1, lane & 7);
+    // Luma only. Top-row slots of the luma tile (tile row -1): 9 words [x-1].w3 | [x].w0..3 | [x+1].w0..3 at
+    // byte 12 + 4k. Lanes 0..3 fetch the four luma words of line x+1 of the row above and publish this row's.
+    const PixLane pl = make_pix_lane(lane);
+    bool dead = false;
+    uint8_t* const fresh_dst = lane < 4 ? &ts.luma[12 + 4 * (5 + lane)] : nullptr;       // where the fetched word goes
+    const uint8_t* const pub_src = lane < 4 ? &ts.luma[luma_at(4 * lane, 15)] : nullptr; // the published word
+    // top-row shift when the walker advances: lanes 0..4, slots k+4 -> k
+    uint8_t* const shift_dst = lane < 5 ? &ts.luma[12 + 4 * lane] : nullptr;
+    // lanes 0..15 store and carry one luma pixel row each
+    const int my_first = luma_at(0, lane & 15), my_last = luma_at(15, lane & 15), my_left = luma_at(-1, lane & 15);
     unsigned n = 0;
     const int W1 = W - 1;
-    const unsigned long long* line_above = nullptr;  // + lane; line x+1 for luma lanes, line x for chroma lanes
+    const unsigned long long* line_above = nullptr;  // + lane; line x+1 of the row above
     unsigned long long* line_mine = nullptr;
     uint8_t* st_ptr = nullptr;
     bool availB = false, publish = false;
@@ -366,15 +574,20 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         // row start
         const int frame = slot.frame;
         const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
-        uint8_t* const Y = a.out + (size_t)frame * n_mb * 384;
         availB = row > 0;
         publish = row + 1 < H;
         line_above = a.line + (mb_row0 - W) * kLineWords + lane;
         line_mine = a.line + mb_row0 * kLineWords + lane;
-        if (lane < 16) st_ptr = Y + (size_t)(16 * row + lane) * strideY;
-        else st_ptr = Y + n_mb * 256 + (size_t)((lane >> 3) & 1) * n_mb * 64 + (size_t)(8 * row + (lane & 7)) * strideC;
+        st_ptr = a.out + (size_t)frame * n_mb * 384 + (size_t)(16 * row + (lane & 15)) * strideY;
         if (availB) {
-          // luma line 0 of the row above becomes "line x" of macroblock 0 (long wait: that row may not have started)
+          // Start lag (see kStartLag), then luma line 0 of the row above becomes "line x" of macroblock 0
+          if (kStartLag > 2) {
+            const int ahead = min(kStartLag - 1, W1);
+            const unsigned long long* far = line_above + (size_t)ahead * kLineWords;
+            unsigned long long vf = 0;
+            if (lane == 0) vf = ld_relaxed_gpu_u64(far);
+            wait_line_words(far, vf, lane, 0, 1, tag, true, a.status, dead);
+          }
           unsigned long long v0 = 0;
           if (lane < 4) v0 = ld_relaxed_gpu_u64(line_above);
           const uint32_t w = wait_line_words(line_above, v0, lane, 0, 4, tag, true, a.status, dead);
@@ -384,63 +597,72 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
           if (lane < 5) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
           __syncwarp();
           if (lane < 5) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
-          // luma lanes look one line ahead from here on
-          if (lane < 4) line_above += kLineWords;
-          if ((lane < 4 && W1 > 0) || (lane >= 4 && lane < 8)) lv = ld_relaxed_gpu_u64(line_above);
+          // look one line ahead from here on
+          if (lane < 4) {
+            line_above += kLineWords;
+            if (W1 > 0) lv = ld_relaxed_gpu_u64(line_above);
+          }
         }
       }
       CLK_MARK(1);  // row start (incl. long wait for line 0)
-      const int mbcls = slot.mbcls, mode16 = slot.mode16 & 3, cm = slot.mode16 >> 8;
+      TRACE_MARK(0);
+      const int mbcls = slot.mbcls, mode16 = slot.mode16 & 3;
       const uint32_t modes_lo = slot.modes_lo, modes_hi = slot.modes_hi;
       const bool availA = x > 0, availC = availB && x < W1, availD = availA && availB;
-      if (availB) {
-        // luma lanes: line x+1 (only if it exists); chroma lanes: line x
-        const int lo = availC ? 0 : 4;
-        const uint32_t w = wait_line_words(line_above, lv, lane, lo, 8, tag, false, a.status, dead);
-        if (lane >= lo && lane < 8) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
-        // fetch for the next macroblock of this row, overlapped with this macroblock's prediction
-        line_above += kLineWords;
-        if ((lane < 4 && x + 2 <= W1) || (lane >= 4 && lane < 8 && x + 1 <= W1)) lv = ld_relaxed_gpu_u64(line_above);
+      // needs line x+1 of the row above (top-right neighbour), if it exists
+      if (availC) {
+        const uint32_t w = wait_line_words(line_above, lv, lane, 0, 4, tag, false, a.status, dead);
+        if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
       }
       __syncwarp();
-      CLK_MARK(2);  // wait for the lines of the row above
+      CLK_MARK(2);  // wait for the luma line of the row above
+      TRACE_MARK(1);
 
       if (mbcls == 0) {
-        predict_i4x4(tab, ts.luma, slot.res, lane, modes_lo, modes_hi,
+        predict_i4x4(tab, ts.luma, slot.res, pl, modes_lo, modes_hi,
                      (availA ? 1 : 0) | (availB ? 2 : 0) | (availC ? 4 : 0) | (availD ? 8 : 0));
         CLK_MARK(3);
       } else if (mbcls == 1) {
-        predict_i8x8(tab, ts.luma, slot.res, lane, modes_lo, modes_hi, availA, availB, availC, availD);
+        predict_i8x8(tab, ts.luma, ts.e8, slot.res, pl, lane, modes_lo, modes_hi, availA, availB, availC, availD);
         CLK_MARK(4);
       } else {
-        predict_i16x16(ts.luma, slot.res, lane, mode16, availA, availB);
+        predict_i16x16(ts.luma, ts.lcol, slot.res, lane, mode16, availA, availB);
         CLK_MARK(5);
       }
-      predict_chroma(ts.chroma, slot.cres, lane, cm, availA, availB, availD);
-      CLK_MARK(6);  // chroma prediction
+      // The row below is waiting for exactly this: publish the bottom line before anything else, and only then
+      // fetch the line for the next macroblock (as late as possible: in a tightly coupled wavefront an earlier
+      // load would only see that the row above has not got there yet).
+      if (lane < 4) {
+        if (publish)
+          st_relaxed_gpu_u64(line_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
+        if (availB) {
+          line_above += kLineWords;
+          if (x + 2 <= W1) lv = ld_relaxed_gpu_u64(line_above);
+        }
+      }
+      line_mine += kLineWords;
+      TRACE_MARK(2);
 
-      // store the macroblock (16 x 16 B luma rows, 2 x 8 x 8 B chroma rows) and publish its bottom line
+      // store the macroblock's 16 x 16 B luma rows
       if (lane < 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&my_tile[my_first]);
+        const uint4 v = *reinterpret_cast<const uint4*>(&ts.luma[my_first]);
         __stcs(reinterpret_cast<uint4*>(st_ptr), v);
         st_ptr += 16;
-      } else {
-        const uint2 v = *reinterpret_cast<const uint2*>(&my_tile[my_first]);
-        __stcs(reinterpret_cast<uint2*>(st_ptr), v);
-        st_ptr += 8;
       }
-      if (publish && lane < 8)
-        st_relaxed_gpu_u64(line_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
-      line_mine += kLineWords;
-      // carry: right-most column -> left-neighbour column, top-row slots shift by one macroblock
-      const int cv = my_tile[my_last];
+      // carry: right-most column -> left-neighbour column (tile column -1 and its contiguous copy),
+      // top-row slots shift by one macroblock
+      const int cv = ts.luma[my_last];
       uint32_t sv = 0;
-      if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + shift_by);
+      if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
       __syncwarp();
-      my_tile[my_left] = (uint8_t)cv;
+      if (lane < 16) {
+        ts.luma[my_left] = (uint8_t)cv;
+        ts.lcol[lane] = (uint8_t)cv;
+      }
       if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ts.empty[si]);
+      TRACE_MARK(3);
+      bar_arrive_empty(si);
       n++;
       CLK_MARK(7);  // stores + publish + carry
     }
@@ -530,10 +752,13 @@ struct dryv_recon_ctx {
   bool tables_valid = false;
   // wavefront control block
   unsigned long long* d_line = nullptr;  // bottom-line hand-off buffer, kLineWords words per macroblock
+  uint8_t* d_modes = nullptr;            // resolved prediction modes, kModeBytes per macroblock
   size_t line_cap = 0;                   // in macroblocks
   uint32_t tag = 0;                      // launch tag, incremented per wavefront launch (0 = never written)
   unsigned int* d_ticket = nullptr;  // [0] ticket, [1] status
   unsigned long long* d_prof = nullptr;  // stage clocks (development builds)
+  unsigned int* d_trace = nullptr;       // timeline trace (development builds), 4 words per macroblock of picture 0
+  size_t trace_mbs = 0;
   int* h_status = nullptr;           // pinned
   // staging for dryv_recon_submit (two slots)
   uint8_t* d_in[2] = {nullptr, nullptr};
@@ -582,11 +807,15 @@ int ensure_control(dryv_recon_ctx* ctx, size_t mbs) {
   if (mbs > ctx->line_cap) {
     CU(cudaDeviceSynchronize());
     if (ctx->d_line) cudaFree(ctx->d_line);
+    if (ctx->d_modes) cudaFree(ctx->d_modes);
     ctx->d_line = nullptr;
+    ctx->d_modes = nullptr;
     ctx->line_cap = 0;
     const size_t bytes = mbs * dryv::kLineWords * sizeof(unsigned long long);
     CU(cudaMalloc(&ctx->d_line, bytes));
     CU(cudaMemset(ctx->d_line, 0, bytes));  // tag 0 is never used by a launch
+    CU(cudaMalloc(&ctx->d_modes, mbs * dryv::kModeBytes));
+    CU(cudaMemset(ctx->d_modes, 0x22, mbs * dryv::kModeBytes));
     ctx->line_cap = mbs;
   }
   return DRYV_OK;
@@ -605,11 +834,15 @@ KernelArgs make_args(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   a.out = out;
   a.tables = ctx->d_tables;
   a.line = ctx->d_line;
+  a.modes = ctx->d_modes;
   a.tag = ctx->tag;
   a.ticket = ctx->d_ticket;
   a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
 #ifdef DRYV_STAGE_CLOCKS
   a.prof = ctx->d_prof;
+#endif
+#ifdef DRYV_TRACE
+  a.trace = ctx->d_trace;
 #endif
   a.W = pp->pic_width_in_mbs;
   a.H = pp->pic_height_in_mbs;
@@ -634,12 +867,16 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   if (++ctx->tag == 0) ctx->tag = 1;  // every launch validates line words with its own tag: no per-launch clearing
   CU(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
   KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out);
+  // pre-pass: prediction-mode derivation, one CTA per picture
+  const int mode_threads = (((int)pp->pic_height_in_mbs + 31) / 32) * 32;  // one warp per band of 32 MB rows
+  dryv::resolve_modes_kernel<<<n_frames, mode_threads, 0, s>>>(a);
+  CU(cudaGetLastError());
   size_t want = rows;  // one row team (CTA) per macroblock row at most
   size_t cap = (size_t)ctx->sm_count * ctx->wave_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
   dryv::recon_wavefront_kernel<<<grid, dryv::kTeamThreads, 0, s>>>(a);
   CU(cudaGetLastError());
-  ctx->launches++;
+  ctx->launches += 2;
   return DRYV_OK;
 }
 
@@ -689,6 +926,9 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
        cudaMemset(ctx->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_status, sizeof(int)) == cudaSuccess &&
        cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)) == cudaSuccess;
+  // shared memory, not L1, is what the row teams live on: ask for the largest carve-out
+  ok = ok && cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wave_ctas_per_sm, dryv::recon_wavefront_kernel,
                                                            dryv::kTeamThreads, 0) == cudaSuccess &&
        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resid_ctas_per_sm, dryv::recon_residual_add_kernel,
@@ -720,6 +960,7 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
   if (ctx->d_line) cudaFree(ctx->d_line);
+  if (ctx->d_modes) cudaFree(ctx->d_modes);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -904,6 +1145,23 @@ size_t dryv_recon_device_tables(const dryv_pic_params* pp, void* out, size_t cap
   delete t;
   return sizeof(DeviceTables);
 }
+
+#ifdef DRYV_TRACE
+// development builds only: allocate / read the per-macroblock timeline of picture 0
+int dryv_recon_debug_trace(dryv_recon_ctx* ctx, unsigned int* out, size_t mbs) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!out) {
+    if (ctx->d_trace) cudaFree(ctx->d_trace);
+    ctx->d_trace = nullptr;
+    if (cudaMalloc(&ctx->d_trace, mbs * 16) != cudaSuccess) return DRYV_ERR_CUDA;
+    cudaMemset(ctx->d_trace, 0, mbs * 16);
+    ctx->trace_mbs = mbs;
+    return DRYV_OK;
+  }
+  if (mbs > ctx->trace_mbs) return DRYV_ERR_ARG;
+  return cudaMemcpy(out, ctx->d_trace, mbs * 16, cudaMemcpyDeviceToHost) == cudaSuccess ? DRYV_OK : DRYV_ERR_CUDA;
+}
+#endif
 
 #ifdef DRYV_STAGE_CLOCKS
 // development builds only (not part of include/dryv_recon.h): read and reset the stage clocks

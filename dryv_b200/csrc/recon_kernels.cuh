@@ -1,16 +1,20 @@
 // recon_kernels.cuh — sm_100a device code of the AVC intra reconstruction path.
 //
-// One warp owns one macroblock row of one picture ("row walker") and walks it left to right. Per MB:
-//   1. residual stage  (no dependencies): 128-bit loads of the MB's 768 B of int16 levels, inverse
-//      zig-zag as a register permutation, dequant, luma-DC / chroma-DC Hadamard (warp shuffles), the
-//      4x4 transform with one block per lane entirely in registers (24 lanes = 16 luma + 8 chroma
-//      blocks) or the 8x8 transform with 8 lanes per block and a shared-memory transpose; int16
-//      residuals land in a per-warp shared-memory tile.
-//   2. wait until the row above has finished MB x+1 (x+2y wavefront, per-row progress counter,
-//      ld.acquire / st.release at gpu scope).
-//   3. prediction + residual add + clip into a shared-memory pixel tile (left column carried over in
-//      shared memory from the previous MB, top strip re-read from the frame).
-//   4. 128-bit row stores of the finished MB, then the row's progress counter is published.
+// Three kernels (entry points in recon.cu):
+//   resolve_modes_kernel   pixel-independent pre-pass: Intra4x4/8x8 prediction-mode derivation for a
+//                          whole picture as a lock-step anti-diagonal walk over the 4x4-cell grid.
+//   recon_wavefront_kernel persistent "row teams" (one CTA = two warps) walking macroblock rows in
+//                          x+2y wavefront order:
+//       front warp  128-bit loads of the MB's 768 B of int16 levels, inverse zig-zag as a register
+//                   permutation, dequant, luma-DC / chroma-DC Hadamard (warp shuffles), 4x4 transform
+//                   with one block per lane in registers (24 lanes = 16 luma + 8 chroma blocks) or the
+//                   8x8 transform with 8 lanes per block; int16 residuals land in a ring slot. It has no
+//                   dependency on any other macroblock and runs ahead of the pixels.
+//       pixel warp  waits for the bottom line of the row above (64-bit payload|tag words, relaxed
+//                   loads), predicts + adds the residual + clips into a shared-memory pixel tile, stores
+//                   128-bit rows, publishes its own bottom line. Prediction is a gather from the tile:
+//                   no shuffles, per-lane sample addresses come from host-built tap tables.
+//   recon_residual_add_kernel  dequant + transform + add to a supplied prediction picture.
 // No tensor cores: the H.264 transforms are shift/add butterflies with exact integer rounding.
 //
 // Reference behaviour reproduced (paths relative to the reference root, src/video/frame/):
@@ -28,7 +32,7 @@ namespace dryv {
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 
-constexpr int kLumaStride = 48;          // pixel (x, y) at (y + 1) * 48 + 16 + x, x in -4..31 (row -1), y in -1..15
+constexpr int kLumaStride = kLumaTileStride;  // pixel (x, y) at (y + 1) * 48 + 16 + x, x in -4..31 (row -1), y in -1..15
 constexpr int kLumaTileBytes = 17 * kLumaStride;
 constexpr int kChromaStride = 24;        // pixel (x, y) at (y + 1) * 24 + 8 + x, x in -4..15 (row -1), y in -1..7
 constexpr int kChromaTileBytes = 9 * kChromaStride;
@@ -45,15 +49,12 @@ struct ResidCtaSmem {
 };
 
 // wavefront kernel: a "row team" = one CTA of two warps walking one macroblock row.
-//   front warp: residual (luma + chroma) and prediction-mode derivation
-//   pixel warp: luma + chroma prediction, stores
-// The front warp hands each macroblock to the luma warp through a ring of kSlots slots.
+// The front warp hands each macroblock to the pixel warp through a ring of kSlots slots.
 constexpr int kSlots = 4;
 constexpr int kTeamThreads = 64;
 struct Slot {
   alignas(16) int16_t res[256];  // luma residual [16][16]
-  alignas(16) int16_t cres[128]; // chroma residual [2][8][8]
-  uint32_t modes_lo, modes_hi;   // resolved Intra4x4/8x8 modes of the raster 4x4 grid cells 0..7 / 8..15, 4 bits each
+  uint32_t modes_lo, modes_hi;   // resolved Intra4x4/8x8 modes in schedule order (resolve_modes_kernel)
   int32_t frame, row, x;         // row < 0: no more work
   int32_t mbcls, mode16;         // 0/1/2 = Intra4x4/8x8/16x16; Intra16x16 prediction mode | intra_chroma_pred_mode << 8
   int32_t pad[1];
@@ -62,20 +63,29 @@ static_assert(sizeof(Slot) % 16 == 0, "slot alignment");
 struct TeamSmem {
   DeviceTables tab;
   Slot slot[kSlots];
+  alignas(16) int16_t coef[4][DRYV_COEFFS_PER_MB];  // level ring filled by cp.async (front warp)
+  alignas(16) int16_t cres[128];                    // chroma residual [2][8][8] of the front warp's current MB
   alignas(16) uint8_t luma[kLumaTileBytes];         // luma pixel tile (pixel warp)
-  alignas(16) uint8_t chroma[2 * kChromaTileBytes]; // chroma pixel tiles (pixel warp)
+  alignas(16) uint8_t chroma[2 * kChromaTileBytes]; // chroma pixel tiles (front warp)
+  alignas(16) uint8_t lcol[16];                     // right-most luma column of the previous MB, contiguous
+  alignas(16) uint8_t ccol[16];                     // right-most Cb | Cr columns of the previous MB
+  alignas(16) uint8_t e8[32];                       // filtered edge vector p' of the current Intra8x8 block
   alignas(16) uint8_t scratch[kScratchBytes];
   alignas(8) unsigned long long full[kSlots];       // mbarriers: slot filled by the front warp
-  alignas(8) unsigned long long empty[kSlots];      // mbarriers: slot released by the pixel warp
 };
 
 enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
 
-// Bottom line a macroblock hands to the row below: 4 luma words (16 px), 2 Cb, 2 Cr words (8 px each)
-// and one word with the resolved prediction modes of its bottom 4x4 blocks. Every 32-bit payload
-// travels with the launch tag in one 64-bit word, so a single relaxed 64-bit load both fetches the
-// data and proves it is there: no fence, no separate flag, no second round trip.
-constexpr int kLineWords = 9;
+// Bottom line a macroblock hands to the row below: 4 luma words (16 px), 2 Cb, 2 Cr words (8 px each).
+// Every 32-bit payload travels with the launch tag in one 64-bit word, so a single relaxed 64-bit load
+// both fetches the data and proves it is there: no fence, no separate flag, no second round trip.
+constexpr int kLineWords = 8;
+
+// Resolved prediction modes of one macroblock (written by resolve_modes_kernel), 8 bytes, one nibble per
+// 4x4 block in the order the Intra4x4 schedule consumes them:
+//   bytes 0..3: half-warp A, steps 0..7; byte 4: half-warp A, steps 8, 9; bytes 5..7: half-warp B, steps 2..7
+// (an Intra8x8 macroblock stores each block's mode in the four cells it covers).
+constexpr int kModeBytes = 8;
 
 struct KernelArgs {
   const uint8_t* mb_type;
@@ -88,9 +98,11 @@ struct KernelArgs {
   const uint8_t* pred_in;   // residual-add kernel only
   const DeviceTables* tables;
   unsigned long long* line; // [n_frames * H * W][kLineWords] bottom line of each MB: payload | tag << 32
+  uint8_t* modes;           // [n_frames * H * W][kModeBytes]
   uint32_t tag;             // launch tag: a line word is valid when its upper half equals it
   unsigned int* ticket;     // row ticket counter
   unsigned long long* prof; // stage clocks (development builds), may be null
+  unsigned int* trace;      // per-macroblock timeline of picture 0 (development builds), may be null
   int* status;
   int W, H, n_frames;
   int cb_off, cr_off;
@@ -340,218 +352,290 @@ __device__ __forceinline__ void residual_stage(const DeviceTables& tab, uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// Prediction stage helpers
+// Prediction stage (pixel warp). Every neighbour sample is read from the shared-memory pixel tiles:
+// the tile is the gather network, there are no shuffles on the pixel path.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int luma_at(int x, int y) { return (y + 1) * kLumaStride + 16 + x; }
-__device__ __forceinline__ int chroma_at(int x, int y) { return (y + 1) * kChromaStride + 8 + x; }
+__host__ __device__ constexpr int luma_at(int x, int y) { return (y + 1) * kLumaStride + 16 + x; }
+__host__ __device__ constexpr int chroma_at(int x, int y) { return (y + 1) * kChromaStride + 8 + x; }
+
+constexpr int kTap4Row = 32 * 3 * 2;          // bytes per (variant, mode) row of DeviceTables::tap4
+constexpr int kTap4Variant = 9 * kTap4Row;    // bytes per variant
+constexpr int kTap8Row = 32 * 8;              // bytes per mode row of DeviceTables::tap8
 
 // legal-mode mask of the nine 4x4/8x8 modes given neighbour availability (the reference writes no
-// prediction when the mode's neighbours are missing, so the prediction stays 0: SURVEY quirk Q4)
+// prediction when the mode's neighbours are missing, so the prediction stays 0: SURVEY quirk Q4).
+// Bit 0 (Vertical) doubles as "top available", bit 1 (Horizontal) as "left available".
 __device__ __forceinline__ uint32_t legal_mask(bool t, bool l, bool c) {
   return 0x004u | (t ? 0x089u : 0u) | (l ? 0x102u : 0u) | ((t && l && c) ? 0x070u : 0u);
 }
 
-// Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110. Ten dependency steps (DeviceTables::i4step),
-// two blocks per step where the decode-order availability rules allow it; one pixel per lane, 16 lanes
-// per block. Kept as a rolled loop: the kernel is instruction-fetch sensitive.
-//   av = A | B<<1 | C<<2 | D<<3 (macroblock availability), modes_lo/hi = 4-bit modes per raster cell.
-__device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma, int lane,
-                                             uint32_t modes_lo, uint32_t modes_hi, int av) {
+// Per-lane constants of the pixel warp.
+struct PixLane {
+  int half;                // Intra4x4: half-warp A (0) / B (1)
+  int i4_pix;              // tile offset of this lane's pixel relative to the step's (half-warp A) block origin
+  int i4_edge;             // half * kI4HalfDelta
+  int i4_res2;             // byte offset of this lane's residual relative to half-warp A's block
+  int i4_tab, i4_tab5;     // byte offset of this lane's entry inside a tap4 row (+ variant stride for half B: step 5)
+  int e8_s, e8_p, e8_n;    // Intra8x8 reference filter: tile offsets (relative to the block origin) of this
+                           // lane's raw edge sample, its predecessor and its successor
+  int i8_pix, i8_res2, i8_tab;
+};
+
+__device__ __forceinline__ PixLane make_pix_lane(int lane) {
+  PixLane pl;
   const int half = lane >> 4, p = lane & 15, px = p & 3, py = p >> 2;
-  // edge sample fetched by this lane, relative to the block origin: 0..7 top / top-right (4..7 fall back to
-  // sample 3 when top-right is missing), 8..11 left, 12 corner, 13..15 contribute 0
-  const int edge_off = p < 8 ? (p - kLumaStride) : (p < 12 ? (p - 8) * kLumaStride - 1 : -kLumaStride - 1);
-  const int edge_off_notr = (p >= 4 && p < 8) ? (3 - kLumaStride) : edge_off;
-  const int guard_bit = p < 8 ? 25 : (p < 12 ? 26 : (p == 12 ? 27 : 31));  // availability bit guarding the sample
-  const int pix_off = py * kLumaStride + px;
-  const int res_lane = py * 16 + px;
-  const uint32_t* steps = &tab.i4step[av][0][half];
-  uint32_t nxt = steps[0];
-#pragma unroll 1
-  for (int s = 0; s < 10; s++) {
-    const uint32_t cur = nxt;
-    nxt = steps[s < 9 ? 2 * s + 2 : 18];
-    const int org = cur & 1023;
-    const int msh = (cur >> 10) & 31;
-    const int mode = (((cur & 0x8000u) ? modes_hi : modes_lo) >> msh) & 15;
-    int ev = lt[org + ((cur & (1u << 28)) ? edge_off : edge_off_notr)];
-    if (!((cur >> guard_bit) & 1u)) ev = 0;  // unavailable samples (and lanes 13..15) count as 0
-    const uint32_t taps = tab.lut4[mode > 8 ? 2 : mode][p];
-    // residual of this lane's pixel: cell -> (cell >> 2) * 64 + (cell & 3) * 4 = msh-derived
-    const int cell = (msh >> 2) | ((cur >> 12) & 8);
-    const int res = res_luma[(cell >> 2) * 64 + (cell & 3) * 4 + res_lane];
-    // __shfl_sync with width 16 takes the source lane modulo 16: no masking of the tap fields needed
-    const int e0 = __shfl_sync(0xffffffffu, ev, taps, 16);
-    const int e1 = __shfl_sync(0xffffffffu, ev, taps >> 4, 16);
-    const int e2 = __shfl_sync(0xffffffffu, ev, taps >> 8, 16);
-    const int t3 = e0 + e1 + e2;
-    int pred = (t3 + e1 + 2) >> 2;
-    if (__any_sync(0xffffffffu, mode == 2)) {
-      // DC (pred4x4.rs:116-167): second summation round over the three partial sums held by lanes 0..2
-      const int q = __shfl_sync(0xffffffffu, t3, 0, 16) + __shfl_sync(0xffffffffu, t3, 1, 16) +
-                    __shfl_sync(0xffffffffu, t3, 2, 16);
-      const int nav = ((cur >> 25) & 1) + ((cur >> 26) & 1);  // available sides: top, left
-      const int dcv = nav == 2 ? ((q + 4) >> 3) : (nav == 1 ? ((q + 2) >> 2) : 128);
-      if (mode == 2) pred = dcv;
-    }
-    if (!((cur >> (16 + mode)) & 1u) || mode > 8) pred = 0;  // mode needs a missing neighbour: prediction stays 0 (Q4)
-    if (cur & (1u << 29)) lt[org + pix_off] = (uint8_t)clip255(pred + res);
-    __syncwarp();
+  pl.half = half;
+  pl.i4_pix = half * kI4HalfDelta + py * kLumaStride + px;
+  pl.i4_edge = half * kI4HalfDelta;
+  pl.i4_res2 = 2 * (half * (8 - 4 * 16) + py * 16 + px);
+  pl.i4_tab = lane * 6;
+  pl.i4_tab5 = pl.i4_tab + (half ? kTap4Variant : 0);
+  // edge sample `lane` of an 8x8 block: 0..15 top, 16..23 left, 24 corner (pred8x8.rs:166-200)
+  int s, pv, nx;
+  if (lane < 16) {
+    s = -kLumaStride + lane;
+    pv = lane == 0 ? -kLumaStride - 1 : s - 1;
+    nx = lane == 15 ? s : s + 1;
+  } else if (lane < 24) {
+    const int k = lane - 16;
+    s = kLumaStride * k - 1;
+    pv = k == 0 ? -kLumaStride - 1 : s - kLumaStride;
+    nx = k == 7 ? s : s + kLumaStride;
+  } else if (lane == 24) {
+    s = -kLumaStride - 1;
+    pv = -kLumaStride;  // p[0,-1]
+    nx = -1;            // p[-1,0]
+  } else {
+    s = pv = nx = -kLumaStride - 1;
   }
+  pl.e8_s = s;
+  pl.e8_p = pv;
+  pl.e8_n = nx;
+  pl.i8_pix = (lane >> 2) * kLumaStride + (lane & 3) * 2;
+  pl.i8_res2 = 2 * ((lane >> 2) * 16 + (lane & 3) * 2);
+  pl.i8_tab = lane * 8;
+  return pl;
 }
 
-// Intra8x8 luma, pred8x8.rs:152-696 + pred8x8.rs:34-46. Four sequential blocks, two pixels per lane.
-__device__ __forceinline__ void predict_i8x8(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma, int lane,
-                                             uint32_t modes_lo, uint32_t modes_hi, bool availA, bool availB,
-                                             bool availC, bool availD) {
-  const int py = lane >> 2, px = (lane & 3) * 2;
-#pragma unroll 1
-  for (int b = 0; b < 4; b++) {
-    const int bx = (b & 1) * 8, by = (b >> 1) * 8;
-    const int mode = (((b & 2) ? modes_hi : modes_lo) >> ((b & 1) * 8)) & 15;  // cells 0, 2, 8, 10
-    const bool aL = bx > 0 || availA;
-    const bool aT = by > 0 || availB;
-    const bool aTL = b == 0 ? availD : (b == 1 ? availB : (b == 2 ? availA : true));
-    const bool aTR = b == 0 ? availB : (b == 1 ? availC : (b == 2));
-    const int m = mode > 8 ? 2 : mode;
-    const uint32_t tw = *reinterpret_cast<const uint32_t*>(&tab.lut8[m][py * 8 + px]);
-    const uint32_t rw = *reinterpret_cast<const uint32_t*>(&res_luma[(by + py) * 16 + bx + px]);
-    // raw edge sample of this lane: 0..15 top, 16..23 left, 24 corner
-    int ex, ey;
-    if (lane < 16) { ex = bx + ((lane >= 8 && !aTR) ? 7 : lane); ey = by - 1; }
-    else if (lane < 24) { ex = bx - 1; ey = by + (lane - 16); }
-    else { ex = bx - 1; ey = by - 1; }
-    const int raw = lt[luma_at(ex, ey)];
-    // reference sample filter, pred8x8.rs:222-288 (with the x = 0 overwrite of quirk Q2)
-    int srcp, srcn;  // lanes supplying the previous / next sample of the 3-tap filter
-    if (lane < 16) { srcp = lane == 0 ? E8_CORNER : lane - 1; srcn = lane == 15 ? 15 : lane + 1; }
-    else if (lane < 24) { srcp = lane == 16 ? (aTL ? E8_CORNER : 16) : lane - 1; srcn = lane == 23 ? 23 : lane + 1; }
-    else { srcp = aT ? 0 : lane; srcn = aL ? 16 : lane; }
-    int pv = __shfl_sync(0xffffffffu, raw, srcp & 31);
-    const int nv = __shfl_sync(0xffffffffu, raw, srcn & 31);
-    if (lane == 0 && !aTL) pv = -1;  // Q2: raw p[-1,-1] sentinel enters the filter
-    int ev = (pv + 2 * raw + nv + 2) >> 2;
-    if (mode == 2) {  // DC, pred8x8.rs:326-425 (warp-uniform): sums of the filtered top 0..7 and left 0..7
-      int sum = ev + __shfl_xor_sync(0xffffffffu, ev, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-      const int sumT = __shfl_sync(0xffffffffu, sum, 0);
-      const int sumL = __shfl_sync(0xffffffffu, sum, 16);
-      int dc;
-      if (aT && aL) dc = (sumT + sumL + 8) >> 4;
-      else if (aL) dc = (sumL + 4) >> 3;
-      else if (aT) dc = (sumT + 4) >> 3;
-      else dc = 128;
-      if (lane == E8_DC) ev = dc;
-    }
-    const bool ok = mode <= 8 && ((legal_mask(aT, aL, aTL) >> mode) & 1u);
-    int pr[2];
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const uint32_t taps = (tw >> (16 * q)) & 0xffffu;
-      const int e0 = __shfl_sync(0xffffffffu, ev, taps & 31);
-      const int e1 = __shfl_sync(0xffffffffu, ev, (taps >> 5) & 31);
-      const int e2 = __shfl_sync(0xffffffffu, ev, (taps >> 10) & 31);
-      pr[q] = ok ? ((e0 + 2 * e1 + e2 + 2) >> 2) : 0;
-    }
-    const int o0 = clip255(pr[0] + lo16(rw)), o1 = clip255(pr[1] + hi16(rw));
-    *reinterpret_cast<uint16_t*>(&lt[luma_at(bx + px, by + py)]) = (uint16_t)(o0 | (o1 << 8));
-    __syncwarp();
-  }
+// ---- Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110 -------------------------------------------
+// Ten dependency steps, two blocks per step where the decode-order availability rules allow it
+// (kI4BlkA / kI4BlkB); one pixel per lane, 16 lanes per block. Fully unrolled: block origins are
+// immediates, the three sample addresses of the next step are fetched while this step computes.
+template <int S>
+struct I4 {
+  static constexpr int b = kI4BlkA[S];
+  static constexpr int bx = ((b >> 2) & 1) * 8 + (b & 1) * 4;
+  static constexpr int by = (b >> 3) * 8 + ((b >> 1) & 1) * 4;
+  static constexpr int org = luma_at(bx, by);
+  static constexpr int res = by * 16 + bx;
+};
+
+template <int S>
+__device__ __forceinline__ void i4_taps(const uint8_t* tap4, int vreg, uint32_t m8, uint32_t m_hi, int& mode,
+                                        uint32_t& a0, uint32_t& a1, uint32_t& a2) {
+  mode = S < 8 ? (int)((m8 >> (4 * (S & 7))) & 15u) : (int)((m_hi >> (4 * (S & 1))) & 15u);
+  const uint8_t* tp = tap4 + mode * kTap4Row + vreg;
+  a0 = *reinterpret_cast<const uint16_t*>(tp);
+  a1 = *reinterpret_cast<const uint16_t*>(tp + 2);
+  a2 = *reinterpret_cast<const uint16_t*>(tp + 4);
 }
 
-// Intra16x16 luma, pred16x16.rs:79-425 + pred16x16.rs:64-75. Lane = (row, half): 8 pixels.
-__device__ __forceinline__ void predict_i16x16(uint8_t* lt, const int16_t* res_luma, int lane, int mode, bool availA,
-                                               bool availB) {
+template <int S>
+__device__ __forceinline__ void i4_body(uint8_t* lt, const PixLane& pl, const uint8_t* resp, int mode, uint32_t a0,
+                                        uint32_t a1, uint32_t a2, uint32_t mask) {
+  constexpr int org = I4<S>::org;
+  const uint8_t* base = lt + (org - kTap4Bias);
+  const int e0 = base[a0], e1 = base[a1], e2 = base[a2];
+  const int r = *reinterpret_cast<const int16_t*>(resp + 2 * I4<S>::res);
+  int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
+  if (mode == 2) {  // DC, pred4x4.rs:116-167
+    const uint8_t* eb = lt + org + pl.i4_edge;
+    const uint32_t tw = *reinterpret_cast<const uint32_t*>(eb - kLumaStride);
+    const int sT = dp4a_us(tw, 0x01010101, 0);
+    const int sL = eb[-1] + eb[kLumaStride - 1] + eb[2 * kLumaStride - 1] + eb[3 * kLumaStride - 1];
+    const bool aT = mask & 1u, aL = mask & 2u;
+    pred = (aT && aL) ? ((sT + sL + 4) >> 3) : (aT ? ((sT + 2) >> 2) : (aL ? ((sL + 2) >> 2) : 128));
+  }
+  if (!((mask >> mode) & 1u)) pred = 0;  // mode needs a missing neighbour: prediction stays 0 (Q4)
+  lt[org + pl.i4_pix] = (uint8_t)clip255(pred + r);
+}
+
+//   av = A | B<<1 | C<<2 | D<<3 (macroblock availability); modes_lo / modes_hi: see kModeBytes.
+__device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma,
+                                             const PixLane& pl, uint32_t modes_lo, uint32_t modes_hi, int av) {
+  const bool A = av & 1, B = av & 2, C = av & 4, D = av & 8;
+  const bool h = pl.half != 0;
+  const uint32_t mask0 = legal_mask(B, A, D);     // block 0
+  const uint32_t maskT = B ? 0x1ffu : 0x106u;     // blocks 1, 4, 5: left is inside the MB, top and corner in B
+  const uint32_t maskL = A ? 0x1ffu : 0x08du;     // blocks 2, 8, 10: top is inside the MB, left and corner in A
+  const uint32_t m2 = h ? maskT : maskL, m3 = h ? maskT : 0x1ffu, m4 = h ? 0x1ffu : maskL;
+  const uint8_t* tap4 = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0][0]);
+  // top-right availability (pred4x4.rs:39-43): blocks 0, 1, 4 from B, block 5 from C, blocks 3, 7, 11, 13, 15 never
+  const int v_b = B ? 0 : kTap4Variant, v_c = C ? 0 : kTap4Variant;
+  const int t0 = pl.i4_tab, t1 = pl.i4_tab + kTap4Variant;
+  const int v0 = t0 + v_b, v2 = t0 + (h ? v_b : 0), v3 = t0 + (h ? v_c : kTap4Variant);
+  const uint32_t m8 = h ? modes_hi : modes_lo, m_hi = modes_hi;
+  const uint8_t* resp = reinterpret_cast<const uint8_t*>(res_luma) + pl.i4_res2;
+  int mode;
+  uint32_t a0, a1, a2;
+  i4_taps<0>(tap4, v0, m8, m_hi, mode, a0, a1, a2);
+#define DRYV_I4_STEP(S, MASK, ONLY_A, VNEXT)                                        \
+  {                                                                                 \
+    int nm = 0;                                                                     \
+    uint32_t b0 = 0, b1 = 0, b2 = 0;                                                \
+    if (S < 9) i4_taps<(S < 9 ? S + 1 : 9)>(tap4, VNEXT, m8, m_hi, nm, b0, b1, b2); \
+    if (!(ONLY_A) || !h) i4_body<S>(lt, pl, resp, mode, a0, a1, a2, MASK);          \
+    __syncwarp();                                                                   \
+    mode = nm;                                                                      \
+    a0 = b0;                                                                        \
+    a1 = b1;                                                                        \
+    a2 = b2;                                                                        \
+  }
+  DRYV_I4_STEP(0, mask0, true, v0)
+  DRYV_I4_STEP(1, maskT, true, v2)
+  DRYV_I4_STEP(2, m2, false, v3)
+  DRYV_I4_STEP(3, m3, false, t0)
+  DRYV_I4_STEP(4, m4, false, pl.i4_tab5)
+  DRYV_I4_STEP(5, 0x1ffu, false, t0)
+  DRYV_I4_STEP(6, m4, false, t1)
+  DRYV_I4_STEP(7, 0x1ffu, false, t0)
+  DRYV_I4_STEP(8, 0x1ffu, true, t1)
+  DRYV_I4_STEP(9, 0x1ffu, true, t0)
+#undef DRYV_I4_STEP
+}
+
+// ---- Intra8x8 luma, pred8x8.rs:152-696 + pred8x8.rs:34-46 ---------------------------------------------
+// Four sequential blocks. Phase 1: lanes 0..24 filter one reference sample each (pred8x8.rs:222-288, with
+// the x = 0 overwrite of quirk Q2) into e8[]. Phase 2: two pixels per lane gathered from e8[].
+template <int BLK>
+__device__ __forceinline__ void i8_block(const DeviceTables& tab, uint8_t* lt, uint8_t* e8, const PixLane& pl,
+                                         const uint8_t* resp8, int lane, int mode, bool aT, bool aL, bool aTL,
+                                         bool aTR) {
+  constexpr int bx = (BLK & 1) * 8, by = (BLK >> 1) * 8;
+  constexpr int o8 = luma_at(bx, by);
+  constexpr int t7 = -kLumaStride + 7;
+  int oS = pl.e8_s, oP = pl.e8_p, oN = pl.e8_n;
+  if (!aTR) {  // p[8..15,-1] unavailable: replicate p[7,-1] (pred8x8.rs:202-220)
+    if (lane >= 8 && lane < 16) oS = oP = oN = t7;
+    if (lane == 7) oN = t7;
+  }
+  if (!aTL && lane == 16) oP = oS;
+  if (lane == 24) {
+    if (!aT) oP = oS;
+    if (!aL) oN = oS;
+  }
+  const uint8_t* b = lt + o8;
+  const int raw = b[oS], nv = b[oN];
+  int pv = b[oP];
+  if (!aTL && lane == 0) pv = -1;  // Q2: the raw p[-1,-1] sentinel enters the filter
+  e8[lane] = (uint8_t)((pv + 2 * raw + nv + 2) >> 2);
+  const uint8_t* tp = &tab.tap8[0][0][0] + mode * kTap8Row + pl.i8_tab;
+  const uint32_t i0 = tp[0], i1 = tp[1], i2 = tp[2], i3 = tp[3], i4 = tp[4], i5 = tp[5];
+  const uint32_t rw = *reinterpret_cast<const uint32_t*>(resp8 + 2 * (by * 16 + bx));
+  __syncwarp();
+  int pr0, pr1;
+  if (mode == 2) {  // DC, pred8x8.rs:326-425 (warp-uniform): sums of the filtered top 0..7 and left 0..7
+    const uint32_t* ew = reinterpret_cast<const uint32_t*>(e8);
+    const int sT = dp4a_us(ew[1], 0x01010101, dp4a_us(ew[0], 0x01010101, 0));
+    const int sL = dp4a_us(ew[5], 0x01010101, dp4a_us(ew[4], 0x01010101, 0));
+    pr0 = (aT && aL) ? ((sT + sL + 8) >> 4) : (aL ? ((sL + 4) >> 3) : (aT ? ((sT + 4) >> 3) : 128));
+    pr1 = pr0;
+  } else {
+    pr0 = ((int)e8[i0] + 2 * (int)e8[i1] + (int)e8[i2] + 2) >> 2;
+    pr1 = ((int)e8[i3] + 2 * (int)e8[i4] + (int)e8[i5] + 2) >> 2;
+  }
+  if (!((legal_mask(aT, aL, aTL) >> mode) & 1u)) pr0 = pr1 = 0;
+  const int o0 = clip255(pr0 + lo16(rw)), o1 = clip255(pr1 + hi16(rw));
+  *reinterpret_cast<uint16_t*>(&lt[o8 + pl.i8_pix]) = (uint16_t)(o0 | (o1 << 8));
+  __syncwarp();
+}
+
+__device__ __forceinline__ void predict_i8x8(const DeviceTables& tab, uint8_t* lt, uint8_t* e8,
+                                             const int16_t* res_luma, const PixLane& pl, int lane, uint32_t modes_lo,
+                                             uint32_t modes_hi, bool A, bool B, bool C, bool D) {
+  const uint8_t* resp8 = reinterpret_cast<const uint8_t*>(res_luma) + pl.i8_res2;
+  // block modes: cells (0,0), (2,0), (0,2), (2,2) = A step 0, B step 2, A step 4, B step 6
+  i8_block<0>(tab, lt, e8, pl, resp8, lane, (int)(modes_lo & 15u), B, A, D, B);
+  i8_block<1>(tab, lt, e8, pl, resp8, lane, (int)((modes_hi >> 8) & 15u), B, true, B, C);
+  i8_block<2>(tab, lt, e8, pl, resp8, lane, (int)((modes_lo >> 16) & 15u), true, A, A, true);
+  i8_block<3>(tab, lt, e8, pl, resp8, lane, (int)((modes_hi >> 24) & 15u), true, true, true, false);
+}
+
+// ---- Intra16x16 luma, pred16x16.rs:79-425 + pred16x16.rs:64-75. Lane = (row, half): 8 pixels ----------
+//   lcol: the left neighbour column as 16 contiguous bytes.
+__device__ __forceinline__ void predict_i16x16(uint8_t* lt, const uint8_t* lcol, const int16_t* res_luma, int lane,
+                                               int mode, bool availA, bool availB) {
   const int row = lane >> 1, h = lane & 1;
-  const uint32_t t0 = *reinterpret_cast<const uint32_t*>(&lt[luma_at(8 * h, -1)]);
-  const uint32_t t1 = *reinterpret_cast<const uint32_t*>(&lt[luma_at(8 * h + 4, -1)]);
-  const int left = lt[luma_at(-1, row)];
+  const uint4 tv = *reinterpret_cast<const uint4*>(&lt[luma_at(0, -1)]);
+  const uint4 rv = *reinterpret_cast<const uint4*>(&res_luma[row * 16 + 8 * h]);
   int pr[8];
   if (mode == 0) {  // vertical
+    const uint32_t t0 = h ? tv.z : tv.x, t1 = h ? tv.w : tv.y;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { pr[k] = (t0 >> (8 * k)) & 0xff; pr[4 + k] = (t1 >> (8 * k)) & 0xff; }
-    if (!availB) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) pr[k] = 0;
+    for (int k = 0; k < 4; k++) {
+      pr[k] = availB ? (int)((t0 >> (8 * k)) & 0xff) : 0;
+      pr[4 + k] = availB ? (int)((t1 >> (8 * k)) & 0xff) : 0;
     }
   } else if (mode == 1) {  // horizontal
+    const int left = lcol[row];
 #pragma unroll
     for (int k = 0; k < 8; k++) pr[k] = availA ? left : 0;
-  } else if (mode == 2) {  // DC
-    int st = dp4a_us(t0, 0x01010101, 0);
-    st = dp4a_us(t1, 0x01010101, st);
-    st += __shfl_xor_sync(0xffffffffu, st, 1);
-    int sl = left;
-    sl += __shfl_xor_sync(0xffffffffu, sl, 2);
-    sl += __shfl_xor_sync(0xffffffffu, sl, 4);
-    sl += __shfl_xor_sync(0xffffffffu, sl, 8);
-    sl += __shfl_xor_sync(0xffffffffu, sl, 16);
-    int dc;
-    if (availA && availB) dc = (st + sl + 16) >> 5;
-    else if (availA) dc = (sl + 8) >> 4;
-    else if (availB) dc = (st + 8) >> 4;
-    else dc = 128;
+  } else {
+    const uint4 lv = *reinterpret_cast<const uint4*>(lcol);
+    if (mode == 2) {  // DC
+      const int st = dp4a_us(tv.w, 0x01010101, dp4a_us(tv.z, 0x01010101, dp4a_us(tv.y, 0x01010101, dp4a_us(tv.x, 0x01010101, 0))));
+      const int sl = dp4a_us(lv.w, 0x01010101, dp4a_us(lv.z, 0x01010101, dp4a_us(lv.y, 0x01010101, dp4a_us(lv.x, 0x01010101, 0))));
+      int dc;
+      if (availA && availB) dc = (st + sl + 16) >> 5;
+      else if (availA) dc = (sl + 8) >> 4;
+      else if (availB) dc = (st + 8) >> 4;
+      else dc = 128;
 #pragma unroll
-    for (int k = 0; k < 8; k++) pr[k] = dc;
-  } else {  // plane (needs A and B; the corner is read unchecked like pred16x16.rs:404, quirk Q5)
-    const int corner = lt[luma_at(-1, -1)];
-    // H = sum_{x'=0..7} (x'+1) * (p[8+x',-1] - p[6-x',-1]),  p[-1,-1] = corner
-    int hp;
-    if (h) hp = dp4a_us(t1, 0x08070605, dp4a_us(t0, 0x04030201, 0));
-    else hp = dp4a_us(t1, 0x00ffFEFD, dp4a_us(t0, 0xFCFBFAF9, -8 * corner));  // -7..-4 | -3,-2,-1,0
-    const int H = hp + __shfl_xor_sync(0xffffffffu, hp, 1);
-    // V likewise over the left column: weight(row) = row - 7 (row 7 -> 0), corner weight -8
-    int vp = (row - 7) * left;  // both halves reduce over their own 16 rows
-    vp += __shfl_xor_sync(0xffffffffu, vp, 2);
-    vp += __shfl_xor_sync(0xffffffffu, vp, 4);
-    vp += __shfl_xor_sync(0xffffffffu, vp, 8);
-    vp += __shfl_xor_sync(0xffffffffu, vp, 16);
-    const int V = vp - 8 * corner;
-    const int l15 = __shfl_sync(0xffffffffu, left, 30);
-    const int t15 = __shfl_sync(0xffffffffu, (int)(t1 >> 24), 1);
-    const int a = 16 * (l15 + t15);
-    const int bb = (5 * H + 32) >> 6;
-    const int cc = (5 * V + 32) >> 6;
-    const bool ok = availA && availB;
-    int base = a + bb * (8 * h - 7) + cc * (row - 7) + 16;
+      for (int k = 0; k < 8; k++) pr[k] = dc;
+    } else {  // plane (needs A and B; the corner is read unchecked like pred16x16.rs:404, quirk Q5)
+      const int corner = lt[luma_at(-1, -1)];
+      // H = sum_{x'=0..7} (x'+1) * (p[8+x',-1] - p[6-x',-1]),  p[-1,-1] = corner ; V likewise over the left column
+      const int H = dp4a_us(tv.w, 0x08070605, dp4a_us(tv.z, 0x04030201, dp4a_us(tv.y, 0x00ffFEFD, dp4a_us(tv.x, 0xFCFBFAF9, -8 * corner))));
+      const int V = dp4a_us(lv.w, 0x08070605, dp4a_us(lv.z, 0x04030201, dp4a_us(lv.y, 0x00ffFEFD, dp4a_us(lv.x, 0xFCFBFAF9, -8 * corner))));
+      const int a = 16 * ((int)(lv.w >> 24) + (int)(tv.w >> 24));
+      const int bb = (5 * H + 32) >> 6;
+      const int cc = (5 * V + 32) >> 6;
+      const bool ok = availA && availB;
+      const int base = a + bb * (8 * h - 7) + cc * (row - 7) + 16;
 #pragma unroll
-    for (int k = 0; k < 8; k++) pr[k] = ok ? clip255((base + bb * k) >> 5) : 0;
+      for (int k = 0; k < 8; k++) pr[k] = ok ? clip255((base + bb * k) >> 5) : 0;
+    }
   }
-  const uint4 rv = *reinterpret_cast<const uint4*>(&res_luma[row * 16 + 8 * h]);
   const int o0 = clip255(pr[0] + lo16(rv.x)), o1 = clip255(pr[1] + hi16(rv.x));
   const int o2 = clip255(pr[2] + lo16(rv.y)), o3 = clip255(pr[3] + hi16(rv.y));
   const int o4 = clip255(pr[4] + lo16(rv.z)), o5 = clip255(pr[5] + hi16(rv.z));
   const int o6 = clip255(pr[6] + lo16(rv.w)), o7 = clip255(pr[7] + hi16(rv.w));
-  __syncwarp();  // every lane has read the neighbours it needs before the tile is overwritten
+  // rows 0..15 / columns 0..15 are written, row -1 and the left column vector are read: no hazard
   *reinterpret_cast<uint2*>(&lt[luma_at(8 * h, row)]) = make_uint2(pack4(o0, o1, o2, o3), pack4(o4, o5, o6, o7));
   __syncwarp();
 }
 
-// Chroma Cb + Cr, trans_chroma.rs:96-366 + trans_chroma.rs:81-92. Lane = (plane, row, half): 4 pixels.
-//   ct: two chroma tiles of kChromaTileBytes each; res_chroma: int16 [2][8][8]
-__device__ __forceinline__ void predict_chroma(uint8_t* ct, const int16_t* res_chroma, int lane, int mode, bool availA,
-                                               bool availB, bool availD) {
+// ---- Chroma Cb + Cr, trans_chroma.rs:96-366 + trans_chroma.rs:81-92. Lane = (plane, row, half): 4 px ---
+//   ct: two chroma tiles of kChromaTileBytes each; ccol: left neighbour columns, 8 bytes per plane;
+//   res_chroma: int16 [2][8][8]
+__device__ __forceinline__ void predict_chroma(uint8_t* ct, const uint8_t* ccol, const int16_t* res_chroma, int lane,
+                                               int mode, bool availA, bool availB, bool availD) {
   const int pl = lane >> 4, row = (lane >> 1) & 7, h = lane & 1;
   uint8_t* tile = ct + pl * kChromaTileBytes;
+  const uint8_t* cv = ccol + pl * 8;
   const uint32_t tw = *reinterpret_cast<const uint32_t*>(&tile[chroma_at(4 * h, -1)]);
-  const int left = tile[chroma_at(-1, row)];
+  const uint2 rv = *reinterpret_cast<const uint2*>(&res_chroma[pl * 64 + row * 8 + 4 * h]);
   int pr[4];
   if (mode == 0) {
     // DC per 4x4 chroma block with the reference's ">= 0" / "> 0" tests (quirk Q3)
-    const int sumT = dp4a_us(tw, 0x01010101, 0);
-    int sumL = left;
-    sumL += __shfl_xor_sync(0xffffffffu, sumL, 2);
-    sumL += __shfl_xor_sync(0xffffffffu, sumL, 4);  // over the 4 rows of this block row
+    const int by4 = row >> 2;
+    const uint32_t lw = *reinterpret_cast<const uint32_t*>(cv + 4 * by4);  // left samples of this block row
+    const int sumT = dp4a_us(tw, 0x01010101, 0), sumL = dp4a_us(lw, 0x01010101, 0);
     // "> 0" variants: unavailable or zero-valued
     const bool t_all_gt = availB && !((tw - 0x01010101u) & ~tw & 0x80808080u);
     const bool t3_gt = availB && (tw >> 24) != 0;
-    const unsigned lz = __ballot_sync(0xffffffffu, left > 0);
-    const int gbase = (lane & ~6) & ~1;                 // lane of row (row & 4), half 0 of this plane
-    const unsigned grp = (lz >> gbase) & 0x55u;          // rows r0..r0+3 at bit 2*k
-    const bool l_all_gt = availA && grp == 0x55u;
-    const bool l3_gt = availA && ((grp >> 6) & 1u);
-    const int by4 = row >> 2;
+    const bool l_all_gt = availA && !((lw - 0x01010101u) & ~lw & 0x80808080u);
+    const bool l3_gt = availA && (lw >> 24) != 0;
     int val;
     if (h == by4) {  // blocks 0 and 3, trans_chroma.rs:174-226
       if (availB && availA) val = (sumT + sumL + 4) >> 3;
@@ -570,6 +654,7 @@ __device__ __forceinline__ void predict_chroma(uint8_t* ct, const int16_t* res_c
 #pragma unroll
     for (int k = 0; k < 4; k++) pr[k] = val;
   } else if (mode == 1) {
+    const int left = cv[row];
 #pragma unroll
     for (int k = 0; k < 4; k++) pr[k] = availA ? left : 0;
   } else if (mode == 2) {
@@ -577,16 +662,11 @@ __device__ __forceinline__ void predict_chroma(uint8_t* ct, const int16_t* res_c
     for (int k = 0; k < 4; k++) pr[k] = availB ? (int)((tw >> (8 * k)) & 0xff) : 0;
   } else {  // plane, trans_chroma.rs:319-364 (needs top, left and the corner)
     const int corner = tile[chroma_at(-1, -1)];
-    int hp = h ? dp4a_us(tw, 0x04030201, 0) : dp4a_us(tw, 0x00ffFEFD, -4 * corner);  // -3,-2,-1,0
-    const int H = hp + __shfl_xor_sync(0xffffffffu, hp, 1);
-    int vp = (row - 3) * left;  // both halves reduce over their own 8 rows
-    vp += __shfl_xor_sync(0xffffffffu, vp, 2);
-    vp += __shfl_xor_sync(0xffffffffu, vp, 4);
-    vp += __shfl_xor_sync(0xffffffffu, vp, 8);
-    const int V = vp - 4 * corner;
-    const int l7 = __shfl_sync(0xffffffffu, left, (lane & 16) | 14);
-    const int t7 = __shfl_sync(0xffffffffu, (int)(tw >> 24), (lane & 16) | 1);
-    const int a = 16 * (l7 + t7);
+    const uint2 tv = *reinterpret_cast<const uint2*>(&tile[chroma_at(0, -1)]);
+    const uint2 lv = *reinterpret_cast<const uint2*>(cv);
+    const int H = dp4a_us(tv.y, 0x04030201, dp4a_us(tv.x, 0x00ffFEFD, -4 * corner));
+    const int V = dp4a_us(lv.y, 0x04030201, dp4a_us(lv.x, 0x00ffFEFD, -4 * corner));
+    const int a = 16 * ((int)(lv.y >> 24) + (int)(tv.y >> 24));
     const int bb = (34 * H + 32) >> 6;
     const int cc = (34 * V + 32) >> 6;
     const bool ok = availA && availB && availD;
@@ -594,46 +674,10 @@ __device__ __forceinline__ void predict_chroma(uint8_t* ct, const int16_t* res_c
 #pragma unroll
     for (int k = 0; k < 4; k++) pr[k] = ok ? clip255((base + bb * k) >> 5) : 0;
   }
-  const uint2 rv = *reinterpret_cast<const uint2*>(&res_chroma[pl * 64 + row * 8 + 4 * h]);
   const int o0 = clip255(pr[0] + lo16(rv.x)), o1 = clip255(pr[1] + hi16(rv.x));
   const int o2 = clip255(pr[2] + lo16(rv.y)), o3 = clip255(pr[3] + hi16(rv.y));
-  __syncwarp();
   *reinterpret_cast<uint32_t*>(&tile[chroma_at(4 * h, row)]) = pack4(o0, o1, o2, o3);
   __syncwarp();
-}
-
-// Prediction-mode derivation for Intra4x4 / Intra8x8 MBs, pred4x4.rs:363-427 / pred8x8.rs:698-764.
-// Works on the 4x4 grid of 4x4 blocks (raster): lane g < 16 owns grid cell (g & 3, g >> 2). An Intra8x8
-// MB stores each block's mode in the four cells it covers, which makes "A is Intra8x8 -> its 8x8 mode"
-// and "A is Intra4x4 -> block 4*blk8+1" (and the B rules) plain cell look-ups.
-//   syn      : this lane's prev/rem byte (pred_syntax entry of the block covering the cell)
-//   a_col    : mode of the cell left of grid column 0 in this lane's grid row (from the previous MB; 2 if not NxN)
-//   b_row    : mode of the cell above grid row 0 in this lane's grid column (from the row above; 2 if not NxN)
-__device__ __forceinline__ int resolve_modes(int lane, int mbcls, int syn, int a_col, int b_row, bool availA,
-                                             bool availB) {
-  const int g = lane & 15, gx = g & 3, gy = g >> 2;
-  int m = 2;
-  if (mbcls == 2) return 2;  // warp-uniform
-  const int step = mbcls == 1 ? 2 : 1;  // Intra8x8: cells move in 2x2 groups
-  const int ox = gx & ~(step - 1), oy = gy & ~(step - 1);  // origin cell of the block covering this cell
-  const bool haveA = ox > 0 || availA, haveB = oy > 0 || availB;
-  // the block covering this cell takes A from its origin row and B from its origin column
-  a_col = __shfl_sync(0xffffffffu, a_col, (oy * 4) | (lane & 16));
-  b_row = __shfl_sync(0xffffffffu, b_row, ox | (lane & 16));
-  const int prev = (syn >> 3) & 1, rem = syn & 7;
-  const int ndiag = mbcls == 1 ? 3 : 7;
-#pragma unroll 1
-  for (int d = 0; d < ndiag; d++) {
-    // neighbour cells: left of the block origin in the origin's row, above the origin in its column
-    int a = __shfl_sync(0xffffffffu, m, (oy * 4 + max(ox - 1, 0)) | (lane & 16));
-    int b = __shfl_sync(0xffffffffu, m, (max(oy - 1, 0) * 4 + ox) | (lane & 16));
-    if (ox == 0) a = a_col;
-    if (oy == 0) b = b_row;
-    const int pred = (haveA && haveB) ? min(a, b) : 2;
-    const int cand = prev ? pred : (rem < pred ? rem : rem + 1);
-    m = (((ox + oy) >> (step - 1)) == d) ? cand : m;
-  }
-  return m;
 }
 
 }  // namespace dryv

@@ -12,27 +12,34 @@
 
 namespace dryv {
 
-// Edge-sample numbering used by the tap tables.
-//   4x4: 0..7 = p[0..7,-1] (top, top-right), 8..11 = p[-1,0..3] (left), 12 = p[-1,-1], 13 = always 0;
-//        mode 2 (DC) holds the first of two summation rounds: lanes 0..2 add three edge samples each
-//   8x8: 0..15 = p'[0..15,-1], 16..23 = p'[-1,0..7], 24 = p'[-1,-1], 25 = DC value
-// Every predicted sample of every mode is (E[i0] + 2*E[i1] + E[i2] + 2) >> 2 for a triple of edge
-// indices: a 2-tap average (a + b + 1) >> 1 is the triple (a, b, a), a copy is (a, a, a).
-enum { E4_LEFT = 8, E4_CORNER = 12, E4_ZERO = 13, E8_LEFT = 16, E8_CORNER = 24, E8_DC = 25 };
+// Prediction as a gather: every predicted sample of every Intra4x4 / Intra8x8 mode other than DC is
+// (E[i0] + 2*E[i1] + E[i2] + 2) >> 2 for a triple of edge samples (a 2-tap average (a + b + 1) >> 1 is the
+// triple (a, b, a), a copy is (a, a, a)). The tables hold, per mode and lane, WHERE those three samples are:
+//   tap4: byte offsets into the shared-memory luma tile, relative to the step's block origin (the block of
+//         half-warp A; half-warp B always works on the block 8 px right / 4 px up of it), biased by +256.
+//         Edge samples of a 4x4 block: top i (0..7) at -48 + i, left k (0..3) at 48 k - 1, corner at -49.
+//         Variant 1 ("no top-right") maps top 4..7 onto top 3 (pred4x4.rs:66-76).
+//   tap8: indices into the filtered edge vector p' of an 8x8 block: 0..15 top, 16..23 left, 24 corner.
+enum { E4_LEFT = 8, E4_CORNER = 12, E8_LEFT = 16, E8_CORNER = 24 };
+constexpr int kLumaTileStride = 48;
+constexpr int kI4HalfDelta = 8 - 4 * kLumaTileStride;  // tile offset of half-warp B's block relative to half-warp A's
+constexpr int kTap4Bias = 256;
+
+// Intra4x4 schedule: ten dependency steps, blocks (spec 4x4 block order) of half-warp A / B per step.
+constexpr int kI4BlkA[10] = {0, 1, 2, 3, 8, 9, 10, 11, 14, 15};
+constexpr int kI4BlkB[10] = {-1, -1, 4, 5, 6, 7, 12, 13, -1, -1};
 
 struct DeviceTables {
-  int32_t t4[52][16];      // [qP][zig-zag k] = LevelScale4x4[qP%6][pos(k)] << max(qP/6 - 4, 0)
-  uint16_t ls8[6][64];     // [qP%6][i*8+j]   = LevelScale8x8
-  uint16_t lut4[9][16];    // [mode][y*4+x]   = i0 | i1<<4 | i2<<8
-  uint16_t lut8[9][64];    // [mode][y*8+x]   = i0 | i1<<5 | i2<<10
-  uint8_t zz8inv[8][8];    // [i][j] -> zig-zag index
-  uint8_t qpc[52];         // qPI -> QPC
-  uint8_t pad[12];
-  // Intra4x4 dependency schedule, specialised per macroblock availability av = A | B<<1 | C<<2 | D<<3:
-  // [av][step][half] -> tile origin (10 bits) | mode nibble shift (0..28) << 10 | modes-hi-word flag << 15 |
-  // legal-mode mask (9 bits) << 16 | top << 25 | left << 26 | corner << 27 | top-right << 28 | active << 29
-  uint32_t i4step[16][10][2];
+  int32_t t4[52][16];         // [qP][zig-zag k] = LevelScale4x4[qP%6][pos(k)] << max(qP/6 - 4, 0)
+  uint16_t ls8[6][64];        // [qP%6][i*8+j]   = LevelScale8x8
+  uint16_t tap4[2][9][32][3]; // [variant][mode][lane][tap]
+  uint8_t tap8[9][32][8];     // [mode][lane][pixel q (0,1) * 3 + tap], 2 pad bytes
+  uint8_t zz8inv[8][8];       // [i][j] -> zig-zag index
+  uint8_t qpc[52];            // qPI -> QPC
+  uint8_t i4sched[10][2];     // copy of kI4BlkA / kI4BlkB (0xff = none), for the host-side tests
+  uint8_t pad[8];
 };
+static_assert(sizeof(DeviceTables) % 16 == 0, "DeviceTables is copied with 128-bit loads");
 
 void build_device_tables(const dryv_pic_params& pp, DeviceTables* t);
 

@@ -67,9 +67,15 @@ def test_write_yuv_file_creates_temp_dir(recon_lib, tmp_path):
 
 
 class Tables(C.Structure):
-    _fields_ = [("t4", (C.c_int32 * 16) * 52), ("ls8", (C.c_uint16 * 64) * 6), ("lut4", (C.c_uint16 * 16) * 9),
-                ("lut8", (C.c_uint16 * 64) * 9), ("zz8inv", (C.c_uint8 * 8) * 8), ("qpc", C.c_uint8 * 52),
-                ("pad", C.c_uint8 * 12), ("i4step", ((C.c_uint32 * 2) * 10) * 16)]
+    _fields_ = [("t4", (C.c_int32 * 16) * 52), ("ls8", (C.c_uint16 * 64) * 6),
+                ("tap4", (((C.c_uint16 * 3) * 32) * 9) * 2), ("tap8", ((C.c_uint8 * 8) * 32) * 9),
+                ("zz8inv", (C.c_uint8 * 8) * 8), ("qpc", C.c_uint8 * 52), ("i4sched", (C.c_uint8 * 2) * 10),
+                ("pad", C.c_uint8 * 8)]
+
+
+TILE_STRIDE = 48
+HALF_DELTA = 8 - 4 * TILE_STRIDE  # half-warp B works on the block 8 px right / 4 px up of half-warp A's
+TAP4_BIAS = 256
 
 
 def get_tables(lib, pp):
@@ -100,38 +106,59 @@ def test_zigzag_and_tap_tables(recon_lib):
     # the reference's own table starts 0,1 / 1,0 / 2,0 / 1,1 (frame/mod.rs:215-219) and ends ... 7,6 / 7,7
     assert spec_model.ZZ8[:5] == [(0, 0), (0, 1), (1, 0), (2, 0), (1, 1)] and spec_model.ZZ8[-2:] == [(7, 6), (7, 7)]
 
-    # every tap triple reproduces the closed-form predictor on random edges (4x4: modes other than DC)
+    # every tap triple reproduces the closed-form predictor on random edges (modes other than DC, which the
+    # kernels compute from the block's top word and left column directly)
     rng = np.random.default_rng(1)
-    for n, lut, bits, left0, corner in ((4, t.lut4, 4, 8, 12), (8, t.lut8, 5, 16, 24)):
+    for n in (4, 8):
         T = rng.integers(0, 256, 2 * n).tolist()
         L = rng.integers(0, 256, n).tolist()
         TL = int(rng.integers(0, 256))
         E = T + L + [TL]
         for mode in (0, 1, 3, 4, 5, 6, 7, 8):
             want = spec_model.pred_nxn(n, mode, T, L, TL)
-            for y in range(n):
-                for x in range(n):
-                    w = lut[mode][y * n + x]
-                    i0, i1, i2 = w & (2 ** bits - 1), (w >> bits) & (2 ** bits - 1), (w >> (2 * bits)) & (2 ** bits - 1)
-                    assert (E[i0] + 2 * E[i1] + E[i2] + 2) >> 2 == want[y, x], (n, mode, x, y)
+            if n == 8:
+                for lane in range(32):
+                    y, x = lane >> 2, (lane & 3) * 2
+                    for q in range(2):
+                        i0, i1, i2 = (t.tap8[mode][lane][q * 3 + k] for k in range(3))
+                        assert (E[i0] + 2 * E[i1] + E[i2] + 2) >> 2 == want[y, x + q], (n, mode, x + q, y)
+                continue
+            # 4x4: the table holds tile byte offsets; place the edge samples in a scratch tile and gather
+            for variant in range(2):
+                Tv = T[:4] + [T[3]] * 4 if variant else T
+                wantv = spec_model.pred_nxn(4, mode, Tv, L, TL)
+                for lane in range(32):
+                    half, p = lane >> 4, lane & 15
+                    org = 1024 + half * HALF_DELTA  # origin of this lane's block inside a big scratch tile
+                    tile = {}
+                    for i in range(8):
+                        tile[org - TILE_STRIDE + i] = T[i]
+                    for k in range(4):
+                        tile[org + TILE_STRIDE * k - 1] = L[k]
+                    tile[org - TILE_STRIDE - 1] = TL
+                    e = [tile[1024 - TAP4_BIAS + t.tap4[variant][mode][lane][k]] for k in range(3)]
+                    assert (e[0] + 2 * e[1] + e[2] + 2) >> 2 == wantv[p >> 2, p & 3], (variant, mode, lane)
 
 
 def test_intra4x4_schedule_respects_decode_order(recon_lib):
     """A block may only be scheduled after every neighbour it can read (left, top, top-left, and top-right
-    unless the reference treats it as unavailable) — the availability rules of pred4x4.rs:39-43."""
+    unless the reference treats it as unavailable) — the availability rules of pred4x4.rs:39-43 — and the
+    block of half-warp B always sits 8 px right / 4 px up of half-warp A's."""
     t = get_tables(recon_lib, PicParams.make(1, 1))
-    step_of = {}
+    pos = lambda b: (((b >> 2) & 1) * 2 + (b & 1), (b >> 3) * 2 + ((b >> 1) & 1))  # noqa: E731
+    step_of, blk_at = {}, {}
     for s in range(10):
-        for h in range(2):
-            w = t.i4step[15][s][h]
-            if (w >> 29) & 1:
-                org = w & 1023
-                by, bx = (org - 16) // 48 - 1, (org - 16) % 48
-                step_of[(bx // 4, by // 4)] = (s, w)
+        a, b = t.i4sched[s][0], t.i4sched[s][1]
+        step_of[pos(a)] = s
+        blk_at[pos(a)] = a
+        if b != 0xff:
+            step_of[pos(b)] = s
+            blk_at[pos(b)] = b
+            assert (pos(b)[0] - pos(a)[0], pos(b)[1] - pos(a)[1]) == (2, -1)
     assert len(step_of) == 16
-    for (gx, gy), (s, w) in step_of.items():
-        tr = (w >> 28) & 1
-        for dx, dy, needed in ((-1, 0, True), (0, -1, True), (-1, -1, True), (1, -1, bool(tr))):
+    for (gx, gy), s in step_of.items():
+        tr = blk_at[(gx, gy)] not in (3, 7, 11, 13, 15)
+        for dx, dy, needed in ((-1, 0, True), (0, -1, True), (-1, -1, True), (1, -1, tr)):
             nx, ny = gx + dx, gy + dy
             if needed and 0 <= nx < 4 and 0 <= ny < 4:
-                assert step_of[(nx, ny)][0] < s
+                assert step_of[(nx, ny)] < s

@@ -22,10 +22,6 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const void* p) {
   return v;
 }
 
-#ifndef DRYV_PREFETCH_MBS
-#define DRYV_PREFETCH_MBS 6
-#endif
-constexpr int kPrefetchMbs = DRYV_PREFETCH_MBS;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 constexpr int kCoefAhead = 3;                 // macroblocks of look-ahead on the level fetch
@@ -193,24 +189,37 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned long long* b, uint32_
 #ifndef DRYV_LINE_LONG_NS
 #define DRYV_LINE_LONG_NS 500u
 #endif
+#ifndef DRYV_POLL_PACE
+#define DRYV_POLL_PACE 0
+#endif
+constexpr int kPollPace = DRYV_POLL_PACE;
 __device__ __forceinline__ uint32_t wait_line_words(const unsigned long long* p, unsigned long long first, int lane,
                                                     int lo, int hi, uint32_t tag, bool long_wait, int* status,
-                                                    bool& dead) {
+                                                    bool& dead, uint32_t& pace_addr) {
   unsigned long long v = first;
   const bool mine = lane >= lo && lane < hi;
   if (dead || __all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) return (uint32_t)v;
+  // Slow path. Every lane polls (lanes outside [lo, hi) re-read word `lo`), which keeps the loop free of
+  // divergence: load, compare, vote, count, branch.
+  const unsigned long long* q = p - lane + (mine ? lane : lo);
   const unsigned ns = long_wait ? DRYV_LINE_LONG_NS : DRYV_LINE_SLEEP_NS;
   unsigned spins = 0;
   for (;;) {
-    if (ns) __nanosleep(ns);  // short waits poll back to back: one L2 round trip per iteration is pause enough
-    if (mine) v = ld_relaxed_gpu_u64(p);
-    if (__all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) break;
-    if ((++spins & 0x3ffu) == 0u) {
-      if (spins > (1u << 20) || ld_relaxed_gpu_s32(status) == STATUS_WATCHDOG) {
-        if (lane == 0) atomicExch(status, STATUS_WATCHDOG);
-        dead = true;
-        break;
-      }
+    if (ns) __nanosleep(ns);
+    if (kPollPace > 0) {
+      // Optional pacing (development knob): a chain of dependent shared-memory loads on a word that holds its own
+      // address. Measured: it does not help, the poll loops are not what limits the working warps.
+      uint32_t a = pace_addr;
+#pragma unroll
+      for (int i = 0; i < kPollPace; i++) asm volatile("ld.volatile.shared.u32 %0, [%0];" : "+r"(a) : : "memory");
+      pace_addr = a;
+    }
+    v = ld_relaxed_gpu_u64(q);
+    if (__all_sync(0xffffffffu, (uint32_t)(v >> 32) == tag)) break;
+    if (++spins > (1u << 22)) {  // watchdog: far beyond any legitimate wait
+      if (lane == 0) atomicExch(status, STATUS_WATCHDOG);
+      dead = true;
+      break;
     }
   }
   return (uint32_t)v;
@@ -360,8 +369,12 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
 // and only checks the tags later: no fences, no flags, and nobody reads the picture back. Luma needs
 // line x+1 of the row above (top-right neighbour: x+2y wavefront); chroma only needs line x.
 // ------------------------------------------------------------------------------------------------
+// Start lag: how many macroblocks the row above must have finished before a row starts. The x+2y order needs
+// two. Larger values were measured (3, 4, 6, 8): they lengthen the pipeline fill by (lag - 2) macroblock times
+// per row and buy nothing, because per-macroblock cost varies by 3x between Intra16x16 and Intra4x4 and the
+// slack is gone within a few macroblocks. Kept as a development knob.
 #ifndef DRYV_START_LAG
-#define DRYV_START_LAG 4
+#define DRYV_START_LAG 2
 #endif
 constexpr int kStartLag = DRYV_START_LAG;
 #ifndef DRYV_TEAMS_PER_SM
@@ -373,10 +386,13 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     const uint4* src = reinterpret_cast<const uint4*>(a.tables);
     uint4* dst = reinterpret_cast<uint4*>(&ts.tab);
     for (int i = threadIdx.x; i < (int)(sizeof(DeviceTables) / 16); i += kTeamThreads) dst[i] = src[i];
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
       for (int i = 0; i < kSlots; i++) mbar_init(&ts.full[i], 1);
+      ts.pace = smem_u32(&ts.pace);  // a word that holds its own shared-memory address (see wait_line_words)
+    }
   }
   __syncthreads();
+  uint32_t pace_addr = smem_u32(&ts.pace);
   const int lane = threadIdx.x & 31;
   const bool is_front = threadIdx.x < 32;
   const DeviceTables& tab = ts.tab;
@@ -498,7 +514,9 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         // walk of a row depends only on the chroma walk of the row above and stays off the luma critical path
         const bool availA = x > 0;
         if (availB) {
-          const uint32_t w = wait_line_words(c_above, lvc, lane, 4, 8, tag, x == 0, a.status, dead);
+          // always the sleeping flavour: the front warp runs ahead of the pixel warp, so this wait is not on the
+          // critical path, and a tight poll here would take issue slots from the pixel warps of the SM
+          const uint32_t w = wait_line_words(c_above, lvc, lane, 4, 8, tag, true, a.status, dead, pace_addr);
           if (lane >= 4 && lane < 8) {
             *reinterpret_cast<uint32_t*>(c_fresh) = w;
             c_above += kLineWords;
@@ -586,11 +604,11 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
             const unsigned long long* far = line_above + (size_t)ahead * kLineWords;
             unsigned long long vf = 0;
             if (lane == 0) vf = ld_relaxed_gpu_u64(far);
-            wait_line_words(far, vf, lane, 0, 1, tag, true, a.status, dead);
+            wait_line_words(far, vf, lane, 0, 1, tag, true, a.status, dead, pace_addr);
           }
           unsigned long long v0 = 0;
           if (lane < 4) v0 = ld_relaxed_gpu_u64(line_above);
-          const uint32_t w = wait_line_words(line_above, v0, lane, 0, 4, tag, true, a.status, dead);
+          const uint32_t w = wait_line_words(line_above, v0, lane, 0, 4, tag, true, a.status, dead, pace_addr);
           if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
           __syncwarp();
           uint32_t sv = 0;
@@ -611,7 +629,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
       const bool availA = x > 0, availC = availB && x < W1, availD = availA && availB;
       // needs line x+1 of the row above (top-right neighbour), if it exists
       if (availC) {
-        const uint32_t w = wait_line_words(line_above, lv, lane, 0, 4, tag, false, a.status, dead);
+        const uint32_t w = wait_line_words(line_above, lv, lane, 0, 4, tag, false, a.status, dead, pace_addr);
         if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
       }
       __syncwarp();

@@ -72,6 +72,7 @@ struct TeamSmem {
   alignas(16) uint8_t e8[32];                       // filtered edge vector p' of the current Intra8x8 block
   alignas(16) uint8_t scratch[kScratchBytes];
   alignas(8) unsigned long long full[kSlots];       // mbarriers: slot filled by the front warp
+  uint32_t pace;                                    // holds its own address: pacing chain of the poll loops
 };
 
 enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
@@ -358,8 +359,7 @@ __device__ __forceinline__ void residual_stage(const DeviceTables& tab, uint8_t*
 __host__ __device__ constexpr int luma_at(int x, int y) { return (y + 1) * kLumaStride + 16 + x; }
 __host__ __device__ constexpr int chroma_at(int x, int y) { return (y + 1) * kChromaStride + 8 + x; }
 
-constexpr int kTap4Row = 32 * 3 * 2;          // bytes per (variant, mode) row of DeviceTables::tap4
-constexpr int kTap4Variant = 9 * kTap4Row;    // bytes per variant
+constexpr int kTap4Row = 16 * 3 * 2;          // bytes per (variant, mode) row of DeviceTables::tap4
 constexpr int kTap8Row = 32 * 8;              // bytes per mode row of DeviceTables::tap8
 
 // legal-mode mask of the nine 4x4/8x8 modes given neighbour availability (the reference writes no
@@ -372,10 +372,9 @@ __device__ __forceinline__ uint32_t legal_mask(bool t, bool l, bool c) {
 // Per-lane constants of the pixel warp.
 struct PixLane {
   int half;                // Intra4x4: half-warp A (0) / B (1)
-  int i4_pix;              // tile offset of this lane's pixel relative to the step's (half-warp A) block origin
-  int i4_edge;             // half * kI4HalfDelta
-  int i4_res2;             // byte offset of this lane's residual relative to half-warp A's block
-  int i4_tab, i4_tab5;     // byte offset of this lane's entry inside a tap4 row (+ variant stride for half B: step 5)
+  int i4_pix;              // tile offset of this lane's pixel relative to its block origin
+  int i4_res2;             // byte offset of this lane's residual relative to its block's
+  int i4_tab;              // byte offset of this lane's entry inside a tap4 row
   int e8_s, e8_p, e8_n;    // Intra8x8 reference filter: tile offsets (relative to the block origin) of this
                            // lane's raw edge sample, its predecessor and its successor
   int i8_pix, i8_res2, i8_tab;
@@ -385,11 +384,9 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
   PixLane pl;
   const int half = lane >> 4, p = lane & 15, px = p & 3, py = p >> 2;
   pl.half = half;
-  pl.i4_pix = half * kI4HalfDelta + py * kLumaStride + px;
-  pl.i4_edge = half * kI4HalfDelta;
-  pl.i4_res2 = 2 * (half * (8 - 4 * 16) + py * 16 + px);
-  pl.i4_tab = lane * 6;
-  pl.i4_tab5 = pl.i4_tab + (half ? kTap4Variant : 0);
+  pl.i4_pix = py * kLumaStride + px;
+  pl.i4_res2 = 2 * (py * 16 + px);
+  pl.i4_tab = p * 6;
   // edge sample `lane` of an 8x8 block: 0..15 top, 16..23 left, 24 corner (pred8x8.rs:166-200)
   int s, pv, nx;
   if (lane < 16) {
@@ -419,146 +416,114 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
 
 // ---- Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110 -------------------------------------------
 // Ten dependency steps, two blocks per step where the decode-order availability rules allow it
-// (kI4BlkA / kI4BlkB); one pixel per lane, 16 lanes per block. Fully unrolled: block origins are
-// immediates, the three sample addresses of the next step are fetched while this step computes.
-template <int S>
-struct I4 {
-  static constexpr int b = kI4BlkA[S];
-  static constexpr int bx = ((b >> 2) & 1) * 8 + (b & 1) * 4;
-  static constexpr int by = (b >> 3) * 8 + ((b >> 1) & 1) * 4;
-  static constexpr int org = luma_at(bx, by);
-  static constexpr int res = by * 16 + bx;
-};
-
-template <int S>
-__device__ __forceinline__ void i4_taps(const uint8_t* tap4, int vreg, uint32_t m8, uint32_t m_hi, int& mode,
-                                        uint32_t& a0, uint32_t& a1, uint32_t& a2) {
-  mode = S < 8 ? (int)((m8 >> (4 * (S & 7))) & 15u) : (int)((m_hi >> (4 * (S & 1))) & 15u);
-  const uint8_t* tp = tap4 + mode * kTap4Row + vreg;
-  a0 = *reinterpret_cast<const uint16_t*>(tp);
-  a1 = *reinterpret_cast<const uint16_t*>(tp + 2);
-  a2 = *reinterpret_cast<const uint16_t*>(tp + 4);
-}
-
-template <int S>
-__device__ __forceinline__ void i4_body(uint8_t* lt, const PixLane& pl, const uint8_t* resp, int mode, uint32_t a0,
-                                        uint32_t a1, uint32_t a2, uint32_t mask) {
-  constexpr int org = I4<S>::org;
-  const uint8_t* base = lt + (org - kTap4Bias);
-  const int e0 = base[a0], e1 = base[a1], e2 = base[a2];
-  const int r = *reinterpret_cast<const int16_t*>(resp + 2 * I4<S>::res);
-  int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
-  if (mode == 2) {  // DC, pred4x4.rs:116-167
-    const uint8_t* eb = lt + org + pl.i4_edge;
-    const uint32_t tw = *reinterpret_cast<const uint32_t*>(eb - kLumaStride);
-    const int sT = dp4a_us(tw, 0x01010101, 0);
-    const int sL = eb[-1] + eb[kLumaStride - 1] + eb[2 * kLumaStride - 1] + eb[3 * kLumaStride - 1];
-    const bool aT = mask & 1u, aL = mask & 2u;
-    pred = (aT && aL) ? ((sT + sL + 4) >> 3) : (aT ? ((sT + 2) >> 2) : (aL ? ((sL + 2) >> 2) : 128));
-  }
-  if (!((mask >> mode) & 1u)) pred = 0;  // mode needs a missing neighbour: prediction stays 0 (Q4)
-  lt[org + pl.i4_pix] = (uint8_t)clip255(pred + r);
-}
-
+// (kI4BlkA / kI4BlkB); one pixel per lane, 16 lanes per block. A rolled loop over DeviceTables::i4tab: the
+// kernel is instruction-fetch bound when a dozen teams share an SM, so code size matters more
+// than the handful of instructions per step an unrolled version saves. The three sample addresses and the
+// residual of the next step are fetched while this step computes.
 //   av = A | B<<1 | C<<2 | D<<3 (macroblock availability); modes_lo / modes_hi: see kModeBytes.
 __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma,
                                              const PixLane& pl, uint32_t modes_lo, uint32_t modes_hi, int av) {
-  const bool A = av & 1, B = av & 2, C = av & 4, D = av & 8;
-  const bool h = pl.half != 0;
-  const uint32_t mask0 = legal_mask(B, A, D);     // block 0
-  const uint32_t maskT = B ? 0x1ffu : 0x106u;     // blocks 1, 4, 5: left is inside the MB, top and corner in B
-  const uint32_t maskL = A ? 0x1ffu : 0x08du;     // blocks 2, 8, 10: top is inside the MB, left and corner in A
-  const uint32_t m2 = h ? maskT : maskL, m3 = h ? maskT : 0x1ffu, m4 = h ? 0x1ffu : maskL;
-  const uint8_t* tap4 = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0][0]);
-  // top-right availability (pred4x4.rs:39-43): blocks 0, 1, 4 from B, block 5 from C, blocks 3, 7, 11, 13, 15 never
-  const int v_b = B ? 0 : kTap4Variant, v_c = C ? 0 : kTap4Variant;
-  const int t0 = pl.i4_tab, t1 = pl.i4_tab + kTap4Variant;
-  const int v0 = t0 + v_b, v2 = t0 + (h ? v_b : 0), v3 = t0 + (h ? v_c : kTap4Variant);
-  const uint32_t m8 = h ? modes_hi : modes_lo, m_hi = modes_hi;
+  const uint32_t* steps = &tab.i4tab[av][0][pl.half];
+  const uint8_t* tap4 = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0][0]) + pl.i4_tab;
   const uint8_t* resp = reinterpret_cast<const uint8_t*>(res_luma) + pl.i4_res2;
-  int mode;
+  const uint8_t* ltb = lt - kTap4Bias;
+  uint32_t mm = pl.half ? modes_hi : modes_lo;  // this half-warp's mode nibbles, consumed from the bottom
+  uint32_t cur = steps[0];
   uint32_t a0, a1, a2;
-  i4_taps<0>(tap4, v0, m8, m_hi, mode, a0, a1, a2);
-#define DRYV_I4_STEP(S, MASK, ONLY_A, VNEXT)                                        \
-  {                                                                                 \
-    int nm = 0;                                                                     \
-    uint32_t b0 = 0, b1 = 0, b2 = 0;                                                \
-    if (S < 9) i4_taps<(S < 9 ? S + 1 : 9)>(tap4, VNEXT, m8, m_hi, nm, b0, b1, b2); \
-    if (!(ONLY_A) || !h) i4_body<S>(lt, pl, resp, mode, a0, a1, a2, MASK);          \
-    __syncwarp();                                                                   \
-    mode = nm;                                                                      \
-    a0 = b0;                                                                        \
-    a1 = b1;                                                                        \
-    a2 = b2;                                                                        \
+  int mode = (int)(mm & 15u);
+  {
+    const uint8_t* tp = tap4 + (mode + ((cur >> 16) & 15u)) * kTap4Row;
+    a0 = *reinterpret_cast<const uint16_t*>(tp);
+    a1 = *reinterpret_cast<const uint16_t*>(tp + 2);
+    a2 = *reinterpret_cast<const uint16_t*>(tp + 4);
   }
-  DRYV_I4_STEP(0, mask0, true, v0)
-  DRYV_I4_STEP(1, maskT, true, v2)
-  DRYV_I4_STEP(2, m2, false, v3)
-  DRYV_I4_STEP(3, m3, false, t0)
-  DRYV_I4_STEP(4, m4, false, pl.i4_tab5)
-  DRYV_I4_STEP(5, 0x1ffu, false, t0)
-  DRYV_I4_STEP(6, m4, false, t1)
-  DRYV_I4_STEP(7, 0x1ffu, false, t0)
-  DRYV_I4_STEP(8, 0x1ffu, true, t1)
-  DRYV_I4_STEP(9, 0x1ffu, true, t0)
-#undef DRYV_I4_STEP
+#pragma unroll 1
+  for (int s = 0; s < 10; s++) {
+    const uint32_t org = cur & 1023u, mask = (cur >> 20) & 0x1ffu;
+    const int e0 = ltb[org + a0], e1 = ltb[org + a1], e2 = ltb[org + a2];
+    const int r = *reinterpret_cast<const int16_t*>(resp + ((cur >> 7) & 0x1f8u));
+    const bool active = (int)cur < 0;
+    const int m = mode;
+    // next step: mode nibble (half-warp A's steps 8 and 9 live in the low byte of modes_hi) and sample addresses
+    const uint32_t nxt = steps[s < 9 ? 2 * s + 2 : 18];
+    mm = s == 7 ? modes_hi : (mm >> 4);
+    mode = (int)(mm & 15u);
+    {
+      const uint8_t* tp = tap4 + (mode + ((nxt >> 16) & 15u)) * kTap4Row;
+      a0 = *reinterpret_cast<const uint16_t*>(tp);
+      a1 = *reinterpret_cast<const uint16_t*>(tp + 2);
+      a2 = *reinterpret_cast<const uint16_t*>(tp + 4);
+    }
+    int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
+    if (m == 2) {  // DC, pred4x4.rs:116-167
+      const uint8_t* eb = lt + org;
+      const uint32_t tw = *reinterpret_cast<const uint32_t*>(eb - kLumaStride);
+      const int sT = dp4a_us(tw, 0x01010101, 0);
+      const int sL = eb[-1] + eb[kLumaStride - 1] + eb[2 * kLumaStride - 1] + eb[3 * kLumaStride - 1];
+      const bool aT = mask & 1u, aL = mask & 2u;
+      pred = (aT && aL) ? ((sT + sL + 4) >> 3) : (aT ? ((sT + 2) >> 2) : (aL ? ((sL + 2) >> 2) : 128));
+    }
+    if (!((mask >> m) & 1u)) pred = 0;  // mode needs a missing neighbour: prediction stays 0 (Q4)
+    if (active) lt[org + pl.i4_pix] = (uint8_t)clip255(pred + r);
+    cur = nxt;
+    __syncwarp();
+  }
 }
 
 // ---- Intra8x8 luma, pred8x8.rs:152-696 + pred8x8.rs:34-46 ---------------------------------------------
-// Four sequential blocks. Phase 1: lanes 0..24 filter one reference sample each (pred8x8.rs:222-288, with
-// the x = 0 overwrite of quirk Q2) into e8[]. Phase 2: two pixels per lane gathered from e8[].
-template <int BLK>
-__device__ __forceinline__ void i8_block(const DeviceTables& tab, uint8_t* lt, uint8_t* e8, const PixLane& pl,
-                                         const uint8_t* resp8, int lane, int mode, bool aT, bool aL, bool aTL,
-                                         bool aTR) {
-  constexpr int bx = (BLK & 1) * 8, by = (BLK >> 1) * 8;
-  constexpr int o8 = luma_at(bx, by);
-  constexpr int t7 = -kLumaStride + 7;
-  int oS = pl.e8_s, oP = pl.e8_p, oN = pl.e8_n;
-  if (!aTR) {  // p[8..15,-1] unavailable: replicate p[7,-1] (pred8x8.rs:202-220)
-    if (lane >= 8 && lane < 16) oS = oP = oN = t7;
-    if (lane == 7) oN = t7;
-  }
-  if (!aTL && lane == 16) oP = oS;
-  if (lane == 24) {
-    if (!aT) oP = oS;
-    if (!aL) oN = oS;
-  }
-  const uint8_t* b = lt + o8;
-  const int raw = b[oS], nv = b[oN];
-  int pv = b[oP];
-  if (!aTL && lane == 0) pv = -1;  // Q2: the raw p[-1,-1] sentinel enters the filter
-  e8[lane] = (uint8_t)((pv + 2 * raw + nv + 2) >> 2);
-  const uint8_t* tp = &tab.tap8[0][0][0] + mode * kTap8Row + pl.i8_tab;
-  const uint32_t i0 = tp[0], i1 = tp[1], i2 = tp[2], i3 = tp[3], i4 = tp[4], i5 = tp[5];
-  const uint32_t rw = *reinterpret_cast<const uint32_t*>(resp8 + 2 * (by * 16 + bx));
-  __syncwarp();
-  int pr0, pr1;
-  if (mode == 2) {  // DC, pred8x8.rs:326-425 (warp-uniform): sums of the filtered top 0..7 and left 0..7
-    const uint32_t* ew = reinterpret_cast<const uint32_t*>(e8);
-    const int sT = dp4a_us(ew[1], 0x01010101, dp4a_us(ew[0], 0x01010101, 0));
-    const int sL = dp4a_us(ew[5], 0x01010101, dp4a_us(ew[4], 0x01010101, 0));
-    pr0 = (aT && aL) ? ((sT + sL + 8) >> 4) : (aL ? ((sL + 4) >> 3) : (aT ? ((sT + 4) >> 3) : 128));
-    pr1 = pr0;
-  } else {
-    pr0 = ((int)e8[i0] + 2 * (int)e8[i1] + (int)e8[i2] + 2) >> 2;
-    pr1 = ((int)e8[i3] + 2 * (int)e8[i4] + (int)e8[i5] + 2) >> 2;
-  }
-  if (!((legal_mask(aT, aL, aTL) >> mode) & 1u)) pr0 = pr1 = 0;
-  const int o0 = clip255(pr0 + lo16(rw)), o1 = clip255(pr1 + hi16(rw));
-  *reinterpret_cast<uint16_t*>(&lt[o8 + pl.i8_pix]) = (uint16_t)(o0 | (o1 << 8));
-  __syncwarp();
-}
-
+// Four sequential blocks (a rolled loop, see predict_i4x4). Phase 1: lanes 0..24 filter one reference sample
+// each (pred8x8.rs:222-288, with the x = 0 overwrite of quirk Q2) into e8[]. Phase 2: two pixels per lane
+// gathered from e8[].
 __device__ __forceinline__ void predict_i8x8(const DeviceTables& tab, uint8_t* lt, uint8_t* e8,
                                              const int16_t* res_luma, const PixLane& pl, int lane, uint32_t modes_lo,
                                              uint32_t modes_hi, bool A, bool B, bool C, bool D) {
   const uint8_t* resp8 = reinterpret_cast<const uint8_t*>(res_luma) + pl.i8_res2;
-  // block modes: cells (0,0), (2,0), (0,2), (2,2) = A step 0, B step 2, A step 4, B step 6
-  i8_block<0>(tab, lt, e8, pl, resp8, lane, (int)(modes_lo & 15u), B, A, D, B);
-  i8_block<1>(tab, lt, e8, pl, resp8, lane, (int)((modes_hi >> 8) & 15u), B, true, B, C);
-  i8_block<2>(tab, lt, e8, pl, resp8, lane, (int)((modes_lo >> 16) & 15u), true, A, A, true);
-  i8_block<3>(tab, lt, e8, pl, resp8, lane, (int)((modes_hi >> 24) & 15u), true, true, true, false);
+  constexpr int t7 = -kLumaStride + 7;
+  // availability of (top, left, corner, top-right), 4 bits per block
+  //   block 0: B A D B   block 1: B 1 B C   block 2: 1 A A 1   block 3: 1 1 1 0
+  const uint32_t avw = (B ? 0x0059u : 0u) | (A ? 0x0602u : 0u) | (D ? 0x0004u : 0u) | (C ? 0x0080u : 0u) | 0x7920u;
+#pragma unroll 1
+  for (int blk = 0; blk < 4; blk++) {
+    const int o8 = luma_at((blk & 1) * 8, (blk >> 1) * 8);
+    const uint32_t fl = avw >> (4 * blk);
+    const bool aT = fl & 1u, aL = fl & 2u, aTL = fl & 4u, aTR = fl & 8u;
+    // block modes: cells (0,0), (2,0), (0,2), (2,2) = A step 0, B step 2, A step 4, B step 6
+    const int mode = (int)((((blk & 1) ? modes_hi : modes_lo) >> (8 * blk)) & 15u);
+    int oS = pl.e8_s, oP = pl.e8_p, oN = pl.e8_n;
+    if (!aTR) {  // p[8..15,-1] unavailable: replicate p[7,-1] (pred8x8.rs:202-220)
+      if (lane >= 8 && lane < 16) oS = oP = oN = t7;
+      if (lane == 7) oN = t7;
+    }
+    if (!aTL && lane == 16) oP = oS;
+    if (lane == 24) {
+      if (!aT) oP = oS;
+      if (!aL) oN = oS;
+    }
+    const uint8_t* b = lt + o8;
+    const int raw = b[oS], nv = b[oN];
+    int pv = b[oP];
+    if (!aTL && lane == 0) pv = -1;  // Q2: the raw p[-1,-1] sentinel enters the filter
+    e8[lane] = (uint8_t)((pv + 2 * raw + nv + 2) >> 2);
+    const uint8_t* tp = &tab.tap8[0][0][0] + mode * kTap8Row + pl.i8_tab;
+    const uint32_t i0 = tp[0], i1 = tp[1], i2 = tp[2], i3 = tp[3], i4 = tp[4], i5 = tp[5];
+    const uint32_t rw = *reinterpret_cast<const uint32_t*>(resp8 + 2 * (((blk >> 1) * 8) * 16 + (blk & 1) * 8));
+    __syncwarp();
+    int pr0, pr1;
+    if (mode == 2) {  // DC, pred8x8.rs:326-425 (warp-uniform): sums of the filtered top 0..7 and left 0..7
+      const uint32_t* ew = reinterpret_cast<const uint32_t*>(e8);
+      const int sT = dp4a_us(ew[1], 0x01010101, dp4a_us(ew[0], 0x01010101, 0));
+      const int sL = dp4a_us(ew[5], 0x01010101, dp4a_us(ew[4], 0x01010101, 0));
+      pr0 = (aT && aL) ? ((sT + sL + 8) >> 4) : (aL ? ((sL + 4) >> 3) : (aT ? ((sT + 4) >> 3) : 128));
+      pr1 = pr0;
+    } else {
+      pr0 = ((int)e8[i0] + 2 * (int)e8[i1] + (int)e8[i2] + 2) >> 2;
+      pr1 = ((int)e8[i3] + 2 * (int)e8[i4] + (int)e8[i5] + 2) >> 2;
+    }
+    if (!((legal_mask(aT, aL, aTL) >> mode) & 1u)) pr0 = pr1 = 0;
+    const int o0 = clip255(pr0 + lo16(rw)), o1 = clip255(pr1 + hi16(rw));
+    *reinterpret_cast<uint16_t*>(&lt[o8 + pl.i8_pix]) = (uint16_t)(o0 | (o1 << 8));
+    __syncwarp();
+  }
 }
 
 // ---- Intra16x16 luma, pred16x16.rs:79-425 + pred16x16.rs:64-75. Lane = (row, half): 8 pixels ----------

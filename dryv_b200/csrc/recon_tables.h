@@ -15,14 +15,12 @@ namespace dryv {
 // Prediction as a gather: every predicted sample of every Intra4x4 / Intra8x8 mode other than DC is
 // (E[i0] + 2*E[i1] + E[i2] + 2) >> 2 for a triple of edge samples (a 2-tap average (a + b + 1) >> 1 is the
 // triple (a, b, a), a copy is (a, a, a)). The tables hold, per mode and lane, WHERE those three samples are:
-//   tap4: byte offsets into the shared-memory luma tile, relative to the step's block origin (the block of
-//         half-warp A; half-warp B always works on the block 8 px right / 4 px up of it), biased by +256.
+//   tap4: byte offsets into the shared-memory luma tile, relative to the block origin, biased by +256.
 //         Edge samples of a 4x4 block: top i (0..7) at -48 + i, left k (0..3) at 48 k - 1, corner at -49.
 //         Variant 1 ("no top-right") maps top 4..7 onto top 3 (pred4x4.rs:66-76).
 //   tap8: indices into the filtered edge vector p' of an 8x8 block: 0..15 top, 16..23 left, 24 corner.
 enum { E4_LEFT = 8, E4_CORNER = 12, E8_LEFT = 16, E8_CORNER = 24 };
 constexpr int kLumaTileStride = 48;
-constexpr int kI4HalfDelta = 8 - 4 * kLumaTileStride;  // tile offset of half-warp B's block relative to half-warp A's
 constexpr int kTap4Bias = 256;
 
 // Intra4x4 schedule: ten dependency steps, blocks (spec 4x4 block order) of half-warp A / B per step.
@@ -32,12 +30,17 @@ constexpr int kI4BlkB[10] = {-1, -1, 4, 5, 6, 7, 12, 13, -1, -1};
 struct DeviceTables {
   int32_t t4[52][16];         // [qP][zig-zag k] = LevelScale4x4[qP%6][pos(k)] << max(qP/6 - 4, 0)
   uint16_t ls8[6][64];        // [qP%6][i*8+j]   = LevelScale8x8
-  uint16_t tap4[2][9][32][3]; // [variant][mode][lane][tap]
+  uint16_t tap4[2][9][16][3]; // [variant][mode][pixel y*4+x][tap]
   uint8_t tap8[9][32][8];     // [mode][lane][pixel q (0,1) * 3 + tap], 2 pad bytes
   uint8_t zz8inv[8][8];       // [i][j] -> zig-zag index
   uint8_t qpc[52];            // qPI -> QPC
   uint8_t i4sched[10][2];     // copy of kI4BlkA / kI4BlkB (0xff = none), for the host-side tests
   uint8_t pad[8];
+  // Intra4x4 schedule specialised per macroblock availability av = A | B<<1 | C<<2 | D<<3:
+  // [av][step][half] -> tile offset of the block origin (10 bits) | (byte offset of the block's residual / 8) << 10
+  // (6 bits) | tap4 row offset of the variant, in rows (0 or 9) << 16 (4 bits) | legal-mode mask << 20 (9 bits;
+  // bit 0 doubles as "top available", bit 1 as "left available") | active << 31
+  uint32_t i4tab[16][10][2];
 };
 static_assert(sizeof(DeviceTables) % 16 == 0, "DeviceTables is copied with 128-bit loads");
 

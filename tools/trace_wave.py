@@ -13,7 +13,8 @@ from dryv_b200 import recon, synth  # noqa: E402
 from dryv_b200.abi import PicParams  # noqa: E402
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-extra = sys.argv[2:]
+p4, p8 = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (40, 25)
+extra = sys.argv[4:]
 so = os.path.join(recon.CSRC, "libdryv_recon_trace.so")
 subprocess.check_call(["/usr/local/cuda/bin/nvcc"] + recon.NVCC_FLAGS + ["-DDRYV_TRACE"] + extra +
                       [os.path.join(recon.CSRC, "recon.cu"), os.path.join(recon.CSRC, "recon_tables.cpp"), "-o", so])
@@ -21,7 +22,7 @@ recon.LIB_PATH = so
 ctx = recon.ReconContext(0)
 pp = PicParams.make(120, 68)
 W, H = 120, 68
-b = synth.generate(pp, frames, 3000)
+b = synth.generate(pp, frames, 3000, pct_i4x4=p4, pct_i8x8=p8)
 ds = recon.DeviceSoa(b)
 d_out = torch.zeros((frames, pp.frame_bytes), dtype=torch.uint8, device="cuda")
 ctx.lib.dryv_recon_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -37,6 +38,7 @@ t = tr.astype(np.int64)
 t0 = t[0, 0, 0]
 t = (t - t0) & 0xffffffff
 cls = np.where(b.mb_type[:W * H] != 0, 2, b.transform_size_8x8_flag[:W * H]).reshape(H, W)
+print(f"mix I4x4 {p4}% I8x8 {p8}%")
 print(f"frames {frames}: picture 0 spans {t[..., 3].max() / 1e3:.1f} us (first MB ready -> last MB done)")
 start = t[:, 0, 0]
 lag = np.diff(start)
@@ -50,7 +52,8 @@ print("per MB (ns), mean: wait-lines %.0f  predict %.0f  store+publish %.0f  gap
       % (wait_lines.mean(), pred.mean(), tail.mean(), gap[:, 1:].mean(), (t[:, -1, 3] - t[:, 0, 0]).mean() / W))
 for k, name in enumerate(("I4x4", "I8x8", "I16x16")):
     m = cls == k
-    print(f"  {name}: predict {pred[m].mean():.0f} ns  wait-lines {wait_lines[m].mean():.0f} ns")
+    if m.any():
+        print(f"  {name}: predict {pred[m].mean():.0f} ns  wait-lines {wait_lines[m].mean():.0f} ns")
 print("fraction of MBs with wait-lines > 300 ns: %.2f ; > 1000 ns: %.2f" % ((wait_lines > 300).mean(), (wait_lines > 1000).mean()))
 rows = [1, 2, 10, 30, 60]
 for r in rows:

@@ -498,6 +498,12 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
           slot.modes_lo = mv_c.x;
           slot.modes_hi = mv_c.y;
         }
+        if (h.mbcls == 0) {
+          // Intra4x4: per-block tap rows (mode, top-right variant, legality and DC flavour in one byte)
+          const uint32_t mlo = __shfl_sync(0xffffffffu, mv_c.x, 24), mhi = __shfl_sync(0xffffffffu, mv_c.y, 24);
+          const int av = (x > 0 ? 1 : 0) | (availB ? 2 : 0) | ((availB && x + 1 < W) ? 4 : 0) | ((x > 0 && availB) ? 8 : 0);
+          slot.rows[lane] = lane < 16 ? (uint8_t)i4_tap_row(tab, lane, mlo, mhi, av) : (uint8_t)0;
+        }
         if (lane == 0) {
           slot.frame = frame;
           slot.row = row;
@@ -637,8 +643,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
       TRACE_MARK(1);
 
       if (mbcls == 0) {
-        predict_i4x4(tab, ts.luma, slot.res, pl, modes_lo, modes_hi,
-                     (availA ? 1 : 0) | (availB ? 2 : 0) | (availC ? 4 : 0) | (availD ? 8 : 0));
+        predict_i4x4(tab, ts.luma, slot.res, pl, slot.rows + 8 * pl.half);
         CLK_MARK(3);
       } else if (mbcls == 1) {
         predict_i8x8(tab, ts.luma, ts.e8, slot.res, pl, lane, modes_lo, modes_hi, availA, availB, availC, availD);

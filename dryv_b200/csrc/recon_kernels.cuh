@@ -55,6 +55,7 @@ constexpr int kTeamThreads = 64;
 struct Slot {
   alignas(16) int16_t res[256];  // luma residual [16][16]
   uint32_t modes_lo, modes_hi;   // resolved Intra4x4/8x8 modes in schedule order (resolve_modes_kernel)
+  alignas(16) uint8_t rows[32];  // Intra4x4: tap rows, half-warp A's steps 0..9 then half-warp B's steps 2..7; rest 0
   int32_t frame, row, x;         // row < 0: no more work
   int32_t mbcls, mode16;         // 0/1/2 = Intra4x4/8x8/16x16; Intra16x16 prediction mode | intra_chroma_pred_mode << 8
   int32_t pad[1];
@@ -359,7 +360,7 @@ __device__ __forceinline__ void residual_stage(const DeviceTables& tab, uint8_t*
 __host__ __device__ constexpr int luma_at(int x, int y) { return (y + 1) * kLumaStride + 16 + x; }
 __host__ __device__ constexpr int chroma_at(int x, int y) { return (y + 1) * kChromaStride + 8 + x; }
 
-constexpr int kTap4Row = 16 * 3 * 2;          // bytes per (variant, mode) row of DeviceTables::tap4
+constexpr int kTap4Row = 16 * 4 * 2;          // bytes per row of DeviceTables::tap4
 constexpr int kTap8Row = 32 * 8;              // bytes per mode row of DeviceTables::tap8
 
 // legal-mode mask of the nine 4x4/8x8 modes given neighbour availability (the reference writes no
@@ -386,7 +387,7 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
   pl.half = half;
   pl.i4_pix = py * kLumaStride + px;
   pl.i4_res2 = 2 * (py * 16 + px);
-  pl.i4_tab = p * 6;
+  pl.i4_tab = p * 8;
   // edge sample `lane` of an 8x8 block: 0..15 top, 16..23 left, 24 corner (pred8x8.rs:166-200)
   int s, pv, nx;
   if (lane < 16) {
@@ -416,58 +417,70 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
 
 // ---- Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110 -------------------------------------------
 // Ten dependency steps, two blocks per step where the decode-order availability rules allow it
-// (kI4BlkA / kI4BlkB); one pixel per lane, 16 lanes per block. A rolled loop over DeviceTables::i4tab: the
-// kernel is instruction-fetch bound when a dozen teams share an SM, so code size matters more
-// than the handful of instructions per step an unrolled version saves. The three sample addresses and the
-// residual of the next step are fetched while this step computes.
-//   av = A | B<<1 | C<<2 | D<<3 (macroblock availability); modes_lo / modes_hi: see kModeBytes.
+// (kI4BlkA / kI4BlkB); one pixel per lane, 16 lanes per block. A rolled loop: the kernel is instruction-fetch
+// bound when a dozen teams share an SM, so code size matters more than the handful of
+// instructions an unrolled version saves. Everything that depends on the mode or on availability was folded
+// into the tap row chosen by the front warp (i4_tap_row): a step is loads, three adds and a clamp.
+//   rows: this half-warp's ten tap-row bytes (Slot::rows + 0 or 8)
+struct I4Regs {
+  const uint8_t *a0, *a1, *a2;  // the three samples of this lane's pixel
+  uint8_t* dst;                 // the pixel
+  int kind, r;                  // tap-row kind, residual
+  bool active;
+};
+__device__ __forceinline__ void i4_fetch(I4Regs& q, const I4Step* e, const uint8_t* tap4, int row, const uint8_t* ltb,
+                                         uint8_t* ltp, const uint8_t* resp) {
+  const uint16_t* tp = reinterpret_cast<const uint16_t*>(tap4 + row * kTap4Row);
+  const uint32_t org = e->org;
+  const uint8_t* ob = ltb + org;
+  q.a0 = ob + tp[0];
+  q.a1 = ob + tp[1];
+  q.a2 = ob + tp[2];
+  q.kind = tp[3];
+  q.r = *reinterpret_cast<const int16_t*>(resp + e->res2);
+  q.dst = ltp + org;
+  q.active = e->active != 0;
+}
 __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma,
-                                             const PixLane& pl, uint32_t modes_lo, uint32_t modes_hi, int av) {
-  const uint32_t* steps = &tab.i4tab[av][0][pl.half];
-  const uint8_t* tap4 = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0][0]) + pl.i4_tab;
+                                             const PixLane& pl, const uint8_t* rows) {
+  const I4Step* st = &tab.i4tab[0][pl.half];
+  const uint8_t* tap4 = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0]) + pl.i4_tab;
   const uint8_t* resp = reinterpret_cast<const uint8_t*>(res_luma) + pl.i4_res2;
   const uint8_t* ltb = lt - kTap4Bias;
-  uint32_t mm = pl.half ? modes_hi : modes_lo;  // this half-warp's mode nibbles, consumed from the bottom
-  uint32_t cur = steps[0];
-  uint32_t a0, a1, a2;
-  int mode = (int)(mm & 15u);
-  {
-    const uint8_t* tp = tap4 + (mode + ((cur >> 16) & 15u)) * kTap4Row;
-    a0 = *reinterpret_cast<const uint16_t*>(tp);
-    a1 = *reinterpret_cast<const uint16_t*>(tp + 2);
-    a2 = *reinterpret_cast<const uint16_t*>(tp + 4);
-  }
+  uint8_t* ltp = lt + pl.i4_pix;
+  // software pipeline: the table look-ups of step s+1 (which do not depend on any pixel) are issued under the
+  // latency of the pixel loads of step s, so a step's dependent chain is pixel load -> three adds -> clamp -> store
+  I4Regs cur;
+  i4_fetch(cur, st, tap4, rows[0], ltb, ltp, resp);
 #pragma unroll 1
   for (int s = 0; s < 10; s++) {
-    const uint32_t org = cur & 1023u, mask = (cur >> 20) & 0x1ffu;
-    const int e0 = ltb[org + a0], e1 = ltb[org + a1], e2 = ltb[org + a2];
-    const int r = *reinterpret_cast<const int16_t*>(resp + ((cur >> 7) & 0x1f8u));
-    const bool active = (int)cur < 0;
-    const int m = mode;
-    // next step: mode nibble (half-warp A's steps 8 and 9 live in the low byte of modes_hi) and sample addresses
-    const uint32_t nxt = steps[s < 9 ? 2 * s + 2 : 18];
-    mm = s == 7 ? modes_hi : (mm >> 4);
-    mode = (int)(mm & 15u);
-    {
-      const uint8_t* tp = tap4 + (mode + ((nxt >> 16) & 15u)) * kTap4Row;
-      a0 = *reinterpret_cast<const uint16_t*>(tp);
-      a1 = *reinterpret_cast<const uint16_t*>(tp + 2);
-      a2 = *reinterpret_cast<const uint16_t*>(tp + 4);
-    }
-    int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
-    if (m == 2) {  // DC, pred4x4.rs:116-167
-      const uint8_t* eb = lt + org;
-      const uint32_t tw = *reinterpret_cast<const uint32_t*>(eb - kLumaStride);
-      const int sT = dp4a_us(tw, 0x01010101, 0);
+    const int e0 = *cur.a0, e1 = *cur.a1, e2 = *cur.a2;
+    I4Regs nxt;
+    const int sn = s < 9 ? s + 1 : 9;
+    i4_fetch(nxt, st + 2 * sn, tap4, rows[sn], ltb, ltp, resp);
+    int pred = (e0 + 2 * e1 + e2 + 2) >> 2, kind = cur.kind;
+    if (kind >= kI4KindDc) {  // DC, pred4x4.rs:116-167
+      const uint8_t* eb = cur.dst - pl.i4_pix;
+      const int sT = dp4a_us(*reinterpret_cast<const uint32_t*>(eb - kLumaStride), 0x01010101, 0);
       const int sL = eb[-1] + eb[kLumaStride - 1] + eb[2 * kLumaStride - 1] + eb[3 * kLumaStride - 1];
-      const bool aT = mask & 1u, aL = mask & 2u;
-      pred = (aT && aL) ? ((sT + sL + 4) >> 3) : (aT ? ((sT + 2) >> 2) : (aL ? ((sL + 2) >> 2) : 128));
+      pred = kind == kI4KindDc ? ((sT + sL + 4) >> 3)
+                               : (kind == kI4KindDcTop ? ((sT + 2) >> 2) : (kind == kI4KindDcLeft ? ((sL + 2) >> 2) : 128));
+      kind = 1;
     }
-    if (!((mask >> m) & 1u)) pred = 0;  // mode needs a missing neighbour: prediction stays 0 (Q4)
-    if (active) lt[org + pl.i4_pix] = (uint8_t)clip255(pred + r);
+    if (cur.active) *cur.dst = (uint8_t)clip255(pred * kind + cur.r);
     cur = nxt;
     __syncwarp();
   }
+}
+
+// Front-warp side of predict_i4x4: lane k < 16 turns the mode of the block behind Slot::rows[k] into its tap
+// row. modes_lo / modes_hi: see kModeBytes; av = A | B<<1 | C<<2 | D<<3.
+__device__ __forceinline__ int i4_tap_row(const DeviceTables& tab, int k, uint32_t modes_lo, uint32_t modes_hi, int av) {
+  const uint32_t m = ((k < 8 ? modes_lo : modes_hi) >> (4 * (k & 7))) & 15u;
+  const uint32_t info = tab.i4row[av][k];
+  if (!((info >> m) & 1u)) return kI4RowIllegal;
+  if (m == 2) return (info & 1u) ? ((info & 2u) ? 2 : kI4RowDcTop) : ((info & 2u) ? kI4RowDcLeft : kI4RowDcNone);
+  return (int)(m + 9u * ((info >> 9) & 1u));
 }
 
 // ---- Intra8x8 luma, pred8x8.rs:152-696 + pred8x8.rs:34-46 ---------------------------------------------

@@ -66,11 +66,15 @@ def test_write_yuv_file_creates_temp_dir(recon_lib, tmp_path):
     assert np.array_equal(np.fromfile(path, np.uint8), frame)
 
 
+class I4Step(C.Structure):
+    _fields_ = [("org", C.c_uint16), ("res2", C.c_uint16), ("active", C.c_uint16), ("pad", C.c_uint16)]
+
+
 class Tables(C.Structure):
     _fields_ = [("t4", (C.c_int32 * 16) * 52), ("ls8", (C.c_uint16 * 64) * 6),
-                ("tap4", (((C.c_uint16 * 3) * 16) * 9) * 2), ("tap8", ((C.c_uint8 * 8) * 32) * 9),
+                ("tap4", ((C.c_uint16 * 4) * 16) * 22), ("tap8", ((C.c_uint8 * 8) * 32) * 9),
                 ("zz8inv", (C.c_uint8 * 8) * 8), ("qpc", C.c_uint8 * 52), ("i4sched", (C.c_uint8 * 2) * 10),
-                ("pad", C.c_uint8 * 8), ("i4tab", ((C.c_uint32 * 2) * 10) * 16)]
+                ("pad", C.c_uint8 * 8), ("i4tab", (I4Step * 2) * 10), ("i4row", (C.c_uint16 * 16) * 16)]
 
 
 TILE_STRIDE = 48
@@ -134,7 +138,8 @@ def test_zigzag_and_tap_tables(recon_lib):
                     for k in range(4):
                         tile[org + TILE_STRIDE * k - 1] = L[k]
                     tile[org - TILE_STRIDE - 1] = TL
-                    e = [tile[org - TAP4_BIAS + t.tap4[variant][mode][p][k]] for k in range(3)]
+                    e = [tile[org - TAP4_BIAS + t.tap4[9 * variant + mode][p][k]] for k in range(3)]
+                    assert t.tap4[9 * variant + mode][p][3] == 1
                     assert (e[0] + 2 * e[1] + e[2] + 2) >> 2 == wantv[p >> 2, p & 3], (variant, mode, p)
 
 
@@ -154,24 +159,26 @@ def test_intra4x4_schedule_respects_decode_order(recon_lib):
             blk_at[pos(b)] = b
             assert (pos(b)[0] - pos(a)[0], pos(b)[1] - pos(a)[1]) == (2, -1)
     assert len(step_of) == 16
-    # the per-availability step table agrees with the schedule and with the availability rules
-    for av in range(16):
-        A, B, Cc, D = bool(av & 1), bool(av & 2), bool(av & 4), bool(av & 8)
-        for s in range(10):
-            for h in range(2):
-                w = t.i4tab[av][s][h]
-                b = t.i4sched[s][h]
-                assert (w >> 31) == (0 if b == 0xff else 1)
-                if b == 0xff:
-                    continue
-                gx, gy = pos(b)
-                assert (w & 1023) == (4 * gy + 1) * TILE_STRIDE + 16 + 4 * gx
-                assert ((w >> 10) & 63) * 8 == 2 * (4 * gy * 16 + 4 * gx)
+    # the step table and the per-availability row info agree with the schedule and the availability rules
+    for s in range(10):
+        for h in range(2):
+            e, b = t.i4tab[s][h], t.i4sched[s][h]
+            assert e.active == (0 if b == 0xff else 1)
+            if b == 0xff:
+                continue
+            gx, gy = pos(b)
+            assert e.org == (4 * gy + 1) * TILE_STRIDE + 16 + 4 * gx and e.res2 == 2 * (4 * gy * 16 + 4 * gx)
+            for av in range(16):
+                A, B, Cc, D = bool(av & 1), bool(av & 2), bool(av & 4), bool(av & 8)
                 aT, aL = gy > 0 or B, gx > 0 or A
                 aTL = True if (gx > 0 and gy > 0) else (B if gx > 0 else (A if gy > 0 else D))
                 aTR = False if b in (3, 7, 11, 13, 15) else (Cc if b == 5 else (B if b in (0, 1, 4) else True))
                 legal = 0x004 | (0x089 if aT else 0) | (0x102 if aL else 0) | (0x070 if (aT and aL and aTL) else 0)
-                assert ((w >> 20) & 0x1ff) == legal and ((w >> 16) & 15) == (0 if aTR else 9)
+                w = t.i4row[av][8 + s if h else s]
+                assert (w & 0x1ff) == legal and (w >> 9) == (0 if aTR else 1)
+    # row kinds: 0 illegal, 1 three-tap gather, 2..5 the DC flavours
+    kinds = [t.tap4[r][0][3] for r in range(22)]
+    assert kinds == [1, 1, 2, 1, 1, 1, 1, 1, 1] * 2 + [0, 3, 4, 5]
     for (gx, gy), s in step_of.items():
         tr = blk_at[(gx, gy)] not in (3, 7, 11, 13, 15)
         for dx, dy, needed in ((-1, 0, True), (0, -1, True), (-1, -1, True), (1, -1, tr)):

@@ -32,6 +32,9 @@ METRIC = "idr_reconstruct_mpixels_per_s"
 UNIT = "Mpixels/s"
 BYTES_PER_MB_FULL = 1172   # 768 levels + 20 syntax + 384 pixels out (SURVEY.md §8d / BASELINE.md §3)
 BYTES_PER_MB_RESID = 1540  # 768 + 4 + 384 prediction in + 384 out
+# DRAM bytes of one recon_wavefront_kernel launch on the default workload, from the committed ncu capture
+# (profiles/r01_v8_wavefront_summary.txt: 434.77 MB read + 225.19 MB written)
+TRAFFIC_BYTES_PER_LAUNCH = 659_952_640
 
 
 def parse_args():
@@ -243,6 +246,9 @@ def main():
     ctx.wait()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
+    # the dominant kernel alone (CUDA events recorded around it on the launching stream, inside the timed region)
+    wave_ms = ctx.wavefront_times_ms(min(64, args.steps))
+    wave_ms_avg = sum(wave_ms) / max(1, len(wave_ms))
 
     # ---- e2e through the host-buffer C ABI call: pinned H2D + kernels + D2H inside the timed region
     e2e_ms = None
@@ -260,10 +266,10 @@ def main():
         e2e_ms = tot / args.steps
     clocks = sampler.stop()
 
-    t = torch.tensor([ms_total, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms if e2e_ms is not None else 0.0, wave_ms_avg], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_max = float(t[0]), float(t[1])
+    ms_total, e2e_ms_max, wave_ms_avg = float(t[0]), float(t[1]), float(t[2])
     ms_per_step = ms_total / args.steps
     total_px = world * n_frames * pp.luma_pixels
     value = total_px / (ms_per_step * 1e-3) / 1e6
@@ -281,7 +287,9 @@ def main():
 
     peak, peak_src = measured_peak_gbs()
     n_mb_step = n_frames * pp.n_mb
-    kernel_s = ms_per_step * 1e-3  # one wavefront kernel (+ two tiny memsets) per step on the timed stream
+    # a step = ticket memset + resolve_modes_kernel (prediction-mode pre-pass) + recon_wavefront_kernel; the
+    # roofline figure is quoted on the dominant kernel's own average duration
+    kernel_s = wave_ms_avg * 1e-3
     achieved = n_mb_step * BYTES_PER_MB_FULL / kernel_s / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -292,8 +300,12 @@ def main():
         "gpu_launches": int(launches),
         "parity_vs_oracle_first_picture": parity,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "kernel": "dryv::recon_wavefront_kernel",
+                     "traffic": TRAFFIC_BYTES_PER_LAUNCH if (n_frames, args.width_mbs, args.height_mbs) == (64, 120, 68) else None,
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                                       "(profiles/r01_v8_wavefront_summary.txt); algorithmic bytes per launch = "
+                                       f"{n_mb_step * BYTES_PER_MB_FULL}",
+                     "peak_source": peak_src, "kernel": "dryv::recon_wavefront_kernel",
+                     "kernel_ms": wave_ms_avg, "kernel_share_of_step": wave_ms_avg / ms_per_step,
                      "algorithmic_bytes_per_mb": BYTES_PER_MB_FULL, "mbs_per_launch": n_mb_step},
     }
     if e2e_ms is not None:

@@ -768,6 +768,10 @@ struct dryv_recon_ctx {
   cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_kernel[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
   cudaEvent_t e_sub_begin = nullptr, e_sub_end = nullptr;
   bool sub_timed = false;
+  // CUDA-event pairs around the most recent wavefront-kernel launches (bench: roofline of the dominant kernel)
+  static constexpr int kTimedLaunches = 64;
+  cudaEvent_t e_wave[kTimedLaunches][2] = {};
+  uint64_t wave_launches = 0;
   // tables
   DeviceTables* d_tables = nullptr;
   DeviceTables* h_tables = nullptr;  // pinned
@@ -897,8 +901,12 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   size_t want = rows;  // one row team (CTA) per macroblock row at most
   size_t cap = (size_t)ctx->sm_count * ctx->wave_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
+  cudaEvent_t* ev = ctx->e_wave[ctx->wave_launches % dryv_recon_ctx::kTimedLaunches];
+  CU(cudaEventRecord(ev[0], s));
   dryv::recon_wavefront_kernel<<<grid, dryv::kTeamThreads, 0, s>>>(a);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(ev[1], s));
+  ctx->wave_launches++;
   ctx->launches += 2;
   return DRYV_OK;
 }
@@ -942,6 +950,8 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
          cudaEventCreateWithFlags(&ctx->e_kernel[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->e_d2h[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreate(&ctx->e_sub_begin) == cudaSuccess && cudaEventCreate(&ctx->e_sub_end) == cudaSuccess;
+  for (int i = 0; i < dryv_recon_ctx::kTimedLaunches && ok; i++)
+    ok = cudaEventCreate(&ctx->e_wave[i][0]) == cudaSuccess && cudaEventCreate(&ctx->e_wave[i][1]) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_tables, sizeof(DeviceTables)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_tables, sizeof(DeviceTables)) == cudaSuccess &&
        cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)) == cudaSuccess &&
@@ -974,6 +984,10 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
     if (ctx->e_d2h[i]) cudaEventDestroy(ctx->e_d2h[i]);
     if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
     if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+  }
+  for (int i = 0; i < dryv_recon_ctx::kTimedLaunches; i++) {
+    if (ctx->e_wave[i][0]) cudaEventDestroy(ctx->e_wave[i][0]);
+    if (ctx->e_wave[i][1]) cudaEventDestroy(ctx->e_wave[i][1]);
   }
   if (ctx->e_sub_begin) cudaEventDestroy(ctx->e_sub_begin);
   if (ctx->e_sub_end) cudaEventDestroy(ctx->e_sub_end);
@@ -1159,6 +1173,18 @@ int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char
 }
 
 uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dryv_recon_wavefront_times(dryv_recon_ctx* ctx, float* out_ms, int cap) {
+  if (!ctx || !out_ms || cap <= 0) return DRYV_ERR_ARG;
+  int n = (int)(ctx->wave_launches < (uint64_t)dryv_recon_ctx::kTimedLaunches ? ctx->wave_launches
+                                                                              : (uint64_t)dryv_recon_ctx::kTimedLaunches);
+  if (n > cap) n = cap;
+  for (int i = 0; i < n; i++) {  // out_ms[0] = the most recent launch
+    cudaEvent_t* ev = ctx->e_wave[(ctx->wave_launches - 1 - i) % dryv_recon_ctx::kTimedLaunches];
+    if (cudaEventElapsedTime(&out_ms[i], ev[0], ev[1]) != cudaSuccess) return DRYV_ERR_CUDA;
+  }
+  return n;
+}
 
 size_t dryv_recon_device_tables(const dryv_pic_params* pp, void* out, size_t cap) {
   if (!pp) return 0;

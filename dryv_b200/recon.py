@@ -25,6 +25,7 @@ EXPORTS = [
     "dryv_recon_last_error", "dryv_recon_alloc_pinned", "dryv_recon_free_pinned", "dryv_recon_submit",
     "dryv_recon_wait", "dryv_recon_reconstruct_device", "dryv_recon_residual_add_device",
     "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms", "dryv_recon_device_tables",
+    "dryv_recon_wavefront_times",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -93,6 +94,8 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_device_tables.argtypes = [C.POINTER(PicParams), vp, sz]
     lib.dryv_recon_launch_count.restype = C.c_uint64
     lib.dryv_recon_launch_count.argtypes = [vp]
+    lib.dryv_recon_wavefront_times.restype = C.c_int
+    lib.dryv_recon_wavefront_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     _lib = lib
     return lib
 
@@ -219,6 +222,14 @@ class ReconContext:
     @property
     def launch_count(self) -> int:
         return int(self.lib.dryv_recon_launch_count(self.h))
+
+    def wavefront_times_ms(self, n: int = 64) -> list:
+        """CUDA-event durations of the most recent wavefront-kernel launches, newest first (call after wait())."""
+        buf = (C.c_float * n)()
+        got = self.lib.dryv_recon_wavefront_times(self.h, buf, n)
+        if got < 0:
+            raise ReconError(got, "dryv_recon_wavefront_times")
+        return [float(buf[i]) for i in range(got)]
 
 
 def write_yuv_file(frame: np.ndarray, path: str):

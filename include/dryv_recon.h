@@ -150,6 +150,12 @@ size_t dryv_recon_device_tables(const dryv_pic_params* pp, void* out, size_t cap
 /* Number of kernel launches issued by this context so far (bench bookkeeping). */
 uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx);
 
+/* Device-measured durations (CUDA events on the launching stream), in milliseconds, of the most recent
+ * wavefront-kernel launches of this context, newest first; at most 64 are kept. Returns how many were written
+ * (<= cap) or a negative error code. Valid after dryv_recon_wait. Bench bookkeeping: the roofline figure is
+ * quoted on this kernel alone. */
+int dryv_recon_wavefront_times(dryv_recon_ctx* ctx, float* out_ms, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <errno.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 
@@ -248,6 +249,12 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
   const size_t n_mb = (size_t)W * H;
   const size_t frame_mb0 = (size_t)blockIdx.x * n_mb;
   const int lane = threadIdx.x & 31, band = threadIdx.x >> 5;
+  // Programmatic dependent launch: the wavefront kernel may start as soon as every CTA of this grid is resident;
+  // it consumes the mode records as they appear (each one carries the launch tag).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef DRYV_TRACE
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[(size_t)a.W * a.H * 4] = gtimer_ns();
+#endif
   if (threadIdx.x < 32) bandprog[threadIdx.x] = 0;
   // pull the picture's syntax (16 + 2 bytes per macroblock) into L2 up front: the walk below is a latency
   // chain with two macroblocks of register look-ahead, which covers an L2 hit but not a DRAM miss
@@ -339,14 +346,20 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
       leftcol = c[0][3] | (c[1][3] << 4) | (c[2][3] << 8) | (c[3][3] << 12);
       bottom = c[3][0] | (c[3][1] << 4) | (c[3][2] << 8) | (c[3][3] << 12);
       if (cls != 2) {
-        // record layout: see kModeBytes (recon_kernels.cuh)
+        // record layout: see kModeWords (recon_kernels.cuh)
         uint32_t lo = 0, hi = c[3][2] | (c[3][3] << 4);
 #pragma unroll
         for (int gy = 0; gy < 4; gy++) lo |= (c[gy][0] | (c[gy][1] << 4)) << (8 * gy);
 #pragma unroll
         for (int gy = 0; gy < 3; gy++) hi |= (c[gy][2] | (c[gy][3] << 4)) << (8 * (gy + 1));
-        *reinterpret_cast<uint2*>(a.modes + (mb_row0 + x) * kModeBytes) = make_uint2(lo, hi);
+        unsigned long long* rec = a.modes + (mb_row0 + x) * kModeWords;
+        const unsigned long long tg = (unsigned long long)a.tag << 32;
+        st_relaxed_gpu_u64(rec, tg | lo);
+        st_relaxed_gpu_u64(rec + 1, tg | hi);
       }
+#ifdef DRYV_TRACE
+      if (a.trace && blockIdx.x == 0 && y == H - 1 && x == W - 1) a.trace[(size_t)a.W * a.H * 4 + 1] = gtimer_ns();
+#endif
       if (last_row) {
         bandline[band & 1][x] = (uint16_t)bottom;
         __threadfence_block();
@@ -446,18 +459,18 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
       // Lanes 0..23 copy (and later read back) the 32 bytes of their own 4x4 block.
       const uint8_t* hp = hdr_base + mb_row0;
       const uint8_t* cp = reinterpret_cast<const uint8_t*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 32;
-      const uint2* mp = reinterpret_cast<const uint2*>(a.modes + mb_row0 * kModeBytes);
+      const unsigned long long* mp = a.modes + mb_row0 * kModeWords + (lane & 1);  // lanes 24 / 25: lo / hi word
       for (int k = 0; k < kCoefAhead; k++) {
         if (lane < 24 && k < W) cp_async_32(&ts.coef[k % kCoefStages][lane * 16], cp + (size_t)k * (DRYV_COEFFS_PER_MB * 2));
         cp_async_commit();
       }
       uint32_t hdr_n = lane < 4 ? (uint32_t)__ldg(hp) : 0u;
-      uint2 mv_n = make_uint2(0, 0);
-      if (lane == 24) mv_n = __ldg(mp);
+      unsigned long long mv_n = 0;
+      if (lane == 24 || lane == 25) mv_n = ld_relaxed_gpu_u64(mp);
 
       for (int x = 0; x < W; x++) {
         const uint32_t hdr_c = hdr_n;
-        const uint2 mv_c = mv_n;
+        unsigned long long mv_c = mv_n;
         {
           const int k = x + kCoefAhead;
           if (lane < 24 && k < W) cp_async_32(&ts.coef[k % kCoefStages][lane * 16], cp + (size_t)k * (DRYV_COEFFS_PER_MB * 2));
@@ -466,14 +479,13 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         if ((x & 15) == 0 && x + 24 < W) {
           // the byte-per-MB arrays and the modes: L2 prefetch now and then
           if (lane >= 8 && lane < 12) prefetch_l2(header_base(a, lane - 8) + mb_row0 + x + 24);
-          if (lane == 12) prefetch_l2(a.modes + (mb_row0 + x + 8) * kModeBytes);
-          if (lane == 13) prefetch_l2(a.modes + (mb_row0 + x + 16) * kModeBytes);
+
         }
         if (x + 1 < W) {
           hp += 1;
-          mp += 1;
+          mp += kModeWords;
           if (lane < 4) hdr_n = (uint32_t)__ldg(hp);
-          if (lane == 24) mv_n = __ldg(mp);
+          if (lane == 24 || lane == 25) mv_n = ld_relaxed_gpu_u64(mp);
         }
         cp_async_wait<kCoefAhead>();  // this macroblock's copy has landed (each lane reads what it copied itself)
         uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
@@ -494,15 +506,21 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         residual_stage(tab, ts.scratch, slot.res, ts.cres, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
         CLK_MARK(2);  // residual stage
 
-        if (lane == 24) {
-          slot.modes_lo = mv_c.x;
-          slot.modes_hi = mv_c.y;
-        }
-        if (h.mbcls == 0) {
+        if (h.mbcls != 2) {
+          // the mode record of this macroblock (fetched one macroblock ago): the pre-pass may still be running,
+          // so check the tags and poll if it has not got here yet (it walks a row about three times faster)
+          const unsigned long long* mq = mp - (x + 1 < W ? kModeWords : 0);
+          const uint32_t w = wait_line_words(mq - (lane & 1) + lane - 24, mv_c, lane, 24, 26, tag, true, a.status, dead, pace_addr);
+          const uint32_t mlo = __shfl_sync(0xffffffffu, w, 24), mhi = __shfl_sync(0xffffffffu, w, 25);
+          if (lane == 24) {
+            slot.modes_lo = mlo;
+            slot.modes_hi = mhi;
+          }
           // Intra4x4: per-block tap rows (mode, top-right variant, legality and DC flavour in one byte)
-          const uint32_t mlo = __shfl_sync(0xffffffffu, mv_c.x, 24), mhi = __shfl_sync(0xffffffffu, mv_c.y, 24);
+          if (h.mbcls == 0) {
           const int av = (x > 0 ? 1 : 0) | (availB ? 2 : 0) | ((availB && x + 1 < W) ? 4 : 0) | ((x > 0 && availB) ? 8 : 0);
-          slot.rows[lane] = lane < 16 ? (uint8_t)i4_tap_row(tab, lane, mlo, mhi, av) : (uint8_t)0;
+            slot.rows[lane] = lane < 16 ? (uint8_t)i4_tap_row(tab, lane, mlo, mhi, av) : (uint8_t)0;
+          }
         }
         if (lane == 0) {
           slot.frame = frame;
@@ -772,6 +790,7 @@ struct dryv_recon_ctx {
   static constexpr int kTimedLaunches = 64;
   cudaEvent_t e_wave[kTimedLaunches][2] = {};
   uint64_t wave_launches = 0;
+  bool use_pdl = true;  // development switch: DRYV_NO_PDL=1 serialises the pre-pass and the wavefront kernel
   // tables
   DeviceTables* d_tables = nullptr;
   DeviceTables* h_tables = nullptr;  // pinned
@@ -779,7 +798,7 @@ struct dryv_recon_ctx {
   bool tables_valid = false;
   // wavefront control block
   unsigned long long* d_line = nullptr;  // bottom-line hand-off buffer, kLineWords words per macroblock
-  uint8_t* d_modes = nullptr;            // resolved prediction modes, kModeBytes per macroblock
+  unsigned long long* d_modes = nullptr; // resolved prediction modes, kModeWords tagged words per macroblock
   size_t line_cap = 0;                   // in macroblocks
   uint32_t tag = 0;                      // launch tag, incremented per wavefront launch (0 = never written)
   unsigned int* d_ticket = nullptr;  // [0] ticket, [1] status
@@ -841,8 +860,8 @@ int ensure_control(dryv_recon_ctx* ctx, size_t mbs) {
     const size_t bytes = mbs * dryv::kLineWords * sizeof(unsigned long long);
     CU(cudaMalloc(&ctx->d_line, bytes));
     CU(cudaMemset(ctx->d_line, 0, bytes));  // tag 0 is never used by a launch
-    CU(cudaMalloc(&ctx->d_modes, mbs * dryv::kModeBytes));
-    CU(cudaMemset(ctx->d_modes, 0x22, mbs * dryv::kModeBytes));
+    CU(cudaMalloc(&ctx->d_modes, mbs * dryv::kModeWords * sizeof(unsigned long long)));
+    CU(cudaMemset(ctx->d_modes, 0, mbs * dryv::kModeWords * sizeof(unsigned long long)));  // tag 0 is never used
     ctx->line_cap = mbs;
   }
   return DRYV_OK;
@@ -894,6 +913,8 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   if (++ctx->tag == 0) ctx->tag = 1;  // every launch validates line words with its own tag: no per-launch clearing
   CU(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
   KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out);
+  cudaEvent_t* ev = ctx->e_wave[ctx->wave_launches % dryv_recon_ctx::kTimedLaunches];
+  CU(cudaEventRecord(ev[0], s));
   // pre-pass: prediction-mode derivation, one CTA per picture
   const int mode_threads = (((int)pp->pic_height_in_mbs + 31) / 32) * 32;  // one warp per band of 32 MB rows
   dryv::resolve_modes_kernel<<<n_frames, mode_threads, 0, s>>>(a);
@@ -901,10 +922,19 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   size_t want = rows;  // one row team (CTA) per macroblock row at most
   size_t cap = (size_t)ctx->sm_count * ctx->wave_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
-  cudaEvent_t* ev = ctx->e_wave[ctx->wave_launches % dryv_recon_ctx::kTimedLaunches];
-  CU(cudaEventRecord(ev[0], s));
-  dryv::recon_wavefront_kernel<<<grid, dryv::kTeamThreads, 0, s>>>(a);
-  CU(cudaGetLastError());
+  // The wavefront kernel is a programmatic dependent of the pre-pass: it starts once every pre-pass CTA is
+  // resident and consumes mode records as they appear (tagged words, no grid-wide wait).
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(dryv::kTeamThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, dryv::recon_wavefront_kernel, a));
   CU(cudaEventRecord(ev[1], s));
   ctx->wave_launches++;
   ctx->launches += 2;
@@ -942,6 +972,7 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
     return bail(DRYV_ERR_CUDA);
   }
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->use_pdl = getenv("DRYV_NO_PDL") == nullptr;
   bool ok = cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;

@@ -83,11 +83,13 @@ enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
 // both fetches the data and proves it is there: no fence, no separate flag, no second round trip.
 constexpr int kLineWords = 8;
 
-// Resolved prediction modes of one macroblock (written by resolve_modes_kernel), 8 bytes, one nibble per
-// 4x4 block in the order the Intra4x4 schedule consumes them:
-//   bytes 0..3: half-warp A, steps 0..7; byte 4: half-warp A, steps 8, 9; bytes 5..7: half-warp B, steps 2..7
-// (an Intra8x8 macroblock stores each block's mode in the four cells it covers).
-constexpr int kModeBytes = 8;
+// Resolved prediction modes of one macroblock (written by resolve_modes_kernel): one nibble per 4x4 block in the
+// order the Intra4x4 schedule consumes them,
+//   lo word: half-warp A, steps 0..7;  hi word: bits 0..7 half-warp A, steps 8, 9; bits 8..31 half-warp B, steps 2..7
+// (an Intra8x8 macroblock stores each block's mode in the four cells it covers). Like the line words, each 32-bit
+// half travels with the launch tag in one 64-bit word, so the wavefront kernel can consume the record while the
+// pre-pass is still running (the two kernels overlap through programmatic dependent launch) without any fence.
+constexpr int kModeWords = 2;
 
 struct KernelArgs {
   const uint8_t* mb_type;
@@ -100,7 +102,7 @@ struct KernelArgs {
   const uint8_t* pred_in;   // residual-add kernel only
   const DeviceTables* tables;
   unsigned long long* line; // [n_frames * H * W][kLineWords] bottom line of each MB: payload | tag << 32
-  uint8_t* modes;           // [n_frames * H * W][kModeBytes]
+  unsigned long long* modes; // [n_frames * H * W][kModeWords]: payload | tag << 32
   uint32_t tag;             // launch tag: a line word is valid when its upper half equals it
   unsigned int* ticket;     // row ticket counter
   unsigned long long* prof; // stage clocks (development builds), may be null
@@ -474,7 +476,7 @@ __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* l
 }
 
 // Front-warp side of predict_i4x4: lane k < 16 turns the mode of the block behind Slot::rows[k] into its tap
-// row. modes_lo / modes_hi: see kModeBytes; av = A | B<<1 | C<<2 | D<<3.
+// row. modes_lo / modes_hi: see kModeWords; av = A | B<<1 | C<<2 | D<<3.
 __device__ __forceinline__ int i4_tap_row(const DeviceTables& tab, int k, uint32_t modes_lo, uint32_t modes_hi, int av) {
   const uint32_t m = ((k < 8 ? modes_lo : modes_hi) >> (4 * (k & 7))) & 15u;
   const uint32_t info = tab.i4row[av][k];

@@ -29,16 +29,20 @@ ctx.lib.dryv_recon_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
 for _ in range(3):
     ctx.reconstruct_device(ds, d_out)
 ctx.wait()
-assert ctx.lib.dryv_recon_debug_trace(ctx.h, None, W * H) == 0
+assert ctx.lib.dryv_recon_debug_trace(ctx.h, None, W * H + 1) == 0
 ctx.reconstruct_device(ds, d_out)
 ctx.wait()
-tr = np.zeros((H, W, 4), np.uint32)
-assert ctx.lib.dryv_recon_debug_trace(ctx.h, tr.ctypes.data, W * H) == 0
+trx = np.zeros((H * W + 1, 4), np.uint32)
+assert ctx.lib.dryv_recon_debug_trace(ctx.h, trx.ctypes.data, W * H + 1) == 0
+tr = trx[:H * W].reshape(H, W, 4)
+m0, m1 = int(trx[H * W, 0]), int(trx[H * W, 1])
 t = tr.astype(np.int64)
 t0 = t[0, 0, 0]
 t = (t - t0) & 0xffffffff
 cls = np.where(b.mb_type[:W * H] != 0, 2, b.transform_size_8x8_flag[:W * H]).reshape(H, W)
 print(f"mix I4x4 {p4}% I8x8 {p8}%")
+print(f"mode pre-pass of picture 0: starts {((m0 - int(t0)) & 0xffffffff) - (1 << 32 if ((m0 - int(t0)) & 0xffffffff) > 1 << 31 else 0)} ns, "
+      f"ends {((m1 - int(t0)) & 0xffffffff) - (1 << 32 if ((m1 - int(t0)) & 0xffffffff) > 1 << 31 else 0)} ns relative to the first macroblock of the wavefront")
 print(f"frames {frames}: picture 0 spans {t[..., 3].max() / 1e3:.1f} us (first MB ready -> last MB done)")
 start = t[:, 0, 0]
 lag = np.diff(start)

@@ -386,12 +386,18 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
 // two. Larger values were measured (3, 4, 6, 8): they lengthen the pipeline fill by (lag - 2) macroblock times
 // per row and buy nothing, because per-macroblock cost varies by 3x between Intra16x16 and Intra4x4 and the
 // slack is gone within a few macroblocks. Kept as a development knob.
+#ifndef DRYV_CHROMA_LONG_WAIT
+#define DRYV_CHROMA_LONG_WAIT 1
+#endif
 #ifndef DRYV_START_LAG
 #define DRYV_START_LAG 2
 #endif
 constexpr int kStartLag = DRYV_START_LAG;
+// Teams per SM = the register budget handed to ptxas. Measured (64 x 1080p, ms per step): 12 teams (79 regs) 0.950,
+// 11 (92) 0.968, 10 (96) 0.900, 9 (96) 0.895, 8 (127) 0.905, 7 (124) 0.907, 6 (143) 1.001. Ten teams of 96 registers:
+// the residual stage stops re-materialising its 16+16 element arrays, and two fewer teams do not cost throughput.
 #ifndef DRYV_TEAMS_PER_SM
-#define DRYV_TEAMS_PER_SM 12
+#define DRYV_TEAMS_PER_SM 10
 #endif
 __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefront_kernel(const KernelArgs a) {
   __shared__ alignas(16) TeamSmem ts;
@@ -540,7 +546,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         if (availB) {
           // always the sleeping flavour: the front warp runs ahead of the pixel warp, so this wait is not on the
           // critical path, and a tight poll here would take issue slots from the pixel warps of the SM
-          const uint32_t w = wait_line_words(c_above, lvc, lane, 4, 8, tag, true, a.status, dead, pace_addr);
+          const uint32_t w = wait_line_words(c_above, lvc, lane, 4, 8, tag, DRYV_CHROMA_LONG_WAIT || x == 0, a.status, dead, pace_addr);
           if (lane >= 4 && lane < 8) {
             *reinterpret_cast<uint32_t*>(c_fresh) = w;
             c_above += kLineWords;

@@ -40,16 +40,17 @@ nmb = frames * pp.n_mb
 cls = np.where(b.mb_type != 0, 2, b.transform_size_8x8_flag)
 n4, n8, n16 = [(cls == k).sum() for k in (0, 1, 2)]
 print(f"frames {frames}, {nmb} MBs ({n4} I4x4, {n8} I8x8, {n16} I16x16)")
-fn = ["prefetch+header", "wait free slot", "residual", "wait modes (above)", "modes+handoff", "-", "-", "row change"]
-ln = ["wait filled slot", "row start", "wait lines (above)", "I4x4 pred (per I4x4 MB)", "I8x8 pred (per I8x8 MB)",
-      "I16x16 pred (per I16 MB)", "chroma pred", "store/publish/carry"]
+fn = ["level fetch + header", "wait free slot (bar.sync, deferred)", "residual", "wait chroma line (above)",
+      "mode record + tap rows + hand-off", "chroma pred + store + carry", "-", "row change"]
+ln = ["wait filled slot", "row start", "wait luma line (above)", "I4x4 pred (per I4x4 MB)", "I8x8 pred (per I8x8 MB)",
+      "I16x16 pred (per I16 MB)", "-", "publish + store + carry"]
 tot_f = sum(clk[:8]) / nmb
 tot_l = sum(clk[8:]) / nmb
 print("front warp: cycles per MB")
 for i in range(8):
     print(f"  {fn[i]:32s} {clk[i] / nmb:9.1f}")
 print(f"  total {tot_f:9.1f}")
-print("luma warp: cycles per MB")
+print("pixel (luma) warp: cycles per MB")
 for i in range(8):
     d = {3: n4, 4: n8, 5: n16}.get(i, nmb)
     print(f"  {ln[i]:32s} {clk[8 + i] / nmb:9.1f}   (per own MB: {clk[8 + i] / max(d, 1):9.1f})")

@@ -68,6 +68,13 @@ class MbSoa(C.Structure):
     ]
 
 
+class LevelsCompact(C.Structure):
+    """dryv_mb_levels_compact: the compact level stream (include/dryv_recon.h)."""
+    _fields_ = [("offset", C.c_void_p), ("stream", C.c_void_p)]
+
+
+COMPACT_MAX_RECORD = 4 + 24 * 2 + COEFFS_PER_MB * 2
+
 FIELDS = ("mb_type", "transform_size_8x8_flag", "intra_chroma_pred_mode", "qp", "pred_syntax", "coeff")
 
 

@@ -776,6 +776,74 @@ __global__ void __launch_bounds__(kThreadsPerCta, 8) recon_residual_add_kernel(c
   if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Compact level stream -> dense level arrays (include/dryv_recon.h, dryv_mb_levels_compact): what the reference's
+// residual_cabac does on the CPU when it scatters the significant levels into zero-filled block arrays
+// (cabac/mod.rs:563-675). One warp per macroblock, lane b < 24 owns slot b (16 levels, 32 bytes): coded-slot mask ->
+// index of the lane's significance mask, warp prefix sum of the population counts -> where the lane's levels start.
+// `base` is the stream offset the device copy starts at (a chunk of a longer host stream), `stream_len` its length.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsPerCta) expand_levels_kernel(const uint32_t* __restrict__ offset,
+                                                                      const uint8_t* __restrict__ stream, uint32_t base,
+                                                                      uint32_t stream_len, size_t n_mbs,
+                                                                      int16_t* __restrict__ coeff, int* status) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = (size_t)gridDim.x * kWarpsPerCta;
+  bool bad = false;
+  for (size_t mb = (size_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); mb < n_mbs; mb += warps) {
+    const uint32_t o = __ldg(offset + mb) - base, e = __ldg(offset + mb + 1) - base;
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+    bool ok = e <= stream_len && o <= e && e - o >= 4u && e - o <= (uint32_t)DRYV_COMPACT_MAX_RECORD && !(o & 3u);
+    if (ok) {
+      const uint32_t len = e - o;
+      const uint8_t* rec = stream + o;
+      const uint32_t hdr = __ldg(reinterpret_cast<const uint32_t*>(rec));
+      const uint32_t cm = hdr & 0xffffffu;
+      const uint32_t wide = hdr >> 31;
+      const uint32_t ncoded = __popc(cm);
+      const uint32_t lv0 = 4u + 2u * ncoded;  // where the levels start
+      ok = !(hdr & 0x7f000000u) && lv0 <= len;
+      uint32_t mask = 0;
+      if (ok && lane < 24 && ((cm >> lane) & 1u))
+        mask = __ldg(reinterpret_cast<const uint16_t*>(rec + 4 + 2 * __popc(cm & ((1u << lane) - 1u))));
+      const uint32_t cnt = __popc(mask);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      ok = ok && lv0 + (total << wide) <= len;
+      if (ok && mask) {
+        const uint8_t* p = rec + lv0 + ((incl - cnt) << wide);
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          // the k-th coefficient's level sits behind the levels of the set bits below k: independent loads
+          int v = 0;
+          if ((mask >> k) & 1u) {
+            const uint32_t i = __popc(mask & ((1u << k) - 1u));
+            v = wide ? (int)(int16_t)__ldg(reinterpret_cast<const uint16_t*>(p) + i) : (int)(int8_t)__ldg(p + i);
+          }
+          if (k & 1) w[k >> 1] |= (uint32_t)v << 16;
+          else w[k >> 1] = (uint32_t)v & 0xffffu;
+        }
+        c0 = make_uint4(w[0], w[1], w[2], w[3]);
+        c1 = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+    if (!ok) bad = true;  // malformed record: the macroblock's levels are written as zeros and the launch is flagged
+    if (lane < 24) {
+      uint4* dst = reinterpret_cast<uint4*>(coeff + mb * DRYV_COEFFS_PER_MB) + lane * 2;
+      dst[0] = c0;
+      dst[1] = c1;
+    }
+  }
+  if (bad) atomicCAS(status, STATUS_OK, STATUS_UNSUPPORTED);
+}
+
 }  // namespace dryv
 
 // ================================================================================================
@@ -788,8 +856,11 @@ struct dryv_recon_ctx {
   int device = 0;
   int sm_count = 0;
   int wave_ctas_per_sm = 0, resid_ctas_per_sm = 0;
-  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_kernel[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
+  // s_compute[0] doubles as the default stream of the device-pointer entry points; dryv_recon_submit alternates
+  // its chunks over both so that the (latency bound) wavefront kernels of neighbouring chunks overlap
+  cudaStream_t s_compute[2] = {nullptr, nullptr}, s_h2d = nullptr, s_d2h = nullptr;
+  static constexpr int kStages = 4;  // staging slots of the submit pipeline
+  cudaEvent_t e_h2d[kStages] = {}, e_kernel[kStages] = {}, e_d2h[kStages] = {};
   cudaEvent_t e_sub_begin = nullptr, e_sub_end = nullptr;
   bool sub_timed = false;
   // CUDA-event pairs around the most recent wavefront-kernel launches (bench: roofline of the dominant kernel)
@@ -802,19 +873,21 @@ struct dryv_recon_ctx {
   DeviceTables* h_tables = nullptr;  // pinned
   dryv_pic_params tables_pp;
   bool tables_valid = false;
-  // wavefront control block
-  unsigned long long* d_line = nullptr;  // bottom-line hand-off buffer, kLineWords words per macroblock
-  unsigned long long* d_modes = nullptr; // resolved prediction modes, kModeWords tagged words per macroblock
-  size_t line_cap = 0;                   // in macroblocks
+  // wavefront control blocks: one per compute stream, so two launches can be in flight
+  struct Control {
+    unsigned long long* d_line = nullptr;  // bottom-line hand-off buffer, kLineWords words per macroblock
+    unsigned long long* d_modes = nullptr; // resolved prediction modes, kModeWords tagged words per macroblock
+    size_t line_cap = 0;                   // in macroblocks
+  } ctl[2];
   uint32_t tag = 0;                      // launch tag, incremented per wavefront launch (0 = never written)
-  unsigned int* d_ticket = nullptr;  // [0] ticket, [1] status
+  unsigned int* d_ticket = nullptr;  // [0] ticket of control block 0, [1] status, [2] ticket of control block 1
   unsigned long long* d_prof = nullptr;  // stage clocks (development builds)
   unsigned int* d_trace = nullptr;       // timeline trace (development builds), 4 words per macroblock of picture 0
   size_t trace_mbs = 0;
   int* h_status = nullptr;           // pinned
-  // staging for dryv_recon_submit (two slots)
-  uint8_t* d_in[2] = {nullptr, nullptr};
-  uint8_t* d_out[2] = {nullptr, nullptr};
+  // staging for dryv_recon_submit / dryv_recon_submit_compact
+  uint8_t* d_in[kStages] = {};
+  uint8_t* d_out[kStages] = {};
   size_t in_cap = 0, out_cap = 0;
   cudaStream_t pending_user = nullptr;
   bool pending_user_valid = false;
@@ -845,7 +918,8 @@ bool pp_ok(const dryv_pic_params* pp) {
 int ensure_tables(dryv_recon_ctx* ctx, const dryv_pic_params* pp, cudaStream_t s) {
   if (ctx->tables_valid && memcmp(&ctx->tables_pp, pp, sizeof *pp) == 0) return DRYV_OK;
   // the pinned host copy may still be in flight from a previous upload on another stream
-  CU(cudaStreamSynchronize(ctx->s_compute));
+  CU(cudaStreamSynchronize(ctx->s_compute[0]));
+  CU(cudaStreamSynchronize(ctx->s_compute[1]));
   if (ctx->pending_user_valid) CU(cudaStreamSynchronize(ctx->pending_user));
   dryv::build_device_tables(*pp, ctx->h_tables);
   CU(cudaMemcpyAsync(ctx->d_tables, ctx->h_tables, sizeof(DeviceTables), cudaMemcpyHostToDevice, s));
@@ -855,26 +929,27 @@ int ensure_tables(dryv_recon_ctx* ctx, const dryv_pic_params* pp, cudaStream_t s
   return DRYV_OK;
 }
 
-int ensure_control(dryv_recon_ctx* ctx, size_t mbs) {
-  if (mbs > ctx->line_cap) {
+int ensure_control(dryv_recon_ctx* ctx, int set, size_t mbs) {
+  dryv_recon_ctx::Control& c = ctx->ctl[set];
+  if (mbs > c.line_cap) {
     CU(cudaDeviceSynchronize());
-    if (ctx->d_line) cudaFree(ctx->d_line);
-    if (ctx->d_modes) cudaFree(ctx->d_modes);
-    ctx->d_line = nullptr;
-    ctx->d_modes = nullptr;
-    ctx->line_cap = 0;
+    if (c.d_line) cudaFree(c.d_line);
+    if (c.d_modes) cudaFree(c.d_modes);
+    c.d_line = nullptr;
+    c.d_modes = nullptr;
+    c.line_cap = 0;
     const size_t bytes = mbs * dryv::kLineWords * sizeof(unsigned long long);
-    CU(cudaMalloc(&ctx->d_line, bytes));
-    CU(cudaMemset(ctx->d_line, 0, bytes));  // tag 0 is never used by a launch
-    CU(cudaMalloc(&ctx->d_modes, mbs * dryv::kModeWords * sizeof(unsigned long long)));
-    CU(cudaMemset(ctx->d_modes, 0, mbs * dryv::kModeWords * sizeof(unsigned long long)));  // tag 0 is never used
-    ctx->line_cap = mbs;
+    CU(cudaMalloc(&c.d_line, bytes));
+    CU(cudaMemset(c.d_line, 0, bytes));  // tag 0 is never used by a launch
+    CU(cudaMalloc(&c.d_modes, mbs * dryv::kModeWords * sizeof(unsigned long long)));
+    CU(cudaMemset(c.d_modes, 0, mbs * dryv::kModeWords * sizeof(unsigned long long)));  // tag 0 is never used
+    c.line_cap = mbs;
   }
   return DRYV_OK;
 }
 
 KernelArgs make_args(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa, uint32_t n_frames,
-                     uint8_t* out) {
+                     uint8_t* out, int set = 0) {
   KernelArgs a;
   memset(&a, 0, sizeof a);
   a.mb_type = soa->mb_type;
@@ -885,10 +960,10 @@ KernelArgs make_args(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   a.coeff = soa->coeff;
   a.out = out;
   a.tables = ctx->d_tables;
-  a.line = ctx->d_line;
-  a.modes = ctx->d_modes;
+  a.line = ctx->ctl[set].d_line;
+  a.modes = ctx->ctl[set].d_modes;
   a.tag = ctx->tag;
-  a.ticket = ctx->d_ticket;
+  a.ticket = ctx->d_ticket + 2 * set;
   a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
 #ifdef DRYV_STAGE_CLOCKS
   a.prof = ctx->d_prof;
@@ -910,15 +985,16 @@ bool soa_ok(const dryv_mb_soa* s) {
 }
 
 // enqueue the wavefront kernel for device-resident buffers on stream s
+// (`set` = which control block: launches that may overlap in time must use different ones)
 int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa, uint32_t n_frames,
-                     uint8_t* d_out, cudaStream_t s) {
+                     uint8_t* d_out, cudaStream_t s, int set = 0) {
   const size_t rows = (size_t)n_frames * pp->pic_height_in_mbs;
   const size_t mbs = rows * pp->pic_width_in_mbs;
-  int rc = ensure_control(ctx, mbs);
+  int rc = ensure_control(ctx, set, mbs);
   if (rc != DRYV_OK) return rc;
   if (++ctx->tag == 0) ctx->tag = 1;  // every launch validates line words with its own tag: no per-launch clearing
-  CU(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
-  KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out);
+  CU(cudaMemsetAsync(ctx->d_ticket + 2 * set, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
+  KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out, set);
   cudaEvent_t* ev = ctx->e_wave[ctx->wave_launches % dryv_recon_ctx::kTimedLaunches];
   CU(cudaEventRecord(ev[0], s));
   // pre-pass: prediction-mode derivation, one CTA per picture
@@ -944,6 +1020,20 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   CU(cudaEventRecord(ev[1], s));
   ctx->wave_launches++;
   ctx->launches += 2;
+  return DRYV_OK;
+}
+
+
+// enqueue the compact-stream expansion for `n_mbs` macroblocks: d_stream points at stream byte `base`
+int launch_expand(dryv_recon_ctx* ctx, const uint32_t* d_offset, const uint8_t* d_stream, uint32_t base, uint32_t len,
+                  size_t n_mbs, int16_t* d_coeff, cudaStream_t s) {
+  size_t want = (n_mbs + dryv::kWarpsPerCta - 1) / dryv::kWarpsPerCta;
+  size_t cap = (size_t)ctx->sm_count * 16;
+  int grid = (int)(want < cap ? want : cap);
+  dryv::expand_levels_kernel<<<grid, dryv::kThreadsPerCta, 0, s>>>(d_offset, d_stream, base, len, n_mbs, d_coeff,
+                                                                 reinterpret_cast<int*>(ctx->d_ticket + 1));
+  CU(cudaGetLastError());
+  ctx->launches++;
   return DRYV_OK;
 }
 
@@ -979,10 +1069,11 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->use_pdl = getenv("DRYV_NO_PDL") == nullptr;
-  bool ok = cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) == cudaSuccess &&
+  bool ok = cudaStreamCreateWithFlags(&ctx->s_compute[0], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->s_compute[1], cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
-  for (int i = 0; i < 2 && ok; i++)
+  for (int i = 0; i < dryv_recon_ctx::kStages && ok; i++)
     ok = cudaEventCreateWithFlags(&ctx->e_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->e_kernel[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->e_d2h[i], cudaEventDisableTiming) == cudaSuccess;
@@ -991,11 +1082,11 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
     ok = cudaEventCreate(&ctx->e_wave[i][0]) == cudaSuccess && cudaEventCreate(&ctx->e_wave[i][1]) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_tables, sizeof(DeviceTables)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_tables, sizeof(DeviceTables)) == cudaSuccess &&
-       cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)) == cudaSuccess &&
+       cudaMalloc(&ctx->d_ticket, 4 * sizeof(unsigned int)) == cudaSuccess &&
        cudaMalloc(&ctx->d_prof, 16 * sizeof(unsigned long long)) == cudaSuccess &&
        cudaMemset(ctx->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_status, sizeof(int)) == cudaSuccess &&
-       cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int)) == cudaSuccess;
+       cudaMemset(ctx->d_ticket, 0, 4 * sizeof(unsigned int)) == cudaSuccess;
   // shared memory, not L1, is what the row teams live on: ask for the largest carve-out
   ok = ok && cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared) == cudaSuccess;
@@ -1015,7 +1106,7 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < dryv_recon_ctx::kStages; i++) {
     if (ctx->e_h2d[i]) cudaEventDestroy(ctx->e_h2d[i]);
     if (ctx->e_kernel[i]) cudaEventDestroy(ctx->e_kernel[i]);
     if (ctx->e_d2h[i]) cudaEventDestroy(ctx->e_d2h[i]);
@@ -1028,13 +1119,16 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
   }
   if (ctx->e_sub_begin) cudaEventDestroy(ctx->e_sub_begin);
   if (ctx->e_sub_end) cudaEventDestroy(ctx->e_sub_end);
-  if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  for (int i = 0; i < 2; i++)
+    if (ctx->s_compute[i]) cudaStreamDestroy(ctx->s_compute[i]);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
-  if (ctx->d_line) cudaFree(ctx->d_line);
-  if (ctx->d_modes) cudaFree(ctx->d_modes);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->ctl[i].d_line) cudaFree(ctx->ctl[i].d_line);
+    if (ctx->ctl[i].d_modes) cudaFree(ctx->ctl[i].d_modes);
+  }
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -1057,7 +1151,7 @@ int dryv_recon_reconstruct_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp
   if (!ctx) return DRYV_ERR_ARG;
   if (!pp_ok(pp) || !soa_ok(d_soa) || !d_out_yuv || n_frames == 0) return fail(ctx, DRYV_ERR_ARG, "bad argument");
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute;
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute[0];
   int rc = ensure_tables(ctx, pp, s);
   if (rc != DRYV_OK) return rc;
   rc = launch_wavefront(ctx, pp, d_soa, n_frames, d_out_yuv, s);
@@ -1076,7 +1170,7 @@ int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* p
   if (!pp_ok(pp) || !soa_ok(d_soa) || !d_out_yuv || !d_pred_yuv || n_frames == 0)
     return fail(ctx, DRYV_ERR_ARG, "bad argument");
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute;
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute[0];
   int rc = ensure_tables(ctx, pp, s);
   if (rc != DRYV_OK) return rc;
   KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out_yuv);
@@ -1095,48 +1189,74 @@ int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* p
   return DRYV_OK;
 }
 
-int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa, uint32_t n_frames,
-                      uint8_t* out_yuv) {
-  if (!ctx) return DRYV_ERR_ARG;
-  if (!pp_ok(pp) || !soa_ok(soa) || !out_yuv || n_frames == 0) return fail(ctx, DRYV_ERR_ARG, "bad argument");
+// Shared pipeline of the two host-buffer entry points. Chunks of pictures travel through kStages staging slots on
+// three kinds of streams: H2D copies, kernels (two compute streams, one wavefront control block each, so the latency
+// bound kernels of neighbouring chunks overlap) and D2H copies.
+static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa,
+                       const dryv_mb_levels_compact* lv, uint32_t n_frames, uint8_t* out_yuv) {
+  constexpr int kStages = dryv_recon_ctx::kStages;
   CU(cudaSetDevice(ctx->device));
-  int rc = ensure_tables(ctx, pp, ctx->s_compute);
+  int rc = ensure_tables(ctx, pp, ctx->s_compute[0]);
   if (rc != DRYV_OK) return rc;
   const size_t n_mb = (size_t)pp->pic_width_in_mbs * pp->pic_height_in_mbs;
-  const size_t in_per_frame = n_mb * (4 + 16 + 768);
   const size_t out_per_frame = n_mb * 384;
-  // chunk = pictures per pipeline stage. Measured on a B200 / PCIe Gen5 box (64 x 1080p, 412 MB in, 201 MB out):
-  // the H2D copy is the floor (7.4 ms alone, 8.0 ms with the D2H running against it); ~72 MB of input per stage
-  // keeps the per-chunk kernels hidden under the copies while the pipeline fill and drain stay short. Pictures
-  // are spread evenly over the stages so there is no runt at the end.
-  const char* chunk_env = getenv("DRYV_CHUNK_MB");  // development knob
-  const size_t chunk_bytes = (size_t)(chunk_env ? atoi(chunk_env) : 72) << 20;
-  const size_t total_in = in_per_frame * n_frames;
-  uint32_t n_chunks = (uint32_t)((total_in + chunk_bytes - 1) / chunk_bytes);
+  const size_t dense_per_frame = n_mb * (4 + 16 + 768);
+  // chunk = pictures per pipeline stage. Measured on a B200 / PCIe Gen5 box (64 x 1080p):
+  //  dense levels (412 MB in, 201 MB out): the H2D copy is the floor (7.4 ms alone, 8.0 ms with the D2H running
+  //    against it); ~72 MB of input per stage keeps the per-chunk kernels hidden under the copies while the pipeline
+  //    fill and drain stay short;
+  //  compact levels: the D2H copy of the pictures is the floor, so stages are sized by output bytes.
+  // Pictures are spread evenly over the stages so there is no runt at the end.
+  uint32_t n_chunks;
+  if (lv) {
+    const char* env = getenv("DRYV_CHUNK_OUT_MB");  // development knob
+    const size_t chunk_bytes = (size_t)(env ? atoi(env) : 24) << 20;
+    n_chunks = (uint32_t)((out_per_frame * n_frames + chunk_bytes - 1) / chunk_bytes);
+  } else {
+    const char* env = getenv("DRYV_CHUNK_MB");  // development knob
+    const size_t chunk_bytes = (size_t)(env ? atoi(env) : 72) << 20;
+    n_chunks = (uint32_t)((dense_per_frame * n_frames + chunk_bytes - 1) / chunk_bytes);
+  }
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > n_frames) n_chunks = n_frames;
-  uint32_t chunk = (n_frames + n_chunks - 1) / n_chunks;
-  const size_t need_in = in_per_frame * chunk, need_out = out_per_frame * chunk;
+  const uint32_t chunk = (n_frames + n_chunks - 1) / n_chunks;
+  // staging slot: dense levels | pred_syntax | mb_type | t8x8 | chroma mode | qp | [offsets | compact stream]
+  size_t stream_max = 0;
+  if (lv) {
+    const size_t total_mbs = n_mb * n_frames;
+    if (lv->offset[0] > lv->offset[total_mbs]) return fail(ctx, DRYV_ERR_ARG, "compact level stream: offsets not monotone");
+    for (uint32_t done = 0; done < n_frames; done += chunk) {
+      const uint32_t nf = (n_frames - done) < chunk ? (n_frames - done) : chunk;
+      const uint32_t o0 = lv->offset[(size_t)done * n_mb], o1 = lv->offset[(size_t)(done + nf) * n_mb];
+      if (o1 < o0 || (o0 & 3u)) return fail(ctx, DRYV_ERR_ARG, "compact level stream: offsets not monotone / not 4-byte aligned");
+      if ((size_t)(o1 - o0) > stream_max) stream_max = o1 - o0;
+    }
+  }
+  const size_t off_bytes = lv ? (((size_t)chunk * n_mb + 1) * 4 + 15) & ~(size_t)15 : 0;
+  const size_t need_in = dense_per_frame * chunk + off_bytes + ((stream_max + 15) & ~(size_t)15);
+  const size_t need_out = out_per_frame * chunk;
   if (need_in > ctx->in_cap || need_out > ctx->out_cap) {
     CU(cudaDeviceSynchronize());
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kStages; i++) {
       if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
       if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
       ctx->d_in[i] = ctx->d_out[i] = nullptr;
     }
+    const size_t cap_in = need_in > ctx->in_cap ? need_in : ctx->in_cap, cap_out = need_out > ctx->out_cap ? need_out : ctx->out_cap;
     ctx->in_cap = ctx->out_cap = 0;
-    for (int i = 0; i < 2; i++) {
-      CU(cudaMalloc(&ctx->d_in[i], need_in));
-      CU(cudaMalloc(&ctx->d_out[i], need_out));
+    for (int i = 0; i < kStages; i++) {
+      CU(cudaMalloc(&ctx->d_in[i], cap_in));
+      CU(cudaMalloc(&ctx->d_out[i], cap_out));
     }
-    ctx->in_cap = need_in;
-    ctx->out_cap = need_out;
+    ctx->in_cap = cap_in;
+    ctx->out_cap = cap_out;
   }
   uint32_t done = 0;
   ctx->sub_timed = false;
   CU(cudaEventRecord(ctx->e_sub_begin, ctx->s_h2d));
   for (uint32_t i = 0; done < n_frames; i++) {
-    const int slot = (int)(i & 1);
+    const int slot = (int)(i % kStages), set = (int)(i & 1);
+    cudaStream_t sc = ctx->s_compute[set];
     const uint32_t nf = (n_frames - done) < chunk ? (n_frames - done) : chunk;
     const size_t mb0 = (size_t)done * n_mb, cnt = (size_t)nf * n_mb;
     uint8_t* base = ctx->d_in[slot];
@@ -1147,21 +1267,35 @@ int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv
     d.transform_size_8x8_flag = base + cnt * (768 + 17);
     d.intra_chroma_pred_mode = base + cnt * (768 + 18);
     d.qp = base + cnt * (768 + 19);
+    uint32_t* d_off = reinterpret_cast<uint32_t*>(base + dense_per_frame * chunk);
+    uint8_t* d_str = base + dense_per_frame * chunk + off_bytes;
     // H2D: the slot's previous kernel must have consumed its inputs
-    if (i >= 2) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->e_kernel[slot], 0));
-    CU(cudaMemcpyAsync(const_cast<int16_t*>(d.coeff), soa->coeff + mb0 * 384, cnt * 768, cudaMemcpyHostToDevice, ctx->s_h2d));
+    if (i >= (uint32_t)kStages) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->e_kernel[slot], 0));
+    uint32_t o0 = 0, o1 = 0;
+    if (lv) {
+      o0 = lv->offset[mb0];
+      o1 = lv->offset[mb0 + cnt];
+      CU(cudaMemcpyAsync(d_off, lv->offset + mb0, (cnt + 1) * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+      if (o1 > o0) CU(cudaMemcpyAsync(d_str, lv->stream + o0, o1 - o0, cudaMemcpyHostToDevice, ctx->s_h2d));
+    } else {
+      CU(cudaMemcpyAsync(const_cast<int16_t*>(d.coeff), soa->coeff + mb0 * 384, cnt * 768, cudaMemcpyHostToDevice, ctx->s_h2d));
+    }
     CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.pred_syntax), soa->pred_syntax + mb0 * 16, cnt * 16, cudaMemcpyHostToDevice, ctx->s_h2d));
     CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.mb_type), soa->mb_type + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
     CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.transform_size_8x8_flag), soa->transform_size_8x8_flag + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
     CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.intra_chroma_pred_mode), soa->intra_chroma_pred_mode + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
     CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.qp), soa->qp + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
     CU(cudaEventRecord(ctx->e_h2d[slot], ctx->s_h2d));
-    // kernel: inputs landed, the slot's previous output has been copied out
-    CU(cudaStreamWaitEvent(ctx->s_compute, ctx->e_h2d[slot], 0));
-    if (i >= 2) CU(cudaStreamWaitEvent(ctx->s_compute, ctx->e_d2h[slot], 0));
-    rc = launch_wavefront(ctx, pp, &d, nf, ctx->d_out[slot], ctx->s_compute);
+    // kernels: inputs landed, the slot's previous output has been copied out
+    CU(cudaStreamWaitEvent(sc, ctx->e_h2d[slot], 0));
+    if (i >= (uint32_t)kStages) CU(cudaStreamWaitEvent(sc, ctx->e_d2h[slot], 0));
+    if (lv) {
+      rc = launch_expand(ctx, d_off, d_str, o0, o1 - o0, cnt, const_cast<int16_t*>(d.coeff), sc);
+      if (rc != DRYV_OK) return rc;
+    }
+    rc = launch_wavefront(ctx, pp, &d, nf, ctx->d_out[slot], sc, set);
     if (rc != DRYV_OK) return rc;
-    CU(cudaEventRecord(ctx->e_kernel[slot], ctx->s_compute));
+    CU(cudaEventRecord(ctx->e_kernel[slot], sc));
     // D2H
     CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->e_kernel[slot], 0));
     CU(cudaMemcpyAsync(out_yuv + (size_t)done * out_per_frame, ctx->d_out[slot], (size_t)nf * out_per_frame,
@@ -1171,6 +1305,46 @@ int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv
   }
   CU(cudaEventRecord(ctx->e_sub_end, ctx->s_d2h));
   ctx->sub_timed = true;
+  return DRYV_OK;
+}
+
+int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa, uint32_t n_frames,
+                      uint8_t* out_yuv) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!pp_ok(pp) || !soa_ok(soa) || !out_yuv || n_frames == 0) return fail(ctx, DRYV_ERR_ARG, "bad argument");
+  return submit_impl(ctx, pp, soa, nullptr, n_frames, out_yuv);
+}
+
+int dryv_recon_submit_compact(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa,
+                              const dryv_mb_levels_compact* levels, uint32_t n_frames, uint8_t* out_yuv) {
+  if (!ctx) return DRYV_ERR_ARG;
+  const bool soa_fields = soa && soa->mb_type && soa->transform_size_8x8_flag && soa->intra_chroma_pred_mode && soa->qp &&
+                          soa->pred_syntax;
+  if (!pp_ok(pp) || !soa_fields || !levels || !levels->offset || !levels->stream || !out_yuv || n_frames == 0)
+    return fail(ctx, DRYV_ERR_ARG, "bad argument");
+  return submit_impl(ctx, pp, soa, levels, n_frames, out_yuv);
+}
+
+int dryv_recon_expand_levels_device(dryv_recon_ctx* ctx, const dryv_mb_levels_compact* d_levels, size_t n_mbs,
+                                    int16_t* d_coeff, void* cuda_stream) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!d_levels || !d_levels->offset || !d_levels->stream || !d_coeff || n_mbs == 0 ||
+      (reinterpret_cast<uintptr_t>(d_coeff) % 16) != 0)
+    return fail(ctx, DRYV_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute[0];
+  // the stream length is only known on the device here: bound it by the last offset
+  uint32_t o_first = 0, o_last = 0;
+  CU(cudaMemcpyAsync(&o_first, d_levels->offset, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(&o_last, d_levels->offset + n_mbs, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (o_last < o_first) return fail(ctx, DRYV_ERR_ARG, "compact level stream: offsets not monotone");
+  int rc = launch_expand(ctx, d_levels->offset, d_levels->stream + o_first, o_first, o_last - o_first, n_mbs, d_coeff, s);
+  if (rc != DRYV_OK) return rc;
+  if (cuda_stream) {
+    ctx->pending_user = s;
+    ctx->pending_user_valid = true;
+  }
   return DRYV_OK;
 }
 
@@ -1185,7 +1359,8 @@ int dryv_recon_wait(dryv_recon_ctx* ctx) {
   if (!ctx) return DRYV_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->s_h2d));
-  CU(cudaStreamSynchronize(ctx->s_compute));
+  CU(cudaStreamSynchronize(ctx->s_compute[0]));
+  CU(cudaStreamSynchronize(ctx->s_compute[1]));
   CU(cudaStreamSynchronize(ctx->s_d2h));
   if (ctx->pending_user_valid) {
     CU(cudaStreamSynchronize(ctx->pending_user));

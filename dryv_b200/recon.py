@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-from .abi import FIELDS, MbSoa, PicParams, SyntaxBatch
+from .abi import COMPACT_MAX_RECORD, FIELDS, LevelsCompact, MbSoa, PicParams, SyntaxBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
@@ -25,7 +25,8 @@ EXPORTS = [
     "dryv_recon_last_error", "dryv_recon_alloc_pinned", "dryv_recon_free_pinned", "dryv_recon_submit",
     "dryv_recon_wait", "dryv_recon_reconstruct_device", "dryv_recon_residual_add_device",
     "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms", "dryv_recon_device_tables",
-    "dryv_recon_wavefront_times",
+    "dryv_recon_wavefront_times", "dryv_recon_pack_levels", "dryv_recon_unpack_levels", "dryv_recon_submit_compact",
+    "dryv_recon_expand_levels_device",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,7 +35,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp", "levels_pack.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "recon_tables.h")] + [
         os.path.join(_HERE, "..", "include", "dryv_recon.h")]
     if not force and os.path.exists(LIB_PATH) and all(
@@ -96,6 +97,14 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_launch_count.argtypes = [vp]
     lib.dryv_recon_wavefront_times.restype = C.c_int
     lib.dryv_recon_wavefront_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    lib.dryv_recon_pack_levels.restype = C.c_int
+    lib.dryv_recon_pack_levels.argtypes = [vp, sz, vp, vp, sz, C.c_int]
+    lib.dryv_recon_unpack_levels.restype = C.c_int
+    lib.dryv_recon_unpack_levels.argtypes = [C.POINTER(LevelsCompact), sz, vp]
+    lib.dryv_recon_submit_compact.restype = C.c_int
+    lib.dryv_recon_submit_compact.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), C.POINTER(LevelsCompact), u32, vp]
+    lib.dryv_recon_expand_levels_device.restype = C.c_int
+    lib.dryv_recon_expand_levels_device.argtypes = [vp, C.POINTER(LevelsCompact), sz, vp, vp]
     _lib = lib
     return lib
 
@@ -136,6 +145,58 @@ def pinned_batch(pp: PicParams, n_frames: int):
               PinnedArray((n, 16), np.uint8), PinnedArray((n, 384), np.int16)]
     b = SyntaxBatch(pp, n_frames, *[o.array for o in owners])
     return b, owners
+
+
+class CompactLevels:
+    """The compact level stream of a batch (dryv_mb_levels_compact): `offset` u32 [n_mbs + 1], `stream` u8."""
+
+    def __init__(self, offset: np.ndarray, stream: np.ndarray, owners=()):
+        self.offset, self.stream, self._owners = offset, stream, owners
+
+    @property
+    def n_mbs(self) -> int:
+        return self.offset.size - 1
+
+    @property
+    def nbytes(self) -> int:
+        """Bytes that travel: the offsets and the used part of the stream."""
+        return int(self.offset.nbytes + int(self.offset[-1]))
+
+    def as_struct(self) -> LevelsCompact:
+        lv = LevelsCompact()
+        lv.offset = self.offset.ctypes.data
+        lv.stream = self.stream.ctypes.data
+        return lv
+
+    def unpack(self) -> np.ndarray:
+        """Host-side inverse (dryv_recon_unpack_levels, diagnostic): dense int16 [n_mbs, 384]."""
+        out = np.empty((self.n_mbs, 384), np.int16)
+        lv = self.as_struct()
+        rc = load_library().dryv_recon_unpack_levels(C.byref(lv), self.n_mbs, out.ctypes.data)
+        if rc != OK:
+            raise ReconError(rc, "malformed compact level stream")
+        return out
+
+
+def pack_levels(coeff: np.ndarray, threads: int = 0, pinned: bool = False) -> CompactLevels:
+    """dryv_recon_pack_levels: dense int16 [n_mbs, 384] -> compact stream (host-side converter, no GPU needed)."""
+    lib = load_library()
+    coeff = np.ascontiguousarray(coeff, np.int16).reshape(-1, 384)
+    n = coeff.shape[0]
+    cap = n * COMPACT_MAX_RECORD
+    scratch = np.empty(cap, np.uint8)
+    off = np.empty(n + 1, np.uint32)
+    rc = lib.dryv_recon_pack_levels(coeff.ctypes.data, n, off.ctypes.data, scratch.ctypes.data, cap,
+                                    threads or (os.cpu_count() or 1))
+    if rc != OK:
+        raise ReconError(rc, "dryv_recon_pack_levels")
+    used = int(off[-1])
+    if pinned:
+        po, ps = PinnedArray(n + 1, np.uint32), PinnedArray(max(used, 4), np.uint8)
+        po.array[:] = off
+        ps.array[:used] = scratch[:used]
+        return CompactLevels(po.array, ps.array, (po, ps))
+    return CompactLevels(off, scratch[:max(used, 4)].copy())
 
 
 class DeviceSoa:
@@ -193,6 +254,31 @@ class ReconContext:
         self._keep = (batch, soa, out)
         self._check(self.lib.dryv_recon_submit(self.h, C.byref(batch.pp), C.byref(soa), batch.n_frames,
                                                out.ctypes.data))
+
+    def submit_compact(self, batch: SyntaxBatch, levels: CompactLevels, out: np.ndarray):
+        """dryv_recon_submit_compact: `batch.coeff` is not read, the levels come from the compact stream."""
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= batch.n_frames * batch.pp.frame_bytes
+        assert levels.n_mbs == batch.n_frames * batch.pp.n_mb
+        soa = batch.as_soa()
+        soa.coeff = None
+        lv = levels.as_struct()
+        self._keep = (batch, soa, levels, lv, out)
+        self._check(self.lib.dryv_recon_submit_compact(self.h, C.byref(batch.pp), C.byref(soa), C.byref(lv),
+                                                       batch.n_frames, out.ctypes.data))
+
+    def reconstruct_compact(self, batch: SyntaxBatch, levels: CompactLevels, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((batch.n_frames, batch.pp.frame_bytes), np.uint8)
+        self.submit_compact(batch, levels, out)
+        self.wait()
+        return out
+
+    def expand_levels_device(self, d_offset, d_stream, n_mbs: int, d_coeff, stream_ptr: int = 0):
+        """The expansion kernel alone on torch device tensors (tests)."""
+        lv = LevelsCompact()
+        lv.offset, lv.stream = d_offset.data_ptr(), d_stream.data_ptr()
+        self._check(self.lib.dryv_recon_expand_levels_device(self.h, C.byref(lv), n_mbs, d_coeff.data_ptr(),
+                                                             stream_ptr or None))
 
     def wait(self):
         self._check(self.lib.dryv_recon_wait(self.h))

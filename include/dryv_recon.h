@@ -134,6 +134,54 @@ int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* p
                                    const dryv_mb_soa* d_soa, uint32_t n_frames,
                                    const uint8_t* d_pred_yuv, uint8_t* d_out_yuv, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Compact level stream: the wire format between the CABAC host and the GPU.
+ *
+ * CABAC hands the reference a significance map plus the non-zero levels of each block and the reference
+ * scatters them into dense zero-filled arrays (residual_cabac, cabac/mod.rs:563-675: significant_coeff_flag map :632-646, levels :653-667; absent blocks
+ * stay all-zero, :669-673). Shipping those dense arrays over PCIe moves mostly zeros (768 B per MB), and the
+ * host-buffer path is PCIe bound, so dryv_recon_submit_compact takes the levels the way CABAC produced
+ * them and a small kernel re-creates the dense `coeff` layout of dryv_mb_soa in HBM.
+ *
+ * One record per macroblock, records in macroblock order, each starting on a 4-byte boundary:
+ *   uint32 header   bits 0..23: slot b (the b-th group of 16 int16 of the MB's `coeff` array, b = 0..23)
+ *                               holds at least one non-zero level;  bit 31: levels are int16 (else int8);
+ *                               bits 24..30 must be 0
+ *   uint16 mask[n]  one per coded slot, ascending b: bit k = coefficient k of the slot is non-zero
+ *   level[...]      the non-zero levels of all coded slots, ascending (b, k); int8 or int16 little endian
+ *   zero padding to the next multiple of 4
+ * offset[i] is the byte offset of macroblock i's record inside `stream`; offset[n_mbs] is the stream size.
+ * A record is at most DRYV_COMPACT_MAX_RECORD bytes; a stream is at most 4 GiB - 1.
+ */
+#define DRYV_COMPACT_MAX_RECORD (4 + 24 * 2 + DRYV_COEFFS_PER_MB * 2)
+
+typedef struct dryv_mb_levels_compact {
+  const uint32_t* offset; /* [n_mbs + 1] */
+  const uint8_t* stream;
+} dryv_mb_levels_compact;
+
+/* Host-side converter dense -> compact for callers that already hold dense arrays (tests, bench); a CABAC
+ * host appends records directly. `offset` must hold n_mbs + 1 entries, `stream` stream_cap bytes
+ * (n_mbs * DRYV_COMPACT_MAX_RECORD always suffices). `threads` <= 1 runs on the calling thread.
+ * Returns DRYV_OK, or DRYV_ERR_ARG when the stream does not fit. Needs no GPU. */
+int dryv_recon_pack_levels(const int16_t* coeff, size_t n_mbs, uint32_t* offset, uint8_t* stream,
+                           size_t stream_cap, int threads);
+
+/* Host-side inverse (diagnostic, used by the CPU tests of the format): compact -> dense int16 [n_mbs][384].
+ * Returns DRYV_ERR_ARG on a malformed stream. Needs no GPU; nothing on the reconstruction path calls it. */
+int dryv_recon_unpack_levels(const dryv_mb_levels_compact* levels, size_t n_mbs, int16_t* coeff);
+
+/* dryv_recon_submit with the levels in the compact format: `soa->coeff` is ignored (may be NULL), every
+ * other field of `soa` is read as in dryv_recon_submit. HOST pointers. */
+int dryv_recon_submit_compact(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa,
+                              const dryv_mb_levels_compact* levels, uint32_t n_frames, uint8_t* out_yuv);
+
+/* The expansion kernel alone, DEVICE pointers: d_levels->offset / stream are device arrays; writes the dense
+ * int16 [n_mbs][384] array at d_coeff (16-byte aligned). Malformed records are reported by dryv_recon_wait
+ * as DRYV_ERR_UNSUPPORTED. */
+int dryv_recon_expand_levels_device(dryv_recon_ctx* ctx, const dryv_mb_levels_compact* d_levels, size_t n_mbs,
+                                    int16_t* d_coeff, void* cuda_stream);
+
 /* Frame::write_to_yuv_file (frame/mod.rs:48-70): writes one reconstructed picture (host memory, the
  * layout above) to `path`, creating the parent directory of "temp/yuv_frame"-style paths if needed. */
 int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char* path);

@@ -12,6 +12,7 @@
 #include <sys/stat.h>
 
 #include <string>
+#include <vector>
 
 #include "recon_kernels.cuh"
 
@@ -852,6 +853,9 @@ __global__ void __launch_bounds__(kThreadsPerCta) expand_levels_kernel(const uin
 using dryv::DeviceTables;
 using dryv::KernelArgs;
 
+#ifndef DRYV_SUBMIT_STAGES
+#define DRYV_SUBMIT_STAGES 4
+#endif
 struct dryv_recon_ctx {
   int device = 0;
   int sm_count = 0;
@@ -859,7 +863,7 @@ struct dryv_recon_ctx {
   // s_compute[0] doubles as the default stream of the device-pointer entry points; dryv_recon_submit alternates
   // its chunks over both so that the (latency bound) wavefront kernels of neighbouring chunks overlap
   cudaStream_t s_compute[2] = {nullptr, nullptr}, s_h2d = nullptr, s_d2h = nullptr;
-  static constexpr int kStages = 4;  // staging slots of the submit pipeline
+  static constexpr int kStages = DRYV_SUBMIT_STAGES;  // staging slots of the submit pipeline
   cudaEvent_t e_h2d[kStages] = {}, e_kernel[kStages] = {}, e_d2h[kStages] = {};
   cudaEvent_t e_sub_begin = nullptr, e_sub_end = nullptr;
   bool sub_timed = false;
@@ -892,6 +896,8 @@ struct dryv_recon_ctx {
   cudaStream_t pending_user = nullptr;
   bool pending_user_valid = false;
   uint64_t launches = 0;
+  // development aid (DRYV_SUBMIT_TRACE=1): per-chunk stage completion events of the last submit, printed by wait
+  std::vector<cudaEvent_t> trace_ev;
   std::string err;
 };
 
@@ -1132,6 +1138,7 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  for (cudaEvent_t e : ctx->trace_ev) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -1220,16 +1227,26 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > n_frames) n_chunks = n_frames;
   const uint32_t chunk = (n_frames + n_chunks - 1) / n_chunks;
+  // Measured dead ends on the compact path (64 x 1080p, 4.9 ms): a short first stage to start the D2H sooner, and 8
+  // staging slots instead of 4 (no change): once the D2H runs, H2D + D2H together move ~75 GB/s over the link (the
+  // same total as a bidirectional copy probe), so the floor is (in + out bytes) / 75 GB/s plus one kernel latency.
+  std::vector<uint32_t> sched;
+  for (uint32_t left = n_frames; left;) {
+    const uint32_t nf = left < chunk ? left : chunk;
+    sched.push_back(nf);
+    left -= nf;
+  }
   // staging slot: dense levels | pred_syntax | mb_type | t8x8 | chroma mode | qp | [offsets | compact stream]
   size_t stream_max = 0;
   if (lv) {
     const size_t total_mbs = n_mb * n_frames;
     if (lv->offset[0] > lv->offset[total_mbs]) return fail(ctx, DRYV_ERR_ARG, "compact level stream: offsets not monotone");
-    for (uint32_t done = 0; done < n_frames; done += chunk) {
-      const uint32_t nf = (n_frames - done) < chunk ? (n_frames - done) : chunk;
+    uint32_t done = 0;
+    for (uint32_t nf : sched) {
       const uint32_t o0 = lv->offset[(size_t)done * n_mb], o1 = lv->offset[(size_t)(done + nf) * n_mb];
       if (o1 < o0 || (o0 & 3u)) return fail(ctx, DRYV_ERR_ARG, "compact level stream: offsets not monotone / not 4-byte aligned");
       if ((size_t)(o1 - o0) > stream_max) stream_max = o1 - o0;
+      done += nf;
     }
   }
   const size_t off_bytes = lv ? (((size_t)chunk * n_mb + 1) * 4 + 15) & ~(size_t)15 : 0;
@@ -1253,11 +1270,21 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
   }
   uint32_t done = 0;
   ctx->sub_timed = false;
+  const bool trace = getenv("DRYV_SUBMIT_TRACE") != nullptr;
+  for (cudaEvent_t e : ctx->trace_ev) cudaEventDestroy(e);
+  ctx->trace_ev.clear();
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ctx->trace_ev.push_back(e);
+  };
   CU(cudaEventRecord(ctx->e_sub_begin, ctx->s_h2d));
-  for (uint32_t i = 0; done < n_frames; i++) {
+  for (uint32_t i = 0; i < (uint32_t)sched.size(); i++) {
     const int slot = (int)(i % kStages), set = (int)(i & 1);
     cudaStream_t sc = ctx->s_compute[set];
-    const uint32_t nf = (n_frames - done) < chunk ? (n_frames - done) : chunk;
+    const uint32_t nf = sched[i];
     const size_t mb0 = (size_t)done * n_mb, cnt = (size_t)nf * n_mb;
     uint8_t* base = ctx->d_in[slot];
     dryv_mb_soa d;
@@ -1286,9 +1313,11 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
     CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.intra_chroma_pred_mode), soa->intra_chroma_pred_mode + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
     CU(cudaMemcpyAsync(const_cast<uint8_t*>(d.qp), soa->qp + mb0, cnt, cudaMemcpyHostToDevice, ctx->s_h2d));
     CU(cudaEventRecord(ctx->e_h2d[slot], ctx->s_h2d));
+    mark(ctx->s_h2d);
     // kernels: inputs landed, the slot's previous output has been copied out
     CU(cudaStreamWaitEvent(sc, ctx->e_h2d[slot], 0));
     if (i >= (uint32_t)kStages) CU(cudaStreamWaitEvent(sc, ctx->e_d2h[slot], 0));
+    mark(sc);
     if (lv) {
       rc = launch_expand(ctx, d_off, d_str, o0, o1 - o0, cnt, const_cast<int16_t*>(d.coeff), sc);
       if (rc != DRYV_OK) return rc;
@@ -1296,11 +1325,13 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
     rc = launch_wavefront(ctx, pp, &d, nf, ctx->d_out[slot], sc, set);
     if (rc != DRYV_OK) return rc;
     CU(cudaEventRecord(ctx->e_kernel[slot], sc));
+    mark(sc);
     // D2H
     CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->e_kernel[slot], 0));
     CU(cudaMemcpyAsync(out_yuv + (size_t)done * out_per_frame, ctx->d_out[slot], (size_t)nf * out_per_frame,
                        cudaMemcpyDeviceToHost, ctx->s_d2h));
     CU(cudaEventRecord(ctx->e_d2h[slot], ctx->s_d2h));
+    mark(ctx->s_d2h);
     done += nf;
   }
   CU(cudaEventRecord(ctx->e_sub_end, ctx->s_d2h));
@@ -1365,6 +1396,16 @@ int dryv_recon_wait(dryv_recon_ctx* ctx) {
   if (ctx->pending_user_valid) {
     CU(cudaStreamSynchronize(ctx->pending_user));
     ctx->pending_user_valid = false;
+  }
+  if (!ctx->trace_ev.empty()) {
+    for (size_t i = 0; i + 3 < ctx->trace_ev.size(); i += 4) {
+      float t[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], ctx->e_sub_begin, ctx->trace_ev[i + k]);
+      fprintf(stderr, "submit trace chunk %zu: h2d done %.3f  kernels start %.3f  done %.3f  d2h done %.3f ms\n", i / 4, t[0],
+              t[1], t[2], t[3]);
+    }
+    for (cudaEvent_t e : ctx->trace_ev) cudaEventDestroy(e);
+    ctx->trace_ev.clear();
   }
   CU(cudaMemcpy(ctx->h_status, ctx->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
   const int st = *ctx->h_status;

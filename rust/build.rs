@@ -17,6 +17,7 @@ fn main() {
     .args(["-shared", "-Xcompiler", "-fPIC"])
     .arg(csrc.join("recon.cu"))
     .arg(csrc.join("recon_tables.cpp"))
+    .arg(csrc.join("levels_pack.cpp"))
     .arg("-o")
     .arg(&lib)
     .status()
@@ -28,4 +29,5 @@ fn main() {
   println!("cargo:rerun-if-changed={}", csrc.join("recon.cu").display());
   println!("cargo:rerun-if-changed={}", csrc.join("recon_kernels.cuh").display());
   println!("cargo:rerun-if-changed={}", csrc.join("recon_tables.cpp").display());
+  println!("cargo:rerun-if-changed={}", csrc.join("levels_pack.cpp").display());
 }

@@ -37,6 +37,14 @@ pub struct dryv_mb_soa {
   pub coeff: *const i16,
 }
 
+/// include/dryv_recon.h `dryv_mb_levels_compact`: the compact level stream (the wire format of the host-buffer path).
+#[repr(C)]
+pub struct dryv_mb_levels_compact {
+  pub offset: *const u32, // [n_mbs + 1] byte offsets into `stream`, multiples of 4
+  pub stream: *const u8,
+}
+pub const DRYV_COMPACT_MAX_RECORD: usize = 4 + 24 * 2 + DRYV_COEFFS_PER_MB * 2;
+
 #[repr(C)]
 pub struct dryv_recon_ctx {
   _private: [u8; 0],
@@ -56,6 +64,22 @@ extern "C" {
     soa: *const dryv_mb_soa,
     n_frames: u32,
     out_yuv: *mut u8,
+  ) -> c_int;
+  pub fn dryv_recon_submit_compact(
+    ctx: *mut dryv_recon_ctx,
+    pp: *const dryv_pic_params,
+    soa: *const dryv_mb_soa, // `coeff` may be null
+    levels: *const dryv_mb_levels_compact,
+    n_frames: u32,
+    out_yuv: *mut u8,
+  ) -> c_int;
+  pub fn dryv_recon_pack_levels(
+    coeff: *const i16,
+    n_mbs: usize,
+    offset: *mut u32,
+    stream: *mut u8,
+    stream_cap: usize,
+    threads: c_int,
   ) -> c_int;
   pub fn dryv_recon_wait(ctx: *mut dryv_recon_ctx) -> c_int;
   pub fn dryv_recon_write_yuv_file(frame_yuv: *const u8, bytes: usize, path: *const c_char) -> c_int;
@@ -207,5 +231,64 @@ impl Drop for SoaBatch {
       dryv_recon_free_pinned(self.base as *mut c_void);
       dryv_recon_free_pinned(self.out as *mut c_void);
     }
+  }
+}
+
+/// Appends compact level records (include/dryv_recon.h, `dryv_mb_levels_compact`) in macroblock order, the way
+/// `residual_cabac` (src/video/cabac/mod.rs:563-675) produces them: per block a significance map and the non-zero
+/// levels. Call `begin_macroblock`, then `push_level(slot, k, level)` for every non-zero level in ascending
+/// (slot, k) order — slot = index of the 16-coefficient group inside the macroblock's `coeff` layout (0..23, see
+/// dryv_mb_soa), k = coefficient index inside it — then `end_macroblock`. Pictures of a batch are appended one
+/// after the other; `levels()` is what `dryv_recon_submit_compact` takes. (For full PCIe speed keep `stream` and
+/// `offset` in memory from dryv_recon_alloc_pinned; plain Vecs are shown for brevity.)
+pub struct CompactLevels {
+  pub offset: Vec<u32>,
+  pub stream: Vec<u8>,
+  masks: [u16; 24],
+  vals: Vec<i16>,
+}
+
+impl CompactLevels {
+  pub fn new() -> Self {
+    Self { offset: vec![0], stream: Vec::new(), masks: [0; 24], vals: Vec::with_capacity(DRYV_COEFFS_PER_MB) }
+  }
+  pub fn begin_macroblock(&mut self) {
+    self.masks = [0; 24];
+    self.vals.clear();
+  }
+  pub fn push_level(&mut self, slot: usize, k: usize, level: isize) {
+    if level != 0 {
+      self.masks[slot] |= 1 << k;
+      self.vals.push(level as i16);
+    }
+  }
+  pub fn end_macroblock(&mut self) {
+    let wide = self.vals.iter().any(|&v| v < -128 || v > 127);
+    let mut hdr: u32 = if wide { 1 << 31 } else { 0 };
+    for b in 0..24 {
+      if self.masks[b] != 0 {
+        hdr |= 1 << b;
+      }
+    }
+    self.stream.extend_from_slice(&hdr.to_le_bytes());
+    for b in 0..24 {
+      if self.masks[b] != 0 {
+        self.stream.extend_from_slice(&self.masks[b].to_le_bytes());
+      }
+    }
+    for &v in &self.vals {
+      if wide {
+        self.stream.extend_from_slice(&v.to_le_bytes());
+      } else {
+        self.stream.push(v as i8 as u8);
+      }
+    }
+    while self.stream.len() % 4 != 0 {
+      self.stream.push(0);
+    }
+    self.offset.push(self.stream.len() as u32);
+  }
+  pub fn levels(&self) -> dryv_mb_levels_compact {
+    dryv_mb_levels_compact { offset: self.offset.as_ptr(), stream: self.stream.as_ptr() }
   }
 }

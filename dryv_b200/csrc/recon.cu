@@ -867,6 +867,13 @@ struct dryv_recon_ctx {
   cudaEvent_t e_h2d[kStages] = {}, e_kernel[kStages] = {}, e_d2h[kStages] = {};
   cudaEvent_t e_sub_begin = nullptr, e_sub_end = nullptr;
   bool sub_timed = false;
+  // submits may be queued back to back (the next batch's H2D runs under this batch's D2H): completion events of the
+  // outstanding ones, oldest first, for dryv_recon_wait_oldest
+  static constexpr int kPending = 4;
+  cudaEvent_t e_done[kPending] = {};
+  int pending_head = 0, pending_count = 0;
+  bool sub_open = false;             // a submit has been queued since the last dryv_recon_wait
+  bool slot_used[kStages] = {};      // the staging slot's events have been recorded at least once
   // CUDA-event pairs around the most recent wavefront-kernel launches (bench: roofline of the dominant kernel)
   static constexpr int kTimedLaunches = 64;
   cudaEvent_t e_wave[kTimedLaunches][2] = {};
@@ -1084,6 +1091,8 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
          cudaEventCreateWithFlags(&ctx->e_kernel[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->e_d2h[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreate(&ctx->e_sub_begin) == cudaSuccess && cudaEventCreate(&ctx->e_sub_end) == cudaSuccess;
+  for (int i = 0; i < dryv_recon_ctx::kPending && ok; i++)
+    ok = cudaEventCreateWithFlags(&ctx->e_done[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < dryv_recon_ctx::kTimedLaunches && ok; i++)
     ok = cudaEventCreate(&ctx->e_wave[i][0]) == cudaSuccess && cudaEventCreate(&ctx->e_wave[i][1]) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_tables, sizeof(DeviceTables)) == cudaSuccess &&
@@ -1123,6 +1132,8 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
     if (ctx->e_wave[i][0]) cudaEventDestroy(ctx->e_wave[i][0]);
     if (ctx->e_wave[i][1]) cudaEventDestroy(ctx->e_wave[i][1]);
   }
+  for (int i = 0; i < dryv_recon_ctx::kPending; i++)
+    if (ctx->e_done[i]) cudaEventDestroy(ctx->e_done[i]);
   if (ctx->e_sub_begin) cudaEventDestroy(ctx->e_sub_begin);
   if (ctx->e_sub_end) cudaEventDestroy(ctx->e_sub_end);
   for (int i = 0; i < 2; i++)
@@ -1280,7 +1291,14 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
     cudaEventRecord(e, st);
     ctx->trace_ev.push_back(e);
   };
-  CU(cudaEventRecord(ctx->e_sub_begin, ctx->s_h2d));
+  // queue depth: block on the oldest outstanding submit when the completion ring is full
+  if (ctx->pending_count == dryv_recon_ctx::kPending) {
+    CU(cudaEventSynchronize(ctx->e_done[ctx->pending_head]));
+    ctx->pending_head = (ctx->pending_head + 1) % dryv_recon_ctx::kPending;
+    ctx->pending_count--;
+  }
+  if (!ctx->sub_open) CU(cudaEventRecord(ctx->e_sub_begin, ctx->s_h2d));  // timing spans every submit queued before the wait
+  ctx->sub_open = true;
   for (uint32_t i = 0; i < (uint32_t)sched.size(); i++) {
     const int slot = (int)(i % kStages), set = (int)(i & 1);
     cudaStream_t sc = ctx->s_compute[set];
@@ -1297,7 +1315,8 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
     uint32_t* d_off = reinterpret_cast<uint32_t*>(base + dense_per_frame * chunk);
     uint8_t* d_str = base + dense_per_frame * chunk + off_bytes;
     // H2D: the slot's previous kernel must have consumed its inputs
-    if (i >= (uint32_t)kStages) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->e_kernel[slot], 0));
+    const bool reused = ctx->slot_used[slot];  // also true for the first chunks of a submit queued behind another one
+    if (reused) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->e_kernel[slot], 0));
     uint32_t o0 = 0, o1 = 0;
     if (lv) {
       o0 = lv->offset[mb0];
@@ -1316,7 +1335,8 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
     mark(ctx->s_h2d);
     // kernels: inputs landed, the slot's previous output has been copied out
     CU(cudaStreamWaitEvent(sc, ctx->e_h2d[slot], 0));
-    if (i >= (uint32_t)kStages) CU(cudaStreamWaitEvent(sc, ctx->e_d2h[slot], 0));
+    if (reused) CU(cudaStreamWaitEvent(sc, ctx->e_d2h[slot], 0));
+    ctx->slot_used[slot] = true;
     mark(sc);
     if (lv) {
       rc = launch_expand(ctx, d_off, d_str, o0, o1 - o0, cnt, const_cast<int16_t*>(d.coeff), sc);
@@ -1335,6 +1355,8 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
     done += nf;
   }
   CU(cudaEventRecord(ctx->e_sub_end, ctx->s_d2h));
+  CU(cudaEventRecord(ctx->e_done[(ctx->pending_head + ctx->pending_count) % dryv_recon_ctx::kPending], ctx->s_d2h));
+  ctx->pending_count++;
   ctx->sub_timed = true;
   return DRYV_OK;
 }
@@ -1386,9 +1408,21 @@ double dryv_recon_last_submit_ms(dryv_recon_ctx* ctx) {
   return (double)ms;
 }
 
+int dryv_recon_wait_oldest(dryv_recon_ctx* ctx) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (ctx->pending_count == 0) return DRYV_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(ctx->e_done[ctx->pending_head]));
+  ctx->pending_head = (ctx->pending_head + 1) % dryv_recon_ctx::kPending;
+  ctx->pending_count--;
+  return DRYV_OK;
+}
+
 int dryv_recon_wait(dryv_recon_ctx* ctx) {
   if (!ctx) return DRYV_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
+  ctx->pending_head = ctx->pending_count = 0;
+  ctx->sub_open = false;
   CU(cudaStreamSynchronize(ctx->s_h2d));
   CU(cudaStreamSynchronize(ctx->s_compute[0]));
   CU(cudaStreamSynchronize(ctx->s_compute[1]));

@@ -26,7 +26,7 @@ EXPORTS = [
     "dryv_recon_wait", "dryv_recon_reconstruct_device", "dryv_recon_residual_add_device",
     "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms", "dryv_recon_device_tables",
     "dryv_recon_wavefront_times", "dryv_recon_pack_levels", "dryv_recon_unpack_levels", "dryv_recon_submit_compact",
-    "dryv_recon_expand_levels_device",
+    "dryv_recon_expand_levels_device", "dryv_recon_wait_oldest",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -83,6 +83,8 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_submit.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, vp]
     lib.dryv_recon_wait.restype = C.c_int
     lib.dryv_recon_wait.argtypes = [vp]
+    lib.dryv_recon_wait_oldest.restype = C.c_int
+    lib.dryv_recon_wait_oldest.argtypes = [vp]
     lib.dryv_recon_reconstruct_device.restype = C.c_int
     lib.dryv_recon_reconstruct_device.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, vp, vp]
     lib.dryv_recon_residual_add_device.restype = C.c_int
@@ -252,6 +254,7 @@ class ReconContext:
         assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= batch.n_frames * batch.pp.frame_bytes
         soa = batch.as_soa()
         self._keep = (batch, soa, out)
+        self.__dict__.setdefault("_keep_all", []).append(self._keep)
         self._check(self.lib.dryv_recon_submit(self.h, C.byref(batch.pp), C.byref(soa), batch.n_frames,
                                                out.ctypes.data))
 
@@ -263,6 +266,7 @@ class ReconContext:
         soa.coeff = None
         lv = levels.as_struct()
         self._keep = (batch, soa, levels, lv, out)
+        self.__dict__.setdefault("_keep_all", []).append(self._keep)
         self._check(self.lib.dryv_recon_submit_compact(self.h, C.byref(batch.pp), C.byref(soa), C.byref(lv),
                                                        batch.n_frames, out.ctypes.data))
 
@@ -282,6 +286,11 @@ class ReconContext:
 
     def wait(self):
         self._check(self.lib.dryv_recon_wait(self.h))
+        self._keep_all = []
+
+    def wait_oldest(self):
+        """Streaming use: returns when the oldest outstanding submit's pictures are complete."""
+        self._check(self.lib.dryv_recon_wait_oldest(self.h))
 
     def reconstruct(self, batch: SyntaxBatch, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:

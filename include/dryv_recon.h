@@ -119,6 +119,16 @@ int dryv_recon_submit(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv
                       uint32_t n_frames, uint8_t* out_yuv);
 int dryv_recon_wait(dryv_recon_ctx* ctx);
 
+/* Streaming use: dryv_recon_submit / dryv_recon_submit_compact may be called again before the previous batch
+ * has been waited for (up to 4 outstanding; a fifth call blocks on the oldest). The batches run in order and
+ * the next batch's H2D copies overlap the previous batch's D2H copies. dryv_recon_wait_oldest returns when the
+ * oldest outstanding batch's pictures are complete in its out_yuv (which, like its inputs, must stay valid and
+ * untouched until then); it returns DRYV_OK at once when nothing is outstanding. Device-side status
+ * (DRYV_ERR_UNSUPPORTED, DRYV_ERR_WATCHDOG) is collected by dryv_recon_wait, which waits for everything.
+ * dryv_recon_last_submit_ms then spans from the first H2D of the first batch queued since the previous
+ * dryv_recon_wait to the last D2H of the last one. */
+int dryv_recon_wait_oldest(dryv_recon_ctx* ctx);
+
 /* Same computation with DEVICE pointers (inputs already resident in HBM, output left in HBM),
  * enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream). Completion and
  * device-side status are collected by dryv_recon_wait (which synchronises that stream). */

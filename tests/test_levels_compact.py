@@ -183,3 +183,32 @@ def test_submit_compact_many_chunks_pinned(gpu_ctx, monkeypatch):
             monkeypatch.setenv("DRYV_CHUNK_OUT_MB", "1")
         assert np.array_equal(out.array, ref)
     assert gpu_ctx.last_submit_ms > 0
+
+
+@pytest.mark.gpu
+def test_queued_submits_and_wait_oldest(gpu_ctx):
+    # streaming use: several batches queued before the first wait; both wire formats; results land in order
+    pp = PicParams.make(40, 23)
+    batches, levels, outs, refs = [], [], [], []
+    for k in range(6):
+        hb, owners = recon.pinned_batch(pp, 5 + k)
+        synth.generate(pp, 5 + k, 900 + k, out=hb)
+        batches.append((hb, owners))
+        levels.append(recon.pack_levels(hb.coeff, pinned=True))
+        outs.append(recon.PinnedArray((5 + k, pp.frame_bytes), np.uint8))
+    for hb, _ in batches:
+        refs.append(gpu_ctx.reconstruct(hb).copy())
+    for k, (hb, _) in enumerate(batches):          # six submits, the queue holds four: the fifth blocks on the oldest
+        if k % 2:
+            gpu_ctx.submit(hb, outs[k].array)
+        else:
+            gpu_ctx.submit_compact(hb, levels[k], outs[k].array)
+    gpu_ctx.wait_oldest()
+    assert np.array_equal(outs[0].array, refs[0]) and np.array_equal(outs[1].array, refs[1])
+    gpu_ctx.wait_oldest()
+    assert np.array_equal(outs[2].array, refs[2])
+    gpu_ctx.wait()
+    for k in range(6):
+        assert np.array_equal(outs[k].array, refs[k]), k
+    assert gpu_ctx.last_submit_ms > 0
+    gpu_ctx.wait_oldest()                           # nothing outstanding: returns at once

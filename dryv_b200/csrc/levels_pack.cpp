@@ -17,57 +17,95 @@ namespace {
 
 constexpr int kSlots = DRYV_COEFFS_PER_MB / 16;
 
-// size in bytes of macroblock `c`'s record
-inline uint32_t record_size(const int16_t* c) {
-  uint32_t ncoded = 0, nnz = 0;
-  bool wide = false;
-  for (int b = 0; b < kSlots; b++) {
-    uint32_t n = 0;
-    for (int k = 0; k < 16; k++) {
-      const int v = c[b * 16 + k];
-      n += v != 0;
-      wide |= v < -128 || v > 127;
-    }
-    ncoded += n != 0;
-    nnz += n;
-  }
-  const uint32_t bytes = 4 + 2 * ncoded + (wide ? 2 * nnz : nnz);
-  return (bytes + 3u) & ~3u;
-}
+// Level codings (header bits 30..31): 0 = int8 per level, 1 = 4-bit code per level + int16 escapes, 2 = int16 per level.
+enum { kModeInt8 = 0, kModeNibble = 1, kModeInt16 = 2 };
 
-inline void write_record(const int16_t* c, uint8_t* rec, uint32_t size) {
-  uint32_t hdr = 0;
-  bool wide = false;
+struct MbStats {
+  uint32_t ncoded = 0, nnz = 0, nesc = 0;  // coded slots, non-zero levels, levels outside -7..7
+  bool wide = false;                       // a level outside int8
   uint16_t mask[kSlots];
+};
+
+inline MbStats scan(const int16_t* c) {
+  MbStats st;
   for (int b = 0; b < kSlots; b++) {
     uint16_t m = 0;
     for (int k = 0; k < 16; k++) {
       const int v = c[b * 16 + k];
-      if (v != 0) m |= (uint16_t)(1u << k);
-      wide |= v < -128 || v > 127;
+      if (!v) continue;
+      m |= (uint16_t)(1u << k);
+      st.nnz++;
+      st.nesc += v < -7 || v > 7;
+      st.wide |= v < -128 || v > 127;
     }
-    mask[b] = m;
-    if (m) hdr |= 1u << b;
+    st.mask[b] = m;
+    st.ncoded += m != 0;
   }
-  if (wide) hdr |= 1u << 31;
+  return st;
+}
+
+// bytes of the level part in each coding, and the smallest legal one
+inline uint32_t level_bytes(const MbStats& st, int mode) {
+  if (mode == kModeInt8) return st.nnz;
+  if (mode == kModeInt16) return 2 * st.nnz;
+  return (((st.nnz + 1) / 2 + 1) & ~1u) + 2 * st.nesc;  // nibbles padded to 2 bytes, then the int16 escapes
+}
+inline int pick_mode(const MbStats& st) {
+  int best = st.wide ? kModeInt16 : kModeInt8;
+  if (level_bytes(st, kModeNibble) < level_bytes(st, best)) best = kModeNibble;
+  return best;
+}
+
+// size in bytes of macroblock `c`'s record
+inline uint32_t record_size(const int16_t* c) {
+  const MbStats st = scan(c);
+  const uint32_t bytes = 4 + 2 * st.ncoded + level_bytes(st, pick_mode(st));
+  return (bytes + 3u) & ~3u;
+}
+
+inline void write_record(const int16_t* c, uint8_t* rec, uint32_t size) {
+  const MbStats st = scan(c);
+  const int mode = pick_mode(st);
+  uint32_t hdr = (uint32_t)mode << 30;
+  for (int b = 0; b < kSlots; b++)
+    if (st.mask[b]) hdr |= 1u << b;
   memcpy(rec, &hdr, 4);
   uint8_t* p = rec + 4;
   for (int b = 0; b < kSlots; b++)
-    if (mask[b]) {
-      memcpy(p, &mask[b], 2);
+    if (st.mask[b]) {
+      memcpy(p, &st.mask[b], 2);
       p += 2;
     }
-  for (int b = 0; b < kSlots; b++)
-    for (int k = 0; k < 16; k++) {
-      const int16_t v = c[b * 16 + k];
+  if (mode == kModeNibble) {
+    const uint32_t nib_bytes = ((st.nnz + 1) / 2 + 1) & ~1u;
+    memset(p, 0, nib_bytes);
+    uint8_t* esc = p + nib_bytes;
+    uint32_t j = 0;
+    for (int i = 0; i < DRYV_COEFFS_PER_MB; i++) {
+      const int16_t v = c[i];
       if (!v) continue;
-      if (wide) {
+      uint32_t code = 0;  // 0 = escape
+      if (v >= -7 && v <= 7) code = v < 0 ? (8u | (uint32_t)-v) : (uint32_t)v;
+      else {
+        memcpy(esc, &v, 2);
+        esc += 2;
+      }
+      p[j >> 1] |= (uint8_t)(code << (4 * (j & 1)));
+      j++;
+    }
+    p = esc;
+  } else {
+    for (int i = 0; i < DRYV_COEFFS_PER_MB; i++) {
+      const int16_t v = c[i];
+      if (!v) continue;
+      if (mode == kModeInt16) {
         memcpy(p, &v, 2);
         p += 2;
       } else {
         *p++ = (uint8_t)(int8_t)v;
       }
     }
+  }
   while (p < rec + size) *p++ = 0;
 }
 
@@ -122,8 +160,9 @@ int dryv_recon_unpack_levels(const dryv_mb_levels_compact* lv, size_t n_mbs, int
     const uint8_t* end = lv->stream + e;
     uint32_t hdr;
     memcpy(&hdr, rec, 4);
-    if (hdr & 0x7f000000u) return DRYV_ERR_ARG;
-    const bool wide = hdr >> 31;
+    if (hdr & 0x3f000000u) return DRYV_ERR_ARG;
+    const int mode = (int)(hdr >> 30);
+    if (mode > kModeInt16) return DRYV_ERR_ARG;
     int ncoded = 0;
     for (int b = 0; b < kSlots; b++) ncoded += (hdr >> b) & 1u;
     const uint8_t* mp = rec + 4;
@@ -131,20 +170,40 @@ int dryv_recon_unpack_levels(const dryv_mb_levels_compact* lv, size_t n_mbs, int
     if (p > end) return DRYV_ERR_ARG;
     int16_t* c = coeff + i * DRYV_COEFFS_PER_MB;
     memset(c, 0, DRYV_COEFFS_PER_MB * sizeof(int16_t));
+    uint32_t nnz = 0;
+    for (int b = 0; b < ncoded; b++) {
+      uint16_t m;
+      memcpy(&m, mp + 2 * b, 2);
+      if (!m) return DRYV_ERR_ARG;  // a coded slot holds at least one level
+      nnz += (uint32_t)__builtin_popcount(m);
+    }
+    const uint8_t* esc = p + (((nnz + 1) / 2 + 1) & ~1u);  // nibble coding only
+    if (mode == kModeNibble && esc > end) return DRYV_ERR_ARG;
+    uint32_t j = 0;
     for (int b = 0; b < kSlots; b++) {
       if (!((hdr >> b) & 1u)) continue;
       uint16_t m;
       memcpy(&m, mp, 2);
       mp += 2;
-      if (!m) return DRYV_ERR_ARG;  // a coded slot holds at least one level
       for (int k = 0; k < 16; k++) {
         if (!((m >> k) & 1u)) continue;
-        if (p + (wide ? 2 : 1) > end) return DRYV_ERR_ARG;
         int16_t v;
-        if (wide) {
+        if (mode == kModeNibble) {
+          const uint32_t code = (p[j >> 1] >> (4 * (j & 1))) & 15u;
+          j++;
+          if (code & 7u) {
+            v = (int16_t)((code & 8u) ? -(int)(code & 7u) : (int)(code & 7u));
+          } else {
+            if (esc + 2 > end) return DRYV_ERR_ARG;
+            memcpy(&v, esc, 2);
+            esc += 2;
+          }
+        } else if (mode == kModeInt16) {
+          if (p + 2 > end) return DRYV_ERR_ARG;
           memcpy(&v, p, 2);
           p += 2;
         } else {
+          if (p + 1 > end) return DRYV_ERR_ARG;
           v = (int16_t)(int8_t)*p++;
         }
         c[b * 16 + k] = v;

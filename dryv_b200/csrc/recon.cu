@@ -801,10 +801,10 @@ __global__ void __launch_bounds__(kThreadsPerCta) expand_levels_kernel(const uin
       const uint8_t* rec = stream + o;
       const uint32_t hdr = __ldg(reinterpret_cast<const uint32_t*>(rec));
       const uint32_t cm = hdr & 0xffffffu;
-      const uint32_t wide = hdr >> 31;
+      const uint32_t mode = hdr >> 30;  // 0: int8 levels, 1: 4-bit codes + int16 escapes, 2: int16 levels
       const uint32_t ncoded = __popc(cm);
       const uint32_t lv0 = 4u + 2u * ncoded;  // where the levels start
-      ok = !(hdr & 0x7f000000u) && lv0 <= len;
+      ok = !(hdr & 0x3f000000u) && mode <= 2u && lv0 <= len;
       uint32_t mask = 0;
       if (ok && lane < 24 && ((cm >> lane) & 1u))
         mask = __ldg(reinterpret_cast<const uint16_t*>(rec + 4 + 2 * __popc(cm & ((1u << lane) - 1u))));
@@ -816,21 +816,66 @@ __global__ void __launch_bounds__(kThreadsPerCta) expand_levels_kernel(const uin
         if (lane >= d) incl += t;
       }
       const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      ok = ok && lv0 + (total << wide) <= len;
-      if (ok && mask) {
-        const uint8_t* p = rec + lv0 + ((incl - cnt) << wide);
-        uint32_t w[8];
+      const uint32_t first = incl - cnt;  // index of this lane's first level among the macroblock's levels
+      uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (mode == 1u) {
+        // 4-bit codes (bit 3 = sign, bits 0..2 = |level| 1..7, 0 = escape), two per byte, low nibble first, padded to
+        // 2 bytes; the escaped levels follow as int16 in stream order
+        const uint32_t nib_bytes = (((total + 1u) >> 1) + 1u) & ~1u;
+        ok = ok && lv0 + nib_bytes <= len;
+        uint32_t codes[16];
+        uint32_t nesc = 0;
+        if (ok) {
+          const uint8_t* p = rec + lv0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          // the k-th coefficient's level sits behind the levels of the set bits below k: independent loads
-          int v = 0;
-          if ((mask >> k) & 1u) {
-            const uint32_t i = __popc(mask & ((1u << k) - 1u));
-            v = wide ? (int)(int16_t)__ldg(reinterpret_cast<const uint16_t*>(p) + i) : (int)(int8_t)__ldg(p + i);
+          for (int k = 0; k < 16; k++) {
+            codes[k] = 0xffu;  // no level
+            if ((mask >> k) & 1u) {
+              const uint32_t j = first + __popc(mask & ((1u << k) - 1u));
+              codes[k] = ((uint32_t)__ldg(p + (j >> 1)) >> (4u * (j & 1u))) & 15u;
+              nesc += (codes[k] & 7u) == 0u;
+            }
           }
-          if (k & 1) w[k >> 1] |= (uint32_t)v << 16;
-          else w[k >> 1] = (uint32_t)v & 0xffffu;
         }
+        uint32_t eincl = nesc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, eincl, d);
+          if (lane >= d) eincl += t;
+        }
+        const uint32_t etotal = __shfl_sync(0xffffffffu, eincl, 31);
+        ok = ok && lv0 + nib_bytes + 2u * etotal <= len;
+        if (ok && mask) {
+          const uint16_t* ep = reinterpret_cast<const uint16_t*>(rec + lv0 + nib_bytes) + (eincl - nesc);
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            int v = 0;
+            if (codes[k] != 0xffu) {
+              const uint32_t m3 = codes[k] & 7u;
+              if (m3) v = (codes[k] & 8u) ? -(int)m3 : (int)m3;
+              else v = (int)(int16_t)__ldg(ep++);
+            }
+            w[k >> 1] |= ((uint32_t)v & 0xffffu) << (16 * (k & 1));
+          }
+        }
+      } else {
+        const uint32_t wide = mode >> 1;
+        ok = ok && lv0 + (total << wide) <= len;
+        if (ok && mask) {
+          const uint8_t* p = rec + lv0 + (first << wide);
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            // the k-th coefficient's level sits behind the levels of the set bits below k: independent loads
+            int v = 0;
+            if ((mask >> k) & 1u) {
+              const uint32_t i = __popc(mask & ((1u << k) - 1u));
+              v = wide ? (int)(int16_t)__ldg(reinterpret_cast<const uint16_t*>(p) + i) : (int)(int8_t)__ldg(p + i);
+            }
+            w[k >> 1] |= ((uint32_t)v & 0xffffu) << (16 * (k & 1));
+          }
+        }
+      }
+      if (ok) {
         c0 = make_uint4(w[0], w[1], w[2], w[3]);
         c1 = make_uint4(w[4], w[5], w[6], w[7]);
       }

@@ -155,11 +155,18 @@ int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* p
  *
  * One record per macroblock, records in macroblock order, each starting on a 4-byte boundary:
  *   uint32 header   bits 0..23: slot b (the b-th group of 16 int16 of the MB's `coeff` array, b = 0..23)
- *                               holds at least one non-zero level;  bit 31: levels are int16 (else int8);
- *                               bits 24..30 must be 0
+ *                               holds at least one non-zero level;  bits 30..31: level coding (below);
+ *                               bits 24..29 must be 0
  *   uint16 mask[n]  one per coded slot, ascending b: bit k = coefficient k of the slot is non-zero
- *   level[...]      the non-zero levels of all coded slots, ascending (b, k); int8 or int16 little endian
+ *   levels          the non-zero levels of all coded slots, ascending (b, k), in one of three codings:
+ *                     0  int8 per level
+ *                     1  one 4-bit code per level, two per byte, low nibble first, padded to a multiple of
+ *                        2 bytes (bit 3 = sign, bits 0..2 = |level| 1..7; 0 = escape), followed by the
+ *                        escaped levels as int16 little endian in the same order
+ *                     2  int16 little endian per level
  *   zero padding to the next multiple of 4
+ * (dryv_recon_pack_levels picks the shortest coding per macroblock: at QP 26, where 98 % of the non-zero
+ * levels are within +-7, a macroblock's levels take ~120 bytes instead of 768.)
  * offset[i] is the byte offset of macroblock i's record inside `stream`; offset[n_mbs] is the stream size.
  * A record is at most DRYV_COMPACT_MAX_RECORD bytes; a stream is at most 4 GiB - 1.
  */

@@ -15,14 +15,25 @@ def reference_pack(coeff):
     for mb in np.asarray(coeff, np.int16).reshape(-1, 24, 16):
         nzm = mb != 0
         coded = nzm.any(axis=1)
-        wide = bool(((mb < -128) | (mb > 127)).any())
-        hdr = sum(1 << b for b in range(24) if coded[b]) | (int(wide) << 31)
+        lv = mb[nzm].astype(np.int32)
+        wide = bool(((lv < -128) | (lv > 127)).any())
+        small = np.abs(lv) <= 7
+        int8 = lv.astype(np.int8).tobytes()
+        int16 = lv.astype("<i2").tobytes()
+        nib = bytearray(((len(lv) + 1) // 2 + 1) & ~1)
+        for j, v in enumerate(lv):
+            code = (abs(int(v)) | (8 if v < 0 else 0)) if small[j] else 0
+            nib[j >> 1] |= code << (4 * (j & 1))
+        nibble = bytes(nib) + lv[~small].astype("<i2").tobytes()
+        mode, levels = (2, int16) if wide else (0, int8)
+        if len(nibble) < len(levels):
+            mode, levels = 1, nibble
+        hdr = sum(1 << b for b in range(24) if coded[b]) | (mode << 30)
         rec = bytearray(np.uint32(hdr).tobytes())
         for b in range(24):
             if coded[b]:
                 rec += np.uint16(sum(1 << k for k in range(16) if nzm[b, k])).tobytes()
-        lv = mb[nzm]
-        rec += lv.astype("<i2").tobytes() if wide else lv.astype(np.int8).tobytes()
+        rec += levels
         rec += bytes(-len(rec) % 4)
         out += rec
         offs.append(len(out))
@@ -31,11 +42,14 @@ def reference_pack(coeff):
 
 def test_pack_matches_documented_layout(recon_lib):
     pp = PicParams.make(5, 4)
-    b = synth.generate(pp, 2, 91, stress_pct=30)
-    lv = recon.pack_levels(b.coeff, threads=1)
-    off, stream = reference_pack(b.coeff)
-    assert np.array_equal(lv.offset, off)
-    assert np.array_equal(lv.stream[:off[-1]], stream)
+    for seed, qp, stress in ((91, 26, 30), (92, 4, 100), (93, 40, 0)):
+        b = synth.generate(pp, 2, seed, qp_base=qp, stress_pct=stress)
+        lv = recon.pack_levels(b.coeff, threads=1)
+        off, stream = reference_pack(b.coeff)
+        assert np.array_equal(lv.offset, off)
+        assert np.array_equal(lv.stream[:off[-1]], stream)
+        modes = set(int(lv.stream[o + 3]) >> 6 for o in lv.offset[:-1])
+        assert modes <= {0, 1, 2}
     assert (lv.offset % 4 == 0).all() and np.diff(lv.offset.astype(np.int64)).max() <= COMPACT_MAX_RECORD
 
 
@@ -51,16 +65,25 @@ def test_pack_unpack_roundtrip(recon_lib, qp, threads):
 
 
 def test_edge_records(recon_lib):
-    c = np.zeros((6, 384), np.int16)
-    c[1, :] = 1                      # every level set, narrow
-    c[2, :] = -32768                 # every level set, wide: the largest record
-    c[3, 383] = 127                  # narrow boundary values
+    c = np.zeros((10, 384), np.int16)
+    c[1, :] = 1                      # every level set, 4-bit codes
+    c[2, :] = -32768                 # every level set, int16: the largest record
+    c[3, 383] = 127                  # int8 boundary values
     c[4, 0] = -128
-    c[5, 17] = 128                   # first wide value
+    c[5, 17] = 128                   # first int16 value
+    c[6, :] = -7                     # 4-bit boundary values
+    c[7, ::3] = 7
+    c[8, :] = 8                      # all escapes would cost more than int8
+    c[9, :5] = [1, -1, 300, 2, -2]   # 4-bit codes with one escape
     lv = recon.pack_levels(c, threads=1)
     sizes = np.diff(lv.offset.astype(np.int64))
-    assert sizes.tolist() == [4, 4 + 48 + 384, COMPACT_MAX_RECORD, 8, 8, 8]
+    assert sizes.tolist() == [4, 4 + 48 + 192, COMPACT_MAX_RECORD, 8, 8, 8, 4 + 48 + 192, 4 + 48 + 64, 4 + 48 + 384,
+                              4 + 2 + 4 + 2]
+    modes = [int(lv.stream[o + 3]) >> 6 for o in lv.offset[:-1]]
+    assert modes == [0, 1, 2, 0, 0, 2, 1, 1, 0, 1]
     assert np.array_equal(lv.unpack(), c)
+    off, stream = reference_pack(c)
+    assert np.array_equal(lv.offset, off) and np.array_equal(lv.stream[:off[-1]], stream)
 
 
 def test_malformed_streams_are_rejected(recon_lib):
@@ -82,7 +105,10 @@ def test_malformed_streams_are_rejected(recon_lib):
     bad[1] += 2                      # not 4-byte aligned
     assert unpack(bad, lv.stream) == recon.ERR_ARG
     st = lv.stream.copy()
-    st[lv.offset[1] + 3] |= 0x40     # reserved header bit
+    st[lv.offset[1] + 3] |= 0x20     # reserved header bit
+    assert unpack(lv.offset, st) == recon.ERR_ARG
+    st = lv.stream.copy()
+    st[lv.offset[1] + 3] |= 0xc0     # level coding 3 does not exist
     assert unpack(lv.offset, st) == recon.ERR_ARG
     st = lv.stream.copy()
     st[lv.offset[1] + 4:lv.offset[1] + 6] = 0   # coded slot with an empty mask
@@ -112,18 +138,24 @@ def test_expand_kernel_matches_dense(gpu_ctx, qp, stress):
 @pytest.mark.gpu
 def test_expand_kernel_edge_records(gpu_ctx):
     import torch
-    c = np.zeros((7, 384), np.int16)
+    c = np.zeros((12, 384), np.int16)
     c[1, :] = -1
     c[2, :] = -32768
     c[3, 383] = 127
     c[4, 0] = -128
     c[5, 17] = 128
     c[6, ::2] = 32767
+    c[7, :] = -7
+    c[8, ::3] = 7
+    c[9, :] = 8
+    c[10, :5] = [1, -1, 300, 2, -2]
+    c[11, :] = np.where(np.arange(384) % 5 == 0, -3000, np.arange(384) % 7 + 1)   # 4-bit codes, escapes in every slot
     lv = recon.pack_levels(c, threads=1)
+    assert sorted(set(int(lv.stream[o + 3]) >> 6 for o in lv.offset[:-1])) == [0, 1, 2]
     d_off = torch.from_numpy(lv.offset.view(np.int32)).cuda()
     d_str = torch.from_numpy(lv.stream).cuda()
-    d_coeff = torch.zeros((7, 384), dtype=torch.int16, device="cuda")
-    gpu_ctx.expand_levels_device(d_off, d_str, 7, d_coeff)
+    d_coeff = torch.zeros((12, 384), dtype=torch.int16, device="cuda")
+    gpu_ctx.expand_levels_device(d_off, d_str, 12, d_coeff)
     gpu_ctx.wait()
     assert np.array_equal(d_coeff.cpu().numpy(), c)
 

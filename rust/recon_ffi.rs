@@ -82,6 +82,8 @@ extern "C" {
     threads: c_int,
   ) -> c_int;
   pub fn dryv_recon_wait(ctx: *mut dryv_recon_ctx) -> c_int;
+  /// streaming use: up to four submits may be outstanding; returns when the oldest one's pictures are complete
+  pub fn dryv_recon_wait_oldest(ctx: *mut dryv_recon_ctx) -> c_int;
   pub fn dryv_recon_write_yuv_file(frame_yuv: *const u8, bytes: usize, path: *const c_char) -> c_int;
 }
 
@@ -262,9 +264,11 @@ impl CompactLevels {
       self.vals.push(level as i16);
     }
   }
+  /// Writes the record with level coding 0 (int8) or 2 (int16); coding 1 (4-bit codes + int16 escapes, see
+  /// include/dryv_recon.h) is what dryv_recon_pack_levels picks when it is shorter and is left out here for brevity.
   pub fn end_macroblock(&mut self) {
     let wide = self.vals.iter().any(|&v| v < -128 || v > 127);
-    let mut hdr: u32 = if wide { 1 << 31 } else { 0 };
+    let mut hdr: u32 = if wide { 2 << 30 } else { 0 };
     for b in 0..24 {
       if self.masks[b] != 0 {
         hdr |= 1 << b;

@@ -27,7 +27,7 @@ class SynthCfg(C.Structure):
         ("stress_pct", C.c_int32),
         ("zero_residual", C.c_int32),
         ("qp_step_per_frame", C.c_int32),
-        ("reserved", C.c_int32),
+        ("standard_only", C.c_int32),
     ]
 
 
@@ -57,10 +57,12 @@ def _load():
 
 def generate(pp: PicParams, n_frames: int, seed0: int, *, qp_base: int = 26, qp_jitter: int = 2,
              pct_i4x4: int = 40, pct_i8x8: int = 25, stress_pct: int = 10, zero_residual: bool = False,
-             qp_step_per_frame: int = 0, threads: int | None = None, out: SyntaxBatch | None = None) -> SyntaxBatch:
+             qp_step_per_frame: int = 0, standard_only: bool = False, threads: int | None = None,
+             out: SyntaxBatch | None = None) -> SyntaxBatch:
     """Pictures f = 0..n_frames-1 are seeded seed0 + f (SplitMix64), MB mix and QP per SURVEY.md §8(d)."""
     lib = _load()
-    cfg = SynthCfg(qp_base, qp_jitter, pct_i4x4, pct_i8x8, stress_pct, int(zero_residual), qp_step_per_frame, 0)
+    cfg = SynthCfg(qp_base, qp_jitter, pct_i4x4, pct_i8x8, stress_pct, int(zero_residual), qp_step_per_frame,
+                   int(standard_only))
     b = out if out is not None else SyntaxBatch.empty(pp, n_frames)
     if threads is None:
         threads = min(os.cpu_count() or 1, 64)

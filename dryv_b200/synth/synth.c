@@ -198,6 +198,7 @@ int dryv_synth_frame(const dryv_pic_params* pp, const dryv_synth_cfg* cfg, uint6
 
       uint32_t tsel = rng_below(&rng, 100);
       int cls = tsel < (uint32_t)cfg->pct_i4x4 ? 0 : (tsel < (uint32_t)(cfg->pct_i4x4 + cfg->pct_i8x8) ? 1 : 2);
+      if (cfg->standard_only && cls == 1 && mx == 0) cls = 0;  /* see dryv_synth_cfg::standard_only */
       me->cls = (uint8_t)cls;
       int qp = cfg->qp_base;
       if (cfg->qp_jitter > 0) qp += (int)rng_below(&rng, 2 * (uint32_t)cfg->qp_jitter + 1) - cfg->qp_jitter;

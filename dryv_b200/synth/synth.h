@@ -15,7 +15,8 @@ typedef struct dryv_synth_cfg {
   int32_t stress_pct;         /* percent MBs with the wide residual profile (clamps to 0/255 regularly) */
   int32_t zero_residual;      /* 1: all levels zero (prediction-only pictures) */
   int32_t qp_step_per_frame;  /* batch only: picture f uses qp_base + f * step (QP sweep) */
-  int32_t reserved;
+  int32_t standard_only;      /* 1: no Intra8x8 macroblock in column 0, the one place where the reference's luma deviates
+                                 from the H.264 text, so that a conformant decoder agrees on the luma */
 } dryv_synth_cfg;
 
 /* One picture; all output arrays are for that picture (n_mb entries, pred_syntax 16/MB, coeff 384/MB). */

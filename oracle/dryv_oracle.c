@@ -10,6 +10,11 @@
  * by reading the reference sources cited below; it is cross-checked against an independent
  * restatement of the H.264 text (oracle/spec_model.py) and against hand-computed vectors under
  * tests/golden/, but not against output of the reference binary itself.
+ * What IS pinned, to an independent conformant decoder: tests/test_libavcodec_crosscheck.py writes real CABAC
+ * High-profile streams from the syntax buffers (tests/avc/stream.py), libavcodec (cv2) decodes them, and this
+ * oracle's luma equals libavcodec's bit for bit wherever the reference follows the standard (everywhere except
+ * Intra8x8 macroblocks in column 0, quirk Q2); a stream + libavcodec luma fixture is committed under
+ * tests/golden/avc/. The reference's deviations themselves (Q1-Q5) rest on reading its source.
  *
  * Every function cites the reference file:line it follows (paths relative to the reference root;
  * "frame/x.rs" = src/video/frame/x.rs, "slice/x.rs" = src/video/slice/x.rs). All arithmetic is

@@ -1,0 +1,556 @@
+// cabac_host.cpp — CPU host side of the reconstruction path (include/dryv_cabac_host.h): Annex-B bytes -> SoA syntax.
+//
+// Restates, for IDR I-slice pictures, what the reference does before it reconstructs a macroblock: NAL split and
+// emulation prevention (src/video/sample/nal.rs:230-253, src/byte/bit.rs:144-149), SPS/PPS
+// (src/video/atom/avcc/sps.rs:42-121, pps.rs:30-58), slice header (src/video/slice/header.rs:145-315), the macroblock
+// loop (src/video/slice/mod.rs:184-317), macroblock_layer / mb_pred / residual (src/video/cabac/mod.rs:89-210, :212-343,
+// :433-675), the syntax-element context selection (:677-1111) and the arithmetic decoding engine (:1207-1308).
+// Written from the text of ITU-T H.264 (7.3, 9.3) as the inverse of the stream writer in tests/avc/stream.py, which
+// libavcodec accepts; organised around a per-macroblock neighbour record instead of the reference's Macroblock structs.
+// Runs on the CPU by design (CABAC is serial inside a slice); pictures are independent and go to separate threads.
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "../../include/dryv_cabac_host.h"
+
+namespace {
+
+#include "cabac_tables.inc"
+
+// ---- bit reader over an RBSP (emulation prevention bytes already removed) ---------------------------------------
+struct Bits {
+  const uint8_t* p;
+  size_t n, pos = 0;  // pos in bits
+  bool bad = false;
+  Bits(const uint8_t* d, size_t len) : p(d), n(len * 8) {}
+  int bit() {
+    if (pos >= n) {
+      bad = true;
+      return 0;
+    }
+    const int b = (p[pos >> 3] >> (7 - (pos & 7))) & 1;
+    pos++;
+    return b;
+  }
+  uint32_t u(int k) {
+    uint32_t v = 0;
+    while (k-- > 0) v = (v << 1) | (uint32_t)bit();
+    return v;
+  }
+  uint32_t ue() {
+    int z = 0;
+    while (!bit() && !bad && z < 32) z++;
+    return z == 0 ? 0 : ((1u << z) - 1 + u(z));
+  }
+  int32_t se() {
+    const uint32_t k = ue();
+    return (k & 1) ? (int32_t)((k + 1) >> 1) : -(int32_t)(k >> 1);
+  }
+  // 7.2 more_rbsp_data(): anything before the last set bit (the stop bit) is data
+  bool more_rbsp_data() const {
+    size_t last = n;
+    while (last > 0 && !((p[(last - 1) >> 3] >> (7 - ((last - 1) & 7))) & 1)) last--;
+    return last > 0 && pos < last - 1;
+  }
+};
+
+struct Nal {
+  int ref_idc, type;
+  std::vector<uint8_t> rbsp;
+};
+
+// Annex B: NAL units separated by 00 00 01 start codes; 00 00 03 -> 00 00 inside a unit
+void split_nals(const uint8_t* d, size_t len, std::vector<Nal>& out) {
+  size_t i = 0;
+  auto start_at = [&](size_t k) { return k + 2 < len && d[k] == 0 && d[k + 1] == 0 && d[k + 2] == 1; };
+  while (i + 2 < len && !start_at(i)) i++;
+  while (i + 3 < len) {
+    i += 3;  // past the start code
+    size_t e = i;
+    while (e < len && !start_at(e)) e++;
+    size_t end = e;
+    while (end > i && d[end - 1] == 0) end--;  // trailing zero bytes belong to the next start code
+    if (end > i) {
+      Nal nal;
+      nal.ref_idc = (d[i] >> 5) & 3;
+      nal.type = d[i] & 31;
+      nal.rbsp.reserve(end - i);
+      int zeros = 0;
+      for (size_t k = i + 1; k < end; k++) {
+        if (zeros >= 2 && d[k] == 3) {
+          zeros = 0;
+          continue;
+        }
+        nal.rbsp.push_back(d[k]);
+        zeros = d[k] == 0 ? zeros + 1 : 0;
+      }
+      out.push_back(std::move(nal));
+    }
+    i = e;
+  }
+}
+
+struct Sps {
+  bool ok = false;
+  int w_mbs = 0, h_mbs = 0, log2_max_frame_num = 4, poc_type = 0, log2_max_poc_lsb = 4, delta_pic_order_always_zero = 0;
+};
+struct Pps {
+  bool ok = false;
+  int bottom_field_pic_order = 0, pic_init_qp = 26, cb_off = 0, cr_off = 0, deblocking_control = 0, redundant_pic_cnt = 0,
+      transform_8x8_mode = 0;
+};
+
+int parse_sps(const Nal& nal, Sps& s) {
+  Bits b(nal.rbsp.data(), nal.rbsp.size());
+  const int profile = (int)b.u(8);
+  b.u(8);
+  b.u(8);
+  b.ue();
+  if (profile == 100 || profile == 110 || profile == 122 || profile == 244 || profile == 44 || profile == 83 || profile == 86 ||
+      profile == 118 || profile == 128 || profile == 138 || profile == 139 || profile == 134 || profile == 135) {
+    if (b.ue() != 1) return DRYV_ERR_UNSUPPORTED;                  // chroma_format_idc: 4:2:0 only
+    if (b.ue() != 0 || b.ue() != 0) return DRYV_ERR_UNSUPPORTED;   // 8-bit only
+    b.u(1);                                                        // qpprime_y_zero_transform_bypass_flag
+    if (b.u(1)) return DRYV_ERR_UNSUPPORTED;                       // seq_scaling_matrix_present_flag
+  }
+  s.log2_max_frame_num = (int)b.ue() + 4;
+  s.poc_type = (int)b.ue();
+  if (s.poc_type == 0) {
+    s.log2_max_poc_lsb = (int)b.ue() + 4;
+  } else if (s.poc_type == 1) {
+    s.delta_pic_order_always_zero = (int)b.u(1);
+    b.se();
+    b.se();
+    const uint32_t cyc = b.ue();
+    for (uint32_t i = 0; i < cyc && !b.bad; i++) b.se();
+  }
+  b.ue();  // max_num_ref_frames
+  b.u(1);  // gaps_in_frame_num_value_allowed_flag
+  s.w_mbs = (int)b.ue() + 1;
+  s.h_mbs = (int)b.ue() + 1;
+  if (!b.u(1)) return DRYV_ERR_UNSUPPORTED;  // frame_mbs_only_flag
+  if (b.bad || s.w_mbs > 1024 || s.h_mbs > 1024) return DRYV_ERR_ARG;
+  s.ok = true;  // direct_8x8_inference, cropping (dryv never crops) and VUI are not needed
+  return DRYV_OK;
+}
+
+int parse_pps(const Nal& nal, Pps& p) {
+  Bits b(nal.rbsp.data(), nal.rbsp.size());
+  b.ue();
+  b.ue();
+  if (!b.u(1)) return DRYV_ERR_UNSUPPORTED;  // entropy_coding_mode_flag: CABAC only (the reference has no CAVLC)
+  p.bottom_field_pic_order = (int)b.u(1);
+  if (b.ue() != 0) return DRYV_ERR_UNSUPPORTED;  // slice groups
+  b.ue();
+  b.ue();
+  b.u(1);
+  b.u(2);
+  p.pic_init_qp = 26 + b.se();
+  b.se();
+  p.cb_off = p.cr_off = b.se();
+  p.deblocking_control = (int)b.u(1);
+  b.u(1);  // constrained_intra_pred_flag: irrelevant inside an I picture
+  p.redundant_pic_cnt = (int)b.u(1);
+  p.transform_8x8_mode = 0;
+  if (b.more_rbsp_data()) {
+    p.transform_8x8_mode = (int)b.u(1);
+    if (b.u(1)) return DRYV_ERR_UNSUPPORTED;  // pic_scaling_matrix_present_flag
+    p.cr_off = b.se();
+  }
+  if (b.bad) return DRYV_ERR_ARG;
+  p.ok = true;
+  return DRYV_OK;
+}
+
+// ---- 9.3.3.2 arithmetic decoding engine + 9.3.1.1 context initialisation -----------------------------------------
+struct Cabac {
+  Bits* in;
+  uint32_t range = 510, offset = 0;
+  uint8_t state[1024], mps[1024];
+  void init(Bits* b, int slice_qp) {
+    in = b;
+    const int q = slice_qp < 0 ? 0 : (slice_qp > 51 ? 51 : slice_qp);
+    for (int i = 0; i < 1024; i++) {
+      int pre = ((kCtxInitM[i] * q) >> 4) + kCtxInitN[i];
+      pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
+      if (pre <= 63) {
+        state[i] = (uint8_t)(63 - pre);
+        mps[i] = 0;
+      } else {
+        state[i] = (uint8_t)(pre - 64);
+        mps[i] = 1;
+      }
+    }
+    range = 510;
+    offset = in->u(9);
+  }
+  int decision(int ctx) {
+    const int s = state[ctx];
+    const uint32_t lps = kRangeTabLps[s * 4 + ((range >> 6) & 3)];
+    range -= lps;
+    int bin;
+    if (offset >= range) {
+      bin = !mps[ctx];
+      offset -= range;
+      range = lps;
+      if (s == 0) mps[ctx] = (uint8_t)!mps[ctx];
+      state[ctx] = kTransIdxLps[s];
+    } else {
+      bin = mps[ctx];
+      state[ctx] = kTransIdxMps[s];
+    }
+    while (range < 256) {
+      range <<= 1;
+      offset = (offset << 1) | (uint32_t)in->bit();
+    }
+    return bin;
+  }
+  int bypass() {
+    offset = (offset << 1) | (uint32_t)in->bit();
+    if (offset >= range) {
+      offset -= range;
+      return 1;
+    }
+    return 0;
+  }
+  int terminate() {
+    range -= 2;
+    if (offset >= range) return 1;
+    while (range < 256) {
+      range <<= 1;
+      offset = (offset << 1) | (uint32_t)in->bit();
+    }
+    return 0;
+  }
+};
+
+// What the context selection of later macroblocks needs to know about a parsed macroblock
+struct MbCtx {
+  uint8_t avail = 0, i16 = 0, t8 = 0, cbp_luma = 0, cbp_chroma = 0, chroma_mode = 0, cbf_dc = 0;
+  uint8_t cbf_cdc[2] = {0, 0};
+  uint8_t cbf_cac[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  uint8_t cbf_luma[16] = {0};
+};
+
+const int kCbfBase[5] = {85, 89, 93, 97, 101};
+const int kSigBase[6] = {105, 120, 134, 149, 152, 402};
+const int kLastBase[6] = {166, 181, 195, 210, 213, 417};
+const int kAbsBase[6] = {227, 237, 247, 257, 266, 426};
+const int kBlkX[16] = {0, 4, 0, 4, 8, 12, 8, 12, 0, 4, 0, 4, 8, 12, 8, 12};
+const int kBlkY[16] = {0, 0, 4, 4, 0, 0, 4, 4, 8, 8, 12, 12, 8, 8, 12, 12};
+inline int blk4_of(int x, int y) { return 8 * (y / 8) + 4 * (x / 8) + 2 * ((y % 8) / 4) + ((x % 8) / 4); }
+
+struct SliceParser {
+  Cabac c;
+  int W, H;
+  std::vector<MbCtx> info;
+  int qp_prev = 26;
+  bool prev_delta_nonzero = false;
+  bool unsupported = false;
+
+  // 7.3.5.3.3 residual_block_cabac: `n` levels in coding order into out[0..n) (already zeroed); returns coded_block_flag
+  int residual_block(int cat, int n, int16_t* out, int stride_unused, int cbf_inc, bool code_cbf) {
+    (void)stride_unused;
+    if (code_cbf && !c.decision(kCbfBase[cat] + cbf_inc)) return 0;
+    uint8_t sig[64];
+    int count = 0, last = n - 1;
+    for (int i = 0; i < n - 1; i++) {
+      const int si = cat == 5 ? kSig8x8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
+      const int li = cat == 5 ? kLast8x8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
+      sig[i] = (uint8_t)c.decision(kSigBase[cat] + si);
+      if (sig[i]) {
+        count++;
+        if (c.decision(kLastBase[cat] + li)) {
+          last = i;
+          break;
+        }
+      }
+    }
+    if (last == n - 1) {
+      sig[n - 1] = 1;  // inferred when no earlier coefficient was flagged last
+      count++;
+    }
+    (void)count;
+    int eq1 = 0, gt1 = 0;
+    for (int i = last; i >= 0; i--) {
+      if (!sig[i]) continue;
+      const int ctx0 = kAbsBase[cat] + (gt1 ? 0 : (1 + eq1 < 4 ? 1 + eq1 : 4));
+      const int lim = 4 - (cat == 3 ? 1 : 0);
+      const int ctxn = kAbsBase[cat] + 5 + (gt1 < lim ? gt1 : lim);
+      int a = 0;
+      if (c.decision(ctx0)) {
+        a = 1;
+        while (a < 14 && c.decision(ctxn)) a++;
+        if (a == 14) {  // 0-th order Exp-Golomb suffix, bypass
+          int k = 0;
+          while (c.bypass() && k < 24) {
+            a += 1 << k;
+            k++;
+          }
+          while (k-- > 0) a += c.bypass() << k;
+        }
+      }
+      const int v = c.bypass() ? -(a + 1) : (a + 1);
+      out[i] = (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v));
+      if (a == 0) eq1++;
+      else gt1++;
+    }
+    return 1;
+  }
+
+  static int cond(const MbCtx* nb, int flag_if_available) { return nb ? flag_if_available : 1; }  // intra MB: unavailable -> 1
+
+  // one macroblock: 7.3.5 macroblock_layer for I slices
+  void macroblock(int addr, uint8_t* mb_type, uint8_t* t8x8, uint8_t* chroma_mode, uint8_t* qp, uint8_t* pred_syntax,
+                  int16_t* coeff) {
+    const int x = addr % W, y = addr / W;
+    const MbCtx* A = x > 0 ? &info[addr - 1] : nullptr;
+    const MbCtx* B = y > 0 ? &info[addr - W] : nullptr;
+    MbCtx me;
+    me.avail = 1;
+    memset(pred_syntax, 0, 16);
+    memset(coeff, 0, DRYV_COEFFS_PER_MB * sizeof(int16_t));
+    // mb_type (9.3.2.5, Table 9-36, I slices)
+    int code = 0, pred16 = 0, cbp_l = 0, cbp_c = 0;
+    if (c.decision(3 + (A && A->i16 ? 1 : 0) + (B && B->i16 ? 1 : 0))) {
+      if (c.terminate()) {  // I_PCM
+        unsupported = true;
+        return;
+      }
+      me.i16 = 1;
+      cbp_l = c.decision(3 + 3) ? 15 : 0;
+      if (c.decision(3 + 4)) cbp_c = c.decision(3 + 5) ? 2 : 1;
+      pred16 = c.decision(3 + 6) << 1;
+      pred16 |= c.decision(3 + 7);
+      code = 1 + pred16 + 4 * cbp_c + (cbp_l ? 12 : 0);
+    }
+    *mb_type = (uint8_t)code;
+    if (!me.i16) {
+      me.t8 = transform8 ? (uint8_t)c.decision(399 + (A && A->t8 ? 1 : 0) + (B && B->t8 ? 1 : 0)) : 0;
+      for (int k = 0; k < (me.t8 ? 4 : 16); k++) {
+        int syn = c.decision(68) << 3;
+        if (!syn) {
+          syn |= c.decision(69);
+          syn |= c.decision(69) << 1;
+          syn |= c.decision(69) << 2;
+        }
+        pred_syntax[k] = (uint8_t)syn;
+      }
+    }
+    *t8x8 = me.t8;
+    // intra_chroma_pred_mode: TU, cMax 3
+    {
+      int cm = 0;
+      if (c.decision(64 + (A && A->chroma_mode ? 1 : 0) + (B && B->chroma_mode ? 1 : 0))) {
+        cm = 1;
+        if (c.decision(64 + 3)) {
+          cm = 2;
+          if (c.decision(64 + 3)) cm = 3;
+        }
+      }
+      me.chroma_mode = (uint8_t)cm;
+      *chroma_mode = (uint8_t)cm;
+    }
+    if (!me.i16) {  // coded_block_pattern (9.3.3.1.1.4)
+      for (int b8 = 0; b8 < 4; b8++) {
+        const int x8 = b8 & 1, y8 = b8 >> 1;
+        const int ca = x8 ? !((cbp_l >> (b8 - 1)) & 1) : (A ? !((A->cbp_luma >> (b8 + 1)) & 1) : 0);
+        const int cb = y8 ? !((cbp_l >> (b8 - 2)) & 1) : (B ? !((B->cbp_luma >> (b8 + 2)) & 1) : 0);
+        cbp_l |= c.decision(73 + ca + 2 * cb) << b8;
+      }
+      if (c.decision(77 + (A && A->cbp_chroma ? 1 : 0) + 2 * (B && B->cbp_chroma ? 1 : 0)))
+        cbp_c = c.decision(77 + 4 + (A && A->cbp_chroma == 2 ? 1 : 0) + 2 * (B && B->cbp_chroma == 2 ? 1 : 0)) ? 2 : 1;
+    }
+    me.cbp_luma = (uint8_t)cbp_l;
+    me.cbp_chroma = (uint8_t)cbp_c;
+    if (me.i16 || cbp_l || cbp_c) {
+      // mb_qp_delta (9.3.2.7 / 9.3.3.1.1.5): unary, mapped
+      int v = 0, ctx = 60 + (prev_delta_nonzero ? 1 : 0);
+      while (c.decision(ctx) && v < 104) {
+        v++;
+        ctx = v == 1 ? 60 + 2 : 60 + 3;
+      }
+      const int delta = (v & 1) ? (v + 1) / 2 : -(v / 2);
+      prev_delta_nonzero = delta != 0;
+      qp_prev = ((qp_prev + delta + 52) % 52);  // cabac/mod.rs:186-191 with QpBdOffsetY = 0
+      // residual (7.3.5.3): luma DC, luma blocks, chroma DC, chroma AC
+      if (me.i16) {
+        int16_t dc[16] = {0};
+        const int inc = cond(A, A && A->i16 ? A->cbf_dc : 0) + 2 * cond(B, B && B->i16 ? B->cbf_dc : 0);
+        me.cbf_dc = (uint8_t)residual_block(0, 16, dc, 0, inc, true);
+        for (int b = 0; b < 16; b++) coeff[b * 16] = dc[b];
+      }
+      for (int b8 = 0; b8 < 4; b8++) {
+        if (!((cbp_l >> b8) & 1)) continue;
+        if (me.t8) {
+          residual_block(5, 64, coeff + b8 * 64, 0, 0, false);
+          for (int k = 0; k < 4; k++) me.cbf_luma[4 * b8 + k] = 1;
+        } else {
+          for (int k = 0; k < 4; k++) {
+            const int blk = 4 * b8 + k, bx = kBlkX[blk], by = kBlkY[blk];
+            const int fa = bx > 0 ? me.cbf_luma[blk4_of(bx - 4, by)] : cond(A, A ? A->cbf_luma[blk4_of(12, by)] : 0);
+            const int fb = by > 0 ? me.cbf_luma[blk4_of(bx, by - 4)] : cond(B, B ? B->cbf_luma[blk4_of(bx, 12)] : 0);
+            me.cbf_luma[blk] = me.i16 ? (uint8_t)residual_block(1, 15, coeff + blk * 16 + 1, 0, fa + 2 * fb, true)
+                                      : (uint8_t)residual_block(2, 16, coeff + blk * 16, 0, fa + 2 * fb, true);
+          }
+        }
+      }
+      if (cbp_c) {
+        for (int pl = 0; pl < 2; pl++) {
+          int16_t dc[4] = {0, 0, 0, 0};
+          const int inc = cond(A, A ? A->cbf_cdc[pl] : 0) + 2 * cond(B, B ? B->cbf_cdc[pl] : 0);
+          me.cbf_cdc[pl] = (uint8_t)residual_block(3, 4, dc, 0, inc, true);
+          for (int k = 0; k < 4; k++) coeff[(16 + 4 * pl + k) * 16] = dc[k];
+        }
+      }
+      if (cbp_c == 2) {
+        for (int pl = 0; pl < 2; pl++)
+          for (int k = 0; k < 4; k++) {
+            const int fa = (k & 1) ? me.cbf_cac[pl][k - 1] : cond(A, A ? A->cbf_cac[pl][k + 1] : 0);
+            const int fb = (k >> 1) ? me.cbf_cac[pl][k - 2] : cond(B, B ? B->cbf_cac[pl][k + 2] : 0);
+            me.cbf_cac[pl][k] = (uint8_t)residual_block(4, 15, coeff + (16 + 4 * pl + k) * 16 + 1, 0, fa + 2 * fb, true);
+          }
+      }
+    } else {
+      prev_delta_nonzero = false;
+    }
+    *qp = (uint8_t)qp_prev;
+    info[addr] = me;
+  }
+
+  int transform8 = 0;
+};
+
+struct Stream {
+  Sps sps;
+  Pps pps;
+  std::vector<const Nal*> idr;
+};
+
+int analyse(const std::vector<Nal>& nals, Stream& st) {
+  for (const Nal& nal : nals) {
+    int rc = DRYV_OK;
+    if (nal.type == 7 && st.idr.empty()) rc = parse_sps(nal, st.sps);
+    else if (nal.type == 8 && st.idr.empty()) rc = parse_pps(nal, st.pps);
+    else if (nal.type == 5) st.idr.push_back(&nal);
+    else if (nal.type == 1) return DRYV_ERR_UNSUPPORTED;  // non-IDR pictures: the path reconstructs IDR pictures only
+    if (rc != DRYV_OK) return rc;
+  }
+  if (!st.sps.ok || !st.pps.ok || st.idr.empty()) return DRYV_ERR_ARG;
+  return DRYV_OK;
+}
+
+int parse_picture(const Stream& st, const Nal& nal, uint8_t* mb_type, uint8_t* t8x8, uint8_t* chroma_mode, uint8_t* qp,
+                  uint8_t* pred_syntax, int16_t* coeff) {
+  Bits b(nal.rbsp.data(), nal.rbsp.size());
+  // slice_header (7.3.3), IDR picture
+  if (b.ue() != 0) return DRYV_ERR_UNSUPPORTED;  // first_mb_in_slice: one slice per picture
+  const uint32_t slice_type = b.ue();
+  if (slice_type != 2 && slice_type != 7) return DRYV_ERR_UNSUPPORTED;
+  b.ue();                             // pic_parameter_set_id
+  b.u(st.sps.log2_max_frame_num);     // frame_num
+  b.ue();                             // idr_pic_id
+  if (st.sps.poc_type == 0) {
+    b.u(st.sps.log2_max_poc_lsb);
+    if (st.pps.bottom_field_pic_order) b.se();
+  } else if (st.sps.poc_type == 1 && !st.sps.delta_pic_order_always_zero) {
+    b.se();
+    if (st.pps.bottom_field_pic_order) b.se();
+  }
+  if (st.pps.redundant_pic_cnt) b.ue();
+  if (nal.ref_idc != 0) b.u(2);       // dec_ref_pic_marking of an IDR picture
+  const int slice_qp = st.pps.pic_init_qp + b.se();
+  if (st.pps.deblocking_control) {
+    if (b.ue() != 1) {                // dryv has no deblocking filter: such a stream would not reconstruct to what it codes
+      b.se();
+      b.se();
+    }
+  }
+  while (b.pos & 7) b.bit();          // cabac_alignment_one_bit
+  if (b.bad || slice_qp < 0 || slice_qp > 51) return DRYV_ERR_ARG;
+  SliceParser sp;
+  sp.W = st.sps.w_mbs;
+  sp.H = st.sps.h_mbs;
+  sp.info.assign((size_t)sp.W * sp.H, MbCtx());
+  sp.transform8 = st.pps.transform_8x8_mode;
+  sp.qp_prev = slice_qp;
+  sp.c.init(&b, slice_qp);
+  const int n = sp.W * sp.H;
+  for (int addr = 0; addr < n; addr++) {
+    sp.macroblock(addr, mb_type + addr, t8x8 + addr, chroma_mode + addr, qp + addr, pred_syntax + (size_t)addr * 16,
+                  coeff + (size_t)addr * DRYV_COEFFS_PER_MB);
+    if (sp.unsupported) return DRYV_ERR_UNSUPPORTED;
+    const int end = sp.c.terminate();  // end_of_slice_flag
+    if (b.bad) return DRYV_ERR_ARG;
+    if (end != (addr == n - 1)) return DRYV_ERR_ARG;  // slice ends early / runs past the picture
+  }
+  return DRYV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dryv_cabac_scan(const uint8_t* annexb, size_t len, dryv_pic_params* pp, uint32_t* n_pictures) {
+  if (!annexb || !pp || !n_pictures || len < 8) return DRYV_ERR_ARG;
+  std::vector<Nal> nals;
+  split_nals(annexb, len, nals);
+  Stream st;
+  const int rc = analyse(nals, st);
+  if (rc != DRYV_OK) return rc;
+  memset(pp, 0, sizeof *pp);
+  pp->pic_width_in_mbs = (uint16_t)st.sps.w_mbs;
+  pp->pic_height_in_mbs = (uint16_t)st.sps.h_mbs;
+  pp->chroma_qp_index_offset = (int8_t)st.pps.cb_off;
+  pp->second_chroma_qp_index_offset = (int8_t)st.pps.cr_off;
+  memset(pp->scaling_list4x4, 16, sizeof pp->scaling_list4x4);  // Flat_4x4_16 / Flat_8x8_16 (slice/header.rs:317-332)
+  memset(pp->scaling_list8x8, 16, sizeof pp->scaling_list8x8);
+  *n_pictures = (uint32_t)st.idr.size();
+  return DRYV_OK;
+}
+
+int dryv_cabac_parse(const uint8_t* annexb, size_t len, const dryv_pic_params* pp, uint32_t n_pictures, uint8_t* mb_type,
+                     uint8_t* transform_size_8x8_flag, uint8_t* intra_chroma_pred_mode, uint8_t* qp, uint8_t* pred_syntax,
+                     int16_t* coeff, int threads) {
+  if (!annexb || !pp || !mb_type || !transform_size_8x8_flag || !intra_chroma_pred_mode || !qp || !pred_syntax || !coeff ||
+      n_pictures == 0)
+    return DRYV_ERR_ARG;
+  std::vector<Nal> nals;
+  split_nals(annexb, len, nals);
+  Stream st;
+  int rc = analyse(nals, st);
+  if (rc != DRYV_OK) return rc;
+  if (st.sps.w_mbs != pp->pic_width_in_mbs || st.sps.h_mbs != pp->pic_height_in_mbs || st.idr.size() != n_pictures)
+    return DRYV_ERR_ARG;
+  const size_t n_mb = (size_t)st.sps.w_mbs * st.sps.h_mbs;
+  std::atomic<uint32_t> next(0);
+  std::atomic<int> status(DRYV_OK);
+  auto work = [&]() {
+    for (;;) {
+      const uint32_t f = next.fetch_add(1);
+      if (f >= n_pictures) break;
+      const size_t o = (size_t)f * n_mb;
+      const int r = parse_picture(st, *st.idr[f], mb_type + o, transform_size_8x8_flag + o, intra_chroma_pred_mode + o, qp + o,
+                                  pred_syntax + o * 16, coeff + o * DRYV_COEFFS_PER_MB);
+      if (r != DRYV_OK) {
+        int expect = DRYV_OK;
+        status.compare_exchange_strong(expect, r);
+      }
+    }
+  };
+  if (threads <= 1 || n_pictures == 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    const uint32_t nt = (uint32_t)threads < n_pictures ? (uint32_t)threads : n_pictures;
+    for (uint32_t t = 0; t < nt; t++) pool.emplace_back(work);
+    for (auto& th : pool) th.join();
+  }
+  return status.load();
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+"""CPU host side of the path (include/dryv_cabac_host.h): Annex-B H.264 bytes -> SyntaxBatch.
+
+The caller of the reconstruction path in the reference is its CABAC parser (src/video/cabac/mod.rs:89-210); this binds the
+C++ restatement of it for IDR I-slice pictures (dryv_b200/csrc/cabac_host.cpp). CPU code by design: entropy decoding stays
+on the host, the GPU gets the syntax buffers."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .abi import PicParams, SyntaxBatch
+from .recon import OK, ReconError, load_library
+
+
+def scan(stream: bytes):
+    """-> (PicParams, number of IDR pictures) of an Annex-B stream."""
+    lib = load_library()
+    buf = np.frombuffer(stream, np.uint8)
+    pp, n = PicParams(), C.c_uint32()
+    rc = lib.dryv_cabac_scan(buf.ctypes.data, buf.size, C.byref(pp), C.byref(n))
+    if rc != OK:
+        raise ReconError(rc, "dryv_cabac_scan: not a supported H.264 stream")
+    return pp, int(n.value)
+
+
+def parse(stream: bytes, threads: int = 0, out: SyntaxBatch | None = None) -> SyntaxBatch:
+    """CABAC-parses every IDR picture of the stream into syntax buffers (dense levels)."""
+    lib = load_library()
+    pp, n = scan(stream)
+    b = out if out is not None else SyntaxBatch.empty(pp, n)
+    buf = np.frombuffer(stream, np.uint8)
+    rc = lib.dryv_cabac_parse(buf.ctypes.data, buf.size, C.byref(pp), n, b.mb_type.ctypes.data,
+                              b.transform_size_8x8_flag.ctypes.data, b.intra_chroma_pred_mode.ctypes.data,
+                              b.qp.ctypes.data, b.pred_syntax.ctypes.data, b.coeff.ctypes.data,
+                              threads or (os.cpu_count() or 1))
+    if rc != OK:
+        raise ReconError(rc, "dryv_cabac_parse")
+    return b

@@ -28,6 +28,7 @@ EXPORTS = [
     "dryv_recon_wavefront_times", "dryv_recon_pack_levels", "dryv_recon_unpack_levels", "dryv_recon_submit_compact",
     "dryv_recon_expand_levels_device", "dryv_recon_wait_oldest",
 ]
+HOST_EXPORTS = ["dryv_cabac_scan", "dryv_cabac_parse"]  # include/dryv_cabac_host.h
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -35,9 +36,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp", "levels_pack.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "recon_tables.h")] + [
-        os.path.join(_HERE, "..", "include", "dryv_recon.h")]
+    srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp", "levels_pack.cpp", "cabac_host.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "recon_tables.h", "cabac_tables.inc")] + [
+        os.path.join(_HERE, "..", "include", "dryv_recon.h"), os.path.join(_HERE, "..", "include", "dryv_cabac_host.h")]
     if not force and os.path.exists(LIB_PATH) and all(
             os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -99,6 +100,10 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_launch_count.argtypes = [vp]
     lib.dryv_recon_wavefront_times.restype = C.c_int
     lib.dryv_recon_wavefront_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    lib.dryv_cabac_scan.restype = C.c_int
+    lib.dryv_cabac_scan.argtypes = [vp, sz, C.POINTER(PicParams), C.POINTER(u32)]
+    lib.dryv_cabac_parse.restype = C.c_int
+    lib.dryv_cabac_parse.argtypes = [vp, sz, C.POINTER(PicParams), u32, vp, vp, vp, vp, vp, vp, C.c_int]
     lib.dryv_recon_pack_levels.restype = C.c_int
     lib.dryv_recon_pack_levels.argtypes = [vp, sz, vp, vp, sz, C.c_int]
     lib.dryv_recon_unpack_levels.restype = C.c_int

@@ -1,0 +1,49 @@
+/*
+ * dryv_cabac_host.h — CPU host side of the reconstruction path: Annex-B H.264 bytes -> the syntax buffers of
+ * include/dryv_recon.h.
+ *
+ * This is the CALLER of the hot path, restated in C++ for IDR I-slice pictures: what the
+ * reference does in
+ *   NAL split / emulation prevention     src/video/sample/nal.rs:230-253, src/byte/bit.rs:144-149
+ *   SPS / PPS                            src/video/atom/avcc/sps.rs:42-121, src/video/atom/avcc/pps.rs:30-58
+ *   slice header                         src/video/slice/header.rs:145-315
+ *   macroblock loop                      src/video/slice/mod.rs:184-317
+ *   CabacContext::macroblock_layer       src/video/cabac/mod.rs:89-210  (up to, and instead of, frame.decode at :208)
+ *   residual / residual_cabac            src/video/cabac/mod.rs:433-675
+ *   arithmetic decoding engine           src/video/cabac/mod.rs:1207-1308
+ * with the macroblock's parsed syntax appended to structure-of-arrays buffers instead of being reconstructed on the
+ * spot. It stays on the CPU, as in the reference (CABAC is serial per slice); independent IDR pictures are parsed on
+ * separate host threads. The MP4 container layer (src/video/atom, src/video/sample/mod.rs) is not restated: input is
+ * an Annex-B byte stream (start-code separated NAL units).
+ *
+ * Supported, like the reference's reconstruction: 8-bit 4:2:0, frame macroblocks, CABAC, one slice per picture
+ * (first_mb_in_slice == 0), I slices with I_NxN (4x4 / 8x8 transform) and I_16x16 macroblocks, no scaling matrices.
+ * Anything else (I_PCM, inter slices, CAVLC, slice groups, scaling lists, ...) returns DRYV_ERR_UNSUPPORTED.
+ */
+#ifndef DRYV_CABAC_HOST_H
+#define DRYV_CABAC_HOST_H
+
+#include "dryv_recon.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Walks the NAL units, parses the (last) SPS and PPS before the first IDR slice into `pp`, and counts the IDR
+ * pictures. Returns DRYV_OK, DRYV_ERR_ARG (no SPS/PPS/IDR, truncated data) or DRYV_ERR_UNSUPPORTED. */
+int dryv_cabac_scan(const uint8_t* annexb, size_t len, dryv_pic_params* pp, uint32_t* n_pictures);
+
+/* Parses every IDR picture of the stream (in stream order) into the caller's structure-of-arrays buffers, laid out as
+ * dryv_mb_soa describes for `n_pictures` pictures of `pp` geometry: mb_type / transform_size_8x8_flag /
+ * intra_chroma_pred_mode / qp: n_pictures * n_mb bytes each; pred_syntax: 16 bytes per macroblock; coeff: 384 int16 per
+ * macroblock (dense; convert with dryv_recon_pack_levels for dryv_recon_submit_compact). `threads` pictures are parsed
+ * concurrently (<= 1: on the calling thread). Returns DRYV_OK, DRYV_ERR_ARG (stream does not match pp / n_pictures,
+ * bitstream ends early) or DRYV_ERR_UNSUPPORTED (mb_type I_PCM, non-I slice, ...). Needs no GPU. */
+int dryv_cabac_parse(const uint8_t* annexb, size_t len, const dryv_pic_params* pp, uint32_t n_pictures,
+                     uint8_t* mb_type, uint8_t* transform_size_8x8_flag, uint8_t* intra_chroma_pred_mode, uint8_t* qp,
+                     uint8_t* pred_syntax, int16_t* coeff, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRYV_CABAC_HOST_H */

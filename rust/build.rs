@@ -18,6 +18,7 @@ fn main() {
     .arg(csrc.join("recon.cu"))
     .arg(csrc.join("recon_tables.cpp"))
     .arg(csrc.join("levels_pack.cpp"))
+    .arg(csrc.join("cabac_host.cpp"))
     .arg("-o")
     .arg(&lib)
     .status()

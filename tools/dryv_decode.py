@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""The whole path on one Annex-B H.264 file, the way `dryv <file>` works on an MP4 (src/main.rs:34-51,
+src/video/decoder.rs:87-150): CABAC-parse the IDR pictures on the CPU (dryv_b200/csrc/cabac_host.cpp), reconstruct them
+on the GPU through the compact level stream, and write the first picture to ./temp/yuv_frame in the reference's byte
+layout (src/video/frame/mod.rs:48-70).
+
+    python tools/dryv_decode.py stream.h264 [out_path]        # needs a B200
+    python tools/dryv_decode.py --make-sample sample.h264     # writes a 640x368 synthetic CABAC stream (no GPU needed)
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--make-sample":
+        from avc import stream
+        from dryv_b200 import synth
+        from dryv_b200.abi import PicParams
+        b = synth.generate(PicParams.make(40, 23), 4, 360, standard_only=True)
+        data = stream.encode_stream(b)
+        open(sys.argv[2], "wb").write(data)
+        print(f"{sys.argv[2]}: {len(data)} bytes, 4 IDR pictures of 640x368")
+        return 0
+    from dryv_b200 import host, recon
+    data = open(sys.argv[1], "rb").read()
+    out_path = sys.argv[2] if len(sys.argv) > 2 else "temp/yuv_frame"
+    t0 = time.perf_counter()
+    batch = host.parse(data)
+    t1 = time.perf_counter()
+    levels = recon.pack_levels(batch.coeff)
+    ctx = recon.ReconContext(0)
+    frames = ctx.reconstruct_compact(batch, levels)
+    t2 = time.perf_counter()
+    recon.write_yuv_file(frames[0], out_path)
+    pp = batch.pp
+    print(f"{batch.n_frames} IDR pictures of {pp.pic_width_in_mbs * 16}x{pp.pic_height_in_mbs * 16}: CABAC parse "
+          f"{(t1 - t0) * 1e3:.1f} ms (CPU), reconstruction {(t2 - t1) * 1e3:.1f} ms incl. context creation (GPU); "
+          f"first picture -> {out_path} ({frames[0].nbytes} bytes)")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

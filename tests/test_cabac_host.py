@@ -134,3 +134,36 @@ def test_fixture_bytes_to_cuda_equals_libavcodec(gpu_ctx):
     _, data, luma = load_fixture()
     parsed = host.parse(data)
     assert np.array_equal(luma_of(gpu_ctx.reconstruct(parsed), parsed.pp), luma)
+
+
+def test_corrupted_streams_never_crash(recon_lib):
+    # every entry point must survive arbitrary bytes: bounded loops, bounds-checked reads, an error code at worst
+    b = synth.generate(PicParams.make(5, 4), 2, 4242, stress_pct=50)
+    data = bytearray(stream.encode_stream(b))
+    pp, n = host.scan(bytes(data))
+    out = synth.generate(pp, n, 0)
+    rng = np.random.default_rng(99)
+    seen = set()
+    for trial in range(300):
+        d = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            kind = int(rng.integers(0, 3))
+            pos = int(rng.integers(0, len(d)))
+            if kind == 0:
+                d[pos] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                d[pos] = int(rng.integers(0, 256))
+            else:
+                del d[pos:pos + int(rng.integers(1, 40))]
+        a = np.frombuffer(bytes(d), np.uint8)
+        pp2, n2 = PicParams(), C.c_uint32()
+        rc = recon_lib.dryv_cabac_scan(a.ctypes.data, a.size, C.byref(pp2), C.byref(n2))
+        assert rc in (recon.OK, recon.ERR_ARG, recon.ERR_UNSUPPORTED)
+        rc = recon_lib.dryv_cabac_parse(a.ctypes.data, a.size, C.byref(pp), n, out.mb_type.ctypes.data,
+                                        out.transform_size_8x8_flag.ctypes.data, out.intra_chroma_pred_mode.ctypes.data,
+                                        out.qp.ctypes.data, out.pred_syntax.ctypes.data, out.coeff.ctypes.data, 2)
+        assert rc in (recon.OK, recon.ERR_ARG, recon.ERR_UNSUPPORTED)
+        seen.add(rc)
+        if rc == recon.OK:      # whatever was parsed must be syntax the reconstruction accepts
+            assert out.mb_type.max() <= 24 and out.intra_chroma_pred_mode.max() <= 3 and out.qp.max() <= 51
+    assert recon.ERR_ARG in seen

@@ -144,7 +144,11 @@ __device__ __forceinline__ void bar_sync_empty(unsigned si) {
     case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
     case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
     case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+    case 5: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
+    case 6: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
   }
 }
 __device__ __forceinline__ void bar_arrive_empty(unsigned si) {
@@ -152,10 +156,14 @@ __device__ __forceinline__ void bar_arrive_empty(unsigned si) {
     case 0: asm volatile("bar.arrive 1, 64;" ::: "memory"); break;
     case 1: asm volatile("bar.arrive 2, 64;" ::: "memory"); break;
     case 2: asm volatile("bar.arrive 3, 64;" ::: "memory"); break;
-    default: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.arrive 5, 64;" ::: "memory"); break;
+    case 5: asm volatile("bar.arrive 6, 64;" ::: "memory"); break;
+    case 6: asm volatile("bar.arrive 7, 64;" ::: "memory"); break;
+    default: asm volatile("bar.arrive 8, 64;" ::: "memory"); break;
   }
 }
-static_assert(kSlots == 4, "named-barrier ids above assume four ring slots");
+static_assert(kSlots >= 2 && kSlots <= 8, "named-barrier ids above cover up to eight ring slots");
 
 // Long waits (the front warp runs kSlots macroblocks ahead and then blocks on the pixel warp for a whole
 // macroblock time): the hinted try_wait above is woken by every mbarrier event of the SM and re-issues ~100

@@ -50,7 +50,13 @@ struct ResidCtaSmem {
 
 // wavefront kernel: a "row team" = one CTA of two warps walking one macroblock row.
 // The front warp hands each macroblock to the pixel warp through a ring of kSlots slots.
-constexpr int kSlots = 4;
+// Ring depth, measured (64 / 16 x 1080p, ms per step): 2 slots 0.900 / 0.504, 3: 0.917 / 0.504, 4: 0.903 / 0.498,
+// 5: 0.924 / 0.505, 6 (9 teams per SM: one named barrier per slot) 0.926 / 0.500, 8 (7 teams) 0.979 / 0.477. Flat: the
+// depth of the ring is not what lets the classes overlap.
+#ifndef DRYV_SLOTS
+#define DRYV_SLOTS 4
+#endif
+constexpr int kSlots = DRYV_SLOTS;
 constexpr int kTeamThreads = 64;
 struct Slot {
   alignas(16) int16_t res[256];  // luma residual [16][16]

@@ -329,6 +329,19 @@ def main():
                      "kernel_ms": wave_ms_avg, "kernel_share_of_step": wave_ms_avg / ms_per_step,
                      "algorithmic_bytes_per_mb": BYTES_PER_MB_FULL, "mbs_per_launch": n_mb_step},
     }
+    # the wavefront occupancy bound: a picture is a chain of W + 2(H - 1) dependent macroblock steps, and
+    # the kernel runs min(rows, SMs x 10 resident row teams) rows at a time
+    teams = min(n_frames * args.height_mbs, torch.cuda.get_device_properties(dev).multi_processor_count * 10)
+    steps = args.width_mbs + 2 * (args.height_mbs - 1)
+    mb_period_us = kernel_s * 1e6 * teams / n_mb_step
+    line["wavefront"] = {
+        "dependent_steps_per_picture": steps, "row_teams": teams,
+        "rows_per_team": n_frames * args.height_mbs / teams,
+        "mb_period_us_per_team": mb_period_us,
+        "critical_path_ms_at_that_period": steps * mb_period_us * 1e-3,
+        "note": "kernel time = rows_per_team x pic_width_in_mbs x mb_period (+ start-up stagger); the period is the serial "
+                "instruction stream of a row team's slower warp (DESIGN.md §5), ~25x what the HBM roofline would allow",
+    }
     if e2e_ms is not None:
         syntax_bytes = int(hbatch.input_bytes - hbatch.coeff.nbytes)
         line["e2e"] = {"value": total_px / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,

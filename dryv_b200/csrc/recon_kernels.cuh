@@ -368,7 +368,7 @@ __device__ __forceinline__ void residual_stage(const DeviceTables& tab, uint8_t*
 __host__ __device__ constexpr int luma_at(int x, int y) { return (y + 1) * kLumaStride + 16 + x; }
 __host__ __device__ constexpr int chroma_at(int x, int y) { return (y + 1) * kChromaStride + 8 + x; }
 
-constexpr int kTap4Row = 16 * 4 * 2;          // bytes per row of DeviceTables::tap4
+constexpr int kTap4Row = 16 * 4 * 4;          // bytes per row of DeviceTables::tap4
 constexpr int kTap8Row = 32 * 8;              // bytes per mode row of DeviceTables::tap8
 
 // legal-mode mask of the nine 4x4/8x8 modes given neighbour availability (the reference writes no
@@ -395,7 +395,7 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
   pl.half = half;
   pl.i4_pix = py * kLumaStride + px;
   pl.i4_res2 = 2 * (py * 16 + px);
-  pl.i4_tab = p * 8;
+  pl.i4_tab = p * 16;
   // edge sample `lane` of an 8x8 block: 0..15 top, 16..23 left, 24 corner (pred8x8.rs:166-200)
   int s, pv, nx;
   if (lane < 16) {
@@ -426,28 +426,22 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
 // ---- Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110 -------------------------------------------
 // Ten dependency steps, two blocks per step where the decode-order availability rules allow it
 // (kI4BlkA / kI4BlkB); one pixel per lane, 16 lanes per block. A rolled loop: the kernel is instruction-fetch
-// bound when a dozen teams share an SM, so code size matters more than the handful of
-// instructions an unrolled version saves. Everything that depends on the mode or on availability was folded
-// into the tap row chosen by the front warp (i4_tap_row): a step is loads, three adds and a clamp.
+// bound when a dozen teams share an SM (an unrolled version with immediates was measured: faster on Intra4x4-only
+// pictures, slower on the mix), so code size matters more than the handful of instructions an unrolled
+// version saves. Everything that depends on the mode or on availability was folded into the tap row chosen by the front
+// warp (i4_tap_row), the schedule entries and tap records are 32-bit fields used as loaded, and a half-warp without a
+// block in a step works on a dummy block in the tile's padding: a step is loads, three adds and a clamp.
 //   rows: this half-warp's ten tap-row bytes (Slot::rows + 0 or 8)
 struct I4Regs {
-  const uint8_t *a0, *a1, *a2;  // the three samples of this lane's pixel
-  uint8_t* dst;                 // the pixel
-  int kind, r;                  // tap-row kind, residual
-  bool active;
+  uint4 tap;      // three sample offsets (biased), kind
+  uint32_t org;   // tile offset of the block origin
+  int r;          // residual
 };
-__device__ __forceinline__ void i4_fetch(I4Regs& q, const I4Step* e, const uint8_t* tap4, int row, const uint8_t* ltb,
-                                         uint8_t* ltp, const uint8_t* resp) {
-  const uint16_t* tp = reinterpret_cast<const uint16_t*>(tap4 + row * kTap4Row);
-  const uint32_t org = e->org;
-  const uint8_t* ob = ltb + org;
-  q.a0 = ob + tp[0];
-  q.a1 = ob + tp[1];
-  q.a2 = ob + tp[2];
-  q.kind = tp[3];
-  q.r = *reinterpret_cast<const int16_t*>(resp + e->res2);
-  q.dst = ltp + org;
-  q.active = e->active != 0;
+__device__ __forceinline__ void i4_fetch(I4Regs& q, const I4Step* e, const uint8_t* tap4, int row, const uint8_t* resp) {
+  q.tap = *reinterpret_cast<const uint4*>(tap4 + row * kTap4Row);
+  const uint2 st = *reinterpret_cast<const uint2*>(e);
+  q.org = st.x;
+  q.r = *reinterpret_cast<const int16_t*>(resp + st.y);
 }
 __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma,
                                              const PixLane& pl, const uint8_t* rows) {
@@ -455,28 +449,28 @@ __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* l
   const uint8_t* tap4 = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0]) + pl.i4_tab;
   const uint8_t* resp = reinterpret_cast<const uint8_t*>(res_luma) + pl.i4_res2;
   const uint8_t* ltb = lt - kTap4Bias;
-  uint8_t* ltp = lt + pl.i4_pix;
-  // software pipeline: the table look-ups of step s+1 (which do not depend on any pixel) are issued under the
-  // latency of the pixel loads of step s, so a step's dependent chain is pixel load -> three adds -> clamp -> store
+  // software pipeline: the table look-ups of step s+1 (which do not depend on any pixel) are issued under the latency
+  // of the pixel loads of step s, so a step's dependent chain is pixel load -> three adds -> clamp -> store
   I4Regs cur;
-  i4_fetch(cur, st, tap4, rows[0], ltb, ltp, resp);
+  i4_fetch(cur, st, tap4, rows[0], resp);
 #pragma unroll 1
   for (int s = 0; s < 10; s++) {
-    const int e0 = *cur.a0, e1 = *cur.a1, e2 = *cur.a2;
-    I4Regs nxt;
-    const int sn = s < 9 ? s + 1 : 9;
-    i4_fetch(nxt, st + 2 * sn, tap4, rows[sn], ltb, ltp, resp);
-    int pred = (e0 + 2 * e1 + e2 + 2) >> 2, kind = cur.kind;
+    const uint8_t* ob = ltb + cur.org;
+    const int e0 = ob[cur.tap.x], e1 = ob[cur.tap.y], e2 = ob[cur.tap.z];
+    int kind = (int)cur.tap.w;
+    const int r = cur.r;
+    uint8_t* dst = lt + cur.org + pl.i4_pix;
+    i4_fetch(cur, st + 2 * (s + 1), tap4, rows[s + 1], resp);  // step 10 = step 9 again (table and Slot::rows padding)
+    int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
     if (kind >= kI4KindDc) {  // DC, pred4x4.rs:116-167
-      const uint8_t* eb = cur.dst - pl.i4_pix;
+      const uint8_t* eb = dst - pl.i4_pix;
       const int sT = dp4a_us(*reinterpret_cast<const uint32_t*>(eb - kLumaStride), 0x01010101, 0);
       const int sL = eb[-1] + eb[kLumaStride - 1] + eb[2 * kLumaStride - 1] + eb[3 * kLumaStride - 1];
       pred = kind == kI4KindDc ? ((sT + sL + 4) >> 3)
                                : (kind == kI4KindDcTop ? ((sT + 2) >> 2) : (kind == kI4KindDcLeft ? ((sL + 2) >> 2) : 128));
       kind = 1;
     }
-    if (cur.active) *cur.dst = (uint8_t)clip255(pred * kind + cur.r);
-    cur = nxt;
+    *dst = (uint8_t)clip255(pred * kind + r);
     __syncwarp();
   }
 }

@@ -27,13 +27,14 @@ constexpr int kTap4Bias = 256;
 constexpr int kI4BlkA[10] = {0, 1, 2, 3, 8, 9, 10, 11, 14, 15};
 constexpr int kI4BlkB[10] = {-1, -1, 4, 5, 6, 7, 12, 13, -1, -1};
 
-// One Intra4x4 schedule entry (see DeviceTables::i4tab).
+// One Intra4x4 schedule entry (see DeviceTables::i4tab): 32-bit fields, used as they are loaded.
+// A half-warp without a block in a step (B in steps 0, 1, 8, 9) gets kI4DummyOrg: it predicts into an unused corner of the
+// luma tile (columns 16.. of rows 0..15 are padding), so the step needs no "active" predicate.
 struct I4Step {
-  uint16_t org;     // tile offset of the block origin
-  uint16_t res2;    // byte offset of the block's residual inside the 16x16 int16 residual tile
-  uint16_t active;  // this half-warp has a block in this step
-  uint16_t pad;
+  uint32_t org;     // tile offset of the block origin
+  uint32_t res2;    // byte offset of the block's residual inside the 16x16 int16 residual tile
 };
+constexpr uint32_t kI4DummyOrg = (4 + 1) * kLumaTileStride + 16 + 20;  // pixel (20, 4): rows 4..7, columns 20..23
 // Rows of DeviceTables::tap4. A row is chosen per block by the front warp from the block's mode and its
 // neighbour availability, so the pixel warp does no legality or availability arithmetic at all.
 //   0..8   modes 0..8, top-right available      9..17  modes 0..8, top-right replaced by top sample 3
@@ -46,13 +47,13 @@ enum { kI4KindIllegal = 0, kI4KindTaps = 1, kI4KindDc = 2, kI4KindDcTop = 3, kI4
 struct DeviceTables {
   int32_t t4[52][16];         // [qP][zig-zag k] = LevelScale4x4[qP%6][pos(k)] << max(qP/6 - 4, 0)
   uint16_t ls8[6][64];        // [qP%6][i*8+j]   = LevelScale8x8
-  uint16_t tap4[kI4Rows][16][4];  // [row][pixel y*4+x] = three sample offsets, kind
+  uint32_t tap4[kI4Rows][16][4];  // [row][pixel y*4+x] = three sample offsets, kind (one 128-bit load, no unpacking)
   uint8_t tap8[9][32][8];     // [mode][lane][pixel q (0,1) * 3 + tap], 2 pad bytes
   uint8_t zz8inv[8][8];       // [i][j] -> zig-zag index
   uint8_t qpc[52];            // qPI -> QPC
   uint8_t i4sched[10][2];     // copy of kI4BlkA / kI4BlkB (0xff = none), for the host-side tests
   uint8_t pad[8];
-  I4Step i4tab[10][2];        // Intra4x4 schedule: [step][half-warp]
+  I4Step i4tab[11][2];        // Intra4x4 schedule: [step][half-warp]; entry 10 repeats 9 (look-ahead of the last step)
   // [av][k], av = A | B<<1 | C<<2 | D<<3: legal-mode mask (9 bits; bit 0 doubles as "top available", bit 1 as
   // "left available") | no-top-right variant << 9 of the block whose tap row is byte k of Slot::rows
   // (k = 0..9: half-warp A's steps, k = 10..15: half-warp B's steps 2..7)

@@ -33,8 +33,8 @@ UNIT = "Mpixels/s"
 BYTES_PER_MB_FULL = 1172   # 768 levels + 20 syntax + 384 pixels out (SURVEY.md §8d / BASELINE.md §3)
 BYTES_PER_MB_RESID = 1540  # 768 + 4 + 384 prediction in + 384 out
 # DRAM bytes of one recon_wavefront_kernel launch on the default workload, from the committed ncu capture
-# (profiles/r01_v13_wavefront_summary.txt: 431.08 MB read + 217.80 MB written)
-TRAFFIC_BYTES_PER_LAUNCH = 648_881_408
+# (profiles/r01_v14_wavefront_summary.txt: 432.22 MB read + 216.21 MB written)
+TRAFFIC_BYTES_PER_LAUNCH = 648_432_384
 
 
 def parse_args():
@@ -323,7 +323,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": TRAFFIC_BYTES_PER_LAUNCH if (n_frames, args.width_mbs, args.height_mbs) == (64, 120, 68) else None,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch "
-                                       "(profiles/r01_v13_wavefront_summary.txt); algorithmic bytes per launch = "
+                                       "(profiles/r01_v14_wavefront_summary.txt); algorithmic bytes per launch = "
                                        f"{n_mb_step * BYTES_PER_MB_FULL}",
                      "peak_source": peak_src, "kernel": "dryv::recon_wavefront_kernel",
                      "kernel_ms": wave_ms_avg, "kernel_share_of_step": wave_ms_avg / ms_per_step,

@@ -63,6 +63,8 @@ struct Nal {
   std::vector<uint8_t> rbsp;
 };
 
+void push_rbsp(int header_byte, const uint8_t* d, size_t n, std::vector<Nal>& out);
+
 // Annex B: NAL units separated by 00 00 01 start codes; 00 00 03 -> 00 00 inside a unit
 void split_nals(const uint8_t* d, size_t len, std::vector<Nal>& out) {
   size_t i = 0;
@@ -74,24 +76,156 @@ void split_nals(const uint8_t* d, size_t len, std::vector<Nal>& out) {
     while (e < len && !start_at(e)) e++;
     size_t end = e;
     while (end > i && d[end - 1] == 0) end--;  // trailing zero bytes belong to the next start code
-    if (end > i) {
-      Nal nal;
-      nal.ref_idc = (d[i] >> 5) & 3;
-      nal.type = d[i] & 31;
-      nal.rbsp.reserve(end - i);
-      int zeros = 0;
-      for (size_t k = i + 1; k < end; k++) {
-        if (zeros >= 2 && d[k] == 3) {
-          zeros = 0;
-          continue;
-        }
-        nal.rbsp.push_back(d[k]);
-        zeros = d[k] == 0 ? zeros + 1 : 0;
-      }
-      out.push_back(std::move(nal));
-    }
+    if (end > i) push_rbsp(d[i], d + i + 1, end - i - 1, out);
     i = e;
   }
+}
+
+// one NAL unit (header byte + payload with emulation prevention) -> Nal with the RBSP
+void push_rbsp(int header_byte, const uint8_t* d, size_t n, std::vector<Nal>& out) {
+  Nal nal;
+  nal.ref_idc = (header_byte >> 5) & 3;
+  nal.type = header_byte & 31;
+  nal.rbsp.reserve(n);
+  int zeros = 0;
+  for (size_t k = 0; k < n; k++) {
+    if (zeros >= 2 && d[k] == 3) {
+      zeros = 0;
+      continue;
+    }
+    nal.rbsp.push_back(d[k]);
+    zeros = d[k] == 0 ? zeros + 1 : 0;
+  }
+  out.push_back(std::move(nal));
+}
+
+// ---- MP4 / QuickTime container (ISO/IEC 14496-12, avcC per 14496-15): the video track's samples as NAL units -------
+// What the reference does in src/video/atom/** (atom tree), src/video/atom/avcc/mod.rs:26-46 (avcC) and
+// src/video/sample/mod.rs:74-110 (stco / stsc / stsz -> sample bytes), src/video/sample/nal.rs:230-253 (length-prefixed
+// NAL units). Only what the path needs: the first 'vide' track with an avc1 sample entry, every sample's NAL units.
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+inline uint64_t be64(const uint8_t* p) { return ((uint64_t)be32(p) << 32) | be32(p + 4); }
+
+struct BoxIter {  // children of a container: [p, end)
+  const uint8_t* p;
+  const uint8_t* end;
+  bool next(uint32_t& type, const uint8_t*& body, const uint8_t*& body_end) {
+    if (end - p < 8) return false;
+    uint64_t size = be32(p);
+    type = be32(p + 4);
+    size_t hdr = 8;
+    if (size == 1) {
+      if (end - p < 16) return false;
+      size = be64(p + 8);
+      hdr = 16;
+    } else if (size == 0) {
+      size = (uint64_t)(end - p);
+    }
+    if (size < hdr || size > (uint64_t)(end - p)) return false;
+    body = p + hdr;
+    body_end = p + size;
+    p += size;
+    return true;
+  }
+};
+constexpr uint32_t fourcc(char a, char b, char c, char d) {
+  return ((uint32_t)(uint8_t)a << 24) | ((uint32_t)(uint8_t)b << 16) | ((uint32_t)(uint8_t)c << 8) | (uint32_t)(uint8_t)d;
+}
+bool find_box(const uint8_t* p, const uint8_t* end, uint32_t want, const uint8_t*& body, const uint8_t*& body_end) {
+  BoxIter it{p, end};
+  uint32_t t;
+  while (it.next(t, body, body_end))
+    if (t == want) return true;
+  return false;
+}
+
+bool looks_like_mp4(const uint8_t* d, size_t len) { return len >= 12 && be32(d + 4) == fourcc('f', 't', 'y', 'p'); }
+
+// -> DRYV_OK and the track's NAL units (SPS, PPS from avcC, then every sample's units), or an error code
+int collect_nals_mp4(const uint8_t* d, size_t len, std::vector<Nal>& out) {
+  const uint8_t *moov, *moov_end;
+  if (!find_box(d, d + len, fourcc('m', 'o', 'o', 'v'), moov, moov_end)) return DRYV_ERR_ARG;
+  BoxIter traks{moov, moov_end};
+  uint32_t t;
+  const uint8_t *b, *e;
+  while (traks.next(t, b, e)) {
+    if (t != fourcc('t', 'r', 'a', 'k')) continue;
+    const uint8_t *mdia, *mdia_e, *hdlr, *hdlr_e, *minf, *minf_e, *stbl, *stbl_e, *stsd, *stsd_e;
+    if (!find_box(b, e, fourcc('m', 'd', 'i', 'a'), mdia, mdia_e)) continue;
+    if (!find_box(mdia, mdia_e, fourcc('h', 'd', 'l', 'r'), hdlr, hdlr_e) || hdlr_e - hdlr < 12 ||
+        be32(hdlr + 8) != fourcc('v', 'i', 'd', 'e'))
+      continue;
+    if (!find_box(mdia, mdia_e, fourcc('m', 'i', 'n', 'f'), minf, minf_e) ||
+        !find_box(minf, minf_e, fourcc('s', 't', 'b', 'l'), stbl, stbl_e) ||
+        !find_box(stbl, stbl_e, fourcc('s', 't', 's', 'd'), stsd, stsd_e) || stsd_e - stsd < 8)
+      return DRYV_ERR_ARG;
+    // stsd: version/flags, entry_count, then sample entries; avc1 = 78 bytes of VisualSampleEntry fields, then boxes
+    const uint8_t *avc1, *avc1_e, *avcc, *avcc_e;
+    if (!find_box(stsd + 8, stsd_e, fourcc('a', 'v', 'c', '1'), avc1, avc1_e)) return DRYV_ERR_UNSUPPORTED;
+    if (avc1_e - avc1 < 78 || !find_box(avc1 + 78, avc1_e, fourcc('a', 'v', 'c', 'C'), avcc, avcc_e) || avcc_e - avcc < 7)
+      return DRYV_ERR_ARG;
+    const int nal_len_size = (avcc[4] & 3) + 1;
+    const uint8_t* q = avcc + 5;
+    for (int pass = 0; pass < 2; pass++) {  // SPS list (count in the low 5 bits), then PPS list
+      if (q >= avcc_e) return DRYV_ERR_ARG;
+      int cnt = pass == 0 ? (*q & 31) : *q;
+      q++;
+      for (int i = 0; i < cnt; i++) {
+        if (avcc_e - q < 2) return DRYV_ERR_ARG;
+        const size_t n = ((size_t)q[0] << 8) | q[1];
+        q += 2;
+        if ((size_t)(avcc_e - q) < n || n < 1) return DRYV_ERR_ARG;
+        push_rbsp(q[0], q + 1, n - 1, out);
+        q += n;
+      }
+    }
+    // sample table: sizes (stsz), chunk offsets (stco / co64), samples per chunk (stsc)
+    const uint8_t *stsz, *stsz_e, *stsc, *stsc_e, *stco, *stco_e;
+    if (!find_box(stbl, stbl_e, fourcc('s', 't', 's', 'z'), stsz, stsz_e) || stsz_e - stsz < 12 ||
+        !find_box(stbl, stbl_e, fourcc('s', 't', 's', 'c'), stsc, stsc_e) || stsc_e - stsc < 8)
+      return DRYV_ERR_ARG;
+    bool co64 = false;
+    if (!find_box(stbl, stbl_e, fourcc('s', 't', 'c', 'o'), stco, stco_e)) {
+      if (!find_box(stbl, stbl_e, fourcc('c', 'o', '6', '4'), stco, stco_e)) return DRYV_ERR_ARG;
+      co64 = true;
+    }
+    if (stco_e - stco < 8) return DRYV_ERR_ARG;
+    const uint32_t fixed_size = be32(stsz + 4), n_samples = be32(stsz + 8);
+    if (!fixed_size && (uint64_t)(stsz_e - stsz - 12) < 4ull * n_samples) return DRYV_ERR_ARG;
+    const uint32_t n_chunks = be32(stco + 4), n_stsc = be32(stsc + 4);
+    if ((uint64_t)(stco_e - stco - 8) < (co64 ? 8ull : 4ull) * n_chunks || (uint64_t)(stsc_e - stsc - 8) < 12ull * n_stsc)
+      return DRYV_ERR_ARG;
+    uint32_t sample = 0, run = 0;
+    for (uint32_t chunk = 1; chunk <= n_chunks && sample < n_samples; chunk++) {
+      while (run + 1 < n_stsc && be32(stsc + 8 + 12 * (run + 1)) <= chunk) run++;  // stsc runs: first_chunk is 1-based
+      const uint32_t per_chunk = n_stsc ? be32(stsc + 8 + 12 * run + 4) : 0;
+      uint64_t off = co64 ? be64(stco + 8 + 8ull * (chunk - 1)) : be32(stco + 8 + 4ull * (chunk - 1));
+      for (uint32_t k = 0; k < per_chunk && sample < n_samples; k++, sample++) {
+        const uint64_t sz = fixed_size ? fixed_size : be32(stsz + 12 + 4ull * sample);
+        if (off > len || sz > len - off) return DRYV_ERR_ARG;
+        const uint8_t* sp = d + off;
+        const uint8_t* se = sp + sz;
+        while (se - sp > nal_len_size) {  // length-prefixed NAL units
+          uint64_t n = 0;
+          for (int i = 0; i < nal_len_size; i++) n = (n << 8) | sp[i];
+          sp += nal_len_size;
+          if (n < 1 || n > (uint64_t)(se - sp)) return DRYV_ERR_ARG;
+          push_rbsp(sp[0], sp + 1, (size_t)n - 1, out);
+          sp += n;
+        }
+        off += sz;
+      }
+    }
+    return DRYV_OK;
+  }
+  return DRYV_ERR_ARG;  // no video track
+}
+
+// Annex-B byte stream or MP4 file -> NAL units
+int collect_nals(const uint8_t* d, size_t len, std::vector<Nal>& out) {
+  if (looks_like_mp4(d, len)) return collect_nals_mp4(d, len, out);
+  split_nals(d, len, out);
+  return DRYV_OK;
 }
 
 struct Sps {
@@ -498,9 +632,10 @@ extern "C" {
 int dryv_cabac_scan(const uint8_t* annexb, size_t len, dryv_pic_params* pp, uint32_t* n_pictures) {
   if (!annexb || !pp || !n_pictures || len < 8) return DRYV_ERR_ARG;
   std::vector<Nal> nals;
-  split_nals(annexb, len, nals);
+  int rc = collect_nals(annexb, len, nals);
+  if (rc != DRYV_OK) return rc;
   Stream st;
-  const int rc = analyse(nals, st);
+  rc = analyse(nals, st);
   if (rc != DRYV_OK) return rc;
   memset(pp, 0, sizeof *pp);
   pp->pic_width_in_mbs = (uint16_t)st.sps.w_mbs;
@@ -520,9 +655,10 @@ int dryv_cabac_parse(const uint8_t* annexb, size_t len, const dryv_pic_params* p
       n_pictures == 0)
     return DRYV_ERR_ARG;
   std::vector<Nal> nals;
-  split_nals(annexb, len, nals);
+  int rc = collect_nals(annexb, len, nals);
+  if (rc != DRYV_OK) return rc;
   Stream st;
-  int rc = analyse(nals, st);
+  rc = analyse(nals, st);
   if (rc != DRYV_OK) return rc;
   if (st.sps.w_mbs != pp->pic_width_in_mbs || st.sps.h_mbs != pp->pic_height_in_mbs || st.idr.size() != n_pictures)
     return DRYV_ERR_ARG;

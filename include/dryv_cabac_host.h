@@ -13,8 +13,14 @@
  *   arithmetic decoding engine           src/video/cabac/mod.rs:1207-1308
  * with the macroblock's parsed syntax appended to structure-of-arrays buffers instead of being reconstructed on the
  * spot. It stays on the CPU, as in the reference (CABAC is serial per slice); independent IDR pictures are parsed on
- * separate host threads. The MP4 container layer (src/video/atom, src/video/sample/mod.rs) is not restated: input is
- * an Annex-B byte stream (start-code separated NAL units).
+ * separate host threads.
+ *
+ * Input (`annexb`, `len` in both calls) is either an Annex-B byte stream (start-code separated NAL units) or a whole MP4 /
+ * QuickTime file, recognised by its leading ftyp box: the file `dryv <file>` opens. Of the container only what the path
+ * needs is restated — the first video track's avc1/avcC sample entry (SPS, PPS, NAL length size) and its sample table
+ * (stsz, stco/co64, stsc) with length-prefixed NAL units — i.e. src/video/atom/root.rs:17-52, atom/stbl.rs:367-420,
+ * atom/avcc/mod.rs:26-46, src/video/sample/mod.rs:74-110 and sample/nal.rs:230-253. Unlike the reference, which decodes the
+ * first sample only (src/video/decoder.rs:88), every IDR picture of the track is parsed.
  *
  * Supported, like the reference's reconstruction: 8-bit 4:2:0, frame macroblocks, CABAC, one slice per picture
  * (first_mb_in_slice == 0), I slices with I_NxN (4x4 / 8x8 transform) and I_16x16 macroblocks, no scaling matrices.

@@ -113,11 +113,13 @@ def test_malformed_and_unsupported_streams(recon_lib):
 
 @pytest.mark.gpu
 def test_bytes_to_yuv_frame_through_the_whole_path(gpu_ctx, tmp_path):
-    # BASELINE configs[0] on a self-made stream: 640x368 CABAC High-profile IDR pictures -> ./temp/yuv_frame
+    # BASELINE configs[0] on a self-made file: 640x368 8-bit 4:2:0 CABAC High-profile MP4 -> ./temp/yuv_frame
     pp = PicParams.make(40, 23)
     b = synth.generate(pp, 3, 360, standard_only=True)
     data = stream.encode_stream(b)
-    parsed = host.parse(data)
+    from avc import mp4
+    movie = mp4.mux(data, 640, 368)          # the kind of file `dryv <file>` opens
+    parsed = host.parse(movie)
     levels = recon.pack_levels(parsed.coeff)
     out = gpu_ctx.reconstruct_compact(parsed, levels)
     assert np.array_equal(out, oracle.reconstruct(b))
@@ -166,4 +168,64 @@ def test_corrupted_streams_never_crash(recon_lib):
         seen.add(rc)
         if rc == recon.OK:      # whatever was parsed must be syntax the reconstruction accepts
             assert out.mb_type.max() <= 24 and out.intra_chroma_pred_mode.max() <= 3 and out.qp.max() <= 51
+    assert recon.ERR_ARG in seen
+
+
+# ---- MP4 container front end (tests/avc/mp4.py muxes, dryv_cabac_scan / dryv_cabac_parse demux) -----------------------
+def test_mp4_file_parses_like_the_annexb_stream(recon_lib):
+    from avc import decode, mp4
+    pp = PicParams.make(9, 6, -1, 2)
+    b = synth.generate(pp, 4, 2718, standard_only=True)
+    data = stream.encode_stream(b)
+    movie = mp4.mux(data, 144, 96)
+    assert movie[4:8] == b"ftyp" and b"avcC" in movie and b"mdat" in movie
+    pp2, n2 = host.scan(movie)
+    assert (pp2.pic_width_in_mbs, pp2.pic_height_in_mbs, pp2.chroma_qp_index_offset, pp2.second_chroma_qp_index_offset,
+            n2) == (9, 6, -1, 2, 4)
+    assert_same_syntax(host.parse(movie), host.parse(data))
+    assert_same_syntax(host.parse(movie), b)
+    if decode.available():      # libavformat + libavcodec agree that this is a valid MP4 with these pictures
+        import cv2
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".mp4", delete=False) as f:
+            f.write(movie)
+        try:
+            cap = cv2.VideoCapture(f.name, cv2.CAP_FFMPEG)
+            assert cap.isOpened() and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 4
+            cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+            ref = luma_of(oracle.reconstruct(b), pp)
+            for k in range(4):
+                ok, fr = cap.read()
+                assert ok and np.array_equal(np.asarray(fr).reshape(-1)[:144 * 96].reshape(96, 144), ref[k])
+        finally:
+            os.unlink(f.name)
+
+
+def test_corrupted_mp4_files_never_crash(recon_lib):
+    from avc import mp4
+    b = synth.generate(PicParams.make(4, 3), 2, 31)
+    movie = bytearray(mp4.mux(stream.encode_stream(b), 64, 48))
+    pp, n = host.scan(bytes(movie))
+    out = synth.generate(pp, n, 0)
+    rng = np.random.default_rng(5)
+    seen = set()
+    for trial in range(300):
+        d = bytearray(movie)
+        for _ in range(int(rng.integers(1, 5))):
+            pos = int(rng.integers(0, len(d)))
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                d[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                d[pos:pos + 4] = int(rng.integers(0, 2 ** 32)).to_bytes(4, "big")
+            else:
+                del d[pos:]
+        if len(d) < 16:
+            continue
+        a = np.frombuffer(bytes(d), np.uint8)
+        rc = recon_lib.dryv_cabac_parse(a.ctypes.data, a.size, C.byref(pp), n, out.mb_type.ctypes.data,
+                                        out.transform_size_8x8_flag.ctypes.data, out.intra_chroma_pred_mode.ctypes.data,
+                                        out.qp.ctypes.data, out.pred_syntax.ctypes.data, out.coeff.ctypes.data, 1)
+        assert rc in (recon.OK, recon.ERR_ARG, recon.ERR_UNSUPPORTED)
+        seen.add(rc)
     assert recon.ERR_ARG in seen

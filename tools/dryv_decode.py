@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""The whole path on one Annex-B H.264 file, the way `dryv <file>` works on an MP4 (src/main.rs:34-51,
-src/video/decoder.rs:87-150): CABAC-parse the IDR pictures on the CPU (dryv_b200/csrc/cabac_host.cpp), reconstruct them
-on the GPU through the compact level stream, and write the first picture to ./temp/yuv_frame in the reference's byte
-layout (src/video/frame/mod.rs:48-70).
+"""The whole path on one MP4 (or Annex-B H.264) file, the way `dryv <file>` works (src/main.rs:34-51,
+src/video/decoder.rs:87-150): demux the video track and CABAC-parse its IDR pictures on the CPU
+(dryv_b200/csrc/cabac_host.cpp), reconstruct them on the GPU through the compact level stream, and write the first picture
+to ./temp/yuv_frame in the reference's byte layout (src/video/frame/mod.rs:48-70).
 
-    python tools/dryv_decode.py stream.h264 [out_path]        # needs a B200
-    python tools/dryv_decode.py --make-sample sample.h264     # writes a 640x368 synthetic CABAC stream (no GPU needed)
+    python tools/dryv_decode.py movie.mp4 [out_path]          # needs a B200
+    python tools/dryv_decode.py --make-sample sample.mp4      # writes a 640x368 synthetic CABAC High-profile MP4 (no GPU)
 """
 import os
 import sys
@@ -23,6 +23,9 @@ def main():
         from dryv_b200.abi import PicParams
         b = synth.generate(PicParams.make(40, 23), 4, 360, standard_only=True)
         data = stream.encode_stream(b)
+        if sys.argv[2].endswith(".mp4"):
+            from avc import mp4
+            data = mp4.mux(data, 640, 368)
         open(sys.argv[2], "wb").write(data)
         print(f"{sys.argv[2]}: {len(data)} bytes, 4 IDR pictures of 640x368")
         return 0

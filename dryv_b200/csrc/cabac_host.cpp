@@ -651,6 +651,13 @@ int dryv_cabac_scan(const uint8_t* annexb, size_t len, dryv_pic_params* pp, uint
 int dryv_cabac_parse(const uint8_t* annexb, size_t len, const dryv_pic_params* pp, uint32_t n_pictures, uint8_t* mb_type,
                      uint8_t* transform_size_8x8_flag, uint8_t* intra_chroma_pred_mode, uint8_t* qp, uint8_t* pred_syntax,
                      int16_t* coeff, int threads) {
+  return dryv_cabac_parse_range(annexb, len, pp, 0, n_pictures, 1, mb_type, transform_size_8x8_flag, intra_chroma_pred_mode, qp,
+                                pred_syntax, coeff, threads);
+}
+
+int dryv_cabac_parse_range(const uint8_t* annexb, size_t len, const dryv_pic_params* pp, uint32_t first_picture,
+                           uint32_t n_pictures, int must_be_all, uint8_t* mb_type, uint8_t* transform_size_8x8_flag,
+                           uint8_t* intra_chroma_pred_mode, uint8_t* qp, uint8_t* pred_syntax, int16_t* coeff, int threads) {
   if (!annexb || !pp || !mb_type || !transform_size_8x8_flag || !intra_chroma_pred_mode || !qp || !pred_syntax || !coeff ||
       n_pictures == 0)
     return DRYV_ERR_ARG;
@@ -660,8 +667,8 @@ int dryv_cabac_parse(const uint8_t* annexb, size_t len, const dryv_pic_params* p
   Stream st;
   rc = analyse(nals, st);
   if (rc != DRYV_OK) return rc;
-  if (st.sps.w_mbs != pp->pic_width_in_mbs || st.sps.h_mbs != pp->pic_height_in_mbs || st.idr.size() != n_pictures)
-    return DRYV_ERR_ARG;
+  if (st.sps.w_mbs != pp->pic_width_in_mbs || st.sps.h_mbs != pp->pic_height_in_mbs) return DRYV_ERR_ARG;
+  if ((uint64_t)first_picture + n_pictures > st.idr.size() || (must_be_all && st.idr.size() != n_pictures)) return DRYV_ERR_ARG;
   const size_t n_mb = (size_t)st.sps.w_mbs * st.sps.h_mbs;
   std::atomic<uint32_t> next(0);
   std::atomic<int> status(DRYV_OK);
@@ -670,7 +677,7 @@ int dryv_cabac_parse(const uint8_t* annexb, size_t len, const dryv_pic_params* p
       const uint32_t f = next.fetch_add(1);
       if (f >= n_pictures) break;
       const size_t o = (size_t)f * n_mb;
-      const int r = parse_picture(st, *st.idr[f], mb_type + o, transform_size_8x8_flag + o, intra_chroma_pred_mode + o, qp + o,
+      const int r = parse_picture(st, *st.idr[first_picture + f], mb_type + o, transform_size_8x8_flag + o, intra_chroma_pred_mode + o, qp + o,
                                   pred_syntax + o * 16, coeff + o * DRYV_COEFFS_PER_MB);
       if (r != DRYV_OK) {
         int expect = DRYV_OK;

@@ -25,16 +25,20 @@ def scan(stream: bytes):
     return pp, int(n.value)
 
 
-def parse(stream: bytes, threads: int = 0, out: SyntaxBatch | None = None) -> SyntaxBatch:
-    """CABAC-parses every IDR picture of the stream into syntax buffers (dense levels)."""
+def parse(stream: bytes, threads: int = 0, out: SyntaxBatch | None = None, first: int = 0,
+          count: int | None = None) -> SyntaxBatch:
+    """CABAC-parses the IDR pictures [first, first + count) of the stream (default: all) into syntax buffers (dense
+    levels). `stream` is an MP4 file or an Annex-B byte stream."""
     lib = load_library()
     pp, n = scan(stream)
-    b = out if out is not None else SyntaxBatch.empty(pp, n)
+    whole = count is None and first == 0
+    count = n - first if count is None else count
+    b = out if out is not None else SyntaxBatch.empty(pp, count)
     buf = np.frombuffer(stream, np.uint8)
-    rc = lib.dryv_cabac_parse(buf.ctypes.data, buf.size, C.byref(pp), n, b.mb_type.ctypes.data,
-                              b.transform_size_8x8_flag.ctypes.data, b.intra_chroma_pred_mode.ctypes.data,
-                              b.qp.ctypes.data, b.pred_syntax.ctypes.data, b.coeff.ctypes.data,
-                              threads or (os.cpu_count() or 1))
+    rc = lib.dryv_cabac_parse_range(buf.ctypes.data, buf.size, C.byref(pp), first, count, 1 if whole else 0,
+                                    b.mb_type.ctypes.data, b.transform_size_8x8_flag.ctypes.data,
+                                    b.intra_chroma_pred_mode.ctypes.data, b.qp.ctypes.data, b.pred_syntax.ctypes.data,
+                                    b.coeff.ctypes.data, threads or (os.cpu_count() or 1))
     if rc != OK:
-        raise ReconError(rc, "dryv_cabac_parse")
+        raise ReconError(rc, "dryv_cabac_parse_range")
     return b

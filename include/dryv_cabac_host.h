@@ -49,6 +49,13 @@ int dryv_cabac_parse(const uint8_t* annexb, size_t len, const dryv_pic_params* p
                      uint8_t* mb_type, uint8_t* transform_size_8x8_flag, uint8_t* intra_chroma_pred_mode, uint8_t* qp,
                      uint8_t* pred_syntax, int16_t* coeff, int threads);
 
+/* The same for pictures [first_picture, first_picture + n_pictures) of the stream only (buffers sized for n_pictures):
+ * what each rank of a multi-GPU host calls for its share of the pictures (dryv_b200/shard.py), nothing is exchanged.
+ * `must_be_all` != 0 additionally requires the range to be the whole stream. */
+int dryv_cabac_parse_range(const uint8_t* annexb, size_t len, const dryv_pic_params* pp, uint32_t first_picture,
+                           uint32_t n_pictures, int must_be_all, uint8_t* mb_type, uint8_t* transform_size_8x8_flag,
+                           uint8_t* intra_chroma_pred_mode, uint8_t* qp, uint8_t* pred_syntax, int16_t* coeff, int threads);
+
 #ifdef __cplusplus
 }
 #endif

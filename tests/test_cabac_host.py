@@ -70,6 +70,8 @@ def test_parse_inverts_the_stream_writer(recon_lib, w, h, n, kw):
     assert np.array_equal(oracle.reconstruct(got), oracle.reconstruct(b))
     if n > 1:
         assert_same_syntax(host.parse(data, threads=4), got)
+        tail = host.parse(data, threads=1, first=1, count=n - 1)     # a rank's share of the pictures
+        assert_same_syntax(tail, got.frames(1, n))
 
 
 def test_parse_of_the_libavcodec_fixture(recon_lib):

@@ -62,3 +62,42 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
     pp = PicParams.make(6, 4)
     ref = oracle.reconstruct(synth.generate(pp, 5, 900))
     assert np.array_equal(got, ref)
+
+
+def _stream_worker(rank, world, port, tmp):
+    import oracle
+    from dryv_b200 import host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    movie = open(os.path.join(tmp, "movie.mp4"), "rb").read()
+    pp, n_total = host.scan(movie)
+    mine = shard.frames_for_rank(n_total, rank, world)
+    out = np.zeros((n_total, pp.frame_bytes), np.uint8)
+    if len(mine):   # every rank demuxes the file but CABAC-parses and reconstructs only its own pictures
+        b = host.parse(movie, threads=1, first=mine.start, count=len(mine))
+        out[mine.start:mine.stop] = oracle.reconstruct(b)
+    t = torch.from_numpy(out.astype(np.int32))
+    dist.all_reduce(t)  # test-only gather; the product path exchanges nothing
+    if rank == 0:
+        np.save(os.path.join(tmp, "gathered_stream.npy"), t.numpy().astype(np.uint8))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_share_one_mp4_file(tmp_path):
+    """The real multi-GPU host flow on CPU: one MP4 file, each rank parses its share of the IDR pictures."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import oracle
+    from avc import mp4, stream
+    from dryv_b200 import synth
+    from dryv_b200.abi import PicParams
+    pp = PicParams.make(6, 4, 1, -1)
+    b = synth.generate(pp, 5, 1234)
+    (tmp_path / "movie.mp4").write_bytes(mp4.mux(stream.encode_stream(b), 96, 64))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_stream_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert np.array_equal(np.load(tmp_path / "gathered_stream.npy"), oracle.reconstruct(b))

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/dryv_cabac_host.h"
+#include "levels_record.h"
 
 namespace {
 
@@ -578,8 +579,15 @@ int analyse(const std::vector<Nal>& nals, Stream& st) {
   return DRYV_OK;
 }
 
+// Compact sink of one picture: the records of its macroblocks back to back, and their sizes
+struct CompactPicture {
+  std::vector<uint8_t> stream;
+  std::vector<uint32_t> size;
+};
+
+// `coeff` (dense, 384 int16 per macroblock) or `compact` (records, include/dryv_recon.h) receives the levels
 int parse_picture(const Stream& st, const Nal& nal, uint8_t* mb_type, uint8_t* t8x8, uint8_t* chroma_mode, uint8_t* qp,
-                  uint8_t* pred_syntax, int16_t* coeff) {
+                  uint8_t* pred_syntax, int16_t* coeff, CompactPicture* compact = nullptr) {
   Bits b(nal.rbsp.data(), nal.rbsp.size());
   // slice_header (7.3.3), IDR picture
   if (b.ue() != 0) return DRYV_ERR_UNSUPPORTED;  // first_mb_in_slice: one slice per picture
@@ -614,10 +622,22 @@ int parse_picture(const Stream& st, const Nal& nal, uint8_t* mb_type, uint8_t* t
   sp.qp_prev = slice_qp;
   sp.c.init(&b, slice_qp);
   const int n = sp.W * sp.H;
+  int16_t one_mb[DRYV_COEFFS_PER_MB];
+  if (compact) {
+    compact->stream.reserve((size_t)n * 256);
+    compact->size.reserve((size_t)n);
+  }
   for (int addr = 0; addr < n; addr++) {
     sp.macroblock(addr, mb_type + addr, t8x8 + addr, chroma_mode + addr, qp + addr, pred_syntax + (size_t)addr * 16,
-                  coeff + (size_t)addr * DRYV_COEFFS_PER_MB);
+                  compact ? one_mb : coeff + (size_t)addr * DRYV_COEFFS_PER_MB);
     if (sp.unsupported) return DRYV_ERR_UNSUPPORTED;
+    if (compact) {  // the macroblock's record, straight from what residual_block decoded
+      const uint32_t sz = dryv_levels::record_size(one_mb);
+      const size_t at = compact->stream.size();
+      compact->stream.resize(at + sz);
+      dryv_levels::write_record(one_mb, compact->stream.data() + at, sz);
+      compact->size.push_back(sz);
+    }
     const int end = sp.c.terminate();  // end_of_slice_flag
     if (b.bad) return DRYV_ERR_ARG;
     if (end != (addr == n - 1)) return DRYV_ERR_ARG;  // slice ends early / runs past the picture
@@ -694,6 +714,78 @@ int dryv_cabac_parse_range(const uint8_t* annexb, size_t len, const dryv_pic_par
     for (auto& th : pool) th.join();
   }
   return status.load();
+}
+
+int dryv_cabac_parse_compact(const uint8_t* annexb, size_t len, const dryv_pic_params* pp, uint32_t first_picture,
+                             uint32_t n_pictures, uint8_t* mb_type, uint8_t* transform_size_8x8_flag,
+                             uint8_t* intra_chroma_pred_mode, uint8_t* qp, uint8_t* pred_syntax, uint32_t* offset,
+                             uint8_t* stream, size_t stream_cap, int threads) {
+  if (!annexb || !pp || !mb_type || !transform_size_8x8_flag || !intra_chroma_pred_mode || !qp || !pred_syntax || !offset ||
+      !stream || n_pictures == 0)
+    return DRYV_ERR_ARG;
+  std::vector<Nal> nals;
+  int rc = collect_nals(annexb, len, nals);
+  if (rc != DRYV_OK) return rc;
+  Stream st;
+  rc = analyse(nals, st);
+  if (rc != DRYV_OK) return rc;
+  if (st.sps.w_mbs != pp->pic_width_in_mbs || st.sps.h_mbs != pp->pic_height_in_mbs) return DRYV_ERR_ARG;
+  if ((uint64_t)first_picture + n_pictures > st.idr.size()) return DRYV_ERR_ARG;
+  const size_t n_mb = (size_t)st.sps.w_mbs * st.sps.h_mbs;
+  std::vector<CompactPicture> pics(n_pictures);
+  std::atomic<uint32_t> next(0);
+  std::atomic<int> status(DRYV_OK);
+  auto work = [&]() {
+    for (;;) {
+      const uint32_t f = next.fetch_add(1);
+      if (f >= n_pictures) break;
+      const size_t o = (size_t)f * n_mb;
+      const int r = parse_picture(st, *st.idr[first_picture + f], mb_type + o, transform_size_8x8_flag + o,
+                                  intra_chroma_pred_mode + o, qp + o, pred_syntax + o * 16, nullptr, &pics[f]);
+      if (r != DRYV_OK) {
+        int expect = DRYV_OK;
+        status.compare_exchange_strong(expect, r);
+      }
+    }
+  };
+  const uint32_t nt = threads <= 1 ? 1u : ((uint32_t)threads < n_pictures ? (uint32_t)threads : n_pictures);
+  if (nt == 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < nt; t++) pool.emplace_back(work);
+    for (auto& th : pool) th.join();
+  }
+  if (status.load() != DRYV_OK) return status.load();
+  // offsets: a prefix sum over the record sizes; then every picture's records are copied to their place
+  uint64_t acc = 0;
+  std::vector<uint64_t> pic_at(n_pictures);
+  offset[0] = 0;
+  for (uint32_t f = 0; f < n_pictures; f++) {
+    pic_at[f] = acc;
+    if (pics[f].size.size() != n_mb) return DRYV_ERR_ARG;
+    for (size_t i = 0; i < n_mb; i++) {
+      acc += pics[f].size[i];
+      if (acc > 0xffffffffull || acc > stream_cap) return DRYV_ERR_ARG;
+      offset[(size_t)f * n_mb + i + 1] = (uint32_t)acc;
+    }
+  }
+  next.store(0);
+  auto copy = [&]() {
+    for (;;) {
+      const uint32_t f = next.fetch_add(1);
+      if (f >= n_pictures) break;
+      memcpy(stream + pic_at[f], pics[f].stream.data(), pics[f].stream.size());
+    }
+  };
+  if (nt == 1) {
+    copy();
+  } else {
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < nt; t++) pool.emplace_back(copy);
+    for (auto& th : pool) th.join();
+  }
+  return DRYV_OK;
 }
 
 }  // extern "C"

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 from .abi import PicParams, SyntaxBatch
-from .recon import OK, ReconError, load_library
+from .abi import COMPACT_MAX_RECORD
+from .recon import OK, CompactLevels, PinnedArray, ReconError, load_library
 
 
 def scan(stream: bytes):
@@ -42,3 +43,31 @@ def parse(stream: bytes, threads: int = 0, out: SyntaxBatch | None = None, first
     if rc != OK:
         raise ReconError(rc, "dryv_cabac_parse_range")
     return b
+
+
+def parse_compact(stream: bytes, threads: int = 0, first: int = 0, count: int | None = None, pinned: bool = False):
+    """CABAC-parses pictures [first, first + count) straight into the compact level stream: -> (SyntaxBatch whose
+    `coeff` is empty, CompactLevels), the pair ReconContext.submit_compact takes."""
+    lib = load_library()
+    pp, n = scan(stream)
+    count = n - first if count is None else count
+    n_mbs = pp.n_mb * count
+    b = SyntaxBatch(pp, count, np.zeros(n_mbs, np.uint8), np.zeros(n_mbs, np.uint8), np.zeros(n_mbs, np.uint8),
+                    np.zeros(n_mbs, np.uint8), np.zeros((n_mbs, 16), np.uint8), np.zeros((0, 384), np.int16))
+    cap = n_mbs * COMPACT_MAX_RECORD
+    scratch = np.empty(cap, np.uint8)
+    off = np.empty(n_mbs + 1, np.uint32)
+    buf = np.frombuffer(stream, np.uint8)
+    rc = lib.dryv_cabac_parse_compact(buf.ctypes.data, buf.size, C.byref(pp), first, count, b.mb_type.ctypes.data,
+                                      b.transform_size_8x8_flag.ctypes.data, b.intra_chroma_pred_mode.ctypes.data,
+                                      b.qp.ctypes.data, b.pred_syntax.ctypes.data, off.ctypes.data, scratch.ctypes.data, cap,
+                                      threads or (os.cpu_count() or 1))
+    if rc != OK:
+        raise ReconError(rc, "dryv_cabac_parse_compact")
+    used = int(off[-1])
+    if pinned:
+        po, ps = PinnedArray(n_mbs + 1, np.uint32), PinnedArray(max(used, 4), np.uint8)
+        po.array[:] = off
+        ps.array[:used] = scratch[:used]
+        return b, CompactLevels(po.array, ps.array, (po, ps))
+    return b, CompactLevels(off, scratch[:max(used, 4)].copy())

@@ -28,7 +28,7 @@ EXPORTS = [
     "dryv_recon_wavefront_times", "dryv_recon_pack_levels", "dryv_recon_unpack_levels", "dryv_recon_submit_compact",
     "dryv_recon_expand_levels_device", "dryv_recon_wait_oldest",
 ]
-HOST_EXPORTS = ["dryv_cabac_scan", "dryv_cabac_parse", "dryv_cabac_parse_range"]  # include/dryv_cabac_host.h
+HOST_EXPORTS = ["dryv_cabac_scan", "dryv_cabac_parse", "dryv_cabac_parse_range", "dryv_cabac_parse_compact"]  # include/dryv_cabac_host.h
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -37,7 +37,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp", "levels_pack.cpp", "cabac_host.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "recon_tables.h", "cabac_tables.inc")] + [
+    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "recon_tables.h", "cabac_tables.inc", "levels_record.h")] + [
         os.path.join(_HERE, "..", "include", "dryv_recon.h"), os.path.join(_HERE, "..", "include", "dryv_cabac_host.h")]
     if not force and os.path.exists(LIB_PATH) and all(
             os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
@@ -104,6 +104,8 @@ def load_library() -> C.CDLL:
     lib.dryv_cabac_scan.argtypes = [vp, sz, C.POINTER(PicParams), C.POINTER(u32)]
     lib.dryv_cabac_parse.restype = C.c_int
     lib.dryv_cabac_parse.argtypes = [vp, sz, C.POINTER(PicParams), u32, vp, vp, vp, vp, vp, vp, C.c_int]
+    lib.dryv_cabac_parse_compact.restype = C.c_int
+    lib.dryv_cabac_parse_compact.argtypes = [vp, sz, C.POINTER(PicParams), u32, u32, vp, vp, vp, vp, vp, vp, vp, sz, C.c_int]
     lib.dryv_cabac_parse_range.restype = C.c_int
     lib.dryv_cabac_parse_range.argtypes = [vp, sz, C.POINTER(PicParams), u32, u32, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
     lib.dryv_recon_pack_levels.restype = C.c_int

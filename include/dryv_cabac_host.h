@@ -56,6 +56,16 @@ int dryv_cabac_parse_range(const uint8_t* annexb, size_t len, const dryv_pic_par
                            uint32_t n_pictures, int must_be_all, uint8_t* mb_type, uint8_t* transform_size_8x8_flag,
                            uint8_t* intra_chroma_pred_mode, uint8_t* qp, uint8_t* pred_syntax, int16_t* coeff, int threads);
 
+/* The same with the levels emitted as the compact stream dryv_recon_submit_compact takes (include/dryv_recon.h,
+ * dryv_mb_levels_compact) instead of dense arrays: the parser has the significance map and the levels in hand, so the
+ * records are written as the blocks are decoded and no dense array is ever filled. `offset` must hold
+ * n_pictures * n_mb + 1 entries, `stream` stream_cap bytes (n_pictures * n_mb * DRYV_COMPACT_MAX_RECORD always suffices);
+ * offset[n_pictures * n_mb] is the number of stream bytes written. */
+int dryv_cabac_parse_compact(const uint8_t* annexb, size_t len, const dryv_pic_params* pp, uint32_t first_picture,
+                             uint32_t n_pictures, uint8_t* mb_type, uint8_t* transform_size_8x8_flag,
+                             uint8_t* intra_chroma_pred_mode, uint8_t* qp, uint8_t* pred_syntax, uint32_t* offset,
+                             uint8_t* stream, size_t stream_cap, int threads);
+
 #ifdef __cplusplus
 }
 #endif

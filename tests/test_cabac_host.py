@@ -74,6 +74,23 @@ def test_parse_inverts_the_stream_writer(recon_lib, w, h, n, kw):
         assert_same_syntax(tail, got.frames(1, n))
 
 
+def test_parse_compact_emits_the_records_pack_levels_would(recon_lib):
+    pp = PicParams.make(9, 7, 1, 0)
+    b = synth.generate(pp, 4, 5150, stress_pct=30)
+    data = stream.encode_stream(b)
+    dense = host.parse(data, threads=1)
+    for threads, first, count in ((1, 0, None), (3, 0, None), (2, 1, 2)):
+        syn, lv = host.parse_compact(data, threads=threads, first=first, count=count)
+        ref = dense.frames(first, first + syn.n_frames)
+        want = recon.pack_levels(ref.coeff, threads=1)
+        assert np.array_equal(lv.offset, want.offset)
+        assert np.array_equal(lv.stream[:int(lv.offset[-1])], want.stream[:int(want.offset[-1])])
+        assert np.array_equal(lv.unpack(), ref.coeff)
+        for f in ("mb_type", "transform_size_8x8_flag", "intra_chroma_pred_mode", "qp", "pred_syntax"):
+            assert np.array_equal(getattr(syn, f), getattr(ref, f)), f
+        assert syn.coeff.size == 0
+
+
 def test_parse_of_the_libavcodec_fixture(recon_lib):
     b, data, luma = load_fixture()
     got = host.parse(data)
@@ -121,8 +138,7 @@ def test_bytes_to_yuv_frame_through_the_whole_path(gpu_ctx, tmp_path):
     data = stream.encode_stream(b)
     from avc import mp4
     movie = mp4.mux(data, 640, 368)          # the kind of file `dryv <file>` opens
-    parsed = host.parse(movie)
-    levels = recon.pack_levels(parsed.coeff)
+    parsed, levels = host.parse_compact(movie)   # demux + CABAC parse straight into the compact level stream
     out = gpu_ctx.reconstruct_compact(parsed, levels)
     assert np.array_equal(out, oracle.reconstruct(b))
     path = tmp_path / "temp" / "yuv_frame"

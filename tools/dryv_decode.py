@@ -33,9 +33,8 @@ def main():
     data = open(sys.argv[1], "rb").read()
     out_path = sys.argv[2] if len(sys.argv) > 2 else "temp/yuv_frame"
     t0 = time.perf_counter()
-    batch = host.parse(data)
+    batch, levels = host.parse_compact(data)   # demux + CABAC parse straight into the compact level stream
     t1 = time.perf_counter()
-    levels = recon.pack_levels(batch.coeff)
     ctx = recon.ReconContext(0)
     frames = ctx.reconstruct_compact(batch, levels)
     t2 = time.perf_counter()

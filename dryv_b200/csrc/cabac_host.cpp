@@ -632,10 +632,12 @@ int parse_picture(const Stream& st, const Nal& nal, uint8_t* mb_type, uint8_t* t
                   compact ? one_mb : coeff + (size_t)addr * DRYV_COEFFS_PER_MB);
     if (sp.unsupported) return DRYV_ERR_UNSUPPORTED;
     if (compact) {  // the macroblock's record, straight from what residual_block decoded
-      const uint32_t sz = dryv_levels::record_size(one_mb);
+      const dryv_levels::MbStats ms = dryv_levels::scan(one_mb);
+      const int mode = dryv_levels::pick_mode(ms);
+      const uint32_t sz = dryv_levels::record_size(ms, mode);
       const size_t at = compact->stream.size();
       compact->stream.resize(at + sz);
-      dryv_levels::write_record(one_mb, compact->stream.data() + at, sz);
+      dryv_levels::write_record(one_mb, ms, mode, compact->stream.data() + at, sz);
       compact->size.push_back(sz);
     }
     const int end = sp.c.terminate();  // end_of_slice_flag

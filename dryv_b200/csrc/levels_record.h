@@ -50,16 +50,18 @@ inline int pick_mode(const MbStats& st) {
   return best;
 }
 
+inline uint32_t record_size(const MbStats& st, int mode) {
+  const uint32_t bytes = 4 + 2 * st.ncoded + level_bytes(st, mode);
+  return (bytes + 3u) & ~3u;
+}
 // size in bytes of macroblock `c`'s record
 inline uint32_t record_size(const int16_t* c) {
   const MbStats st = scan(c);
-  const uint32_t bytes = 4 + 2 * st.ncoded + level_bytes(st, pick_mode(st));
-  return (bytes + 3u) & ~3u;
+  return record_size(st, pick_mode(st));
 }
 
-inline void write_record(const int16_t* c, uint8_t* rec, uint32_t size) {
-  const MbStats st = scan(c);
-  const int mode = pick_mode(st);
+// writes the record of macroblock `c` (whose scan() is `st`) in coding `mode`, `size` = record_size(st, mode) bytes
+inline void write_record(const int16_t* c, const MbStats& st, int mode, uint8_t* rec, uint32_t size) {
   uint32_t hdr = (uint32_t)mode << 30;
   for (int b = 0; b < kSlots; b++)
     if (st.mask[b]) hdr |= 1u << b;
@@ -75,32 +77,38 @@ inline void write_record(const int16_t* c, uint8_t* rec, uint32_t size) {
     memset(p, 0, nib_bytes);
     uint8_t* esc = p + nib_bytes;
     uint32_t j = 0;
-    for (int i = 0; i < DRYV_COEFFS_PER_MB; i++) {
-      const int16_t v = c[i];
-      if (!v) continue;
-      uint32_t code = 0;  // 0 = escape
-      if (v >= -7 && v <= 7) code = v < 0 ? (8u | (uint32_t)-v) : (uint32_t)v;
-      else {
-        memcpy(esc, &v, 2);
-        esc += 2;
+    for (int b = 0; b < kSlots; b++) {
+      for (uint32_t m = st.mask[b]; m; m &= m - 1) {  // set bits in ascending order
+        const int16_t v = c[b * 16 + __builtin_ctz(m)];
+        uint32_t code = 0;  // 0 = escape
+        if (v >= -7 && v <= 7) code = v < 0 ? (8u | (uint32_t)-v) : (uint32_t)v;
+        else {
+          memcpy(esc, &v, 2);
+          esc += 2;
+        }
+        p[j >> 1] |= (uint8_t)(code << (4 * (j & 1)));
+        j++;
       }
-      p[j >> 1] |= (uint8_t)(code << (4 * (j & 1)));
-      j++;
     }
     p = esc;
   } else {
-    for (int i = 0; i < DRYV_COEFFS_PER_MB; i++) {
-      const int16_t v = c[i];
-      if (!v) continue;
-      if (mode == kModeInt16) {
-        memcpy(p, &v, 2);
-        p += 2;
-      } else {
-        *p++ = (uint8_t)(int8_t)v;
+    for (int b = 0; b < kSlots; b++) {
+      for (uint32_t m = st.mask[b]; m; m &= m - 1) {
+        const int16_t v = c[b * 16 + __builtin_ctz(m)];
+        if (mode == kModeInt16) {
+          memcpy(p, &v, 2);
+          p += 2;
+        } else {
+          *p++ = (uint8_t)(int8_t)v;
+        }
       }
     }
   }
   while (p < rec + size) *p++ = 0;
+}
+inline void write_record(const int16_t* c, uint8_t* rec, uint32_t size) {
+  const MbStats st = scan(c);
+  write_record(c, st, pick_mode(st), rec, size);
 }
 
 }  // namespace dryv_levels

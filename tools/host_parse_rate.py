@@ -16,11 +16,12 @@ qp = int(sys.argv[2]) if len(sys.argv) > 2 else 26
 pp = PicParams.make(40, 23)
 b = synth.generate(pp, n, 360, qp_base=qp)
 data = stream.encode_stream(b)
-for threads in (1, os.cpu_count() or 1):
-    best = 1e9
-    for _ in range(5):
-        t = time.perf_counter()
-        host.parse(data, threads=threads)
-        best = min(best, time.perf_counter() - t)
-    print(f"{threads:3d} thread(s): {n / best:8.1f} pictures/s  {n * pp.luma_pixels / best / 1e6:8.1f} Mpixels/s  "
-          f"{len(data) * 8 / best / 1e6:8.1f} Mbit/s  ({len(data) / n / 1024:.1f} KiB per picture at QP {qp})")
+for name, fn in (("dense levels", host.parse), ("compact stream", host.parse_compact)):
+    for threads in (1, os.cpu_count() or 1):
+        best = 1e9
+        for _ in range(5):
+            t = time.perf_counter()
+            fn(data, threads=threads)
+            best = min(best, time.perf_counter() - t)
+        print(f"{name:14s} {threads:3d} thread(s): {n / best:8.1f} pictures/s  {n * pp.luma_pixels / best / 1e6:8.1f} Mpixels/s  "
+              f"{len(data) * 8 / best / 1e6:8.1f} Mbit/s  ({len(data) / n / 1024:.1f} KiB per picture at QP {qp})")

@@ -225,6 +225,14 @@ class DeviceSoa:
             setattr(soa, f, self.tensors[f].data_ptr())
         return soa
 
+    def frames(self, lo: int, hi: int) -> "DeviceSoa":
+        """View of pictures [lo, hi) (no copy)."""
+        n = self.pp.n_mb
+        v = object.__new__(DeviceSoa)
+        v.pp, v.n_frames = self.pp, hi - lo
+        v.tensors = {f: t[lo * n:hi * n] for f, t in self.tensors.items()}
+        return v
+
     @property
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.tensors.values())

@@ -302,12 +302,30 @@ int parse_pps(const Nal& nal, Pps& p) {
 }
 
 // ---- 9.3.3.2 arithmetic decoding engine + 9.3.1.1 context initialisation -----------------------------------------
+// codIOffset is kept scaled: `value` = codIOffset * 2^look + the next `look` bits of the stream, so "offset >= range"
+// is value >= range << look, renormalising by s bits is look -= s, and the stream is read a byte at a time instead of a
+// bit at a time (the arithmetic is that of 9.3.3.2.2 - 9.3.3.2.4 exactly; src/video/cabac/mod.rs:1207-1278 reads bits).
 struct Cabac {
-  Bits* in;
-  uint32_t range = 510, offset = 0;
+  const uint8_t* p = nullptr;    // next byte of the slice data
+  const uint8_t* end = nullptr;
+  size_t overrun = 0;            // zero bytes fed past the end of the data
+  uint32_t range = 510, value = 0;
+  int look = 0;
   uint8_t state[1024], mps[1024];
-  void init(Bits* b, int slice_qp) {
-    in = b;
+  void refill() {  // keeps 8 <= look <= 15: one operation consumes at most 6 bits, and range << look stays below 2^24
+    while (look < 8) {
+      uint32_t byte = 0;
+      if (p < end) byte = *p++;
+      else overrun++;
+      value = (value << 8) | byte;
+      look += 8;
+    }
+  }
+  // bits consumed beyond the end of the data (0 for a well-formed slice)
+  bool overran() const { return overrun * 8 > (size_t)look; }
+  void init(const uint8_t* data, const uint8_t* data_end, int slice_qp) {
+    p = data;
+    end = data_end;
     const int q = slice_qp < 0 ? 0 : (slice_qp > 51 ? 51 : slice_qp);
     for (int i = 0; i < 1024; i++) {
       int pre = ((kCtxInitM[i] * q) >> 4) + kCtxInitN[i];
@@ -321,16 +339,18 @@ struct Cabac {
       }
     }
     range = 510;
-    offset = in->u(9);
+    value = 0;
+    look = -9;  // the first nine bits are codIOffset itself
+    refill();
   }
   int decision(int ctx) {
     const int s = state[ctx];
     const uint32_t lps = kRangeTabLps[s * 4 + ((range >> 6) & 3)];
     range -= lps;
     int bin;
-    if (offset >= range) {
+    if (value >= (range << look)) {
       bin = !mps[ctx];
-      offset -= range;
+      value -= range << look;
       range = lps;
       if (s == 0) mps[ctx] = (uint8_t)!mps[ctx];
       state[ctx] = kTransIdxLps[s];
@@ -338,26 +358,31 @@ struct Cabac {
       bin = mps[ctx];
       state[ctx] = kTransIdxMps[s];
     }
-    while (range < 256) {
-      range <<= 1;
-      offset = (offset << 1) | (uint32_t)in->bit();
+    if (range < 256) {
+      const int sh = __builtin_clz(range) - 23;  // range is 9 bits wide: shift it back into [256, 511]
+      range <<= sh;
+      look -= sh;
+      refill();
     }
     return bin;
   }
   int bypass() {
-    offset = (offset << 1) | (uint32_t)in->bit();
-    if (offset >= range) {
-      offset -= range;
+    look -= 1;
+    refill();
+    if (value >= (range << look)) {
+      value -= range << look;
       return 1;
     }
     return 0;
   }
   int terminate() {
     range -= 2;
-    if (offset >= range) return 1;
-    while (range < 256) {
-      range <<= 1;
-      offset = (offset << 1) | (uint32_t)in->bit();
+    if (value >= (range << look)) return 1;
+    if (range < 256) {
+      const int sh = __builtin_clz(range) - 23;
+      range <<= sh;
+      look -= sh;
+      refill();
     }
     return 0;
   }
@@ -620,7 +645,7 @@ int parse_picture(const Stream& st, const Nal& nal, uint8_t* mb_type, uint8_t* t
   sp.info.assign((size_t)sp.W * sp.H, MbCtx());
   sp.transform8 = st.pps.transform_8x8_mode;
   sp.qp_prev = slice_qp;
-  sp.c.init(&b, slice_qp);
+  sp.c.init(nal.rbsp.data() + (b.pos >> 3), nal.rbsp.data() + nal.rbsp.size(), slice_qp);
   const int n = sp.W * sp.H;
   int16_t one_mb[DRYV_COEFFS_PER_MB];
   if (compact) {
@@ -641,7 +666,7 @@ int parse_picture(const Stream& st, const Nal& nal, uint8_t* mb_type, uint8_t* t
       compact->size.push_back(sz);
     }
     const int end = sp.c.terminate();  // end_of_slice_flag
-    if (b.bad) return DRYV_ERR_ARG;
+    if (sp.c.overran()) return DRYV_ERR_ARG;
     if (end != (addr == n - 1)) return DRYV_ERR_ARG;  // slice ends early / runs past the picture
   }
   return DRYV_OK;

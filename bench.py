@@ -214,11 +214,16 @@ def main():
     ctx = recon.ReconContext(local_rank)
     dsoa = recon.DeviceSoa(hbatch, device=dev)
     d_out = torch.zeros((n_frames, pp.frame_bytes), dtype=torch.uint8, device=dev)
-    # a dedicated (non-default) torch stream: kernels are launched on it through the C ABI and the
-    # torch.cuda.Event pair below is recorded on the same stream
-    stream = torch.cuda.Stream(dev)
+    d_out2 = torch.zeros_like(d_out)
+    d_outs = [d_out, d_out2]
+    # Two dedicated (non-default) torch streams: kernels are launched on them through the C ABI and the torch.cuda.Event
+    # objects below are recorded on the same streams. Consecutive steps alternate over the two streams and the two output
+    # buffers: the batches are independent, so the library lets a step start while the previous one drains (the start-up
+    # stagger of one wavefront fills the tail of the other). Every step still does all of its work.
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    stream = streams[0]
     sptr = stream.cuda_stream
-    assert sptr != 0
+    assert sptr != 0 and streams[1].cuda_stream != 0
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -226,29 +231,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step():
-        ctx.reconstruct_device(dsoa, d_out, sptr)
+    def step(k=0, n_streams=2):
+        i = k % n_streams
+        ctx.reconstruct_device(dsoa, d_outs[i], streams[i].cuda_stream)
 
-    for _ in range(max(3, args.warmup)):
-        step()
+    for k in range(max(3, args.warmup)):
+        step(k)
     ctx.wait()
+
+    # one batch at a time on one stream: the isolated duration of the dominant kernel (CUDA events recorded around each
+    # launch on the launching stream) and the serial step time, reported beside the headline
+    iso_steps = max(3, min(args.steps, 10))
+    e0s, e1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0s.record(stream)
+    for _ in range(iso_steps):
+        step(0, 1)
+    e1s.record(stream)
+    barrier()
+    ctx.wait()
+    ms_serial_step = e0s.elapsed_time(e1s) / iso_steps
+    wave_ms = ctx.wavefront_times_ms(min(64, iso_steps))
+    wave_ms_isolated = sum(wave_ms) / max(1, len(wave_ms))
 
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
     launches0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
     barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
+    ev0.record(streams[0])
+    streams[1].wait_event(ev0)
+    for k in range(args.steps):
+        step(k)
+    ends[0].record(streams[0])
+    ends[1].record(streams[1])
     barrier()
     ctx.wait()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = max(ev0.elapsed_time(ends[0]), ev0.elapsed_time(ends[1]))
     launches = ctx.launch_count - launches0
-    # the dominant kernel alone (CUDA events recorded around it on the launching stream, inside the timed region)
-    wave_ms = ctx.wavefront_times_ms(min(64, args.steps))
-    wave_ms_avg = sum(wave_ms) / max(1, len(wave_ms))
+    # effective time of the dominant kernel per launch inside the timed region (two launches share the GPU at a time, so
+    # the event pair around one launch spans more than its share): the timed region is nothing but these launches
+    wave_ms_avg = ms_total / args.steps
 
     # ---- e2e through the host-buffer C ABI calls: pinned H2D + kernels + D2H inside the timed region.
     # Two wire formats for the levels: the compact stream (significance masks + non-zero levels, the form CABAC
@@ -301,15 +325,16 @@ def main():
 
     # parity spot check outside the timed region: first picture against the oracle
     import oracle
-    got0 = d_out[0].cpu().numpy()
+    got0 = d_outs[(args.steps - 1) & 1][0].cpu().numpy()
     ref0 = oracle.reconstruct(hbatch.frames(0, 1))[0]
-    parity = bool(np.array_equal(got0, ref0))
+    parity = bool(np.array_equal(got0, ref0)) and bool(torch.equal(d_outs[0], d_outs[1]))
 
     peak, peak_src = measured_peak_gbs()
     n_mb_step = n_frames * pp.n_mb
     # a step = ticket memset + resolve_modes_kernel (prediction-mode pre-pass) + recon_wavefront_kernel. The wavefront
-    # kernel is a programmatic dependent of the pre-pass and overlaps it, so the CUDA-event pair brackets both:
-    # kernel_ms is the duration of the overlapped pair, quoted against the wavefront kernel's algorithmic bytes
+    # kernel is a programmatic dependent of the pre-pass and overlaps it; with two batches in flight the GPU time one
+    # launch costs is the timed region divided by the launches in it (kernel_ms); kernel_ms_isolated is the CUDA-event
+    # duration of a launch that has the GPU to itself, quoted against the wavefront kernel's algorithmic bytes as well
     kernel_s = wave_ms_avg * 1e-3
     achieved = n_mb_step * BYTES_PER_MB_FULL / kernel_s / 1e9
     line = {
@@ -319,6 +344,10 @@ def main():
         "config": config_dict(args, world),
         "clocks": clocks,
         "gpu_launches": int(launches),
+        "batches_in_flight": 2,
+        "single_stream": {"ms_per_step": ms_serial_step,
+                          "value": n_frames * pp.luma_pixels / (ms_serial_step * 1e-3) / 1e6,
+                          "note": "rank 0, one batch at a time on one stream (no overlap between consecutive batches)"},
         "parity_vs_oracle_first_picture": parity,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": TRAFFIC_BYTES_PER_LAUNCH if (n_frames, args.width_mbs, args.height_mbs) == (64, 120, 68) else None,
@@ -327,20 +356,23 @@ def main():
                                        f"{n_mb_step * BYTES_PER_MB_FULL}",
                      "peak_source": peak_src, "kernel": "dryv::recon_wavefront_kernel",
                      "kernel_ms": wave_ms_avg, "kernel_share_of_step": wave_ms_avg / ms_per_step,
+                     "kernel_ms_isolated": wave_ms_isolated,
+                     "frac_isolated": n_mb_step * BYTES_PER_MB_FULL / (wave_ms_isolated * 1e-3) / 1e9 / peak,
                      "algorithmic_bytes_per_mb": BYTES_PER_MB_FULL, "mbs_per_launch": n_mb_step},
     }
     # the wavefront occupancy bound: a picture is a chain of W + 2(H - 1) dependent macroblock steps, and
     # the kernel runs min(rows, SMs x 10 resident row teams) rows at a time
     teams = min(n_frames * args.height_mbs, torch.cuda.get_device_properties(dev).multi_processor_count * 10)
     steps = args.width_mbs + 2 * (args.height_mbs - 1)
-    mb_period_us = kernel_s * 1e6 * teams / n_mb_step
+    mb_period_us = wave_ms_isolated * 1e3 * teams / n_mb_step   # from a launch that has the GPU to itself
     line["wavefront"] = {
         "dependent_steps_per_picture": steps, "row_teams": teams,
         "rows_per_team": n_frames * args.height_mbs / teams,
         "mb_period_us_per_team": mb_period_us,
         "critical_path_ms_at_that_period": steps * mb_period_us * 1e-3,
-        "note": "kernel time = rows_per_team x pic_width_in_mbs x mb_period (+ start-up stagger); the period is the serial "
-                "instruction stream of a row team's slower warp (DESIGN.md §5), ~25x what the HBM roofline would allow",
+        "note": "isolated kernel time = rows_per_team x pic_width_in_mbs x mb_period (+ start-up stagger and tail, which "
+                "back-to-back batches on two streams hide); the period is the serial instruction stream of a row team's "
+                "slower warp (DESIGN.md §5), ~25x what the HBM roofline would allow",
     }
     if e2e_ms is not None:
         syntax_bytes = int(hbatch.input_bytes - hbatch.coeff.nbytes)

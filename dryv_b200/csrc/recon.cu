@@ -957,14 +957,21 @@ struct dryv_recon_ctx {
   DeviceTables* h_tables = nullptr;  // pinned
   dryv_pic_params tables_pp;
   bool tables_valid = false;
-  // wavefront control blocks: one per compute stream, so two launches can be in flight
+  // Wavefront control blocks, used round robin: a launch may overlap the launches before it (on other streams), which
+  // is where back-to-back batches gain — the start-up stagger of one wavefront fills the tail of the previous one
+  // (64 x 1080p: 0.89 -> 0.74 ms per batch with two in flight, 8-picture batches 0.38 -> 0.13 ms with four). A block is
+  // reused only after the launch that used it last has finished (its `done` event).
+  static constexpr int kSets = 4;
   struct Control {
     unsigned long long* d_line = nullptr;  // bottom-line hand-off buffer, kLineWords words per macroblock
     unsigned long long* d_modes = nullptr; // resolved prediction modes, kModeWords tagged words per macroblock
     size_t line_cap = 0;                   // in macroblocks
-  } ctl[2];
+    cudaEvent_t done = nullptr;            // recorded behind the last launch that used this block
+    bool used = false;
+  } ctl[kSets];
+  unsigned next_set = 0;
   uint32_t tag = 0;                      // launch tag, incremented per wavefront launch (0 = never written)
-  unsigned int* d_ticket = nullptr;  // [0] ticket of control block 0, [1] status, [2] ticket of control block 1
+  unsigned int* d_ticket = nullptr;  // [2 * set] ticket of control block `set`, [1] status
   unsigned long long* d_prof = nullptr;  // stage clocks (development builds)
   unsigned int* d_trace = nullptr;       // timeline trace (development builds), 4 words per macroblock of picture 0
   size_t trace_mbs = 0;
@@ -1071,13 +1078,14 @@ bool soa_ok(const dryv_mb_soa* s) {
 }
 
 // enqueue the wavefront kernel for device-resident buffers on stream s
-// (`set` = which control block: launches that may overlap in time must use different ones)
 int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa, uint32_t n_frames,
-                     uint8_t* d_out, cudaStream_t s, int set = 0) {
+                     uint8_t* d_out, cudaStream_t s) {
   const size_t rows = (size_t)n_frames * pp->pic_height_in_mbs;
   const size_t mbs = rows * pp->pic_width_in_mbs;
+  const int set = (int)(ctx->next_set++ % dryv_recon_ctx::kSets);
   int rc = ensure_control(ctx, set, mbs);
   if (rc != DRYV_OK) return rc;
+  if (ctx->ctl[set].used) CU(cudaStreamWaitEvent(s, ctx->ctl[set].done, 0));  // the block's previous launch has finished
   if (++ctx->tag == 0) ctx->tag = 1;  // every launch validates line words with its own tag: no per-launch clearing
   CU(cudaMemsetAsync(ctx->d_ticket + 2 * set, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
   KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out, set);
@@ -1104,6 +1112,8 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   cfg.numAttrs = 1;
   CU(cudaLaunchKernelEx(&cfg, dryv::recon_wavefront_kernel, a));
   CU(cudaEventRecord(ev[1], s));
+  CU(cudaEventRecord(ctx->ctl[set].done, s));
+  ctx->ctl[set].used = true;
   ctx->wave_launches++;
   ctx->launches += 2;
   return DRYV_OK;
@@ -1170,11 +1180,13 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
     ok = cudaEventCreate(&ctx->e_wave[i][0]) == cudaSuccess && cudaEventCreate(&ctx->e_wave[i][1]) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_tables, sizeof(DeviceTables)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_tables, sizeof(DeviceTables)) == cudaSuccess &&
-       cudaMalloc(&ctx->d_ticket, 4 * sizeof(unsigned int)) == cudaSuccess &&
+       cudaMalloc(&ctx->d_ticket, 2 * dryv_recon_ctx::kSets * sizeof(unsigned int)) == cudaSuccess &&
        cudaMalloc(&ctx->d_prof, 16 * sizeof(unsigned long long)) == cudaSuccess &&
        cudaMemset(ctx->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_status, sizeof(int)) == cudaSuccess &&
-       cudaMemset(ctx->d_ticket, 0, 4 * sizeof(unsigned int)) == cudaSuccess;
+       cudaMemset(ctx->d_ticket, 0, 2 * dryv_recon_ctx::kSets * sizeof(unsigned int)) == cudaSuccess;
+  for (int i = 0; i < dryv_recon_ctx::kSets && ok; i++)
+    ok = cudaEventCreateWithFlags(&ctx->ctl[i].done, cudaEventDisableTiming) == cudaSuccess;
   // shared memory, not L1, is what the row teams live on: ask for the largest carve-out
   ok = ok && cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared) == cudaSuccess;
@@ -1215,9 +1227,10 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < dryv_recon_ctx::kSets; i++) {
     if (ctx->ctl[i].d_line) cudaFree(ctx->ctl[i].d_line);
     if (ctx->ctl[i].d_modes) cudaFree(ctx->ctl[i].d_modes);
+    if (ctx->ctl[i].done) cudaEventDestroy(ctx->ctl[i].done);
   }
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
@@ -1373,8 +1386,8 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
   if (!ctx->sub_open) CU(cudaEventRecord(ctx->e_sub_begin, ctx->s_h2d));  // timing spans every submit queued before the wait
   ctx->sub_open = true;
   for (uint32_t i = 0; i < (uint32_t)sched.size(); i++) {
-    const int slot = (int)(i % kStages), set = (int)(i & 1);
-    cudaStream_t sc = ctx->s_compute[set];
+    const int slot = (int)(i % kStages);
+    cudaStream_t sc = ctx->s_compute[i & 1];
     const uint32_t nf = sched[i];
     const size_t mb0 = (size_t)done * n_mb, cnt = (size_t)nf * n_mb;
     uint8_t* base = ctx->d_in[slot];
@@ -1415,7 +1428,7 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
       rc = launch_expand(ctx, d_off, d_str, o0, o1 - o0, cnt, const_cast<int16_t*>(d.coeff), sc);
       if (rc != DRYV_OK) return rc;
     }
-    rc = launch_wavefront(ctx, pp, &d, nf, ctx->d_out[slot], sc, set);
+    rc = launch_wavefront(ctx, pp, &d, nf, ctx->d_out[slot], sc);
     if (rc != DRYV_OK) return rc;
     CU(cudaEventRecord(ctx->e_kernel[slot], sc));
     mark(sc);
@@ -1504,6 +1517,8 @@ int dryv_recon_wait(dryv_recon_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->pending_user));
     ctx->pending_user_valid = false;
   }
+  for (int i = 0; i < dryv_recon_ctx::kSets; i++)  // launches on caller streams other than the last one
+    if (ctx->ctl[i].used) CU(cudaEventSynchronize(ctx->ctl[i].done));
   if (!ctx->trace_ev.empty()) {
     for (size_t i = 0; i + 3 < ctx->trace_ev.size(); i += 4) {
       float t[4] = {0, 0, 0, 0};

@@ -201,3 +201,21 @@ def test_pinned_buffers_and_repeated_submits(gpu_ctx):
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_independent_batches_overlap_on_different_streams(gpu_ctx):
+    # up to four launches of a context may be in flight (round-robin control blocks guarded by completion events):
+    # six batches over three streams, different inputs and outputs, every result must be its own
+    import torch
+    pp = PicParams.make(24, 14)
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    batches = [synth.generate(pp, 3 + (k % 2), 6100 + k) for k in range(6)]
+    dsoas = [recon.DeviceSoa(b) for b in batches]
+    outs = [torch.zeros((b.n_frames, pp.frame_bytes), dtype=torch.uint8, device="cuda") for b in batches]
+    torch.cuda.synchronize()
+    for rep in range(2):
+        for k in range(6):
+            gpu_ctx.reconstruct_device(dsoas[k], outs[k], streams[k % 3].cuda_stream)
+    gpu_ctx.wait()      # waits for every launch of the context, whatever stream it went to
+    for k in range(6):
+        assert np.array_equal(outs[k].cpu().numpy(), oracle.reconstruct(batches[k], threads=4)), k

@@ -309,16 +309,26 @@ struct Cabac {
   const uint8_t* p = nullptr;    // next byte of the slice data
   const uint8_t* end = nullptr;
   size_t overrun = 0;            // zero bytes fed past the end of the data
-  uint32_t range = 510, value = 0;
+  uint32_t range = 510;
+  uint64_t value = 0;
   int look = 0;
-  uint8_t state[1024], mps[1024];
-  void refill() {  // keeps 8 <= look <= 15: one operation consumes at most 6 bits, and range << look stays below 2^24
-    while (look < 8) {
-      uint32_t byte = 0;
-      if (p < end) byte = *p++;
-      else overrun++;
-      value = (value << 8) | byte;
-      look += 8;
+  uint8_t state[1024];           // (pStateIdx << 1) | valMPS
+  uint8_t next_mps[128], next_lps[128];
+  void refill() {  // keeps 8 <= look <= 23: one operation consumes at most 6 bits
+    if (look < 8) {
+      uint32_t two = 0;
+      if (end - p >= 2) {
+        two = ((uint32_t)p[0] << 8) | p[1];
+        p += 2;
+      } else {
+        for (int i = 0; i < 2; i++) {
+          two <<= 8;
+          if (p < end) two |= *p++;
+          else overrun++;
+        }
+      }
+      value = (value << 16) | two;
+      look += 16;
     }
   }
   // bits consumed beyond the end of the data (0 for a well-formed slice)
@@ -330,60 +340,51 @@ struct Cabac {
     for (int i = 0; i < 1024; i++) {
       int pre = ((kCtxInitM[i] * q) >> 4) + kCtxInitN[i];
       pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
-      if (pre <= 63) {
-        state[i] = (uint8_t)(63 - pre);
-        mps[i] = 0;
-      } else {
-        state[i] = (uint8_t)(pre - 64);
-        mps[i] = 1;
-      }
+      state[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
+    }
+    for (int st = 0; st < 128; st++) {
+      const int ps = st >> 1, m = st & 1;
+      next_mps[st] = (uint8_t)((kTransIdxMps[ps] << 1) | m);
+      next_lps[st] = (uint8_t)((kTransIdxLps[ps] << 1) | (ps == 0 ? !m : m));
     }
     range = 510;
     value = 0;
     look = -9;  // the first nine bits are codIOffset itself
     refill();
+    refill();
   }
+  // 9.3.3.2.1 without a data-dependent branch: the LPS / MPS outcome is a mask, the renormalisation shift a bit count
   int decision(int ctx) {
-    const int s = state[ctx];
-    const uint32_t lps = kRangeTabLps[s * 4 + ((range >> 6) & 3)];
+    const uint32_t st = state[ctx];
+    const uint32_t lps = kRangeTabLps[(st >> 1) * 4 + ((range >> 6) & 3)];
     range -= lps;
-    int bin;
-    if (value >= (range << look)) {
-      bin = !mps[ctx];
-      value -= range << look;
-      range = lps;
-      if (s == 0) mps[ctx] = (uint8_t)!mps[ctx];
-      state[ctx] = kTransIdxLps[s];
-    } else {
-      bin = mps[ctx];
-      state[ctx] = kTransIdxMps[s];
-    }
-    if (range < 256) {
-      const int sh = __builtin_clz(range) - 23;  // range is 9 bits wide: shift it back into [256, 511]
-      range <<= sh;
-      look -= sh;
-      refill();
-    }
-    return bin;
+    const uint64_t scaled = (uint64_t)range << look;
+    const uint32_t is_lps = value >= scaled;
+    const uint64_t mask = 0ull - (uint64_t)is_lps;
+    value -= scaled & mask;
+    range = is_lps ? lps : range;
+    state[ctx] = is_lps ? next_lps[st] : next_mps[st];
+    const int sh = __builtin_clz(range) - 23;  // 0 when range is already in [256, 511]
+    range <<= sh;
+    look -= sh;
+    refill();
+    return (int)((st & 1u) ^ is_lps);
   }
   int bypass() {
     look -= 1;
+    const uint64_t scaled = (uint64_t)range << look;
+    const uint32_t bin = value >= scaled;
+    value -= scaled & (0ull - (uint64_t)bin);
     refill();
-    if (value >= (range << look)) {
-      value -= range << look;
-      return 1;
-    }
-    return 0;
+    return (int)bin;
   }
   int terminate() {
     range -= 2;
-    if (value >= (range << look)) return 1;
-    if (range < 256) {
-      const int sh = __builtin_clz(range) - 23;
-      range <<= sh;
-      look -= sh;
-      refill();
-    }
+    if (value >= ((uint64_t)range << look)) return 1;
+    const int sh = __builtin_clz(range) - 23;
+    range <<= sh;
+    look -= sh;
+    refill();
     return 0;
   }
 };

@@ -1083,8 +1083,10 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   const size_t rows = (size_t)n_frames * pp->pic_height_in_mbs;
   const size_t mbs = rows * pp->pic_width_in_mbs;
   const int set = (int)(ctx->next_set++ % dryv_recon_ctx::kSets);
-  int rc = ensure_control(ctx, set, mbs);
-  if (rc != DRYV_OK) return rc;
+  for (int i = 0; i < dryv_recon_ctx::kSets; i++) {  // all blocks grow together: no allocation once a batch size has run
+    int rc = ensure_control(ctx, i, mbs);
+    if (rc != DRYV_OK) return rc;
+  }
   if (ctx->ctl[set].used) CU(cudaStreamWaitEvent(s, ctx->ctl[set].done, 0));  // the block's previous launch has finished
   if (++ctx->tag == 0) ctx->tag = 1;  // every launch validates line words with its own tag: no per-launch clearing
   CU(cudaMemsetAsync(ctx->d_ticket + 2 * set, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait

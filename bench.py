@@ -33,8 +33,11 @@ UNIT = "Mpixels/s"
 BYTES_PER_MB_FULL = 1172   # 768 levels + 20 syntax + 384 pixels out (SURVEY.md §8d / BASELINE.md §3)
 BYTES_PER_MB_RESID = 1540  # 768 + 4 + 384 prediction in + 384 out
 # DRAM bytes of one recon_wavefront_kernel launch on the default workload, from the committed ncu capture
-# (profiles/r01_v14_wavefront_summary.txt: 432.22 MB read + 216.21 MB written)
-TRAFFIC_BYTES_PER_LAUNCH = 648_432_384
+# (profiles/r01_v16_wavefront_summary.txt: 424.45 MB read + 215.19 MB written)
+TRAFFIC_BYTES_PER_LAUNCH = 639_644_416
+# independent batches kept in flight by the device-resident timed region: consecutive steps rotate over this many CUDA
+# streams and output buffers (the library's four wavefront control blocks allow up to four)
+N_FLIGHT = 3
 
 
 def parse_args():
@@ -214,16 +217,15 @@ def main():
     ctx = recon.ReconContext(local_rank)
     dsoa = recon.DeviceSoa(hbatch, device=dev)
     d_out = torch.zeros((n_frames, pp.frame_bytes), dtype=torch.uint8, device=dev)
-    d_out2 = torch.zeros_like(d_out)
-    d_outs = [d_out, d_out2]
-    # Two dedicated (non-default) torch streams: kernels are launched on them through the C ABI and the torch.cuda.Event
-    # objects below are recorded on the same streams. Consecutive steps alternate over the two streams and the two output
+    d_outs = [d_out] + [torch.zeros_like(d_out) for _ in range(N_FLIGHT - 1)]
+    # Dedicated (non-default) torch streams: kernels are launched on them through the C ABI and the torch.cuda.Event
+    # objects below are recorded on the same streams. Consecutive steps rotate over the N_FLIGHT streams and as many output
     # buffers: the batches are independent, so the library lets a step start while the previous one drains (the start-up
     # stagger of one wavefront fills the tail of the other). Every step still does all of its work.
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = [torch.cuda.Stream(dev) for _ in range(N_FLIGHT)]
     stream = streams[0]
     sptr = stream.cuda_stream
-    assert sptr != 0 and streams[1].cuda_stream != 0
+    assert all(s.cuda_stream != 0 for s in streams)
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -231,7 +233,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step(k=0, n_streams=2):
+    def step(k=0, n_streams=N_FLIGHT):
         i = k % n_streams
         ctx.reconstruct_device(dsoa, d_outs[i], streams[i].cuda_stream)
 
@@ -258,17 +260,18 @@ def main():
     sampler.start()
     launches0 = ctx.launch_count
     ev0 = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(N_FLIGHT)]
     barrier()
     ev0.record(streams[0])
-    streams[1].wait_event(ev0)
+    for s in streams[1:]:
+        s.wait_event(ev0)
     for k in range(args.steps):
         step(k)
-    ends[0].record(streams[0])
-    ends[1].record(streams[1])
+    for e, s in zip(ends, streams):
+        e.record(s)
     barrier()
     ctx.wait()
-    ms_total = max(ev0.elapsed_time(ends[0]), ev0.elapsed_time(ends[1]))
+    ms_total = max(ev0.elapsed_time(e) for e in ends)
     launches = ctx.launch_count - launches0
     # effective time of the dominant kernel per launch inside the timed region (two launches share the GPU at a time, so
     # the event pair around one launch spans more than its share): the timed region is nothing but these launches
@@ -325,14 +328,14 @@ def main():
 
     # parity spot check outside the timed region: first picture against the oracle
     import oracle
-    got0 = d_outs[(args.steps - 1) & 1][0].cpu().numpy()
+    got0 = d_outs[(args.steps - 1) % N_FLIGHT][0].cpu().numpy()
     ref0 = oracle.reconstruct(hbatch.frames(0, 1))[0]
-    parity = bool(np.array_equal(got0, ref0)) and bool(torch.equal(d_outs[0], d_outs[1]))
+    parity = bool(np.array_equal(got0, ref0)) and all(bool(torch.equal(d_outs[0], o)) for o in d_outs[1:])
 
     peak, peak_src = measured_peak_gbs()
     n_mb_step = n_frames * pp.n_mb
     # a step = ticket memset + resolve_modes_kernel (prediction-mode pre-pass) + recon_wavefront_kernel. The wavefront
-    # kernel is a programmatic dependent of the pre-pass and overlaps it; with two batches in flight the GPU time one
+    # kernel is a programmatic dependent of the pre-pass and overlaps it; with N_FLIGHT batches in flight the GPU time one
     # launch costs is the timed region divided by the launches in it (kernel_ms); kernel_ms_isolated is the CUDA-event
     # duration of a launch that has the GPU to itself, quoted against the wavefront kernel's algorithmic bytes as well
     kernel_s = wave_ms_avg * 1e-3
@@ -344,7 +347,7 @@ def main():
         "config": config_dict(args, world),
         "clocks": clocks,
         "gpu_launches": int(launches),
-        "batches_in_flight": 2,
+        "batches_in_flight": N_FLIGHT,
         "single_stream": {"ms_per_step": ms_serial_step,
                           "value": n_frames * pp.luma_pixels / (ms_serial_step * 1e-3) / 1e6,
                           "note": "rank 0, one batch at a time on one stream (no overlap between consecutive batches)"},
@@ -352,7 +355,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": TRAFFIC_BYTES_PER_LAUNCH if (n_frames, args.width_mbs, args.height_mbs) == (64, 120, 68) else None,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch "
-                                       "(profiles/r01_v14_wavefront_summary.txt); algorithmic bytes per launch = "
+                                       "(profiles/r01_v16_wavefront_summary.txt); algorithmic bytes per launch = "
                                        f"{n_mb_step * BYTES_PER_MB_FULL}",
                      "peak_source": peak_src, "kernel": "dryv::recon_wavefront_kernel",
                      "kernel_ms": wave_ms_avg, "kernel_share_of_step": wave_ms_avg / ms_per_step,
@@ -371,7 +374,7 @@ def main():
         "mb_period_us_per_team": mb_period_us,
         "critical_path_ms_at_that_period": steps * mb_period_us * 1e-3,
         "note": "isolated kernel time = rows_per_team x pic_width_in_mbs x mb_period (+ start-up stagger and tail, which "
-                "back-to-back batches on two streams hide); the period is the serial instruction stream of a row team's "
+                "back-to-back batches on separate streams hide); the period is the serial instruction stream of a row team's "
                 "slower warp (DESIGN.md §5), ~25x what the HBM roofline would allow",
     }
     if e2e_ms is not None:

@@ -425,8 +425,12 @@ constexpr int kStartLag = DRYV_START_LAG;
 // Teams per SM = the register budget handed to ptxas. Measured (64 x 1080p, ms per step): 12 teams (79 regs) 0.950,
 // 11 (92) 0.968, 10 (96) 0.900, 9 (96) 0.895, 8 (127) 0.905, 7 (124) 0.907, 6 (143) 1.001. Ten teams of 96 registers:
 // the residual stage stops re-materialising its 16+16 element arrays, and two fewer teams do not cost throughput.
+// Measured again after the Intra4x4 predictor was rolled (one batch at a time / two batches in flight on two streams):
+// 12 teams 0.958 / 0.772, 11 0.967 / 0.778, 10 0.895 / 0.741, 9 0.890 / 0.737, 8 (and 7: same residency) 0.865 / 0.735,
+// 6 (and 5) 0.933 / 0.835. Eight teams with up to 128 registers; the optimum is flat (poll pacing, sleep lengths and the
+// chroma wait flavour all land within 0.3 % of it, tools/overlap_var.sh).
 #ifndef DRYV_TEAMS_PER_SM
-#define DRYV_TEAMS_PER_SM 10
+#define DRYV_TEAMS_PER_SM 8
 #endif
 __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefront_kernel(const KernelArgs a) {
   __shared__ alignas(16) TeamSmem ts;

@@ -15,7 +15,7 @@ pp = PicParams.make(120, 68)
 b = synth.generate(pp, frames, 3000)
 ds = recon.DeviceSoa(b)
 NS = 4
-ctxs = [recon.ReconContext(0) for _ in range(NS)]
+ctxs = [recon.ReconContext(0)] * NS  # one context: the library rotates its control blocks over the launches
 outs = [torch.zeros((frames, pp.frame_bytes), dtype=torch.uint8, device="cuda") for _ in range(NS)]
 streams = [torch.cuda.Stream() for _ in range(NS)]
 

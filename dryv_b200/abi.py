@@ -75,6 +75,23 @@ class LevelsCompact(C.Structure):
 
 COMPACT_MAX_RECORD = 4 + 24 * 2 + COEFFS_PER_MB * 2
 
+SURFACE_I420, SURFACE_NV12 = 0, 1
+
+
+class Surface(C.Structure):
+    """dryv_surface: the rectangle of the coded picture to hand out and its layout (include/dryv_recon.h)."""
+    _fields_ = [("format", C.c_uint32), ("crop_left", C.c_uint32), ("crop_top", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32)]
+
+    @classmethod
+    def make(cls, width, height, crop_left=0, crop_top=0, fmt=SURFACE_I420):
+        return cls(fmt, crop_left, crop_top, width, height)
+
+    @property
+    def nbytes(self) -> int:
+        return self.width * self.height * 3 // 2
+
+
 FIELDS = ("mb_type", "transform_size_8x8_flag", "intra_chroma_pred_mode", "qp", "pred_syntax", "coeff")
 
 

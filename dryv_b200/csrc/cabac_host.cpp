@@ -232,6 +232,7 @@ int collect_nals(const uint8_t* d, size_t len, std::vector<Nal>& out) {
 struct Sps {
   bool ok = false;
   int w_mbs = 0, h_mbs = 0, log2_max_frame_num = 4, poc_type = 0, log2_max_poc_lsb = 4, delta_pic_order_always_zero = 0;
+  uint32_t crop_l = 0, crop_r = 0, crop_t = 0, crop_b = 0;  // frame_crop_*_offset, in units of two luma samples (4:2:0 frames)
 };
 struct Pps {
   bool ok = false;
@@ -269,7 +270,15 @@ int parse_sps(const Nal& nal, Sps& s) {
   s.h_mbs = (int)b.ue() + 1;
   if (!b.u(1)) return DRYV_ERR_UNSUPPORTED;  // frame_mbs_only_flag
   if (b.bad || s.w_mbs > 1024 || s.h_mbs > 1024) return DRYV_ERR_ARG;
-  s.ok = true;  // direct_8x8_inference, cropping (dryv never crops) and VUI are not needed
+  b.u(1);  // direct_8x8_inference_flag
+  if (b.u(1)) {  // frame_cropping_flag, atom/avcc/sps.rs:252-267: reconstruction ignores it (dryv never crops), dryv_cabac_surface reports it
+    s.crop_l = b.ue();
+    s.crop_r = b.ue();
+    s.crop_t = b.ue();
+    s.crop_b = b.ue();
+  }
+  if (b.bad) return DRYV_ERR_ARG;
+  s.ok = true;  // the VUI is not needed
   return DRYV_OK;
 }
 
@@ -693,6 +702,25 @@ int dryv_cabac_scan(const uint8_t* annexb, size_t len, dryv_pic_params* pp, uint
   memset(pp->scaling_list4x4, 16, sizeof pp->scaling_list4x4);  // Flat_4x4_16 / Flat_8x8_16 (slice/header.rs:317-332)
   memset(pp->scaling_list8x8, 16, sizeof pp->scaling_list8x8);
   *n_pictures = (uint32_t)st.idr.size();
+  return DRYV_OK;
+}
+
+int dryv_cabac_surface(const uint8_t* annexb, size_t len, dryv_surface* out) {
+  if (!annexb || !out || len < 8) return DRYV_ERR_ARG;
+  std::vector<Nal> nals;
+  int rc = collect_nals(annexb, len, nals);
+  if (rc != DRYV_OK) return rc;
+  Stream st;
+  rc = analyse(nals, st);
+  if (rc != DRYV_OK) return rc;
+  const uint64_t W = 16ull * (uint64_t)st.sps.w_mbs, H = 16ull * (uint64_t)st.sps.h_mbs;
+  const uint64_t l = 2ull * st.sps.crop_l, r = 2ull * st.sps.crop_r, t = 2ull * st.sps.crop_t, b = 2ull * st.sps.crop_b;
+  if (l + r >= W || t + b >= H) return DRYV_ERR_ARG;
+  out->format = DRYV_SURFACE_I420;
+  out->crop_left = (uint32_t)l;
+  out->crop_top = (uint32_t)t;
+  out->width = (uint32_t)(W - l - r);
+  out->height = (uint32_t)(H - t - b);
   return DRYV_OK;
 }
 

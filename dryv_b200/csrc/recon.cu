@@ -922,6 +922,72 @@ __global__ void __launch_bounds__(kThreadsPerCta) expand_levels_kernel(const uin
   if (bad) atomicCAS(status, STATUS_OK, STATUS_UNSUPPORTED);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Surface export: crop rectangle of the coded pictures -> packed I420 planes or NV12. A pure
+// streaming pass: every thread moves V output bytes (V chosen on the host from the alignment of crop offset, width and
+// plane offsets); rows of the coded picture that the rectangle leaves out are never read.
+// ------------------------------------------------------------------------------------------------
+template <int V> struct ExportVec;
+template <> struct ExportVec<16> { typedef uint4 type; };
+template <> struct ExportVec<8> { typedef uint2 type; };
+template <> struct ExportVec<4> { typedef uint32_t type; };
+template <> struct ExportVec<2> { typedef uint16_t type; };
+template <> struct ExportVec<1> { typedef uint8_t type; };
+
+struct ExportArgs {
+  const uint8_t* src;   // first wanted sample of picture 0's plane (crop offset applied)
+  const uint8_t* src2;  // interleave only: the Cr plane, same position
+  uint8_t* dst;         // picture 0's destination plane
+  size_t src_frame_stride, dst_frame_stride;
+  uint32_t src_row_stride;  // bytes between rows of the coded plane
+  uint32_t row_bytes;       // bytes per destination row
+  uint32_t rows;            // rows per picture
+  unsigned long long total; // n_frames * rows * (row_bytes / V)
+};
+
+template <int V>
+__global__ void __launch_bounds__(256) export_rows_kernel(const ExportArgs a) {
+  typedef typename ExportVec<V>::type T;
+  const unsigned long long idx = (unsigned long long)blockIdx.x * 256u + threadIdx.x;
+  if (idx >= a.total) return;
+  const uint32_t per_row = a.row_bytes / V;
+  const uint32_t c = (uint32_t)(idx % per_row);
+  const unsigned long long rr = idx / per_row;
+  const uint32_t row = (uint32_t)(rr % a.rows);
+  const size_t f = (size_t)(rr / a.rows);
+  const T v = __ldcs(reinterpret_cast<const T*>(a.src + f * a.src_frame_stride + (size_t)row * a.src_row_stride) + c);
+  __stcs(reinterpret_cast<T*>(a.dst + f * a.dst_frame_stride + (size_t)row * a.row_bytes) + c, v);
+}
+
+// NV12 chroma rows: V output bytes = V/2 Cb samples and V/2 Cr samples, interleaved
+template <int V>
+__global__ void __launch_bounds__(256) export_interleave_kernel(const ExportArgs a) {
+  typedef typename ExportVec<V>::type T;
+  typedef typename ExportVec<V / 2>::type H;
+  const unsigned long long idx = (unsigned long long)blockIdx.x * 256u + threadIdx.x;
+  if (idx >= a.total) return;
+  const uint32_t per_row = a.row_bytes / V;
+  const uint32_t c = (uint32_t)(idx % per_row);
+  const unsigned long long rr = idx / per_row;
+  const uint32_t row = (uint32_t)(rr % a.rows);
+  const size_t f = (size_t)(rr / a.rows);
+  const size_t so = f * a.src_frame_stride + (size_t)row * a.src_row_stride;
+  const H cb = __ldcs(reinterpret_cast<const H*>(a.src + so) + c);
+  const H cr = __ldcs(reinterpret_cast<const H*>(a.src2 + so) + c);
+  T out;
+  if constexpr (V == 16) {
+    out = make_uint4(__byte_perm(cb.x, cr.x, 0x5140), __byte_perm(cb.x, cr.x, 0x7362), __byte_perm(cb.y, cr.y, 0x5140),
+                     __byte_perm(cb.y, cr.y, 0x7362));
+  } else if constexpr (V == 8) {
+    out = make_uint2(__byte_perm(cb, cr, 0x5140), __byte_perm(cb, cr, 0x7362));
+  } else if constexpr (V == 4) {
+    out = __byte_perm((uint32_t)cb, (uint32_t)cr, 0x5140);
+  } else {
+    out = (uint16_t)((uint32_t)cb | ((uint32_t)cr << 8));
+  }
+  __stcs(reinterpret_cast<T*>(a.dst + f * a.dst_frame_stride + (size_t)row * a.row_bytes) + c, out);
+}
+
 }  // namespace dryv
 
 // ================================================================================================
@@ -984,6 +1050,11 @@ struct dryv_recon_ctx {
   uint8_t* d_in[kStages] = {};
   uint8_t* d_out[kStages] = {};
   size_t in_cap = 0, out_cap = 0;
+  // output surface of the submit calls (dryv_recon_set_surface): exported on the GPU into d_exp, copied out from there
+  dryv_surface surface = {};
+  bool surface_set = false;
+  uint8_t* d_exp[kStages] = {};
+  size_t exp_cap = 0;
   cudaStream_t pending_user = nullptr;
   bool pending_user_valid = false;
   uint64_t launches = 0;
@@ -1139,6 +1210,106 @@ int launch_expand(dryv_recon_ctx* ctx, const uint32_t* d_offset, const uint8_t* 
   return DRYV_OK;
 }
 
+
+bool surface_ok(const dryv_surface* s) {
+  return s && (s->format == DRYV_SURFACE_I420 || s->format == DRYV_SURFACE_NV12) && s->width > 0 && s->height > 0 &&
+         !((s->width | s->height | s->crop_left | s->crop_top) & 1u) && s->width <= (1u << 15) && s->height <= (1u << 15) &&
+         s->crop_left <= (1u << 15) && s->crop_top <= (1u << 15);
+}
+size_t surface_bytes(const dryv_surface* s) { return (size_t)s->width * s->height * 3 / 2; }
+
+// largest power of two <= cap that divides every one of the byte quantities
+int common_vector(std::initializer_list<unsigned long long> q, int cap, int floor_v) {
+  int v = cap;
+  for (; v > floor_v; v >>= 1) {
+    bool ok = true;
+    for (unsigned long long x : q) ok = ok && (x % (unsigned)v) == 0;
+    if (ok) break;
+  }
+  return v;
+}
+
+int launch_rows(dryv_recon_ctx* ctx, int v, dryv::ExportArgs a, unsigned long long vectors, cudaStream_t st) {
+  a.total = vectors;
+  if (vectors == 0) return DRYV_OK;
+  const unsigned blocks = (unsigned)((vectors + 255) / 256);
+  switch (v) {
+    case 16: dryv::export_rows_kernel<16><<<blocks, 256, 0, st>>>(a); break;
+    case 8: dryv::export_rows_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    case 4: dryv::export_rows_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    case 2: dryv::export_rows_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+    default: dryv::export_rows_kernel<1><<<blocks, 256, 0, st>>>(a); break;
+  }
+  CU(cudaGetLastError());
+  return DRYV_OK;
+}
+int launch_interleave(dryv_recon_ctx* ctx, int v, dryv::ExportArgs a, unsigned long long vectors, cudaStream_t st) {
+  a.total = vectors;
+  if (vectors == 0) return DRYV_OK;
+  const unsigned blocks = (unsigned)((vectors + 255) / 256);
+  switch (v) {
+    case 16: dryv::export_interleave_kernel<16><<<blocks, 256, 0, st>>>(a); break;
+    case 8: dryv::export_interleave_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    case 4: dryv::export_interleave_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    default: dryv::export_interleave_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+  }
+  CU(cudaGetLastError());
+  return DRYV_OK;
+}
+
+// enqueue the surface export of n_frames coded pictures (d_yuv, `pp` geometry) into d_out on stream st
+int launch_export(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const uint8_t* d_yuv, uint32_t n_frames,
+                  const dryv_surface* s, uint8_t* d_out, cudaStream_t st) {
+  const size_t W = 16u * (size_t)pp->pic_width_in_mbs, H = 16u * (size_t)pp->pic_height_in_mbs;
+  if ((size_t)s->crop_left + s->width > W || (size_t)s->crop_top + s->height > H)
+    return fail(ctx, DRYV_ERR_ARG, "surface rectangle leaves the coded picture");
+  const size_t src_frame = W * H * 3 / 2, dst_frame = surface_bytes(s);
+  const size_t w = s->width, h = s->height, cl = s->crop_left, ct = s->crop_top;
+  const unsigned long long pa = (unsigned long long)reinterpret_cast<uintptr_t>(d_yuv),
+                           pb = (unsigned long long)reinterpret_cast<uintptr_t>(d_out);
+  dryv::ExportArgs a;
+  memset(&a, 0, sizeof a);
+  a.src_frame_stride = src_frame;
+  a.dst_frame_stride = dst_frame;
+  // luma
+  {
+    const int v = common_vector({pa, pb, cl, w, dst_frame}, 16, 1);
+    a.src = d_yuv + ct * W + cl;
+    a.dst = d_out;
+    a.src_row_stride = (uint32_t)W;
+    a.row_bytes = (uint32_t)w;
+    a.rows = (uint32_t)h;
+    int rc = launch_rows(ctx, v, a, (unsigned long long)n_frames * h * (w / v), st);
+    if (rc != DRYV_OK) return rc;
+    ctx->launches++;
+  }
+  const uint8_t* cb = d_yuv + W * H + (ct / 2) * (W / 2) + cl / 2;
+  const uint8_t* cr = cb + (W / 2) * (H / 2);
+  a.src_row_stride = (uint32_t)(W / 2);
+  a.rows = (uint32_t)(h / 2);
+  if (s->format == DRYV_SURFACE_NV12) {
+    const int v = common_vector({pa, pb, cl, w, w * h, dst_frame}, 16, 2);  // V/2 source bytes per plane: cl/2 % (V/2) == 0
+    a.src = cb;
+    a.src2 = cr;
+    a.dst = d_out + w * h;
+    a.row_bytes = (uint32_t)w;
+    int rc = launch_interleave(ctx, v, a, (unsigned long long)n_frames * (h / 2) * (w / v), st);
+    if (rc != DRYV_OK) return rc;
+    ctx->launches++;
+  } else {
+    const int v = common_vector({pa, pb, cl / 2, w / 2, w * h, w * h / 4, dst_frame}, 16, 1);
+    a.row_bytes = (uint32_t)(w / 2);
+    for (int pl = 0; pl < 2; pl++) {
+      a.src = pl ? cr : cb;
+      a.dst = d_out + w * h + (size_t)pl * (w / 2) * (h / 2);
+      int rc = launch_rows(ctx, v, a, (unsigned long long)n_frames * (h / 2) * (w / 2 / v), st);
+      if (rc != DRYV_OK) return rc;
+      ctx->launches++;
+    }
+  }
+  return DRYV_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1218,6 +1389,7 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
     if (ctx->e_d2h[i]) cudaEventDestroy(ctx->e_d2h[i]);
     if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
     if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+    if (ctx->d_exp[i]) cudaFree(ctx->d_exp[i]);
   }
   for (int i = 0; i < dryv_recon_ctx::kTimedLaunches; i++) {
     if (ctx->e_wave[i][0]) cudaEventDestroy(ctx->e_wave[i][0]);
@@ -1311,6 +1483,12 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
   const size_t n_mb = (size_t)pp->pic_width_in_mbs * pp->pic_height_in_mbs;
   const size_t out_per_frame = n_mb * 384;
   const size_t dense_per_frame = n_mb * (4 + 16 + 768);
+  const bool exporting = ctx->surface_set;
+  const dryv_surface surf = ctx->surface;
+  if (exporting && ((size_t)surf.crop_left + surf.width > 16u * (size_t)pp->pic_width_in_mbs ||
+                    (size_t)surf.crop_top + surf.height > 16u * (size_t)pp->pic_height_in_mbs))
+    return fail(ctx, DRYV_ERR_ARG, "surface rectangle leaves the coded picture");
+  const size_t host_per_frame = exporting ? surface_bytes(&surf) : out_per_frame;  // what out_yuv receives per picture
   // chunk = pictures per pipeline stage. Measured on a B200 / PCIe Gen5 box (64 x 1080p):
   //  dense levels (412 MB in, 201 MB out): the H2D copy is the floor (7.4 ms alone, 8.0 ms with the D2H running
   //    against it); ~72 MB of input per stage keeps the per-chunk kernels hidden under the copies while the pipeline
@@ -1355,6 +1533,17 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
   const size_t off_bytes = lv ? (((size_t)chunk * n_mb + 1) * 4 + 15) & ~(size_t)15 : 0;
   const size_t need_in = dense_per_frame * chunk + off_bytes + ((stream_max + 15) & ~(size_t)15);
   const size_t need_out = out_per_frame * chunk;
+  const size_t need_exp = exporting ? host_per_frame * chunk : 0;
+  if (need_exp > ctx->exp_cap) {
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < kStages; i++) {
+      if (ctx->d_exp[i]) cudaFree(ctx->d_exp[i]);
+      ctx->d_exp[i] = nullptr;
+    }
+    ctx->exp_cap = 0;
+    for (int i = 0; i < kStages; i++) CU(cudaMalloc(&ctx->d_exp[i], need_exp));
+    ctx->exp_cap = need_exp;
+  }
   if (need_in > ctx->in_cap || need_out > ctx->out_cap) {
     CU(cudaDeviceSynchronize());
     for (int i = 0; i < kStages; i++) {
@@ -1436,12 +1625,16 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
     }
     rc = launch_wavefront(ctx, pp, &d, nf, ctx->d_out[slot], sc);
     if (rc != DRYV_OK) return rc;
+    if (exporting) {
+      rc = launch_export(ctx, pp, ctx->d_out[slot], nf, &surf, ctx->d_exp[slot], sc);
+      if (rc != DRYV_OK) return rc;
+    }
     CU(cudaEventRecord(ctx->e_kernel[slot], sc));
     mark(sc);
     // D2H
     CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->e_kernel[slot], 0));
-    CU(cudaMemcpyAsync(out_yuv + (size_t)done * out_per_frame, ctx->d_out[slot], (size_t)nf * out_per_frame,
-                       cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU(cudaMemcpyAsync(out_yuv + (size_t)done * host_per_frame, exporting ? ctx->d_exp[slot] : ctx->d_out[slot],
+                       (size_t)nf * host_per_frame, cudaMemcpyDeviceToHost, ctx->s_d2h));
     CU(cudaEventRecord(ctx->e_d2h[slot], ctx->s_d2h));
     mark(ctx->s_d2h);
     done += nf;
@@ -1468,6 +1661,35 @@ int dryv_recon_submit_compact(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
   if (!pp_ok(pp) || !soa_fields || !levels || !levels->offset || !levels->stream || !out_yuv || n_frames == 0)
     return fail(ctx, DRYV_ERR_ARG, "bad argument");
   return submit_impl(ctx, pp, soa, levels, n_frames, out_yuv);
+}
+
+size_t dryv_recon_surface_bytes(const dryv_surface* s) { return surface_ok(s) ? surface_bytes(s) : 0; }
+
+int dryv_recon_export_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const uint8_t* d_yuv, uint32_t n_frames,
+                             const dryv_surface* s, uint8_t* d_out, void* cuda_stream) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!pp_ok(pp) || !d_yuv || !d_out || n_frames == 0 || !surface_ok(s)) return fail(ctx, DRYV_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute[0];
+  int rc = launch_export(ctx, pp, d_yuv, n_frames, s, d_out, st);
+  if (rc != DRYV_OK) return rc;
+  if (cuda_stream) {
+    ctx->pending_user = st;
+    ctx->pending_user_valid = true;
+  }
+  return DRYV_OK;
+}
+
+int dryv_recon_set_surface(dryv_recon_ctx* ctx, const dryv_surface* s) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!s) {
+    ctx->surface_set = false;
+    return DRYV_OK;
+  }
+  if (!surface_ok(s)) return fail(ctx, DRYV_ERR_ARG, "malformed surface");
+  ctx->surface = *s;
+  ctx->surface_set = true;
+  return DRYV_OK;
 }
 
 int dryv_recon_expand_levels_device(dryv_recon_ctx* ctx, const dryv_mb_levels_compact* d_levels, size_t n_mbs,

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .abi import PicParams, SyntaxBatch
+from .abi import PicParams, Surface, SyntaxBatch
 from .abi import COMPACT_MAX_RECORD
 from .recon import OK, CompactLevels, PinnedArray, ReconError, load_library
 
@@ -24,6 +24,18 @@ def scan(stream: bytes):
     if rc != OK:
         raise ReconError(rc, "dryv_cabac_scan: not a supported H.264 stream")
     return pp, int(n.value)
+
+
+def surface(stream: bytes) -> Surface:
+    """The display rectangle the stream's SPS asks for (frame_crop_*_offset) as an I420 Surface; the whole coded picture
+    when the SPS does not crop."""
+    lib = load_library()
+    buf = np.frombuffer(stream, np.uint8)
+    sf = Surface()
+    rc = lib.dryv_cabac_surface(buf.ctypes.data, buf.size, C.byref(sf))
+    if rc != OK:
+        raise ReconError(rc, "dryv_cabac_surface")
+    return sf
 
 
 def parse(stream: bytes, threads: int = 0, out: SyntaxBatch | None = None, first: int = 0,

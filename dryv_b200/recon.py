@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-from .abi import COMPACT_MAX_RECORD, FIELDS, LevelsCompact, MbSoa, PicParams, SyntaxBatch
+from .abi import COMPACT_MAX_RECORD, FIELDS, LevelsCompact, MbSoa, PicParams, Surface, SyntaxBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
@@ -26,9 +26,11 @@ EXPORTS = [
     "dryv_recon_wait", "dryv_recon_reconstruct_device", "dryv_recon_residual_add_device",
     "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms", "dryv_recon_device_tables",
     "dryv_recon_wavefront_times", "dryv_recon_pack_levels", "dryv_recon_unpack_levels", "dryv_recon_submit_compact",
-    "dryv_recon_expand_levels_device", "dryv_recon_wait_oldest",
+    "dryv_recon_expand_levels_device", "dryv_recon_wait_oldest", "dryv_recon_surface_bytes", "dryv_recon_export_device",
+    "dryv_recon_set_surface",
 ]
-HOST_EXPORTS = ["dryv_cabac_scan", "dryv_cabac_parse", "dryv_cabac_parse_range", "dryv_cabac_parse_compact"]  # include/dryv_cabac_host.h
+HOST_EXPORTS = ["dryv_cabac_scan", "dryv_cabac_parse", "dryv_cabac_parse_range", "dryv_cabac_parse_compact",
+                "dryv_cabac_surface"]  # include/dryv_cabac_host.h
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -116,6 +118,14 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_submit_compact.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), C.POINTER(LevelsCompact), u32, vp]
     lib.dryv_recon_expand_levels_device.restype = C.c_int
     lib.dryv_recon_expand_levels_device.argtypes = [vp, C.POINTER(LevelsCompact), sz, vp, vp]
+    lib.dryv_recon_surface_bytes.argtypes = [C.POINTER(Surface)]
+    lib.dryv_recon_surface_bytes.restype = sz
+    lib.dryv_recon_export_device.argtypes = [vp, C.POINTER(PicParams), vp, u32, C.POINTER(Surface), vp, vp]
+    lib.dryv_recon_export_device.restype = C.c_int
+    lib.dryv_recon_set_surface.argtypes = [vp, C.POINTER(Surface)]
+    lib.dryv_recon_set_surface.restype = C.c_int
+    lib.dryv_cabac_surface.argtypes = [vp, sz, C.POINTER(Surface)]
+    lib.dryv_cabac_surface.restype = C.c_int
     _lib = lib
     return lib
 
@@ -266,9 +276,25 @@ class ReconContext:
         if rc != OK:
             raise ReconError(rc, (self.lib.dryv_recon_last_error(self.h) or b"").decode())
 
+    # -- output surface (crop rectangle, I420 / NV12): include/dryv_recon.h, SURVEY.md §8(f) next-3 ---
+    def set_surface(self, surface: "Surface | None"):
+        """What submit / submit_compact hand back from now on: the given surface, or (None) the coded pictures."""
+        self._check(self.lib.dryv_recon_set_surface(self.h, C.byref(surface) if surface is not None else None))
+        self._surface = surface
+
+    def _out_bytes(self, pp: PicParams) -> int:
+        sf = getattr(self, "_surface", None)
+        return sf.nbytes if sf is not None else pp.frame_bytes
+
+    def export_device(self, pp: PicParams, d_yuv, n_frames: int, surface: "Surface", d_out, stream_ptr: int = 0):
+        """dryv_recon_export_device on torch device tensors: coded pictures -> surfaces, asynchronous on the stream."""
+        assert d_out.numel() >= n_frames * surface.nbytes and d_yuv.numel() >= n_frames * pp.frame_bytes
+        self._check(self.lib.dryv_recon_export_device(self.h, C.byref(pp), d_yuv.data_ptr(), n_frames, C.byref(surface),
+                                                      d_out.data_ptr(), stream_ptr or None))
+
     # -- host-buffer path (what a decoder host calls): H2D + kernels + D2H inside --------------------
     def submit(self, batch: SyntaxBatch, out: np.ndarray):
-        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= batch.n_frames * batch.pp.frame_bytes
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= batch.n_frames * self._out_bytes(batch.pp)
         soa = batch.as_soa()
         self._keep = (batch, soa, out)
         self.__dict__.setdefault("_keep_all", []).append(self._keep)
@@ -277,7 +303,7 @@ class ReconContext:
 
     def submit_compact(self, batch: SyntaxBatch, levels: CompactLevels, out: np.ndarray):
         """dryv_recon_submit_compact: `batch.coeff` is not read, the levels come from the compact stream."""
-        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= batch.n_frames * batch.pp.frame_bytes
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= batch.n_frames * self._out_bytes(batch.pp)
         assert levels.n_mbs == batch.n_frames * batch.pp.n_mb
         soa = batch.as_soa()
         soa.coeff = None

@@ -39,6 +39,12 @@ extern "C" {
  * pictures. Returns DRYV_OK, DRYV_ERR_ARG (no SPS/PPS/IDR, truncated data) or DRYV_ERR_UNSUPPORTED. */
 int dryv_cabac_scan(const uint8_t* annexb, size_t len, dryv_pic_params* pp, uint32_t* n_pictures);
 
+/* The display rectangle the stream's SPS asks for (frame_cropping_flag and frame_crop_*_offset, 7.4.2.1.1; the fields the
+ * reference parses in atom/avcc/sps.rs:252-267 and never applies), as a DRYV_SURFACE_I420 surface for
+ * dryv_recon_export_device / dryv_recon_set_surface: the whole coded picture when the SPS does not crop. Returns
+ * DRYV_ERR_ARG if the offsets leave no picture. */
+int dryv_cabac_surface(const uint8_t* annexb, size_t len, dryv_surface* out);
+
 /* Parses every IDR picture of the stream (in stream order) into the caller's structure-of-arrays buffers, laid out as
  * dryv_mb_soa describes for `n_pictures` pictures of `pp` geometry: mb_type / transform_size_8x8_flag /
  * intra_chroma_pred_mode / qp: n_pictures * n_mb bytes each; pred_syntax: 16 bytes per macroblock; coeff: 384 int16 per

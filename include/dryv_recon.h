@@ -202,6 +202,38 @@ int dryv_recon_submit_compact(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
 int dryv_recon_expand_levels_device(dryv_recon_ctx* ctx, const dryv_mb_levels_compact* d_levels, size_t n_mbs,
                                     int16_t* d_coeff, void* cuda_stream);
 
+/* ---- Output surface ---------------------------------------------------------------------
+ * The reference writes the coded picture, macroblock aligned and planar (frame/mod.rs:48-70); "frame cropping" is an
+ * open item of its roadmap (README.md:13) although the crop fields are already parsed (atom/avcc/sps.rs:252-267).
+ * A surface is the rectangle of the coded picture a consumer wants and the layout it wants it in:
+ *   DRYV_SURFACE_I420: Y (width x height), Cb (width/2 x height/2), Cr — planar, rows packed;
+ *   DRYV_SURFACE_NV12: Y (width x height), then height/2 rows of width bytes: Cb, Cr pairs interleaved.
+ * crop_left / crop_top / width / height are in luma samples and even (4:2:0); the rectangle must lie inside the coded
+ * picture. The SPS crop rectangle of a stream (7.4.2.1.1: frame_crop_*_offset x CropUnit, CropUnitX = CropUnitY = 2
+ * for 4:2:0 frame pictures) is returned by dryv_cabac_surface (include/dryv_cabac_host.h). */
+#define DRYV_SURFACE_I420 0u
+#define DRYV_SURFACE_NV12 1u
+typedef struct dryv_surface {
+  uint32_t format;
+  uint32_t crop_left, crop_top;
+  uint32_t width, height;
+} dryv_surface;
+
+/* Bytes of one exported picture (width * height * 3 / 2); 0 if `s` is NULL or malformed (odd / zero fields, unknown format). */
+size_t dryv_recon_surface_bytes(const dryv_surface* s);
+
+/* Device buffers: d_yuv holds n_frames reconstructed pictures of `pp` geometry (dryv_recon_reconstruct_device's output),
+ * d_out receives n_frames surfaces of dryv_recon_surface_bytes each. Asynchronous on `cuda_stream` (0: the context's own),
+ * stream-ordered after the reconstruction when that ran on the same stream. One streaming pass, no host staging. */
+int dryv_recon_export_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const uint8_t* d_yuv, uint32_t n_frames,
+                             const dryv_surface* s, uint8_t* d_out, void* cuda_stream);
+
+/* Selects what dryv_recon_submit / dryv_recon_submit_compact hand back from now on: with a surface set, `out_yuv`
+ * receives n_frames * dryv_recon_surface_bytes(s) bytes (the export runs on the GPU behind each stage's kernels, so the
+ * D2H copy moves the cropped pictures only); s == NULL restores the coded pictures (the default, the reference's layout).
+ * Returns DRYV_ERR_ARG for a malformed surface; that it fits the pictures is checked by the submit that uses it. */
+int dryv_recon_set_surface(dryv_recon_ctx* ctx, const dryv_surface* s);
+
 /* Frame::write_to_yuv_file (frame/mod.rs:48-70): writes one reconstructed picture (host memory, the
  * layout above) to `path`, creating the parent directory of "temp/yuv_frame"-style paths if needed. */
 int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char* path);

@@ -79,7 +79,8 @@ def nal_unit(ref_idc, nal_type, rbsp: bytes) -> bytes:
     return bytes(out)
 
 
-def sps_rbsp(w_mbs, h_mbs):
+def sps_rbsp(w_mbs, h_mbs, crop=None):
+    """crop: None or (left, right, top, bottom) frame_crop_*_offset values (units of two luma samples for 4:2:0 frames)."""
     w = BitWriter()
     w.u(8, 100)   # profile_idc: High
     w.u(8, 0)     # constraint flags + reserved
@@ -98,7 +99,10 @@ def sps_rbsp(w_mbs, h_mbs):
     w.ue(h_mbs - 1)
     w.u(1, 1)     # frame_mbs_only_flag
     w.u(1, 1)     # direct_8x8_inference_flag
-    w.u(1, 0)     # frame_cropping_flag
+    w.u(1, 1 if crop else 0)     # frame_cropping_flag
+    if crop:
+        for v in crop:
+            w.ue(v)   # frame_crop_left / right / top / bottom_offset
     w.u(1, 0)     # vui_parameters_present_flag
     w.trailing()
     return w.tobytes()
@@ -494,12 +498,13 @@ def encode_picture(batch, frame, cbps, idr_pic_id=0) -> bytes:
     return nal_unit(3, 5, w.tobytes())
 
 
-def encode_stream(batch) -> bytes:
-    """Annex-B stream: SPS, PPS, then one IDR picture per frame of `batch` (canonicalises `batch` in place)."""
+def encode_stream(batch, crop=None) -> bytes:
+    """Annex-B stream: SPS, PPS, then one IDR picture per frame of `batch` (canonicalises `batch` in place). `crop`: the
+    SPS frame_crop_{left,right,top,bottom}_offset values, or None for no cropping."""
     pp = batch.pp
     assert all(v == 16 for v in pp.scaling_list4x4) and all(v == 16 for v in pp.scaling_list8x8), "flat lists only"
     cbps = canonicalise(batch)
-    out = nal_unit(3, 7, sps_rbsp(pp.pic_width_in_mbs, pp.pic_height_in_mbs))
+    out = nal_unit(3, 7, sps_rbsp(pp.pic_width_in_mbs, pp.pic_height_in_mbs, crop))
     out += nal_unit(3, 8, pps_rbsp(int(pp.chroma_qp_index_offset), int(pp.second_chroma_qp_index_offset)))
     for f in range(batch.n_frames):
         out += encode_picture(batch, f, cbps, idr_pic_id=f & 1)

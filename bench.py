@@ -435,6 +435,38 @@ def main():
                                  "roofline": {"bound": "hbm", "achieved": rach, "peak": peak, "unit": "GB/s",
                                               "frac": rach / peak, "algorithmic_bytes_per_mb": BYTES_PER_MB_RESID}}
 
+        # side measurement, SURVEY.md §8(f) next-3: the display rectangle of every picture of the batch (the SPS crop of a
+        # 1080p / 2160p stream: the coded height rounded down to a multiple of 8 lines below it) as I420 planes and as NV12;
+        # a streaming pass, checked against oracle/surface.py on the first picture
+        from dryv_b200.abi import SURFACE_I420, SURFACE_NV12, Surface
+        from oracle import surface as osurf
+        W_, H_ = 16 * pp.pic_width_in_mbs, 16 * pp.pic_height_in_mbs
+        h_disp = H_ - 8 if H_ > 16 else H_
+        exp = {}
+        for name, fmt in (("i420", SURFACE_I420), ("nv12", SURFACE_NV12)):
+            sf = Surface.make(W_, h_disp, 0, 0, fmt)
+            d_sf = torch.empty((n_frames, sf.nbytes), dtype=torch.uint8, device=dev)
+            for _ in range(3):
+                ctx.export_device(pp, d_out, n_frames, sf, d_sf, sptr)
+            torch.cuda.synchronize(dev)
+            a0.record(stream)
+            for _ in range(args.steps):
+                ctx.export_device(pp, d_out, n_frames, sf, d_sf, sptr)
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            ctx.wait()
+            ems = a0.elapsed_time(a1) / args.steps
+            ok = bool(np.array_equal(d_sf[0].cpu().numpy(), osurf.export(d_out[0].cpu().numpy(), pp.pic_width_in_mbs,
+                                                                         pp.pic_height_in_mbs, 0, 0, W_, h_disp, fmt)))
+            eb = 2.0 * n_frames * sf.nbytes   # every surface byte is read once and written once
+            exp[name] = {"ms_per_step": ems, "value": n_frames * W_ * h_disp / (ems * 1e-3) / 1e6, "unit": UNIT,
+                         "parity_vs_oracle_first_picture": ok,
+                         "roofline": {"bound": "hbm", "achieved": eb / (ems * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": eb / (ems * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_pixel": 3.0}}
+            del d_sf
+        line["surface_export"] = {"workload": f"{W_}x{h_disp} display rectangle of the {n_frames} coded pictures "
+                                              "(dryv_recon_export_device), device-resident", **exp}
+
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n = n_frames if cores >= 8 else max(1, min(n_frames, 2 * cores))

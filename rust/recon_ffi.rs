@@ -85,6 +85,23 @@ extern "C" {
   /// streaming use: up to four submits may be outstanding; returns when the oldest one's pictures are complete
   pub fn dryv_recon_wait_oldest(ctx: *mut dryv_recon_ctx) -> c_int;
   pub fn dryv_recon_write_yuv_file(frame_yuv: *const u8, bytes: usize, path: *const c_char) -> c_int;
+  /// output surface (crop rectangle, I420 / NV12): with one set, the submit calls hand back
+  /// `n_frames * dryv_recon_surface_bytes(s)` bytes; null restores the coded pictures (what the reference writes)
+  pub fn dryv_recon_surface_bytes(s: *const dryv_surface) -> usize;
+  pub fn dryv_recon_set_surface(ctx: *mut dryv_recon_ctx, s: *const dryv_surface) -> c_int;
+}
+
+/// `dryv_surface` of include/dryv_recon.h. For the SPS display rectangle fill it from the fields the reference already
+/// parses (src/video/atom/avcc/sps.rs:252-267): crop_left = 2 * frame_crop_left_offset, crop_top = 2 * frame_crop_top_offset,
+/// width = 16 * pic_width_in_mbs - 2 * (left + right), height = 16 * pic_height_in_mbs - 2 * (top + bottom).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct dryv_surface {
+  pub format: u32, // 0 = I420 planes, 1 = NV12
+  pub crop_left: u32,
+  pub crop_top: u32,
+  pub width: u32,
+  pub height: u32,
 }
 
 /// Pinned structure-of-arrays buffers for `n_frames` pictures of `n_mb` macroblocks each.

@@ -105,7 +105,7 @@ def test_export_rejects_a_rectangle_outside_the_picture():
     pp = PicParams.make(4, 4)
     ctx = recon.ReconContext(0)
     d_yuv = torch.zeros(pp.frame_bytes, dtype=torch.uint8, device="cuda")
-    d_out = torch.zeros(pp.frame_bytes, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(2 * pp.frame_bytes, dtype=torch.uint8, device="cuda")
     for sf in (Surface.make(64, 64, 2, 0), Surface.make(66, 64), Surface.make(16, 16, 0, 50)):
         with pytest.raises(recon.ReconError) as e:
             ctx.export_device(pp, d_yuv, 1, sf, d_out)

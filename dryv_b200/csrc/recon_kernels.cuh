@@ -52,7 +52,8 @@ struct ResidCtaSmem {
 // The front warp hands each macroblock to the pixel warp through a ring of kSlots slots.
 // Ring depth, measured (64 / 16 x 1080p, ms per step): 2 slots 0.900 / 0.504, 3: 0.917 / 0.504, 4: 0.903 / 0.498,
 // 5: 0.924 / 0.505, 6 (9 teams per SM: one named barrier per slot) 0.926 / 0.500, 8 (7 teams) 0.979 / 0.477. Flat: the
-// depth of the ring is not what lets the classes overlap.
+// depth of the ring is not what lets the classes overlap. Again at eight teams per SM with three batches in flight
+// (64 x 1080p, one batch at a time / overlapped): 3 slots 0.879 / 0.738, 4: 0.866 / 0.725, 5: 0.873 / 0.741, 6: 0.884 / 0.752.
 #ifndef DRYV_SLOTS
 #define DRYV_SLOTS 4
 #endif

@@ -314,16 +314,16 @@ int parse_pps(const Nal& nal, Pps& p) {
 // codIOffset is kept scaled: `value` = codIOffset * 2^look + the next `look` bits of the stream, so "offset >= range"
 // is value >= range << look, renormalising by s bits is look -= s, and the stream is read a byte at a time instead of a
 // bit at a time (the arithmetic is that of 9.3.3.2.2 - 9.3.3.2.4 exactly; src/video/cabac/mod.rs:1207-1278 reads bits).
-struct Cabac {
+// The arithmetic decoder's scalars live apart from the context states: a loop that keeps a local copy of the core has
+// them in registers across the byte stores to the state table (which may alias anything else).
+struct CabacCore {
   const uint8_t* p = nullptr;    // next byte of the slice data
   const uint8_t* end = nullptr;
   size_t overrun = 0;            // zero bytes fed past the end of the data
   uint32_t range = 510;
   uint64_t value = 0;
   int look = 0;
-  uint8_t state[1024];           // (pStateIdx << 1) | valMPS
-  uint8_t next_mps[128], next_lps[128];
-  void refill() {  // keeps 8 <= look <= 23: one operation consumes at most 6 bits
+  inline void refill() {  // keeps 8 <= look <= 23: one operation consumes at most 6 bits
     if (look < 8) {
       uint32_t two = 0;
       if (end - p >= 2) {
@@ -340,30 +340,9 @@ struct Cabac {
       look += 16;
     }
   }
-  // bits consumed beyond the end of the data (0 for a well-formed slice)
-  bool overran() const { return overrun * 8 > (size_t)look; }
-  void init(const uint8_t* data, const uint8_t* data_end, int slice_qp) {
-    p = data;
-    end = data_end;
-    const int q = slice_qp < 0 ? 0 : (slice_qp > 51 ? 51 : slice_qp);
-    for (int i = 0; i < 1024; i++) {
-      int pre = ((kCtxInitM[i] * q) >> 4) + kCtxInitN[i];
-      pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
-      state[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
-    }
-    for (int st = 0; st < 128; st++) {
-      const int ps = st >> 1, m = st & 1;
-      next_mps[st] = (uint8_t)((kTransIdxMps[ps] << 1) | m);
-      next_lps[st] = (uint8_t)((kTransIdxLps[ps] << 1) | (ps == 0 ? !m : m));
-    }
-    range = 510;
-    value = 0;
-    look = -9;  // the first nine bits are codIOffset itself
-    refill();
-    refill();
-  }
-  // 9.3.3.2.1 without a data-dependent branch: the LPS / MPS outcome is a mask, the renormalisation shift a bit count
-  int decision(int ctx) {
+  // 9.3.3.2.1 without a data-dependent branch: the LPS / MPS outcome is a mask, the renormalisation shift a bit count.
+  // `state`: (pStateIdx << 1) | valMPS per context; `next`: [0..127] state after an MPS, [128..255] after an LPS.
+  inline int decision(uint8_t* state, const uint8_t* next, int ctx) {
     const uint32_t st = state[ctx];
     const uint32_t lps = kRangeTabLps[(st >> 1) * 4 + ((range >> 6) & 3)];
     range -= lps;
@@ -372,14 +351,14 @@ struct Cabac {
     const uint64_t mask = 0ull - (uint64_t)is_lps;
     value -= scaled & mask;
     range = is_lps ? lps : range;
-    state[ctx] = is_lps ? next_lps[st] : next_mps[st];
+    state[ctx] = next[st + (is_lps << 7)];
     const int sh = __builtin_clz(range) - 23;  // 0 when range is already in [256, 511]
     range <<= sh;
     look -= sh;
     refill();
     return (int)((st & 1u) ^ is_lps);
   }
-  int bypass() {
+  inline int bypass() {
     look -= 1;
     const uint64_t scaled = (uint64_t)range << look;
     const uint32_t bin = value >= scaled;
@@ -387,7 +366,7 @@ struct Cabac {
     refill();
     return (int)bin;
   }
-  int terminate() {
+  inline int terminate() {
     range -= 2;
     if (value >= ((uint64_t)range << look)) return 1;
     const int sh = __builtin_clz(range) - 23;
@@ -396,6 +375,36 @@ struct Cabac {
     refill();
     return 0;
   }
+};
+
+struct Cabac {
+  CabacCore k;
+  uint8_t state[1024];  // (pStateIdx << 1) | valMPS
+  uint8_t next[256];
+  // bits consumed beyond the end of the data (0 for a well-formed slice)
+  bool overran() const { return k.overrun * 8 > (size_t)k.look; }
+  void init(const uint8_t* data, const uint8_t* data_end, int slice_qp) {
+    k = CabacCore();
+    k.p = data;
+    k.end = data_end;
+    const int q = slice_qp < 0 ? 0 : (slice_qp > 51 ? 51 : slice_qp);
+    for (int i = 0; i < 1024; i++) {
+      int pre = ((kCtxInitM[i] * q) >> 4) + kCtxInitN[i];
+      pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
+      state[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
+    }
+    for (int st = 0; st < 128; st++) {
+      const int ps = st >> 1, m = st & 1;
+      next[st] = (uint8_t)((kTransIdxMps[ps] << 1) | m);
+      next[128 + st] = (uint8_t)((kTransIdxLps[ps] << 1) | (ps == 0 ? !m : m));
+    }
+    k.look = -9;  // the first nine bits are codIOffset itself
+    k.refill();
+    k.refill();
+  }
+  int decision(int ctx) { return k.decision(state, next, ctx); }
+  int bypass() { return k.bypass(); }
+  int terminate() { return k.terminate(); }
 };
 
 // What the context selection of later macroblocks needs to know about a parsed macroblock
@@ -423,18 +432,22 @@ struct SliceParser {
   bool unsupported = false;
 
   // 7.3.5.3.3 residual_block_cabac: `n` levels in coding order into out[0..n) (already zeroed); returns coded_block_flag
-  int residual_block(int cat, int n, int16_t* out, int stride_unused, int cbf_inc, bool code_cbf) {
+  template <int cat>
+  int residual_block(int n, int16_t* out, int stride_unused, int cbf_inc, bool code_cbf) {
     (void)stride_unused;
     if (code_cbf && !c.decision(kCbfBase[cat] + cbf_inc)) return 0;
+    CabacCore eng = c.k;  // registers for the length of the block
+    uint8_t* const state = c.state;
+    const uint8_t* const next = c.next;
     uint8_t sig[64];
     int count = 0, last = n - 1;
     for (int i = 0; i < n - 1; i++) {
       const int si = cat == 5 ? kSig8x8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
       const int li = cat == 5 ? kLast8x8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
-      sig[i] = (uint8_t)c.decision(kSigBase[cat] + si);
+      sig[i] = (uint8_t)eng.decision(state, next, kSigBase[cat] + si);
       if (sig[i]) {
         count++;
-        if (c.decision(kLastBase[cat] + li)) {
+        if (eng.decision(state, next, kLastBase[cat] + li)) {
           last = i;
           break;
         }
@@ -452,23 +465,24 @@ struct SliceParser {
       const int lim = 4 - (cat == 3 ? 1 : 0);
       const int ctxn = kAbsBase[cat] + 5 + (gt1 < lim ? gt1 : lim);
       int a = 0;
-      if (c.decision(ctx0)) {
+      if (eng.decision(state, next, ctx0)) {
         a = 1;
-        while (a < 14 && c.decision(ctxn)) a++;
+        while (a < 14 && eng.decision(state, next, ctxn)) a++;
         if (a == 14) {  // 0-th order Exp-Golomb suffix, bypass
           int k = 0;
-          while (c.bypass() && k < 24) {
+          while (eng.bypass() && k < 24) {
             a += 1 << k;
             k++;
           }
-          while (k-- > 0) a += c.bypass() << k;
+          while (k-- > 0) a += eng.bypass() << k;
         }
       }
-      const int v = c.bypass() ? -(a + 1) : (a + 1);
+      const int v = eng.bypass() ? -(a + 1) : (a + 1);
       out[i] = (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v));
       if (a == 0) eq1++;
       else gt1++;
     }
+    c.k = eng;
     return 1;
   }
 
@@ -551,21 +565,21 @@ struct SliceParser {
       if (me.i16) {
         int16_t dc[16] = {0};
         const int inc = cond(A, A && A->i16 ? A->cbf_dc : 0) + 2 * cond(B, B && B->i16 ? B->cbf_dc : 0);
-        me.cbf_dc = (uint8_t)residual_block(0, 16, dc, 0, inc, true);
+        me.cbf_dc = (uint8_t)residual_block<0>(16, dc, 0, inc, true);
         for (int b = 0; b < 16; b++) coeff[b * 16] = dc[b];
       }
       for (int b8 = 0; b8 < 4; b8++) {
         if (!((cbp_l >> b8) & 1)) continue;
         if (me.t8) {
-          residual_block(5, 64, coeff + b8 * 64, 0, 0, false);
+          residual_block<5>(64, coeff + b8 * 64, 0, 0, false);
           for (int k = 0; k < 4; k++) me.cbf_luma[4 * b8 + k] = 1;
         } else {
           for (int k = 0; k < 4; k++) {
             const int blk = 4 * b8 + k, bx = kBlkX[blk], by = kBlkY[blk];
             const int fa = bx > 0 ? me.cbf_luma[blk4_of(bx - 4, by)] : cond(A, A ? A->cbf_luma[blk4_of(12, by)] : 0);
             const int fb = by > 0 ? me.cbf_luma[blk4_of(bx, by - 4)] : cond(B, B ? B->cbf_luma[blk4_of(bx, 12)] : 0);
-            me.cbf_luma[blk] = me.i16 ? (uint8_t)residual_block(1, 15, coeff + blk * 16 + 1, 0, fa + 2 * fb, true)
-                                      : (uint8_t)residual_block(2, 16, coeff + blk * 16, 0, fa + 2 * fb, true);
+            me.cbf_luma[blk] = me.i16 ? (uint8_t)residual_block<1>(15, coeff + blk * 16 + 1, 0, fa + 2 * fb, true)
+                                      : (uint8_t)residual_block<2>(16, coeff + blk * 16, 0, fa + 2 * fb, true);
           }
         }
       }
@@ -573,7 +587,7 @@ struct SliceParser {
         for (int pl = 0; pl < 2; pl++) {
           int16_t dc[4] = {0, 0, 0, 0};
           const int inc = cond(A, A ? A->cbf_cdc[pl] : 0) + 2 * cond(B, B ? B->cbf_cdc[pl] : 0);
-          me.cbf_cdc[pl] = (uint8_t)residual_block(3, 4, dc, 0, inc, true);
+          me.cbf_cdc[pl] = (uint8_t)residual_block<3>(4, dc, 0, inc, true);
           for (int k = 0; k < 4; k++) coeff[(16 + 4 * pl + k) * 16] = dc[k];
         }
       }
@@ -582,7 +596,7 @@ struct SliceParser {
           for (int k = 0; k < 4; k++) {
             const int fa = (k & 1) ? me.cbf_cac[pl][k - 1] : cond(A, A ? A->cbf_cac[pl][k + 1] : 0);
             const int fb = (k >> 1) ? me.cbf_cac[pl][k - 2] : cond(B, B ? B->cbf_cac[pl][k + 2] : 0);
-            me.cbf_cac[pl][k] = (uint8_t)residual_block(4, 15, coeff + (16 + 4 * pl + k) * 16 + 1, 0, fa + 2 * fb, true);
+            me.cbf_cac[pl][k] = (uint8_t)residual_block<4>(15, coeff + (16 + 4 * pl + k) * 16 + 1, 0, fa + 2 * fb, true);
           }
       }
     } else {

@@ -22,19 +22,28 @@ struct MbStats {
 
 inline MbStats scan(const int16_t* c) {
   MbStats st;
+  uint32_t wide = 0;
   for (int b = 0; b < kSlots; b++) {
-    uint16_t m = 0;
-    for (int k = 0; k < 16; k++) {
-      const int v = c[b * 16 + k];
-      if (!v) continue;
-      m |= (uint16_t)(1u << k);
-      st.nnz++;
-      st.nesc += v < -7 || v > 7;
-      st.wide |= v < -128 || v > 127;
+    const int16_t* s = c + b * 16;
+    uint64_t w[4];
+    memcpy(w, s, 32);
+    if (!(w[0] | w[1] | w[2] | w[3])) {  // most slots of a quantised picture hold nothing
+      st.mask[b] = 0;
+      continue;
     }
-    st.mask[b] = m;
-    st.ncoded += m != 0;
+    uint32_t m = 0, esc = 0;
+    for (int k = 0; k < 16; k++) {  // no data-dependent branch: a zero level counts for nothing below
+      const int v = s[k];
+      m |= (uint32_t)(v != 0) << k;
+      esc += (uint32_t)(v + 7) > 14u;
+      wide |= (uint32_t)(v + 128) > 255u;
+    }
+    st.mask[b] = (uint16_t)m;
+    st.nnz += (uint32_t)__builtin_popcount(m);
+    st.nesc += esc;
+    st.ncoded++;
   }
+  st.wide = wide != 0;
   return st;
 }
 

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "recon_kernels.cuh"
+#include "deblock_kernel.cuh"
 
 namespace dryv {
 
@@ -1055,6 +1056,11 @@ struct dryv_recon_ctx {
   bool surface_set = false;
   uint8_t* d_exp[kStages] = {};
   size_t exp_cap = 0;
+  // deblocking post-pass: per-row progress counters + row ticket; one launch of it at a time (guarded by db_done)
+  int* d_db_progress = nullptr;
+  size_t db_rows_cap = 0;
+  cudaEvent_t db_done = nullptr;
+  bool db_used = false;
   cudaStream_t pending_user = nullptr;
   bool pending_user_valid = false;
   uint64_t launches = 0;
@@ -1364,6 +1370,7 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
        cudaMemset(ctx->d_ticket, 0, 2 * dryv_recon_ctx::kSets * sizeof(unsigned int)) == cudaSuccess;
   for (int i = 0; i < dryv_recon_ctx::kSets && ok; i++)
     ok = cudaEventCreateWithFlags(&ctx->ctl[i].done, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->db_done, cudaEventDisableTiming) == cudaSuccess;
   // shared memory, not L1, is what the row teams live on: ask for the largest carve-out
   ok = ok && cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared) == cudaSuccess;
@@ -1411,6 +1418,8 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
     if (ctx->ctl[i].done) cudaEventDestroy(ctx->ctl[i].done);
   }
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->d_db_progress) cudaFree(ctx->d_db_progress);
+  if (ctx->db_done) cudaEventDestroy(ctx->db_done);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   for (cudaEvent_t e : ctx->trace_ev) cudaEventDestroy(e);
@@ -1663,6 +1672,53 @@ int dryv_recon_submit_compact(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
   return submit_impl(ctx, pp, soa, levels, n_frames, out_yuv);
 }
 
+int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa, uint32_t n_frames,
+                              int slice_alpha_c0_offset_div2, int slice_beta_offset_div2, uint8_t* d_yuv, void* cuda_stream) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (!pp_ok(pp) || !d_soa || !d_soa->qp || !d_soa->transform_size_8x8_flag || !d_yuv || n_frames == 0 ||
+      slice_alpha_c0_offset_div2 < -6 || slice_alpha_c0_offset_div2 > 6 || slice_beta_offset_div2 < -6 || slice_beta_offset_div2 > 6)
+    return fail(ctx, DRYV_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute[0];
+  const size_t rows = (size_t)n_frames * pp->pic_height_in_mbs;
+  if (rows + 1 > ctx->db_rows_cap) {  // [0]: the row ticket, [1 + r]: progress of row r
+    CU(cudaDeviceSynchronize());
+    if (ctx->d_db_progress) cudaFree(ctx->d_db_progress);
+    ctx->d_db_progress = nullptr;
+    ctx->db_rows_cap = 0;
+    CU(cudaMalloc(&ctx->d_db_progress, (rows + 1) * sizeof(int)));
+    ctx->db_rows_cap = rows + 1;
+  }
+  if (ctx->db_used) CU(cudaStreamWaitEvent(st, ctx->db_done, 0));  // the counters serve one launch at a time
+  CU(cudaMemsetAsync(ctx->d_db_progress, 0, (rows + 1) * sizeof(int), st));
+  dryv::DeblockArgs a;
+  memset(&a, 0, sizeof a);
+  a.yuv = d_yuv;
+  a.qp = d_soa->qp;
+  a.t8x8 = d_soa->transform_size_8x8_flag;
+  a.ticket = reinterpret_cast<unsigned int*>(ctx->d_db_progress);
+  a.progress = ctx->d_db_progress + 1;
+  a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
+  a.W = pp->pic_width_in_mbs;
+  a.H = pp->pic_height_in_mbs;
+  a.n_frames = (int)n_frames;
+  a.cb_off = pp->chroma_qp_index_offset;
+  a.cr_off = pp->second_chroma_qp_index_offset;
+  a.off_a = 2 * slice_alpha_c0_offset_div2;
+  a.off_b = 2 * slice_beta_offset_div2;
+  const size_t want = (rows + dryv::kDbWarps - 1) / dryv::kDbWarps, cap = (size_t)ctx->sm_count * 8;
+  dryv::deblock_wavefront_kernel<<<(unsigned)(want < cap ? want : cap), 32 * dryv::kDbWarps, 0, st>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->db_done, st));
+  ctx->db_used = true;
+  ctx->launches++;
+  if (cuda_stream) {
+    ctx->pending_user = st;
+    ctx->pending_user_valid = true;
+  }
+  return DRYV_OK;
+}
+
 size_t dryv_recon_surface_bytes(const dryv_surface* s) { return surface_ok(s) ? surface_bytes(s) : 0; }
 
 int dryv_recon_export_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const uint8_t* d_yuv, uint32_t n_frames,
@@ -1747,6 +1803,7 @@ int dryv_recon_wait(dryv_recon_ctx* ctx) {
   }
   for (int i = 0; i < dryv_recon_ctx::kSets; i++)  // launches on caller streams other than the last one
     if (ctx->ctl[i].used) CU(cudaEventSynchronize(ctx->ctl[i].done));
+  if (ctx->db_used) CU(cudaEventSynchronize(ctx->db_done));
   if (!ctx->trace_ev.empty()) {
     for (size_t i = 0; i + 3 < ctx->trace_ev.size(); i += 4) {
       float t[4] = {0, 0, 0, 0};

@@ -27,7 +27,7 @@ EXPORTS = [
     "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms", "dryv_recon_device_tables",
     "dryv_recon_wavefront_times", "dryv_recon_pack_levels", "dryv_recon_unpack_levels", "dryv_recon_submit_compact",
     "dryv_recon_expand_levels_device", "dryv_recon_wait_oldest", "dryv_recon_surface_bytes", "dryv_recon_export_device",
-    "dryv_recon_set_surface",
+    "dryv_recon_set_surface", "dryv_recon_deblock_device",
 ]
 HOST_EXPORTS = ["dryv_cabac_scan", "dryv_cabac_parse", "dryv_cabac_parse_range", "dryv_cabac_parse_compact",
                 "dryv_cabac_surface"]  # include/dryv_cabac_host.h
@@ -118,6 +118,8 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_submit_compact.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), C.POINTER(LevelsCompact), u32, vp]
     lib.dryv_recon_expand_levels_device.restype = C.c_int
     lib.dryv_recon_expand_levels_device.argtypes = [vp, C.POINTER(LevelsCompact), sz, vp, vp]
+    lib.dryv_recon_deblock_device.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, C.c_int, C.c_int, vp, vp]
+    lib.dryv_recon_deblock_device.restype = C.c_int
     lib.dryv_recon_surface_bytes.argtypes = [C.POINTER(Surface)]
     lib.dryv_recon_surface_bytes.restype = sz
     lib.dryv_recon_export_device.argtypes = [vp, C.POINTER(PicParams), vp, u32, C.POINTER(Surface), vp, vp]
@@ -285,6 +287,12 @@ class ReconContext:
     def _out_bytes(self, pp: PicParams) -> int:
         sf = getattr(self, "_surface", None)
         return sf.nbytes if sf is not None else pp.frame_bytes
+
+    def deblock_device(self, dsoa: "DeviceSoa", d_yuv, alpha_div2: int = 0, beta_div2: int = 0, stream_ptr: int = 0):
+        """dryv_recon_deblock_device: the optional H.264 in-loop filter over reconstructed pictures, in place (not dryv parity)."""
+        soa = dsoa.as_soa()
+        self._check(self.lib.dryv_recon_deblock_device(self.h, C.byref(dsoa.pp), C.byref(soa), dsoa.n_frames, alpha_div2,
+                                                       beta_div2, d_yuv.data_ptr(), stream_ptr or None))
 
     def export_device(self, pp: PicParams, d_yuv, n_frames: int, surface: "Surface", d_out, stream_ptr: int = 0):
         """dryv_recon_export_device on torch device tensors: coded pictures -> surfaces, asynchronous on the stream."""

@@ -234,6 +234,18 @@ int dryv_recon_export_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, con
  * Returns DRYV_ERR_ARG for a malformed surface; that it fits the pictures is checked by the submit that uses it. */
 int dryv_recon_set_surface(dryv_recon_ctx* ctx, const dryv_surface* s);
 
+/* ---- Deblocking post-pass — NOT part of dryv parity --------------------------------------
+ * The reference has no in-loop filter (README.md:15; it parses disable_deblocking_filter_idc and the two offsets in
+ * slice/header.rs:609-640 and ignores them), so its output — and everything above in this header — is the unfiltered
+ * reconstruction. For streams that ask for the filter this applies H.264 8.7 to n_frames reconstructed intra pictures IN
+ * PLACE (device memory, the dryv_recon_reconstruct_device layout): bS 4 on macroblock edges, 3 on transform edges, every
+ * edge filtered (disable_deblocking_filter_idc 0; with one slice per picture 2 is the same). d_soa: the batch's device
+ * syntax buffers, of which qp and transform_size_8x8_flag are read. The offsets are the slice header's
+ * slice_alpha_c0_offset_div2 / slice_beta_offset_div2 (-6..6). Asynchronous on `cuda_stream` (0: the context's own);
+ * errors (watchdog) are reported by dryv_recon_wait. */
+int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa, uint32_t n_frames,
+                              int slice_alpha_c0_offset_div2, int slice_beta_offset_div2, uint8_t* d_yuv, void* cuda_stream);
+
 /* Frame::write_to_yuv_file (frame/mod.rs:48-70): writes one reconstructed picture (host memory, the
  * layout above) to `path`, creating the parent directory of "temp/yuv_frame"-style paths if needed. */
 int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char* path);

@@ -475,8 +475,9 @@ class SliceWriter:
         return self.bits
 
 
-def encode_picture(batch, frame, cbps, idr_pic_id=0) -> bytes:
-    """One IDR access unit (slice NAL only) of picture `frame`."""
+def encode_picture(batch, frame, cbps, idr_pic_id=0, deblock=None) -> bytes:
+    """One IDR access unit (slice NAL only) of picture `frame`. deblock: None (filter disabled, what dryv decodes) or
+    (slice_alpha_c0_offset_div2, slice_beta_offset_div2) for a stream that asks for the in-loop filter."""
     base = frame * batch.pp.n_mb
     slice_qp = int(batch.qp[base])
     w = BitWriter()
@@ -488,7 +489,12 @@ def encode_picture(batch, frame, cbps, idr_pic_id=0) -> bytes:
     w.u(1, 0)               # no_output_of_prior_pics_flag
     w.u(1, 0)               # long_term_reference_flag
     w.se(slice_qp - 26)     # slice_qp_delta
-    w.ue(1)                 # disable_deblocking_filter_idc: no deblocking (dryv has none)
+    if deblock is None:
+        w.ue(1)             # disable_deblocking_filter_idc: no deblocking (dryv has none)
+    else:
+        w.ue(0)             # filter every edge
+        w.se(deblock[0])    # slice_alpha_c0_offset_div2
+        w.se(deblock[1])    # slice_beta_offset_div2
     while len(w.bits) % 8:
         w.bits.append(1)    # cabac_alignment_one_bit
     sw = SliceWriter(batch, frame, cbps, slice_qp)
@@ -498,7 +504,7 @@ def encode_picture(batch, frame, cbps, idr_pic_id=0) -> bytes:
     return nal_unit(3, 5, w.tobytes())
 
 
-def encode_stream(batch, crop=None) -> bytes:
+def encode_stream(batch, crop=None, deblock=None) -> bytes:
     """Annex-B stream: SPS, PPS, then one IDR picture per frame of `batch` (canonicalises `batch` in place). `crop`: the
     SPS frame_crop_{left,right,top,bottom}_offset values, or None for no cropping."""
     pp = batch.pp
@@ -507,5 +513,5 @@ def encode_stream(batch, crop=None) -> bytes:
     out = nal_unit(3, 7, sps_rbsp(pp.pic_width_in_mbs, pp.pic_height_in_mbs, crop))
     out += nal_unit(3, 8, pps_rbsp(int(pp.chroma_qp_index_offset), int(pp.second_chroma_qp_index_offset)))
     for f in range(batch.n_frames):
-        out += encode_picture(batch, f, cbps, idr_pic_id=f & 1)
+        out += encode_picture(batch, f, cbps, idr_pic_id=f & 1, deblock=deblock)
     return out

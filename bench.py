@@ -467,6 +467,27 @@ def main():
         line["surface_export"] = {"workload": f"{W_}x{h_disp} display rectangle of the {n_frames} coded pictures "
                                               "(dryv_recon_export_device), device-resident", **exp}
 
+        # side measurement, SURVEY.md §8(f) next-4: the optional in-loop deblocking post-pass over the batch's pictures, in
+        # place (not part of dryv parity: the reference has no filter). Parity of the kernel: tests/test_deblock_oracle.py.
+        d_db = d_outs[0].clone()
+        for _ in range(2):
+            ctx.deblock_device(dsoa, d_db, 0, 0, sptr)
+        torch.cuda.synchronize(dev)
+        a0.record(stream)
+        for _ in range(args.steps):
+            ctx.deblock_device(dsoa, d_db, 0, 0, sptr)
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        ctx.wait()
+        dms = a0.elapsed_time(a1) / args.steps
+        dbytes = n_mb_step * (384 + 384 + 2)   # every sample read and written once, qp + transform flag per macroblock
+        line["deblock"] = {"workload": f"H.264 8.7 deblocking of the {n_frames} reconstructed pictures, in place "
+                                       "(dryv_recon_deblock_device; intra: bS 4 / 3 on every edge)",
+                           "ms_per_step": dms, "value": n_frames * pp.luma_pixels / (dms * 1e-3) / 1e6, "unit": UNIT,
+                           "roofline": {"bound": "hbm", "achieved": dbytes / (dms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                        "frac": dbytes / (dms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_mb": 770}}
+        del d_db
+
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n = n_frames if cores >= 8 else max(1, min(n_frames, 2 * cores))

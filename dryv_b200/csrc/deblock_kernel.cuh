@@ -94,11 +94,11 @@ constexpr int kDbChromaStride = 12;  // 4 margin (2 used) + 8
 constexpr int kDbWarps = 4;          // rows (warps) per CTA
 
 struct DeblockTile {
-  uint8_t luma[20 * kDbLumaStride];
-  uint8_t chroma[2][12 * kDbChromaStride];
+  alignas(16) uint8_t luma[20 * kDbLumaStride];
+  alignas(16) uint8_t chroma[2][12 * kDbChromaStride];
 };
 
-__global__ void __launch_bounds__(32 * kDbWarps) deblock_wavefront_kernel(const DeblockArgs a) {
+__global__ void __launch_bounds__(32 * kDbWarps, 8) deblock_wavefront_kernel(const DeblockArgs a) {
   __shared__ DeblockTile tiles[kDbWarps];
   __shared__ unsigned int s_row[kDbWarps];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -143,15 +143,18 @@ __global__ void __launch_bounds__(32 * kDbWarps) deblock_wavefront_kernel(const 
       const int step = t8_row[mx] ? 8 : 4;
       // ---- load the macroblock with a 4-sample (chroma: 2 of 4) margin on the left and on top; L2 loads: the margins were
       // written by other SMs
-      for (int i = lane; i < 20 * 20; i += 32) {
-        const int r = i / 20, c = i % 20;
-        const int gy = 16 * my + r - 4, gx = 16 * mx + c - 4;
-        t.luma[r * kDbLumaStride + c] = (gy >= 0 && gx >= 0) ? __ldcg(Y + (size_t)gy * lw + gx) : (uint8_t)0;
+      // (32-bit words of luma, 16-bit words of chroma: the margins start 4 / 2 samples left of the macroblock)
+      for (int i = lane; i < 20 * 5; i += 32) {
+        const int r = i / 5, wc = i % 5;
+        const int gy = 16 * my + r - 4, gx = 16 * mx + 4 * wc - 4;
+        *reinterpret_cast<uint32_t*>(t.luma + r * kDbLumaStride + 4 * wc) =
+            (gy >= 0 && gx >= 0) ? __ldcg(reinterpret_cast<const uint32_t*>(Y + (size_t)gy * lw + gx)) : 0u;
       }
-      for (int i = lane; i < 2 * 10 * 10; i += 32) {
-        const int pl = i / 100, r = (i % 100) / 10, c = i % 10;
-        const int gy = 8 * my + r - 2, gx = 8 * mx + c - 2;
-        t.chroma[pl][(r + 2) * kDbChromaStride + c + 2] = (gy >= 0 && gx >= 0) ? __ldcg(C[pl] + (size_t)gy * cw + gx) : (uint8_t)0;
+      for (int i = lane; i < 2 * 10 * 5; i += 32) {
+        const int pl = i / 50, r = (i % 50) / 5, hc = i % 5;
+        const int gy = 8 * my + r - 2, gx = 8 * mx + 2 * hc - 2;
+        *reinterpret_cast<uint16_t*>(t.chroma[pl] + (r + 2) * kDbChromaStride + 2 * hc + 2) =
+            (gy >= 0 && gx >= 0) ? __ldcg(reinterpret_cast<const uint16_t*>(C[pl] + (size_t)gy * cw + gx)) : (uint16_t)0;
       }
       __syncwarp();
       // ---- vertical edges, left to right: lane = line
@@ -194,24 +197,29 @@ __global__ void __launch_bounds__(32 * kDbWarps) deblock_wavefront_kernel(const 
       __syncwarp();
       // ---- write back what may have changed: the macroblock, three columns of the left neighbour (this macroblock's rows),
       // three rows of the upper neighbour (this macroblock's columns); chroma: one column / one row
-      for (int i = lane; i < 16 * 19; i += 32) {
-        const int r = i / 19, c = i % 19 - 3;
-        if (c < 0 && mx == 0) continue;
-        Y[(size_t)(16 * my + r) * lw + 16 * mx + c] = t.luma[(4 + r) * kDbLumaStride + 4 + c];
+      // (whole words: the outermost margin sample of a word is written back unchanged, and nobody else touches it before
+      // this macroblock is published)
+      for (int i = lane; i < 16 * 5; i += 32) {
+        const int r = i / 5, wc = i % 5;
+        if (wc == 0 && mx == 0) continue;
+        *reinterpret_cast<uint32_t*>(Y + (size_t)(16 * my + r) * lw + 16 * mx + 4 * wc - 4) =
+            *reinterpret_cast<const uint32_t*>(t.luma + (4 + r) * kDbLumaStride + 4 * wc);
       }
-      if (my > 0)
-        for (int i = lane; i < 3 * 16; i += 32) {
-          const int r = i / 16 - 3, c = i % 16;
-          Y[(size_t)(16 * my + r) * lw + 16 * mx + c] = t.luma[(4 + r) * kDbLumaStride + 4 + c];
-        }
-      for (int i = lane; i < 2 * 8 * 9; i += 32) {
-        const int pl = i / 72, r = (i % 72) / 9, c = i % 9 - 1;
-        if (c < 0 && mx == 0) continue;
-        C[pl][(size_t)(8 * my + r) * cw + 8 * mx + c] = t.chroma[pl][(4 + r) * kDbChromaStride + 4 + c];
+      if (my > 0 && lane < 12) {
+        const int r = lane / 4 - 3, wc = lane % 4;
+        *reinterpret_cast<uint32_t*>(Y + (size_t)(16 * my + r) * lw + 16 * mx + 4 * wc) =
+            *reinterpret_cast<const uint32_t*>(t.luma + (4 + r) * kDbLumaStride + 4 + 4 * wc);
       }
-      if (my > 0 && lane < 16) {
-        const int pl = lane >> 3, c = lane & 7;
-        C[pl][(size_t)(8 * my - 1) * cw + 8 * mx + c] = t.chroma[pl][3 * kDbChromaStride + 4 + c];
+      for (int i = lane; i < 2 * 8 * 5; i += 32) {
+        const int pl = i / 40, r = (i % 40) / 5, hc = i % 5;
+        if (hc == 0 && mx == 0) continue;
+        *reinterpret_cast<uint16_t*>(C[pl] + (size_t)(8 * my + r) * cw + 8 * mx + 2 * hc - 2) =
+            *reinterpret_cast<const uint16_t*>(t.chroma[pl] + (4 + r) * kDbChromaStride + 2 + 2 * hc);
+      }
+      if (my > 0 && lane < 8) {
+        const int pl = lane >> 2, hc = lane & 3;
+        *reinterpret_cast<uint16_t*>(C[pl] + (size_t)(8 * my - 1) * cw + 8 * mx + 2 * hc) =
+            *reinterpret_cast<const uint16_t*>(t.chroma[pl] + 3 * kDbChromaStride + 4 + 2 * hc);
       }
       // ---- publish: every lane's stores are visible before the counter moves
       __threadfence();

@@ -1676,7 +1676,8 @@ int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
                               int slice_alpha_c0_offset_div2, int slice_beta_offset_div2, uint8_t* d_yuv, void* cuda_stream) {
   if (!ctx) return DRYV_ERR_ARG;
   if (!pp_ok(pp) || !d_soa || !d_soa->qp || !d_soa->transform_size_8x8_flag || !d_yuv || n_frames == 0 ||
-      slice_alpha_c0_offset_div2 < -6 || slice_alpha_c0_offset_div2 > 6 || slice_beta_offset_div2 < -6 || slice_beta_offset_div2 > 6)
+      (reinterpret_cast<uintptr_t>(d_yuv) & 3u) || slice_alpha_c0_offset_div2 < -6 || slice_alpha_c0_offset_div2 > 6 ||
+      slice_beta_offset_div2 < -6 || slice_beta_offset_div2 > 6)
     return fail(ctx, DRYV_ERR_ARG, "bad argument");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute[0];

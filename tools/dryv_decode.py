@@ -5,6 +5,8 @@ src/video/decoder.rs:87-150): demux the video track and CABAC-parse its IDR pict
 to ./temp/yuv_frame in the reference's byte layout (src/video/frame/mod.rs:48-70).
 
     python tools/dryv_decode.py movie.mp4 [out_path]          # needs a B200
+    python tools/dryv_decode.py --display [--nv12] movie.mp4 [out_path]   # the SPS display rectangle instead of the coded
+                                                              # picture (the reference's open "frame cropping" item)
     python tools/dryv_decode.py --make-sample sample.mp4      # writes a 640x368 synthetic CABAC High-profile MP4 (no GPU)
 """
 import os
@@ -30,13 +32,27 @@ def main():
         print(f"{sys.argv[2]}: {len(data)} bytes, 4 IDR pictures of 640x368")
         return 0
     from dryv_b200 import host, recon
-    data = open(sys.argv[1], "rb").read()
-    out_path = sys.argv[2] if len(sys.argv) > 2 else "temp/yuv_frame"
+    from dryv_b200.abi import SURFACE_NV12
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    display, nv12 = "--display" in sys.argv, "--nv12" in sys.argv
+    data = open(args[0], "rb").read()
+    out_path = args[1] if len(args) > 1 else "temp/yuv_frame"
     t0 = time.perf_counter()
     batch, levels = host.parse_compact(data)   # demux + CABAC parse straight into the compact level stream
     t1 = time.perf_counter()
     ctx = recon.ReconContext(0)
-    frames = ctx.reconstruct_compact(batch, levels)
+    if display or nv12:
+        import numpy as np
+        sf = host.surface(data)                # the rectangle the SPS asks for (the whole picture if it does not crop)
+        if not display:
+            sf.crop_left = sf.crop_top = 0
+            sf.width, sf.height = 16 * batch.pp.pic_width_in_mbs, 16 * batch.pp.pic_height_in_mbs
+        if nv12:
+            sf.format = SURFACE_NV12
+        ctx.set_surface(sf)
+        frames = ctx.reconstruct_compact(batch, levels, np.empty((batch.n_frames, sf.nbytes), np.uint8))
+    else:
+        frames = ctx.reconstruct_compact(batch, levels)
     t2 = time.perf_counter()
     recon.write_yuv_file(frames[0], out_path)
     pp = batch.pp

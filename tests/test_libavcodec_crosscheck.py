@@ -8,7 +8,12 @@ streams from the syntax buffers, libavcodec decodes them, and
     Intra8x8 in macroblock column 0) cannot fire, and where it can, the first differing macroblock must be such a one;
   * a committed fixture (stream + libavcodec's luma, tests/golden/avc/) holds the oracle — and, with -m gpu, the CUDA
     path — to libavcodec's output even where cv2 is missing.
-cv2 exposes the decoder's luma plane only (tests/avc/decode.py), so chroma stays pinned by the spec model alone."""
+cv2 exposes the decoder's luma plane only (tests/avc/decode.py); chroma is pinned through the BGR pictures instead: our planar
+pictures, written as a YUV4MPEG2 file, go through the same libavformat + swscale conversion as the decoded stream, and
+  * the standard model must give the same BGR pictures as libavcodec on every stream (one flipped chroma LSB is seen);
+  * the C oracle must do so wherever dryv's one chroma deviation (the "> 0" availability tests of the
+    chroma DC predictor) cannot fire, i.e. while no reconstructed chroma sample is 0; where it fires, luma is untouched and
+    the first differing chroma macroblock is DC-predicted."""
 import os
 
 import numpy as np
@@ -120,3 +125,71 @@ def test_cuda_path_equals_libavcodec_live(gpu_ctx):
     pp, b, data = make(dict(w=20, h=12, n=4, seed=13), standard_only=True)
     got = decode.decode_luma(data, b.n_frames, pp.pic_width_in_mbs * 16, pp.pic_height_in_mbs * 16)
     assert np.array_equal(got, luma_of(gpu_ctx.reconstruct(b), pp))
+
+
+# ---- chroma: the planes themselves are not reachable through cv2, the BGR pictures swscale makes of them are (avc/decode.py) --
+def bgr_equal(frames, pp, data):
+    """libavcodec's decode of `data`, converted to BGR, equals the same conversion of our planar pictures."""
+    W, H = pp.pic_width_in_mbs * 16, pp.pic_height_in_mbs * 16
+    theirs = decode.decode_bgr(data, len(frames))
+    ours = decode.bgr_of_pictures(frames, W, H)
+    return theirs.shape == ours.shape and bool(np.array_equal(theirs, ours))
+
+
+@needs_libavcodec
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_libavcodec_equals_standard_model_in_chroma_too(case):
+    pp, b, data = make(case)
+    assert bgr_equal(spec_model.reconstruct(b, quirks=False), pp, data)
+
+
+@needs_libavcodec
+def test_bgr_comparison_sees_single_chroma_lsbs():
+    """Sensitivity of the comparison above: flipping the lowest bit of one chroma sample changes the BGR picture."""
+    pp, b, data = make(dict(w=5, h=4, n=1, seed=3, pct_i4x4=0, pct_i8x8=0))
+    good = spec_model.reconstruct(b, quirks=False)
+    assert bgr_equal(good, pp, data)
+    rng = np.random.default_rng(1)
+    n_luma = pp.n_mb * 256
+    seen = 0
+    for pos in rng.integers(n_luma, pp.frame_bytes, 12):
+        bad = good.copy()
+        bad[0, pos] ^= 1
+        seen += not bgr_equal(bad, pp, data)
+    assert seen >= 11     # a sample whose whole neighbourhood is clipped in B / R may hide
+
+
+@needs_libavcodec
+def test_q3_is_the_only_chroma_difference():
+    """dryv's chroma deviates from the standard only through Q3 (the "> 0" availability tests of the chroma DC predictor,
+    trans_chroma.rs:209-268): the C oracle equals libavcodec in every plane on pictures where no reconstructed chroma
+    sample is 0 next to a DC-predicted block, and where it differs the first difference is a DC-predicted chroma block."""
+    # mid-range content, no stress macroblocks: no chroma sample reaches 0, Q3 cannot fire, Q2 is excluded by standard_only
+    pp, b, data = make(dict(w=7, h=5, n=3, seed=6, stress_pct=0), standard_only=True)
+    ours = oracle.reconstruct(b)
+    n_luma = pp.n_mb * 256
+    assert ours[:, n_luma:].min() > 0
+    assert bgr_equal(ours, pp, data)
+    # with stress macroblocks chroma clamps to 0 and Q3 fires: the oracle follows the quirks model, not the standard
+    pp, b, data = make(dict(w=6, h=4, n=3, seed=5, stress_pct=60), standard_only=True)
+    ours = oracle.reconstruct(b)
+    assert np.array_equal(ours, spec_model.reconstruct(b, quirks=True))
+    std = spec_model.reconstruct(b, quirks=False)
+    assert bgr_equal(std, pp, data)
+    diff = ours != std
+    assert not diff[:, :pp.n_mb * 256].any()         # luma untouched
+    assert diff.any()                                # Q3 fired; the first differing chroma macroblock uses DC prediction
+    if True:
+        W, H = pp.pic_width_in_mbs, pp.pic_height_in_mbs
+        f = int(np.argwhere(diff.any(axis=1))[0][0])
+        cb = diff[f, pp.n_mb * 256:pp.n_mb * 320].reshape(H, 8, W, 8).any(axis=(1, 3))
+        cr = diff[f, pp.n_mb * 320:].reshape(H, 8, W, 8).any(axis=(1, 3))
+        y, x = np.argwhere(cb | cr)[0]
+        assert b.intra_chroma_pred_mode[f * pp.n_mb + y * W + x] == 0
+
+
+@pytest.mark.gpu
+@needs_libavcodec
+def test_cuda_path_equals_libavcodec_live_in_chroma_too(gpu_ctx):
+    pp, b, data = make(dict(w=7, h=5, n=3, seed=6, stress_pct=0), standard_only=True)   # Q2 / Q3 cannot fire (see above)
+    assert bgr_equal(gpu_ctx.reconstruct(b), pp, data)

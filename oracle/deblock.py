@@ -4,8 +4,8 @@ The H.264 in-loop deblocking filter (8.7) for the pictures this path produces: i
 edges, 3 inside), frame pictures, 4:2:0, 8 bit, one slice, disable_deblocking_filter_idc = 0. The reference has no
 deblocking filter (README.md:15 lists it as open; its slice header parses the fields, src/video/slice/header.rs:609-640),
 so it must stay OFF for dryv parity; this restates the standard's text and is pinned to libavcodec's output on streams that
-enable the filter (tests/test_deblock_oracle.py, luma — cv2 exposes no chroma). Pure Python loops over macroblocks:
-small pictures only.
+enable the filter (tests/test_deblock_oracle.py: luma directly, chroma through the BGR pictures of tests/avc/decode.py).
+Pure Python loops over macroblocks: small pictures only.
 """
 import numpy as np
 

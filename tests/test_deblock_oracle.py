@@ -138,3 +138,31 @@ def test_bytes_to_deblocked_pictures_equal_libavcodec():
     theirs = decode.decode_luma(s, 3, 128, 96)
     assert np.array_equal(d.cpu().numpy()[:, :128 * 96].reshape(3, 96, 128), theirs)
     ctx.close()
+
+
+@needs_libavcodec
+@pytest.mark.parametrize("case", [
+    dict(w=5, h=4, n=2, seed=31, qp_base=30),
+    dict(w=6, h=4, n=2, seed=32, qp_base=38, cb=4, cr=-5),
+    dict(w=6, h=4, n=1, seed=33, qp_base=34, pct_i4x4=0, pct_i8x8=100, cb=-6, cr=7),
+    dict(w=7, h=5, n=2, seed=34, qp_base=44, stress_pct=30, offs=(2, -3)),
+    dict(w=4, h=3, n=1, seed=35, qp_base=24, offs=(-2, 5), cb=12, cr=-12),
+], ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_deblock_oracle_equals_libavcodec_in_chroma_too(case):
+    """Chroma through the BGR pictures (avc/decode.py): the filtered planes, written as YUV4MPEG2, must convert to the BGR
+    pictures libavcodec's decode of the filter-enabled stream converts to. The unfiltered input is the standard model's
+    reconstruction (dryv's chroma quirk Q3 is not libavcodec's behaviour)."""
+    from oracle import spec_model
+    c = dict(case)
+    w, h, n = c.pop("w"), c.pop("h"), c.pop("n")
+    offs = c.pop("offs", (0, 0))
+    pp = PicParams.make(w, h, c.pop("cb", 0), c.pop("cr", 0))
+    b = synth.generate(pp, n, 9200 + c.pop("seed"), standard_only=True, **c)
+    s = stream.encode_stream(b, deblock=offs)
+    frames = spec_model.reconstruct(b, quirks=False)
+    out = np.stack([dbl.deblock(frames[f], w, h, b.qp[f * pp.n_mb:(f + 1) * pp.n_mb],
+                                b.transform_size_8x8_flag[f * pp.n_mb:(f + 1) * pp.n_mb], int(pp.chroma_qp_index_offset),
+                                int(pp.second_chroma_qp_index_offset), offs[0], offs[1]) for f in range(n)])
+    theirs = decode.decode_bgr(s, n)
+    assert np.array_equal(theirs, decode.bgr_of_pictures(out, 16 * w, 16 * h))
+    assert not np.array_equal(theirs, decode.bgr_of_pictures(frames, 16 * w, 16 * h))   # the filter is visible in BGR

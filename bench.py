@@ -141,6 +141,8 @@ def config_dict(args, n_gpus):
         "mb_mix": "40% Intra4x4 / 25% Intra8x8 / 35% Intra16x16, 10% stress MBs",
         "sharding": f"frames x{n_gpus} (independent IDR pictures per GPU, no collective)",
         "l2": "per-step working set (levels+syntax in, pictures out) is larger than the 126 MB L2, no flush needed",
+        "step_overlap": f"GPU arm, device-resident value: consecutive steps rotate over {N_FLIGHT} CUDA streams and output "
+                        "buffers, so independent batches overlap; single_stream is one batch at a time",
     }
 
 

@@ -1303,7 +1303,9 @@ int launch_export(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const uint8_t*
     if (rc != DRYV_OK) return rc;
     ctx->launches++;
   } else {
-    const int v = common_vector({pa, pb, cl / 2, w / 2, w * h, w * h / 4, dst_frame}, 16, 1);
+    // W / 2: the coded chroma row stride is 8 * pic_width_in_mbs, so with an odd macroblock count rows alternate between
+    // 16- and 8-byte alignment
+    const int v = common_vector({pa, pb, cl / 2, w / 2, W / 2, w * h, w * h / 4, dst_frame}, 16, 1);
     a.row_bytes = (uint32_t)(w / 2);
     for (int pl = 0; pl < 2; pl++) {
       a.src = pl ? cr : cb;

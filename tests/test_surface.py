@@ -74,6 +74,7 @@ SURFACES = [
     (8, 6, 2, 4, 90, 50),            # 2-byte luma, byte-wise I420 chroma
     (8, 6, 126, 94, 2, 2),           # the last 2x2 samples
     (1, 1, 0, 0, 16, 16), (1, 1, 6, 10, 6, 2), (40, 23, 0, 0, 640, 360),
+    (5, 4, 0, 0, 64, 64), (5, 3, 16, 0, 64, 32),   # odd macroblock count: coded chroma rows are only 8-byte aligned
 ]
 
 

@@ -116,6 +116,15 @@ __device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// Bulk copy global -> shared (TMA engine, no tensor map: the bytes are contiguous): one lane arms the mbarrier with the
+// byte count and issues the copy; the consumers wait on the mbarrier. 16-byte aligned addresses, size a multiple of 16.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+  const uint32_t d = smem_u32(smem_dst), b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gmem_src), "r"(bytes), "r"(b)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
   const uint32_t addr = smem_u32(b);
   asm volatile(
@@ -753,61 +762,159 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
 
 // ------------------------------------------------------------------------------------------------
 // Residual only (BASELINE config "dequant + IDCT + residual add"): out = clip(pred_in + residual).
-// One warp per macroblock, grid-stride; no dependencies between macroblocks.
+// No dependencies between macroblocks. One warp walks groups of four consecutive macroblocks (residual_stage.cuh):
+//   * the group's 3072 B of levels arrive by ONE bulk copy (cp.async.bulk, mbarrier complete_tx) issued by one lane, one
+//     group ahead of their use, into a two-stage ring;
+//   * residual_group turns them into biased residual fields in shared memory (luma of two macroblocks / chroma of four
+//     per pass, all 32 lanes busy);
+//   * per macroblock one luma pass (8 samples per lane) and one chroma pass (4 samples per lane) add the prediction and
+//     clip, two samples per VIADDMNMX, and store.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsPerCta, 8) recon_residual_add_kernel(const KernelArgs a) {
-  __shared__ alignas(16) ResidCtaSmem cs;
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.tables);
-    uint4* dst = reinterpret_cast<uint4*>(&cs.tab);
-    for (int i = threadIdx.x; i < (int)(sizeof(DeviceTables) / 16); i += kThreadsPerCta) dst[i] = src[i];
+struct ResidWarpSmem {
+  alignas(16) int16_t lv[2][kGroupMbs * DRYV_COEFFS_PER_MB];  // level ring (bulk-copy destinations)
+  alignas(16) uint16_t res_luma[kGroupMbs][kResLumaTile];     // residual fields
+  // chroma residual fields; the 8x8 passes, which run before the chroma pass writes them, transpose through the same bytes
+  alignas(16) uint16_t res_chroma[kGroupMbs][kResChromaMb];
+  alignas(16) uint32_t hdr[kGroupMbs];                        // class | qp << 8
+  alignas(8) unsigned long long full[2];                      // mbarriers of the level ring
+};
+static_assert(sizeof(uint16_t) * kGroupMbs * kResChromaMb >= sizeof(int) * kScratchWords, "scratch aliases the chroma tiles");
+struct ResidCtaSmem {
+  alignas(16) unsigned char tab[kResidTableBytes];  // the residual part of DeviceTables
+  ResidWarpSmem warp[kWarpsPerCta];
+};
+
+// Position of a group: groups never straddle macroblock rows (the last group of a row is short when W % 4 != 0), so the
+// macroblocks of a group are neighbours in the picture as well as in the level array.
+struct GroupWalk {
+  uint32_t gx, row, frame;  // group index inside the row, macroblock row, picture
+  uint32_t W, H, gpr;
+  __device__ __forceinline__ void init(uint32_t g, uint32_t W_, uint32_t H_) {
+    W = W_;
+    H = H_;
+    gpr = (W + kGroupMbs - 1) / kGroupMbs;
+    const uint32_t rowidx = g / gpr;
+    gx = g - rowidx * gpr;
+    frame = rowidx / H;
+    row = rowidx - frame * H;
   }
-  __syncthreads();
+  __device__ __forceinline__ void next() {
+    if (++gx == gpr) {
+      gx = 0;
+      if (++row == H) {
+        row = 0;
+        frame++;
+      }
+    }
+  }
+  __device__ __forceinline__ uint32_t x0() const { return gx * kGroupMbs; }
+  __device__ __forceinline__ int n() const { return (int)min((uint32_t)kGroupMbs, W - x0()); }
+  __device__ __forceinline__ uint32_t mb0() const { return (frame * H + row) * W + x0(); }
+};
+
+#ifndef DRYV_RESID_CTAS
+#define DRYV_RESID_CTAS 4
+#endif
+__global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residual_add_kernel(const KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ResidCtaSmem& cs = *reinterpret_cast<ResidCtaSmem*>(smem_raw);
   const int lane = threadIdx.x & 31;
   ResidWarpSmem& ws = cs.warp[threadIdx.x >> 5];
-  const LaneConst lc = make_lane_const(lane, cs.tab);
-  const uint8_t* const hdr_base = header_base(a, lane);
-  const int W = a.W, H = a.H;
-  const size_t n_mb = (size_t)W * H, total = n_mb * a.n_frames;
-  const int strideY = W * 16, strideC = W * 8;
-  const size_t warps = (size_t)gridDim.x * kWarpsPerCta;
-  int local_status = STATUS_OK;
-  for (size_t mb = (size_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); mb < total; mb += warps) {
-    const size_t frame = mb / n_mb, addr = mb % n_mb;
-    const int x = (int)(addr % W), row = (int)(addr / W);
-    const uint32_t hdr = load_header_lane(hdr_base, lane, mb);
-    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
-    if (lane < 24) {
-      const uint4* cp = reinterpret_cast<const uint4*>(a.coeff + mb * DRYV_COEFFS_PER_MB) + lane * 2;
-      c0 = __ldg(cp);
-      c1 = __ldg(cp + 1);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.tables);
+    uint4* dst = reinterpret_cast<uint4*>(cs.tab);
+    for (int i = threadIdx.x; i < (int)(kResidTableBytes / 16); i += kThreadsPerCta) dst[i] = src[i];
+    if (lane == 0) {
+      mbar_init(&ws.full[0], 1);
+      mbar_init(&ws.full[1], 1);
     }
-    const MbHeader h = decode_header(hdr, &local_status);
-    residual_stage(cs.tab, ws.scratch, ws.res, ws.res + 256, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
-    const size_t fo = frame * n_mb * 384;
-    {  // luma: lane = (row r, half h): 8 pixels
-      const int r = lane >> 1, hf = lane & 1;
-      const size_t o = fo + (size_t)(16 * row + r) * strideY + 16 * x + 8 * hf;
-      const uint2 pv = __ldg(reinterpret_cast<const uint2*>(a.pred_in + o));
-      const uint4 rv = *reinterpret_cast<const uint4*>(&ws.res[r * 16 + 8 * hf]);
-      const int o0 = clip255((int)(pv.x & 0xff) + lo16(rv.x)), o1 = clip255((int)((pv.x >> 8) & 0xff) + hi16(rv.x));
-      const int o2 = clip255((int)((pv.x >> 16) & 0xff) + lo16(rv.y)), o3 = clip255((int)(pv.x >> 24) + hi16(rv.y));
-      const int o4 = clip255((int)(pv.y & 0xff) + lo16(rv.z)), o5 = clip255((int)((pv.y >> 8) & 0xff) + hi16(rv.z));
-      const int o6 = clip255((int)((pv.y >> 16) & 0xff) + lo16(rv.w)), o7 = clip255((int)(pv.y >> 24) + hi16(rv.w));
-      *reinterpret_cast<uint2*>(a.out + o) = make_uint2(pack4(o0, o1, o2, o3), pack4(o4, o5, o6, o7));
+  }
+  __syncthreads();
+  const DeviceTables& tab = *reinterpret_cast<const DeviceTables*>(cs.tab);  // only the residual part is there
+  const ResLane lc = make_res_lane(lane, tab);
+  const uint32_t W = (uint32_t)a.W, H = (uint32_t)a.H, n_mb = W * H;
+  const uint32_t strideY = W * 16, strideC = W * 8;
+  const uint32_t gpr = (W + kGroupMbs - 1) / kGroupMbs;
+  const uint32_t groups = gpr * H * (uint32_t)a.n_frames;
+  // every warp walks a contiguous range of groups
+  const uint32_t warps = gridDim.x * kWarpsPerCta, wid = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const uint32_t g_begin = (uint32_t)((unsigned long long)groups * wid / warps);
+  const uint32_t g_end = (uint32_t)((unsigned long long)groups * (wid + 1) / warps);
+  // header lanes: lane = field * 4 + macroblock of the group; field 0 mb_type, 1 transform_size_8x8_flag, 2 chroma mode, 3 qp
+  const uint8_t* const hdr_base = header_base(a, lane >> 2);
+  const uint32_t hdr_lim = (lane >> 2) == 0 ? 24u : ((lane >> 2) == 2 ? 3u : ((lane >> 2) == 3 ? 51u : 255u));
+  bool unsupported = false;
+  GroupWalk cur, nxt;
+  cur.init(g_begin, W, H);
+  nxt = cur;
+  auto fetch = [&](const GroupWalk& p, int st) {
+    bulk_load(ws.lv[st], a.coeff + (size_t)p.mb0() * DRYV_COEFFS_PER_MB, (uint32_t)p.n() * (DRYV_COEFFS_PER_MB * 2), &ws.full[st]);
+  };
+  auto load_hdr = [&](const GroupWalk& p) -> uint32_t {
+    return (lane < 16 && (lane & 3) < p.n()) ? (uint32_t)__ldg(hdr_base + p.mb0() + (lane & 3)) : 0u;
+  };
+  uint32_t hv = 0;
+  if (g_begin < g_end) {
+    if (lane == 0) fetch(cur, 0);
+    hv = load_hdr(cur);
+  }
+  // per-lane sample offsets inside a macroblock: luma lane = (row r, half h): 8 samples; chroma lane = (plane, row r, half): 4
+  const size_t lane_lo = (size_t)(lane >> 1) * strideY + 8 * (lane & 1);
+  const size_t lane_co = (size_t)n_mb * 256 + (size_t)(lane >> 4) * n_mb * 64 + (size_t)((lane >> 1) & 7) * strideC + 4 * (lane & 1);
+  for (uint32_t g = g_begin, it = 0; g < g_end; g++, it++) {
+    const int st = it & 1;
+    nxt.next();
+    const bool more = g + 1 < g_end;
+    if (more && lane == 0) fetch(nxt, st ^ 1);
+    const int n = cur.n();
+    uint32_t m4, m8;
+    {  // headers of the group's macroblocks
+      uint32_t v = hv;
+      if (more) hv = load_hdr(nxt);  // next group's, one iteration ahead
+      if (v > hdr_lim) {  // I_PCM / inter / out-of-range syntax: flagged, never decoded
+        unsupported = true;
+        v = (lane >> 2) == 2 ? (v & 3u) : hdr_lim;
+      }
+      const int m = lane & 3;
+      const uint32_t mbt = __shfl_sync(0xffffffffu, v, m), t8 = __shfl_sync(0xffffffffu, v, 4 + m),
+                     qp = __shfl_sync(0xffffffffu, v, 12 + m);
+      const uint32_t cls = mbt == 0 ? (t8 ? 1u : 0u) : 2u;  // slice/macroblock.rs:682-716
+      if (lane < kGroupMbs) ws.hdr[lane] = cls | (qp << 8);
+      m8 = __ballot_sync(0xffffffffu, lane < n && cls == 1u);
+      m4 = ((1u << n) - 1u) & ~m8;
+      __syncwarp();
     }
-    {  // chroma: lane = (plane, row r, half): 4 pixels
-      const int pl = lane >> 4, r = (lane >> 1) & 7, hf = lane & 1;
-      const size_t o = fo + n_mb * 256 + (size_t)pl * n_mb * 64 + (size_t)(8 * row + r) * strideC + 8 * x + 4 * hf;
-      const uint32_t pv = __ldg(reinterpret_cast<const uint32_t*>(a.pred_in + o));
-      const uint2 rv = *reinterpret_cast<const uint2*>(&ws.res[256 + pl * 64 + r * 8 + 4 * hf]);
-      const int o0 = clip255((int)(pv & 0xff) + lo16(rv.x)), o1 = clip255((int)((pv >> 8) & 0xff) + hi16(rv.x));
-      const int o2 = clip255((int)((pv >> 16) & 0xff) + lo16(rv.y)), o3 = clip255((int)(pv >> 24) + hi16(rv.y));
-      *reinterpret_cast<uint32_t*>(a.out + o) = pack4(o0, o1, o2, o3);
+    // the prediction samples of the whole group, issued before the transforms so that their latency is covered
+    const size_t fo = (size_t)cur.frame * n_mb * 384;
+    const size_t lo = fo + (size_t)(16u * cur.row) * strideY + 16u * cur.x0() + lane_lo;
+    const size_t co = fo + (size_t)(8u * cur.row) * strideC + 8u * cur.x0() + lane_co;
+    uint2 pl[kGroupMbs];
+    uint32_t pc[kGroupMbs];
+#pragma unroll
+    for (int m = 0; m < kGroupMbs; m++) {
+      const int mm = m < n ? m : 0;
+      pl[m] = __ldg(reinterpret_cast<const uint2*>(a.pred_in + lo + 16 * mm));
+      pc[m] = __ldg(reinterpret_cast<const uint32_t*>(a.pred_in + co + 8 * mm));
+    }
+    mbar_wait(&ws.full[st], (it >> 1) & 1);
+    residual_group(tab, a.tables, lc, lane, ws.hdr, m4, m8, ws.lv[st], n, reinterpret_cast<int*>(&ws.res_chroma[0][0]),
+                   &ws.res_luma[0][0], kResLumaTile, &ws.res_chroma[0][0], kResChromaMb, a.cb_off, a.cr_off);
+#pragma unroll
+    for (int m = 0; m < kGroupMbs; m++) {
+      if (m < n) {
+        const uint2* rp = reinterpret_cast<const uint2*>(&ws.res_luma[m][(lane >> 1) * kResLumaStride + 8 * (lane & 1)]);
+        const uint2 r0 = rp[0], r1 = rp[1];
+        __stcs(reinterpret_cast<uint2*>(a.out + lo + 16 * m),
+               make_uint2(add_clip4(r0.x, r0.y, pl[m].x), add_clip4(r1.x, r1.y, pl[m].y)));
+        const uint2 rc = *reinterpret_cast<const uint2*>(
+            &ws.res_chroma[m][(lane >> 4) * kResChromaPlane + ((lane >> 1) & 7) * 8 + 4 * (lane & 1)]);
+        __stcs(reinterpret_cast<uint32_t*>(a.out + co + 8 * m), add_clip4(rc.x, rc.y, pc[m]));
+      }
     }
     __syncwarp();
+    cur = nxt;
   }
-  if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
+  if (unsupported) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
 }
 
 
@@ -1378,8 +1485,12 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
                                   cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wave_ctas_per_sm, dryv::recon_wavefront_kernel,
                                                            dryv::kTeamThreads, 0) == cudaSuccess &&
+       cudaFuncSetAttribute(dryv::recon_residual_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(dryv::ResidCtaSmem)) == cudaSuccess &&
+       cudaFuncSetAttribute(dryv::recon_residual_add_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resid_ctas_per_sm, dryv::recon_residual_add_kernel,
-                                                     dryv::kThreadsPerCta, 0) == cudaSuccess;
+                                                     dryv::kThreadsPerCta, sizeof(dryv::ResidCtaSmem)) == cudaSuccess;
   if (!ok || ctx->wave_ctas_per_sm < 1 || ctx->resid_ctas_per_sm < 1) {
     dryv_recon_destroy(ctx);
     return DRYV_ERR_CUDA;
@@ -1469,10 +1580,12 @@ int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* p
   KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out_yuv);
   a.pred_in = d_pred_yuv;
   const size_t mbs = (size_t)n_frames * pp->pic_width_in_mbs * pp->pic_height_in_mbs;
-  size_t want = (mbs + dryv::kWarpsPerCta - 1) / dryv::kWarpsPerCta;
+  if (mbs >= (1ull << 31)) return fail(ctx, DRYV_ERR_ARG, "more than 2^31 macroblocks in one launch");
+  const size_t n_groups = (size_t)n_frames * pp->pic_height_in_mbs * ((pp->pic_width_in_mbs + dryv::kGroupMbs - 1) / dryv::kGroupMbs);
+  size_t want = (n_groups + dryv::kWarpsPerCta - 1) / dryv::kWarpsPerCta;
   size_t cap = (size_t)ctx->sm_count * ctx->resid_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
-  dryv::recon_residual_add_kernel<<<grid, dryv::kThreadsPerCta, 0, s>>>(a);
+  dryv::recon_residual_add_kernel<<<grid, dryv::kThreadsPerCta, sizeof(dryv::ResidCtaSmem), s>>>(a);
   CU(cudaGetLastError());
   ctx->launches++;
   if (cuda_stream) {

@@ -26,6 +26,7 @@
 #include <stdint.h>
 
 #include "recon_tables.h"
+#include "residual_stage.cuh"
 
 namespace dryv {
 
@@ -37,16 +38,6 @@ constexpr int kLumaTileBytes = 17 * kLumaStride;
 constexpr int kChromaStride = 24;        // pixel (x, y) at (y + 1) * 24 + 8 + x, x in -4..15 (row -1), y in -1..7
 constexpr int kChromaTileBytes = 9 * kChromaStride;
 constexpr int kScratchBytes = 1152;      // 8x8 coefficient slab (4 * 144 B) aliased with the transpose buffer (4 * 72 words)
-
-// residual-only kernel: one warp per macroblock
-struct ResidWarpSmem {
-  alignas(16) int16_t res[384];  // luma [16][16] | cb [8][8] | cr [8][8]
-  alignas(16) uint8_t scratch[kScratchBytes];
-};
-struct ResidCtaSmem {
-  DeviceTables tab;
-  ResidWarpSmem warp[kWarpsPerCta];
-};
 
 // wavefront kernel: a "row team" = one CTA of two warps walking one macroblock row.
 // The front warp hands each macroblock to the pixel warp through a ring of kSlots slots.
@@ -163,28 +154,6 @@ __device__ __forceinline__ void idct4(int& a, int& b, int& c, int& d) {
   c = e1 - e2;
   d = e0 - e3;
 }
-// 8-point inverse transform, pred8x8.rs:85-112
-__device__ __forceinline__ void idct8(int* d) {
-  int e0 = d[0] + d[4];
-  int e1 = -d[3] + d[5] - d[7] - (d[7] >> 1);
-  int e2 = d[0] - d[4];
-  int e3 = d[1] + d[7] - d[3] - (d[3] >> 1);
-  int e4 = (d[2] >> 1) - d[6];
-  int e5 = -d[1] + d[7] + d[5] + (d[5] >> 1);
-  int e6 = d[2] + (d[6] >> 1);
-  int e7 = d[3] + d[5] + d[1] + (d[1] >> 1);
-  int f0 = e0 + e6, f1 = e1 + (e7 >> 2), f2 = e2 + e4, f3 = e3 + (e5 >> 2);
-  int f4 = e2 - e4, f5 = (e3 >> 2) - e5, f6 = e0 - e6, f7 = e7 - (e1 >> 2);
-  d[0] = f0 + f7;
-  d[1] = f2 + f5;
-  d[2] = f4 + f3;
-  d[3] = f6 + f1;
-  d[4] = f6 - f1;
-  d[5] = f4 - f3;
-  d[6] = f2 - f5;
-  d[7] = f0 - f7;
-}
-
 // Per-lane constants that do not change over the kernel.
 struct LaneConst {
   int res_off;      // int16 offset of this lane's 4x4 block inside the luma (lanes 0..15) / chroma (16..23) residual tile

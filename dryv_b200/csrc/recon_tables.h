@@ -6,6 +6,7 @@
 //   * zig-zag scans       (reference: inverse_scanner4x4 / inverse_scanner_8x8, src/video/frame/mod.rs:185-284)
 //   * tap tables for the nine Intra4x4 / Intra8x8 modes (reference: pred4x4.rs:92-359, pred8x8.rs:294-692)
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/dryv_recon.h"
@@ -44,22 +45,48 @@ constexpr uint32_t kI4DummyOrg = (4 + 1) * kLumaTileStride + 16 + 20;  // pixel 
 enum { kI4RowIllegal = 18, kI4RowDcTop = 19, kI4RowDcLeft = 20, kI4RowDcNone = 21, kI4Rows = 22 };
 enum { kI4KindIllegal = 0, kI4KindTaps = 1, kI4KindDc = 2, kI4KindDcTop = 3, kI4KindDcLeft = 4, kI4KindDcNone = 5 };
 
+// Laid out by who reads what: the residual passes need the first part only (recon_residual_add_kernel copies just
+// that to shared memory), the row teams of the wavefront kernel the first two; t4 (the general dequantisation, used
+// only for qP without a byte-scale form) stays in global memory.
 struct DeviceTables {
-  int32_t t4[52][16];         // [qP][zig-zag k] = LevelScale4x4[qP%6][pos(k)] << max(qP/6 - 4, 0)
+  // ---- residual stage ----
   uint16_t ls8[6][64];        // [qP%6][i*8+j]   = LevelScale8x8
-  uint32_t tap4[kI4Rows][16][4];  // [row][pixel y*4+x] = three sample offsets, kind (one 128-bit load, no unpacking)
-  uint8_t tap8[9][32][8];     // [mode][lane][pixel q (0,1) * 3 + tap], 2 pad bytes
-  uint8_t zz8inv[8][8];       // [i][j] -> zig-zag index
+  // Byte-scale form of t4 for the packed residual stage (residual_stage.cuh). Where the dequantisation of qP
+  // (transform.rs:143-155) is an exact multiplication d = level * m * 2^e with byte factors m (and m a multiple of 4 when
+  // e > 0, so that the two halvings of the row and column passes stay exact in units of 2^e), word w of t4b[qP] holds
+  // the factor of level 2w in byte 0 and the factor of level 2w+1 in byte 3: the operand of one dp2a.lo / dp2a.hi per
+  // level, which extracts the int16 level from its packed word and multiplies it in a single instruction. Flat lists:
+  // LevelScale << (qP/6 - 4) = normAdjust << qP/6, so m = normAdjust << qP/6 (e = 0) below qP 12 and m = 4 * normAdjust,
+  // e = qP/6 - 2 from there on. t4b_e[qP] = e, or 0xff when qP has no such form (the stage then uses t4).
+  uint32_t t4b[52][8];
+  int32_t ls00[8];            // [qP%6] = LevelScale4x4[qP%6][0][0] (the DC transforms), 6 used
+  uint8_t t4b_e[52];
   uint8_t qpc[52];            // qPI -> QPC
-  uint8_t i4sched[10][2];     // copy of kI4BlkA / kI4BlkB (0xff = none), for the host-side tests
-  uint8_t pad[8];
-  I4Step i4tab[11][2];        // Intra4x4 schedule: [step][half-warp]; entry 10 repeats 9 (look-ahead of the last step)
+  uint8_t zz8inv[8][8];       // [i][j] -> zig-zag index
+  // positions of the set bits of a 4-bit mask, lowest first, one nibble each (0xf = none): pairs the macroblocks of a
+  // group of four that take the same residual pass
+  uint16_t setbits4[16];
+  uint8_t pad0[8];
+  // ---- prediction (row teams) ----
   // [av][k], av = A | B<<1 | C<<2 | D<<3: legal-mode mask (9 bits; bit 0 doubles as "top available", bit 1 as
-  // "left available") | no-top-right variant << 9 of the block whose tap row is byte k of Slot::rows
+  // "left available") | no-top-right variant << 9 of the block whose tap row is byte k of the slot's row bytes
   // (k = 0..9: half-warp A's steps, k = 10..15: half-warp B's steps 2..7)
   uint16_t i4row[16][16];
+  uint32_t tap4[kI4Rows][16][4];  // [row][pixel y*4+x] = three sample offsets, kind (one 128-bit load, no unpacking)
+  uint8_t tap8[9][32][8];     // [mode][lane][pixel q (0,1) * 3 + tap], 2 pad bytes
+  I4Step i4tab[11][2];        // Intra4x4 schedule: [step][half-warp]; entry 10 repeats 9 (look-ahead of the last step)
+  uint8_t i4sched[10][2];     // copy of kI4BlkA / kI4BlkB (0xff = none), for the host-side tests
+  uint8_t pad1[12];
+  // ---- global memory only ----
+  int32_t t4[52][16];         // [qP][zig-zag k] = LevelScale4x4[qP%6][pos(k)] << max(qP/6 - 4, 0)
 };
 static_assert(sizeof(DeviceTables) % 16 == 0, "DeviceTables is copied with 128-bit loads");
+static_assert(offsetof(DeviceTables, t4b) % 16 == 0 && offsetof(DeviceTables, tap4) % 16 == 0 &&
+                  offsetof(DeviceTables, ls8) % 16 == 0 && offsetof(DeviceTables, i4row) % 16 == 0 &&
+                  offsetof(DeviceTables, t4) % 16 == 0 && offsetof(DeviceTables, i4tab) % 8 == 0,
+              "tables read with vector loads / copied in 128-bit pieces");
+constexpr size_t kResidTableBytes = offsetof(DeviceTables, i4row);  // what the residual passes read
+constexpr size_t kTeamTableBytes = offsetof(DeviceTables, t4);      // what a row team reads
 
 void build_device_tables(const dryv_pic_params& pp, DeviceTables* t);
 

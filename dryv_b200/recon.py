@@ -39,7 +39,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp", "levels_pack.cpp", "cabac_host.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "deblock_kernel.cuh", "recon_tables.h", "cabac_tables.inc", "levels_record.h")] + [
+    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "residual_stage.cuh", "deblock_kernel.cuh", "recon_tables.h", "cabac_tables.inc", "levels_record.h")] + [
         os.path.join(_HERE, "..", "include", "dryv_recon.h"), os.path.join(_HERE, "..", "include", "dryv_cabac_host.h")]
     if not force and os.path.exists(LIB_PATH) and all(
             os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):

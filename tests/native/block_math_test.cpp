@@ -1,0 +1,131 @@
+// block_math_test.cpp — CPU unit test of the lane-local arithmetic of dryv_b200/csrc/residual_stage.cuh (TEST CODE).
+// The header is compiled for the host (its instruction wrappers fall back to plain C++), and every 4x4 block function is
+// compared with the oracle's scaling_and_transform4x4 (oracle/dryv_oracle.c) on random and extreme blocks: flat and
+// non-flat scaling lists, qP 0..51, Intra4x4 / Intra16x16 (DC supplied) / chroma blocks. The packed column pass, its
+// range guard and the 32-bit path it falls back to are all exercised; the result must be clamp(r, -512, 511) + 512.
+//   build: g++ -O1 -std=c++17 -I. tests/native/block_math_test.cpp dryv_b200/csrc/recon_tables.cpp oracle/libdryv_oracle.so
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../dryv_b200/csrc/residual_stage.cuh"
+#include "../../oracle/dryv_oracle.h"
+
+using namespace dryv;
+
+static uint64_t rng_state = 0x1234567ull;
+static uint64_t rnd() {
+  uint64_t z = (rng_state += 0x9E3779B97F4A7C15ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+static int clampi(long v, long lo, long hi) { return (int)(v < lo ? lo : (v > hi ? hi : v)); }
+
+int main() {
+  static DeviceTables tab;
+  long n_blocks = 0, n_wide = 0, n_fast_deq = 0;
+  for (int lists = 0; lists < 3; lists++) {
+    dryv_pic_params pp;
+    memset(&pp, 0, sizeof pp);
+    pp.pic_width_in_mbs = pp.pic_height_in_mbs = 1;
+    for (int k = 0; k < 16; k++) pp.scaling_list4x4[k] = lists == 0 ? 16 : (lists == 1 ? (uint8_t)(6 + 3 * k) : (uint8_t)(1 + (rnd() % 255)));
+    for (int k = 0; k < 64; k++) pp.scaling_list8x8[k] = 16;
+    pp.chroma_qp_index_offset = lists == 1 ? -3 : 2;
+    pp.second_chroma_qp_index_offset = lists == 2 ? 7 : 0;
+    build_device_tables(pp, &tab);
+    for (int qp = 0; qp < 52; qp++) {
+      for (int mode = 0; mode < 4; mode++) {
+        for (int trial = 0; trial < 400; trial++) {
+          int16_t lv[16];
+          // magnitude classes: small (typical), medium, large (guard must route to the 32-bit path), int16 extremes with
+          // flat lists only (the 32-bit path itself is int32: see include/dryv_recon.h on the supported level range)
+          const int cls = trial % 10;
+          int amp = cls == 0 ? 4 : (cls == 1 ? 40 : (cls == 2 ? 300 : (cls == 3 ? 2047 : (cls == 4 ? 1 : 12))));
+          if (cls >= 6) {  // dequantised magnitudes around the guard's threshold (row-pass outputs near +-8192)
+            const int target[4] = {700, 2000, 3500, 5000};
+            int qq = qp;
+            if (mode >= 2) {
+              int q = qp + (mode == 2 ? pp.chroma_qp_index_offset : pp.second_chroma_qp_index_offset);
+              qq = tab.qpc[q < 0 ? 0 : (q > 51 ? 51 : q)];
+            }
+            const long sc = ((long)tab.t4[qq][0] >> (qq / 6 < 4 ? 4 - qq / 6 : 0));
+            amp = (int)(target[cls - 6] / (sc > 0 ? sc : 1));
+            if (amp < 1) amp = 1;
+          }
+          for (int k = 0; k < 16; k++) {
+            int v = (int)(rnd() % (2 * amp + 1)) - amp;
+            if (cls == 5 && (rnd() & 3)) v = 0;
+            lv[k] = (int16_t)v;
+          }
+          if (trial == 399) for (int k = 0; k < 16; k++) lv[k] = (k & 1) ? 2047 : -2047;
+          // oracle: mode 0 I4x4 luma, 1 I16x16 luma (lv[0] is the dequantised DC), 2 Cb, 3 Cr (DC supplied too)
+          int16_t in[16];
+          memcpy(in, lv, sizeof in);
+          int dcv = 0;
+          if (mode >= 1) {
+            dcv = (int)(rnd() % 8001) - 4000;
+            if (cls == 3) dcv *= 8;
+            if (cls >= 6) dcv = (int)(rnd() % 12001) - 6000;
+            in[0] = (int16_t)clampi(dcv, -32768, 32767);
+            dcv = in[0];
+          }
+          int32_t want[16];
+          if (dryv_oracle_block4x4(&pp, qp, mode, in, want) != 0) { printf("oracle failed\n"); return 1; }
+          int qpl = qp;
+          if (mode >= 2) {
+            int q = qp + (mode == 2 ? pp.chroma_qp_index_offset : pp.second_chroma_qp_index_offset);
+            q = q < 0 ? 0 : (q > 51 ? 51 : q);
+            qpl = tab.qpc[q];
+          }
+          uint32_t cw[8], out[8];
+          for (int w = 0; w < 8; w++) cw[w] = (uint32_t)(uint16_t)lv[2 * w] | ((uint32_t)(uint16_t)lv[2 * w + 1] << 16);
+          const int e = tab.t4b_e[qpl];
+          const bool fast = e != 0xff;
+          const int qpd = qpl / 6;
+          int tt[16];
+          for (int k = 0; k < 16; k++) tt[k] = tab.t4[qpl][k];
+          if (fast) block4x4_bytes(cw, tab.t4b[qpl], e, mode >= 1, dcv, out);
+          else block4x4_general(cw, tt, qpd < 4 ? 4 - qpd : 0, mode >= 1, dcv, out);
+          n_fast_deq += fast;
+          if (fast) {  // statistics: how often the guard fires on the byte-scale path
+            const int rb = kRowBias >> e;
+            int d[16], f[4][4];
+            for (int w = 0; w < 8; w++) {
+              d[2 * w] = dp2a_lo_su(cw[w], tab.t4b[qpl][w], w == 0 ? rb + (32 >> e) : (w == 1 ? rb : 0));
+              d[2 * w + 1] = dp2a_hi_su(cw[w], tab.t4b[qpl][w], (w == 1 || w == 4) ? rb : 0);
+            }
+            if (mode >= 1) d[0] = ((dcv + 32) >> e) + rb;
+            n_wide += (rows4x4(d, f) & ~((16384u >> e) - 1u)) != 0;
+          }
+          n_blocks++;
+          for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) {
+              const int got = (int)((out[2 * i + (j >> 1)] >> (16 * (j & 1))) & 0xffffu);
+              // beyond int32 the 32-bit path is outside its contract: skip blocks whose oracle result needs more
+              const int exp = clampi(want[i * 4 + j], -512, 511) + 512;
+              if (got != exp) {
+                printf("MISMATCH lists %d qp %d mode %d trial %d (%d,%d): got %d want %d (r = %d)\n", lists, qp, mode, trial, i, j,
+                       got, exp, want[i * 4 + j]);
+                return 1;
+              }
+            }
+        }
+      }
+    }
+  }
+  // add_clip4: every prediction byte against a sweep of residual fields
+  for (int p = 0; p < 256; p++)
+    for (int r = -512; r < 512; r++) {
+      const uint32_t pb = (uint32_t)p | ((uint32_t)((p * 7 + 3) & 0xff) << 8) | ((uint32_t)(255 - p) << 16) | ((uint32_t)((p * 13) & 0xff) << 24);
+      const int rr[4] = {r, -r - 1, (r * 3) % 512, 511 - ((r + 512) % 1024)};
+      const uint32_t r01 = (uint32_t)(rr[0] + 512) | ((uint32_t)(rr[1] + 512) << 16), r23 = (uint32_t)(rr[2] + 512) | ((uint32_t)(rr[3] + 512) << 16);
+      const uint32_t got = add_clip4(r01, r23, pb);
+      for (int k = 0; k < 4; k++) {
+        const int exp = clampi((long)((pb >> (8 * k)) & 0xff) + rr[k], 0, 255);
+        if ((int)((got >> (8 * k)) & 0xff) != exp) { printf("add_clip4 mismatch p %d r %d k %d\n", p, r, k); return 1; }
+      }
+    }
+  printf("ok: %ld blocks bit-exact (%ld through the byte-scale dequantisation, %ld of those through the 32-bit column pass)\n", n_blocks, n_fast_deq, n_wide);
+  return 0;
+}

@@ -71,10 +71,13 @@ class I4Step(C.Structure):
 
 
 class Tables(C.Structure):
-    _fields_ = [("t4", (C.c_int32 * 16) * 52), ("ls8", (C.c_uint16 * 64) * 6),
-                ("tap4", ((C.c_uint32 * 4) * 16) * 22), ("tap8", ((C.c_uint8 * 8) * 32) * 9),
-                ("zz8inv", (C.c_uint8 * 8) * 8), ("qpc", C.c_uint8 * 52), ("i4sched", (C.c_uint8 * 2) * 10),
-                ("pad", C.c_uint8 * 8), ("i4tab", (I4Step * 2) * 11), ("i4row", (C.c_uint16 * 16) * 16)]
+    # mirrors dryv_b200/csrc/recon_tables.h: residual part | prediction part | t4 (global memory only)
+    _fields_ = [("ls8", (C.c_uint16 * 64) * 6), ("t4b", (C.c_uint32 * 8) * 52), ("ls00", C.c_int32 * 8),
+                ("t4b_e", C.c_uint8 * 52), ("qpc", C.c_uint8 * 52), ("zz8inv", (C.c_uint8 * 8) * 8),
+                ("setbits4", C.c_uint16 * 16), ("pad0", C.c_uint8 * 8),
+                ("i4row", (C.c_uint16 * 16) * 16), ("tap4", ((C.c_uint32 * 4) * 16) * 22),
+                ("tap8", ((C.c_uint8 * 8) * 32) * 9), ("i4tab", (I4Step * 2) * 11), ("i4sched", (C.c_uint8 * 2) * 10),
+                ("pad1", C.c_uint8 * 12), ("t4", (C.c_int32 * 16) * 52)]
 
 
 TILE_STRIDE = 48
@@ -100,6 +103,20 @@ def test_level_scale_tables(recon_lib, custom):
     for m in range(6):
         assert np.array_equal(np.array(t.ls8[m]).reshape(8, 8), spec_model.level_scale8(l8, m))
     assert [int(v) for v in t.qpc] == spec_model.QPC
+    assert [int(v) for v in t.ls00[:6]] == [int(spec_model.level_scale4(l4, m)[0, 0]) for m in range(6)]
+    # byte-scale form (residual_stage.cuh): where it exists, level * factor * 2^e is the standard's dequantisation exactly
+    for qp in range(52):
+        e = t.t4b_e[qp]
+        if custom and e == 0xff:
+            continue
+        assert e != 0xff, "flat lists have the form at every qP"
+        shr = max(4 - qp // 6, 0)
+        for k in range(16):
+            f = (t.t4b[qp][k >> 1] >> (24 * (k & 1))) & 0xff
+            assert (f << e) << shr == t.t4[qp][k] and (e == 0 or f % 4 == 0)
+    for m in range(16):
+        bits = [b for b in range(4) if m & (1 << b)]
+        assert [(t.setbits4[m] >> (4 * i)) & 15 for i in range(4)] == bits + [15] * (4 - len(bits))
 
 
 def test_zigzag_and_tap_tables(recon_lib):

@@ -27,47 +27,14 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const void* p) {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-constexpr int kCoefAhead = 3;                 // macroblocks of look-ahead on the level fetch
-constexpr int kCoefStages = kCoefAhead + 1;   // ring depth
-__device__ __forceinline__ void cp_async_32(void* smem_dst, const void* gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(reinterpret_cast<const uint8_t*>(gmem_src) + 16) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-struct MbHeader {
-  int mbt, t8, cm, qp, mbcls;
-};
-
-// lanes 0..3 fetch mb_type / transform_size_8x8_flag / intra_chroma_pred_mode / qp of macroblock `mb`;
-// `base` is the lane's array (header_base), selected once per kernel
-__device__ __forceinline__ const uint8_t* header_base(const KernelArgs& a, int lane) {
+// lanes (field, macroblock) fetch mb_type / transform_size_8x8_flag / intra_chroma_pred_mode / qp of the macroblocks
+// of a group; `field` picks the lane's array once per kernel
+__device__ __forceinline__ const uint8_t* header_base(const KernelArgs& a, int field) {
   const uint8_t* p = a.qp;
-  if (lane == 0) p = a.mb_type;
-  if (lane == 1) p = a.t8x8;
-  if (lane == 2) p = a.chroma_mode;
+  if (field == 0) p = a.mb_type;
+  if (field == 1) p = a.t8x8;
+  if (field == 2) p = a.chroma_mode;
   return p;
-}
-__device__ __forceinline__ uint32_t load_header_lane(const uint8_t* base, int lane, size_t mb) {
-  return lane < 4 ? (uint32_t)__ldg(base + mb) : 0u;
-}
-__device__ __forceinline__ MbHeader decode_header(uint32_t hdr_lane, int* status) {
-  MbHeader h;
-  h.mbt = __shfl_sync(0xffffffffu, hdr_lane, 0);
-  h.t8 = __shfl_sync(0xffffffffu, hdr_lane, 1);
-  h.cm = __shfl_sync(0xffffffffu, hdr_lane, 2);
-  h.qp = __shfl_sync(0xffffffffu, hdr_lane, 3);
-  if (h.mbt > 24 || h.cm > 3 || h.qp > 51) {  // I_PCM / inter / out-of-range syntax: flagged, never decoded
-    *status = STATUS_UNSUPPORTED;
-    h.mbt = min(h.mbt, 24);
-    h.cm &= 3;
-    h.qp = min(h.qp, 51);
-  }
-  h.mbcls = h.mbt == 0 ? (h.t8 ? 1 : 0) : 2;  // slice/macroblock.rs:682-716
-  return h;
 }
 
 // Timeline trace (development builds only: -DDRYV_TRACE): the pixel warp records, for picture 0, the global
@@ -80,7 +47,7 @@ __device__ __forceinline__ unsigned int gtimer_ns() {
 }
 #define TRACE_MARK(k)                                                                                  \
   do {                                                                                                 \
-    if (a.trace && lane == 0 && slot.frame == 0) a.trace[((size_t)row * W + x) * 4 + (k)] = gtimer_ns(); \
+    if (a.trace && lane == 0 && G.frame == 0) a.trace[((size_t)row * W + x) * 4 + (k)] = gtimer_ns(); \
   } while (0)
 #else
 #define TRACE_MARK(k)
@@ -173,7 +140,7 @@ __device__ __forceinline__ void bar_arrive_empty(unsigned si) {
     default: asm volatile("bar.arrive 8, 64;" ::: "memory"); break;
   }
 }
-static_assert(kSlots >= 2 && kSlots <= 8, "named-barrier ids above cover up to eight ring slots");
+static_assert(kGroupSlots >= 2 && kGroupSlots <= 8, "named-barrier ids above cover up to eight group slots");
 
 // Long waits (the front warp runs kSlots macroblocks ahead and then blocks on the pixel warp for a whole
 // macroblock time): the hinted try_wait above is woken by every mbarrier event of the SM and re-issues ~100
@@ -199,7 +166,7 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned long long* b, uint32_
   while (!mbar_test(b, parity)) __nanosleep(DRYV_FRONT_SLEEP_NS);
 }
 
-// Waits until the line words of lanes [lo, hi) carry this launch's tag; returns the lane's payload.
+// Waits until the words of the lanes with `mine` set carry this launch's tag; returns the lane's payload.
 // `first` is the value of a load issued earlier (so its latency overlapped with other work).
 // On a watchdog trip `dead` is set and every later wait returns immediately (the kernel drains with
 // garbage and the host reports DRYV_ERR_WATCHDOG).
@@ -222,11 +189,10 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned long long* b, uint32_
 #endif
 constexpr int kPollPace = DRYV_POLL_PACE;
 constexpr int kPollUnroll = DRYV_POLL_UNROLL;
-__device__ DRYV_WAIT_INLINE uint32_t wait_line_words(const unsigned long long* p, unsigned long long first, int lane,
-                                                    int lo, int hi, uint32_t tag, bool long_wait, int* status,
-                                                    bool& dead, uint32_t& pace_addr) {
+__device__ DRYV_WAIT_INLINE uint32_t wait_line_words(const unsigned long long* p, unsigned long long first, bool mine,
+                                                    uint32_t tag, bool long_wait, int* status, bool& dead,
+                                                    uint32_t& pace_addr) {
   unsigned long long v = first;
-  const bool mine = lane >= lo && lane < hi;
   if (dead || __all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) return (uint32_t)v;
   // Slow path. Only the lanes that own a word poll, each in its own loop (load, compare, branch: three instructions per
   // poll, no vote); the others wait at the __syncwarp below. Every instruction a waiting warp issues is taken from the
@@ -411,10 +377,12 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
 // ------------------------------------------------------------------------------------------------
 // Full reconstruction: persistent row teams over an x+2y macroblock wavefront.
 //
-// A row team (one CTA, two warps) walks one macroblock row of one picture left to right:
-//   front warp  - 128-bit coefficient loads, dequant + Hadamard + 4x4/8x8 inverse transforms into a ring
-//                 slot. Depends on nothing but its own macroblock, so it runs ahead of the pixels.
-//   pixel warp  - Intra4x4/8x8/16x16 + chroma prediction, residual add + clip, 128-bit row stores.
+// A row team (one CTA, two warps) walks one macroblock row of one picture left to right, a group of four macroblocks
+// at a time:
+//   front warp  - one bulk copy per group for the levels (a group ahead), the residual stage of the group
+//                 (residual_stage.cuh) into a group slot, tap rows of the Intra4x4 blocks, then the chroma of each
+//                 macroblock. Depends on nothing but its own macroblocks for luma, so it runs ahead of the pixels.
+//   pixel warp  - Intra4x4/8x8/16x16 prediction, residual add + clip, 128-bit row stores.
 // Rows hand data down through the line buffer: after a macroblock the team writes its bottom line
 // (4 luma words, 2+2 chroma words), each as payload | launch tag in one 64-bit word. The row below
 // fetches a line with one relaxed 64-bit load per lane, issued a whole macroblock before it is needed,
@@ -432,24 +400,23 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
 #define DRYV_START_LAG 2
 #endif
 constexpr int kStartLag = DRYV_START_LAG;
-// Teams per SM = the register budget handed to ptxas. Measured (64 x 1080p, ms per step): 12 teams (79 regs) 0.950,
-// 11 (92) 0.968, 10 (96) 0.900, 9 (96) 0.895, 8 (127) 0.905, 7 (124) 0.907, 6 (143) 1.001. Ten teams of 96 registers:
-// the residual stage stops re-materialising its 16+16 element arrays, and two fewer teams do not cost throughput.
-// Measured again after the Intra4x4 predictor was rolled (one batch at a time / two batches in flight on two streams):
-// 12 teams 0.958 / 0.772, 11 0.967 / 0.778, 10 0.895 / 0.741, 9 0.890 / 0.737, 8 (and 7: same residency) 0.865 / 0.735,
-// 6 (and 5) 0.933 / 0.835. Eight teams with up to 128 registers; the optimum is flat (poll pacing, sleep lengths and the
-// chroma wait flavour all land within 0.3 % of it, tools/overlap_var.sh).
+// Teams per SM = the register budget handed to ptxas (and 27 KB of shared memory per team).
 #ifndef DRYV_TEAMS_PER_SM
 #define DRYV_TEAMS_PER_SM 8
 #endif
 __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefront_kernel(const KernelArgs a) {
-  __shared__ alignas(16) TeamSmem ts;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TeamSmem& ts = *reinterpret_cast<TeamSmem*>(smem_raw);
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.tables);
-    uint4* dst = reinterpret_cast<uint4*>(&ts.tab);
-    for (int i = threadIdx.x; i < (int)(sizeof(DeviceTables) / 16); i += kTeamThreads) dst[i] = src[i];
+    uint4* dst = reinterpret_cast<uint4*>(ts.tab);
+    for (int i = threadIdx.x; i < (int)(kTeamTableBytes / 16); i += kTeamThreads) dst[i] = src[i];
+    // tap-row bytes 16..31 of every slot stay zero: the look-ahead of the Intra4x4 loop reads up to byte 18
+    for (int i = threadIdx.x; i < kGroupSlots * kGroupMbs * 4; i += kTeamThreads)
+      reinterpret_cast<uint32_t*>(ts.grp[i / (kGroupMbs * 4)].mb[(i / 4) % kGroupMbs].rows + 16)[i % 4] = 0u;
     if (threadIdx.x == 0) {
-      for (int i = 0; i < kSlots; i++) mbar_init(&ts.full[i], 1);
+      for (int i = 0; i < kGroupSlots; i++) mbar_init(&ts.full[i], 1);
+      for (int i = 0; i < kLvStages; i++) mbar_init(&ts.lvfull[i], 1);
       ts.pace = smem_u32(&ts.pace);  // a word that holds its own shared-memory address (see wait_line_words)
     }
   }
@@ -457,7 +424,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
   uint32_t pace_addr = smem_u32(&ts.pace);
   const int lane = threadIdx.x & 31;
   const bool is_front = threadIdx.x < 32;
-  const DeviceTables& tab = ts.tab;
+  const DeviceTables& tab = *reinterpret_cast<const DeviceTables*>(ts.tab);  // everything but t4
   const int W = a.W, H = a.H;
   const size_t n_mb = (size_t)W * H;
   const int strideY = W * 16;
@@ -465,11 +432,15 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
 
   if (is_front) {
     // =========================================== front warp ===========================================
-    const LaneConst lc = make_lane_const(lane, tab);
-    const uint8_t* const hdr_base = header_base(a, lane);
+    const ResLane lc = make_res_lane(lane, tab);
+    // header lanes: lane = field * 4 + macroblock of the group; field 0 mb_type, 1 transform_size_8x8_flag, 2 chroma mode, 3 qp
+    const uint8_t* const hdr_base = header_base(a, lane >> 2);
+    const uint32_t hdr_lim = (lane >> 2) == 0 ? 24u : ((lane >> 2) == 2 ? 3u : ((lane >> 2) == 3 ? 51u : 255u));
     const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
-    int local_status = STATUS_OK;
-    unsigned n = 0;  // macroblocks handed to the pixel warp so far
+    const int gpr = (W + kGroupMbs - 1) / kGroupMbs;
+    bool unsupported = false;
+    unsigned gn = 0;   // groups handed to the pixel warp so far
+    unsigned lvw = 0;  // level fetches consumed so far: fetch k lands in stage k & 1, phase (k >> 1) & 1
     // chroma lane roles: lanes 4..5 / 6..7 fetch and publish the two Cb / Cr words of a bottom line,
     // lanes 8..9 shift the top-row slots [x-1].w1 | [x].w0..1 (byte 4 + 4k of tile row -1) when the walker
     // advances, lanes 16..23 / 24..31 store and carry one Cb / Cr pixel row each
@@ -484,6 +455,10 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     uint8_t* const c_tile = &ts.chroma[((lane >> 3) & 1) * kChromaTileBytes];
     const int c_first = chroma_at(0, lane & 7), c_last = chroma_at(7, lane & 7), c_left = chroma_at(-1, lane & 7);
     const int strideC = W * 8;
+    const bool c_lane = lane >= 4 && lane < 8;
+    // mode-record lanes: lanes 8..15 = (macroblock (lane >> 1) & 3 of the group, word lane & 1)
+    const bool m_lane = lane >= 8 && lane < 16;
+    const int m_mb = (lane >> 1) & 3;
     bool dead = false;
     CLK_DECL;
     for (;;) {
@@ -500,139 +475,158 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
       uint8_t* c_st = a.out + (size_t)frame * n_mb * 384 + n_mb * 256 + (size_t)((lane >> 3) & 1) * n_mb * 64 +
                       (size_t)(8 * row + (lane & 7)) * strideC;
       unsigned long long lvc = 0;
-      if (availB && lane >= 4 && lane < 8) lvc = ld_relaxed_gpu_u64(c_above);
+      if (availB && c_lane) lvc = ld_relaxed_gpu_u64(c_above);
 
-      // Level fetch: cp.async (LDGSTS) copies of the macroblock's 768 B into a ring in shared memory, kCoefAhead
-      // macroblocks ahead of their use. No staging registers and no scoreboard: under load the front warp used to
-      // stall on a one-macroblock-ahead register prefetch (DRAM latency > one macroblock time).
-      // Lanes 0..23 copy (and later read back) the 32 bytes of their own 4x4 block.
-      const uint8_t* hp = hdr_base + mb_row0;
-      const uint8_t* cp = reinterpret_cast<const uint8_t*>(a.coeff + mb_row0 * DRYV_COEFFS_PER_MB) + lane * 32;
-      const unsigned long long* mp = a.modes + mb_row0 * kModeWords + (lane & 1);  // lanes 24 / 25: lo / hi word
-      for (int k = 0; k < kCoefAhead; k++) {
-        if (lane < 24 && k < W) cp_async_32(&ts.coef[k % kCoefStages][lane * 16], cp + (size_t)k * (DRYV_COEFFS_PER_MB * 2));
-        cp_async_commit();
-      }
-      uint32_t hdr_n = lane < 4 ? (uint32_t)__ldg(hp) : 0u;
-      unsigned long long mv_n = 0;
-      if (lane == 24 || lane == 25) mv_n = ld_relaxed_gpu_u64(mp);
+      const int16_t* const lv_row = a.coeff + mb_row0 * DRYV_COEFFS_PER_MB;
+      auto fetch = [&](int g, unsigned k) {  // levels of group g of this row -> stage k & 1
+        const int nn = min(kGroupMbs, W - g * kGroupMbs);
+        bulk_load(ts.lv[k & 1], lv_row + (size_t)g * (kGroupMbs * DRYV_COEFFS_PER_MB), (uint32_t)nn * (DRYV_COEFFS_PER_MB * 2),
+                  &ts.lvfull[k & 1]);
+      };
+      auto load_hdr = [&](int g) -> uint32_t {
+        const int x = g * kGroupMbs + (lane & 3);
+        return (lane < 16 && x < W) ? (uint32_t)__ldg(hdr_base + mb_row0 + x) : 0u;
+      };
+      auto load_modes = [&](int g) -> unsigned long long {
+        const int x = g * kGroupMbs + m_mb;
+        return (m_lane && x < W) ? ld_relaxed_gpu_u64(a.modes + (mb_row0 + x) * kModeWords + (lane & 1)) : 0ull;
+      };
+      if (lane == 0) fetch(0, lvw);
+      uint32_t hv = load_hdr(0);
+      unsigned long long mv = load_modes(0);
 
-      for (int x = 0; x < W; x++) {
-        const uint32_t hdr_c = hdr_n;
-        unsigned long long mv_c = mv_n;
+      for (int g = 0; g < gpr; g++) {
+        const int x0 = g * kGroupMbs, n = min(kGroupMbs, W - x0);
+        const int stage = (int)(lvw & 1u);
+        if (g + 1 < gpr && lane == 0) fetch(g + 1, lvw + 1);  // the other stage held group g - 1: consumed
+        // ---- headers of the group ----
+        uint32_t v = hv;
+        const unsigned long long mvc = mv;
+        if (g + 1 < gpr) {
+          hv = load_hdr(g + 1);
+          mv = load_modes(g + 1);
+        }
+        if (v > hdr_lim) {  // I_PCM / inter / out-of-range syntax: flagged, never decoded
+          unsupported = true;
+          v = (lane >> 2) == 2 ? (v & 3u) : hdr_lim;
+        }
+        uint32_t m4, m8, mI4;
         {
-          const int k = x + kCoefAhead;
-          if (lane < 24 && k < W) cp_async_32(&ts.coef[k % kCoefStages][lane * 16], cp + (size_t)k * (DRYV_COEFFS_PER_MB * 2));
-          cp_async_commit();
-        }
-        if ((x & 15) == 0 && x + 24 < W) {
-          // the byte-per-MB arrays and the modes: L2 prefetch now and then
-          if (lane >= 8 && lane < 12) prefetch_l2(header_base(a, lane - 8) + mb_row0 + x + 24);
-
-        }
-        if (x + 1 < W) {
-          hp += 1;
-          mp += kModeWords;
-          if (lane < 4) hdr_n = (uint32_t)__ldg(hp);
-          if (lane == 24 || lane == 25) mv_n = ld_relaxed_gpu_u64(mp);
-        }
-        cp_async_wait<kCoefAhead>();  // this macroblock's copy has landed (each lane reads what it copied itself)
-        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-        if (lane < 24) {
-          const uint4* src = reinterpret_cast<const uint4*>(&ts.coef[x % kCoefStages][lane * 16]);
-          c0 = src[0];
-          c1 = src[1];
-        }
-        const MbHeader h = decode_header(hdr_c, &local_status);
-
-        // ring slot: wait until the pixel warp has released its previous use
-        const unsigned si = n % kSlots, use = n / kSlots;
-        Slot& slot = ts.slot[si];
-        CLK_MARK(0);  // prefetch + header
-        if (use > 0) bar_sync_empty(si);
-        CLK_MARK(1);  // wait for a free slot
-
-        residual_stage(tab, ts.scratch, slot.res, ts.cres, lc, lane, c0, c1, h.mbcls, h.qp, a.cb_off, a.cr_off);
-        CLK_MARK(2);  // residual stage
-
-        if (h.mbcls != 2) {
-          // the mode record of this macroblock (fetched one macroblock ago): the pre-pass may still be running,
-          // so check the tags and poll if it has not got here yet (it walks a row about three times faster)
-          const unsigned long long* mq = mp - (x + 1 < W ? kModeWords : 0);
-          const uint32_t w = wait_line_words(mq - (lane & 1) + lane - 24, mv_c, lane, 24, 26, tag, true, a.status, dead, pace_addr);
-          const uint32_t mlo = __shfl_sync(0xffffffffu, w, 24), mhi = __shfl_sync(0xffffffffu, w, 25);
-          if (lane == 24) {
-            slot.modes_lo = mlo;
-            slot.modes_hi = mhi;
-          }
-          // Intra4x4: per-block tap rows (mode, top-right variant, legality and DC flavour in one byte)
-          if (h.mbcls == 0) {
-          const int av = (x > 0 ? 1 : 0) | (availB ? 2 : 0) | ((availB && x + 1 < W) ? 4 : 0) | ((x > 0 && availB) ? 8 : 0);
-            slot.rows[lane] = lane < 16 ? (uint8_t)i4_tap_row(tab, lane, mlo, mhi, av) : (uint8_t)0;
-          }
-        }
-        if (lane == 0) {
-          slot.frame = frame;
-          slot.row = row;
-          slot.x = x;
-          slot.mbcls = h.mbcls;
-          slot.mode16 = ((h.mbt - 1) & 3) | (h.cm << 8);
+          const int m = lane & 3;
+          const uint32_t mbt = __shfl_sync(0xffffffffu, v, m), t8 = __shfl_sync(0xffffffffu, v, 4 + m),
+                         cm = __shfl_sync(0xffffffffu, v, 8 + m), qp = __shfl_sync(0xffffffffu, v, 12 + m);
+          const uint32_t cls = mbt == 0 ? (t8 ? 1u : 0u) : 2u;  // slice/macroblock.rs:682-716
+          if (lane < kGroupMbs) ts.hdr[lane] = cls | (qp << 8) | (cm << 16) | (mbt << 24);
+          m8 = __ballot_sync(0xffffffffu, lane < n && cls == 1u);
+          mI4 = __ballot_sync(0xffffffffu, lane < n && cls == 0u);
+          m4 = ((1u << n) - 1u) & ~m8;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ts.full[si]);
-        n++;
+        CLK_MARK(0);  // prefetch + headers
+        // ---- group slot: wait until the pixel warp has released its previous use ----
+        const unsigned gs = gn % kGroupSlots, use = gn / kGroupSlots;
+        GroupSlot& G = ts.grp[gs];
+        if (use > 0) bar_sync_empty(gs);
+        CLK_MARK(1);  // wait for a free slot
+        mbar_wait(&ts.lvfull[stage], (lvw >> 1) & 1u);
+        residual_group(tab, a.tables, lc, lane, ts.hdr, m4, m8, ts.lv[stage], n, reinterpret_cast<int*>(&ts.cres[0][0]),
+                       G.mb[0].res, (int)(sizeof(MbSlot) / sizeof(uint16_t)), &ts.cres[0][0], kResChromaMb, a.cb_off,
+                       a.cr_off);
+        lvw++;
+        CLK_MARK(2);  // residual stage
+        // ---- mode records of the Intra4x4 / Intra8x8 macroblocks (fetched a group ago): the pre-pass may still be
+        // running, so check the tags and poll if a record has not got here yet (it walks a row about three times faster)
+        if (m4 != ((1u << n) - 1u) || mI4) {
+          const bool mine = m_lane && m_mb < n && (ts.hdr[m_mb] & 0xffu) != 2u;
+          const uint32_t w = wait_line_words(a.modes + (mb_row0 + x0 + m_mb) * kModeWords + (lane & 1), mvc, mine, tag, true,
+                                             a.status, dead, pace_addr);
+          if (mine) (&G.mb[m_mb].modes_lo)[lane & 1] = w;
+          __syncwarp();
+          // Intra4x4: per-block tap rows (mode, top-right variant, legality and DC flavour in one byte), two macroblocks per pass
+          if (mI4) {
+            const uint32_t list = tab.setbits4[mI4];
+            const int ni = __popc(mI4);
+            for (int p = 0; 2 * p < ni; p++) {
+              const uint32_t m = (list >> (4 * (2 * p + (lane >> 4)))) & 15u;
+              if (m < (uint32_t)kGroupMbs) {
+                const int x = x0 + (int)m;
+                const int av = (x > 0 ? 1 : 0) | (availB ? 2 : 0) | ((availB && x + 1 < W) ? 4 : 0) | ((x > 0 && availB) ? 8 : 0);
+                const uint2 mw = *reinterpret_cast<const uint2*>(&G.mb[m].modes_lo);
+                G.mb[m].rows[lane & 15] = (uint8_t)i4_tap_row(tab, lane & 15, mw.x, mw.y, av);
+              }
+            }
+          }
+        }
+        if (lane < n) {
+          const uint32_t h = ts.hdr[lane];
+          G.mb[lane].mbcls = (int)(h & 0xffu);
+          G.mb[lane].mode16 = (int)(((h >> 24) - 1u) & 3u);
+        }
+        if (lane == 0) {
+          G.frame = frame;
+          G.row = row;
+          G.x0 = x0;
+          G.n = n;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ts.full[gs]);
+        gn++;
         CLK_MARK(4);  // hand-off
 
-        // ---- chroma of this macroblock: prediction needs line x of the row above (no top-right), so the chroma
+        // ---- chroma of the group's macroblocks: prediction needs line x of the row above (no top-right), so the chroma
         // walk of a row depends only on the chroma walk of the row above and stays off the luma critical path
-        const bool availA = x > 0;
-        if (availB) {
-          // always the sleeping flavour: the front warp runs ahead of the pixel warp, so this wait is not on the
-          // critical path, and a tight poll here would take issue slots from the pixel warps of the SM
-          const uint32_t w = wait_line_words(c_above, lvc, lane, 4, 8, tag, DRYV_CHROMA_LONG_WAIT || x == 0, a.status, dead, pace_addr);
-          if (lane >= 4 && lane < 8) {
-            *reinterpret_cast<uint32_t*>(c_fresh) = w;
-            c_above += kLineWords;
-            if (x + 1 < W) lvc = ld_relaxed_gpu_u64(c_above);
+        for (int m = 0; m < n; m++) {
+          const int x = x0 + m;
+          const int cm = (int)((ts.hdr[m] >> 16) & 0xffu);
+          const bool availA = x > 0;
+          if (availB) {
+            // always the sleeping flavour: the front warp runs ahead of the pixel warp, so this wait is not on the
+            // critical path, and a tight poll here would take issue slots from the pixel warps of the SM
+            const uint32_t w = wait_line_words(c_above, lvc, c_lane, tag, DRYV_CHROMA_LONG_WAIT || x == 0, a.status, dead, pace_addr);
+            if (c_lane) {
+              *reinterpret_cast<uint32_t*>(c_fresh) = w;
+              c_above += kLineWords;
+              if (x + 1 < W) lvc = ld_relaxed_gpu_u64(c_above);
+            }
+            __syncwarp();
           }
-          __syncwarp();
-        }
-        CLK_MARK(3);  // wait for the chroma line of the row above
-        predict_chroma(ts.chroma, ts.ccol, ts.cres, lane, h.cm, availA, availB, availA && availB);
-        if (publish && lane >= 4 && lane < 8)
-          st_relaxed_gpu_u64(c_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(c_pub));
-        c_mine += kLineWords;
-        if (lane >= 16) {
-          const uint2 v = *reinterpret_cast<const uint2*>(&c_tile[c_first]);
-          __stcs(reinterpret_cast<uint2*>(c_st), v);
-          c_st += 8;
-        }
-        {  // carry: right-most column -> left-neighbour column (tile column -1 and its contiguous copy), top-row shift
-          const int cv = c_tile[c_last];
-          uint32_t sv = 0;
-          if (c_shift) sv = *reinterpret_cast<const uint32_t*>(c_shift + 8);
-          __syncwarp();
+          CLK_MARK(3);  // wait for the chroma line of the row above
+          predict_chroma(ts.chroma, ts.ccol, ts.cres[m], lane, cm, availA, availB, availA && availB);
+          if (publish && c_lane)
+            st_relaxed_gpu_u64(c_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(c_pub));
+          c_mine += kLineWords;
           if (lane >= 16) {
-            c_tile[c_left] = (uint8_t)cv;
-            ts.ccol[lane - 16] = (uint8_t)cv;
+            const uint2 pv = *reinterpret_cast<const uint2*>(&c_tile[c_first]);
+            __stcs(reinterpret_cast<uint2*>(c_st), pv);
+            c_st += 8;
           }
-          if (c_shift) *reinterpret_cast<uint32_t*>(c_shift) = sv;
-          __syncwarp();
+          {  // carry: right-most column -> left-neighbour column (tile column -1 and its contiguous copy), top-row shift
+            const int cv = c_tile[c_last];
+            uint32_t sv = 0;
+            if (c_shift) sv = *reinterpret_cast<const uint32_t*>(c_shift + 8);
+            __syncwarp();
+            if (lane >= 16) {
+              c_tile[c_left] = (uint8_t)cv;
+              ts.ccol[lane - 16] = (uint8_t)cv;
+            }
+            if (c_shift) *reinterpret_cast<uint32_t*>(c_shift) = sv;
+            __syncwarp();
+          }
+          CLK_MARK(5);  // chroma prediction + store + carry
         }
-        CLK_MARK(5);  // chroma prediction + store + carry
       }
       CLK_MARK(7);  // row change
     }
     CLK_FLUSH(0);
     // no more rows: tell the pixel warp
     {
-      const unsigned si = n % kSlots, use = n / kSlots;
-      if (use > 0) bar_sync_empty(si);
-      if (lane == 0) ts.slot[si].row = -1;
+      const unsigned gs = gn % kGroupSlots, use = gn / kGroupSlots;
+      if (use > 0) bar_sync_empty(gs);
+      if (lane == 0) ts.grp[gs].row = -1;
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ts.full[si]);
+      if (lane == 0) mbar_arrive(&ts.full[gs]);
     }
-    if (local_status == STATUS_UNSUPPORTED) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
+    if (unsupported) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
   } else {
     // =========================================== pixel warp ===========================================
     // Luma only. Top-row slots of the luma tile (tile row -1): 9 words [x-1].w3 | [x].w0..3 | [x+1].w0..3 at
@@ -645,7 +639,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     uint8_t* const shift_dst = lane < 5 ? &ts.luma[12 + 4 * lane] : nullptr;
     // lanes 0..15 store and carry one luma pixel row each
     const int my_first = luma_at(0, lane & 15), my_last = luma_at(15, lane & 15), my_left = luma_at(-1, lane & 15);
-    unsigned n = 0;
+    unsigned gn = 0;
     const int W1 = W - 1;
     const unsigned long long* line_above = nullptr;  // + lane; line x+1 of the row above
     unsigned long long* line_mine = nullptr;
@@ -654,107 +648,110 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     unsigned long long lv = 0;  // in-flight fetch of this lane's line word for the current macroblock
     CLK_DECL;
     for (;;) {
-      const unsigned si = n % kSlots, use = n / kSlots;
-      Slot& slot = ts.slot[si];
-      mbar_wait(&ts.full[si], use & 1);
+      const unsigned gs = gn % kGroupSlots, use = gn / kGroupSlots;
+      GroupSlot& G = ts.grp[gs];
+      mbar_wait(&ts.full[gs], use & 1);
       CLK_MARK(0);  // wait for a filled slot
-      const int row = slot.row;
+      const int row = G.row;
       if (row < 0) break;
-      const int x = slot.x;
-      if (x == 0) {
-        // row start
-        const int frame = slot.frame;
-        const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
-        availB = row > 0;
-        publish = row + 1 < H;
-        line_above = a.line + (mb_row0 - W) * kLineWords + lane;
-        line_mine = a.line + mb_row0 * kLineWords + lane;
-        st_ptr = a.out + (size_t)frame * n_mb * 384 + (size_t)(16 * row + (lane & 15)) * strideY;
-        if (availB) {
-          // Start lag (see kStartLag), then luma line 0 of the row above becomes "line x" of macroblock 0
-          if (kStartLag > 2) {
-            const int ahead = min(kStartLag - 1, W1);
-            const unsigned long long* far = line_above + (size_t)ahead * kLineWords;
-            unsigned long long vf = 0;
-            if (lane == 0) vf = ld_relaxed_gpu_u64(far);
-            wait_line_words(far, vf, lane, 0, 1, tag, true, a.status, dead, pace_addr);
+      const int x0 = G.x0, n = G.n;
+      for (int m = 0; m < n; m++) {
+        const int x = x0 + m;
+        MbSlot& slot = G.mb[m];
+        if (x == 0) {
+          // row start
+          const int frame = G.frame;
+          const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
+          availB = row > 0;
+          publish = row + 1 < H;
+          line_above = a.line + (mb_row0 - W) * kLineWords + lane;
+          line_mine = a.line + mb_row0 * kLineWords + lane;
+          st_ptr = a.out + (size_t)frame * n_mb * 384 + (size_t)(16 * row + (lane & 15)) * strideY;
+          if (availB) {
+            // Start lag (see kStartLag), then luma line 0 of the row above becomes "line x" of macroblock 0
+            if (kStartLag > 2) {
+              const int ahead = min(kStartLag - 1, W1);
+              const unsigned long long* far = line_above + (size_t)ahead * kLineWords;
+              unsigned long long vf = 0;
+              if (lane == 0) vf = ld_relaxed_gpu_u64(far);
+              wait_line_words(far, vf, lane == 0, tag, true, a.status, dead, pace_addr);
+            }
+            unsigned long long v0 = 0;
+            if (lane < 4) v0 = ld_relaxed_gpu_u64(line_above);
+            const uint32_t w = wait_line_words(line_above, v0, lane < 4, tag, true, a.status, dead, pace_addr);
+            if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+            __syncwarp();
+            uint32_t sv = 0;
+            if (lane < 5) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
+            __syncwarp();
+            if (lane < 5) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
+            // look one line ahead from here on
+            if (lane < 4) {
+              line_above += kLineWords;
+              if (W1 > 0) lv = ld_relaxed_gpu_u64(line_above);
+            }
           }
-          unsigned long long v0 = 0;
-          if (lane < 4) v0 = ld_relaxed_gpu_u64(line_above);
-          const uint32_t w = wait_line_words(line_above, v0, lane, 0, 4, tag, true, a.status, dead, pace_addr);
+        }
+        CLK_MARK(1);  // row start (incl. long wait for line 0)
+        TRACE_MARK(0);
+        const int mbcls = slot.mbcls, mode16 = slot.mode16;
+        const bool availA = x > 0, availC = availB && x < W1, availD = availA && availB;
+        // needs line x+1 of the row above (top-right neighbour), if it exists
+        if (availC) {
+          const uint32_t w = wait_line_words(line_above, lv, lane < 4, tag, false, a.status, dead, pace_addr);
           if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
-          __syncwarp();
-          uint32_t sv = 0;
-          if (lane < 5) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
-          __syncwarp();
-          if (lane < 5) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
-          // look one line ahead from here on
-          if (lane < 4) {
+        }
+        __syncwarp();
+        CLK_MARK(2);  // wait for the luma line of the row above
+        TRACE_MARK(1);
+
+        if (mbcls == 0) {
+          predict_i4x4(tab, ts.luma, slot.res, pl, slot.rows + 8 * pl.half);
+          CLK_MARK(3);
+        } else if (mbcls == 1) {
+          predict_i8x8(tab, ts.luma, ts.e8, slot.res, pl, lane, slot.modes_lo, slot.modes_hi, availA, availB, availC, availD);
+          CLK_MARK(4);
+        } else {
+          predict_i16x16(ts.luma, ts.lcol, slot.res, lane, mode16, availA, availB);
+          CLK_MARK(5);
+        }
+        // The row below is waiting for exactly this: publish the bottom line before anything else, and only then
+        // fetch the line for the next macroblock (as late as possible: in a tightly coupled wavefront an earlier
+        // load would only see that the row above has not got there yet).
+        if (lane < 4) {
+          if (publish)
+            st_relaxed_gpu_u64(line_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
+          if (availB) {
             line_above += kLineWords;
-            if (W1 > 0) lv = ld_relaxed_gpu_u64(line_above);
+            if (x + 2 <= W1) lv = ld_relaxed_gpu_u64(line_above);
           }
         }
-      }
-      CLK_MARK(1);  // row start (incl. long wait for line 0)
-      TRACE_MARK(0);
-      const int mbcls = slot.mbcls, mode16 = slot.mode16 & 3;
-      const uint32_t modes_lo = slot.modes_lo, modes_hi = slot.modes_hi;
-      const bool availA = x > 0, availC = availB && x < W1, availD = availA && availB;
-      // needs line x+1 of the row above (top-right neighbour), if it exists
-      if (availC) {
-        const uint32_t w = wait_line_words(line_above, lv, lane, 0, 4, tag, false, a.status, dead, pace_addr);
-        if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
-      }
-      __syncwarp();
-      CLK_MARK(2);  // wait for the luma line of the row above
-      TRACE_MARK(1);
+        line_mine += kLineWords;
+        TRACE_MARK(2);
 
-      if (mbcls == 0) {
-        predict_i4x4(tab, ts.luma, slot.res, pl, slot.rows + 8 * pl.half);
-        CLK_MARK(3);
-      } else if (mbcls == 1) {
-        predict_i8x8(tab, ts.luma, ts.e8, slot.res, pl, lane, modes_lo, modes_hi, availA, availB, availC, availD);
-        CLK_MARK(4);
-      } else {
-        predict_i16x16(ts.luma, ts.lcol, slot.res, lane, mode16, availA, availB);
-        CLK_MARK(5);
-      }
-      // The row below is waiting for exactly this: publish the bottom line before anything else, and only then
-      // fetch the line for the next macroblock (as late as possible: in a tightly coupled wavefront an earlier
-      // load would only see that the row above has not got there yet).
-      if (lane < 4) {
-        if (publish)
-          st_relaxed_gpu_u64(line_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
-        if (availB) {
-          line_above += kLineWords;
-          if (x + 2 <= W1) lv = ld_relaxed_gpu_u64(line_above);
+        // store the macroblock's 16 x 16 B luma rows
+        if (lane < 16) {
+          const uint4 pv = *reinterpret_cast<const uint4*>(&ts.luma[my_first]);
+          __stcs(reinterpret_cast<uint4*>(st_ptr), pv);
+          st_ptr += 16;
         }
+        // carry: right-most column -> left-neighbour column (tile column -1 and its contiguous copy),
+        // top-row slots shift by one macroblock
+        const int cv = ts.luma[my_last];
+        uint32_t sv = 0;
+        if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
+        __syncwarp();
+        if (lane < 16) {
+          ts.luma[my_left] = (uint8_t)cv;
+          ts.lcol[lane] = (uint8_t)cv;
+        }
+        if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
+        __syncwarp();
+        TRACE_MARK(3);
+        CLK_MARK(7);  // stores + publish + carry
       }
-      line_mine += kLineWords;
-      TRACE_MARK(2);
-
-      // store the macroblock's 16 x 16 B luma rows
-      if (lane < 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&ts.luma[my_first]);
-        __stcs(reinterpret_cast<uint4*>(st_ptr), v);
-        st_ptr += 16;
-      }
-      // carry: right-most column -> left-neighbour column (tile column -1 and its contiguous copy),
-      // top-row slots shift by one macroblock
-      const int cv = ts.luma[my_last];
-      uint32_t sv = 0;
-      if (shift_dst) sv = *reinterpret_cast<const uint32_t*>(shift_dst + 16);
-      __syncwarp();
-      if (lane < 16) {
-        ts.luma[my_left] = (uint8_t)cv;
-        ts.lcol[lane] = (uint8_t)cv;
-      }
-      if (shift_dst) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
-      __syncwarp();
-      TRACE_MARK(3);
-      bar_arrive_empty(si);
-      n++;
-      CLK_MARK(7);  // stores + publish + carry
+      bar_arrive_empty(gs);
+      gn++;
     }
     CLK_FLUSH(8);
   }
@@ -1293,7 +1290,7 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(dryv::kTeamThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = sizeof(dryv::TeamSmem);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1482,9 +1479,11 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
   ok = ok && cudaEventCreateWithFlags(&ctx->db_done, cudaEventDisableTiming) == cudaSuccess;
   // shared memory, not L1, is what the row teams live on: ask for the largest carve-out
   ok = ok && cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+                                  cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+       cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(dryv::TeamSmem)) == cudaSuccess;
   ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wave_ctas_per_sm, dryv::recon_wavefront_kernel,
-                                                           dryv::kTeamThreads, 0) == cudaSuccess &&
+                                                           dryv::kTeamThreads, sizeof(dryv::TeamSmem)) == cudaSuccess &&
        cudaFuncSetAttribute(dryv::recon_residual_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(dryv::ResidCtaSmem)) == cudaSuccess &&
        cudaFuncSetAttribute(dryv::recon_residual_add_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,

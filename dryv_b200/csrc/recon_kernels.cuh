@@ -1,19 +1,19 @@
-// recon_kernels.cuh — sm_100a device code of the AVC intra reconstruction path.
+// recon_kernels.cuh — sm_100a device code of the AVC intra reconstruction path: data structures of the row teams and the
+// prediction stage. (The residual stage — dequantisation, DC Hadamards, inverse transforms — is residual_stage.cuh; the
+// kernels themselves are in recon.cu.)
 //
-// Three kernels (entry points in recon.cu):
-//   resolve_modes_kernel   pixel-independent pre-pass: Intra4x4/8x8 prediction-mode derivation for a
-//                          whole picture as a lock-step anti-diagonal walk over the 4x4-cell grid.
-//   recon_wavefront_kernel persistent "row teams" (one CTA = two warps) walking macroblock rows in
-//                          x+2y wavefront order:
-//       front warp  128-bit loads of the MB's 768 B of int16 levels, inverse zig-zag as a register
-//                   permutation, dequant, luma-DC / chroma-DC Hadamard (warp shuffles), 4x4 transform
-//                   with one block per lane in registers (24 lanes = 16 luma + 8 chroma blocks) or the
-//                   8x8 transform with 8 lanes per block; int16 residuals land in a ring slot. It has no
-//                   dependency on any other macroblock and runs ahead of the pixels.
-//       pixel warp  waits for the bottom line of the row above (64-bit payload|tag words, relaxed
-//                   loads), predicts + adds the residual + clips into a shared-memory pixel tile, stores
-//                   128-bit rows, publishes its own bottom line. Prediction is a gather from the tile:
-//                   no shuffles, per-lane sample addresses come from host-built tap tables.
+// Three kernels:
+//   resolve_modes_kernel   pixel-independent pre-pass: Intra4x4/8x8 prediction-mode derivation for a whole picture.
+//   recon_wavefront_kernel persistent "row teams" (one CTA = two warps) walking macroblock rows in x+2y wavefront order,
+//                          four macroblocks (a group) at a time:
+//       front warp  one bulk copy (cp.async.bulk + mbarrier) of the group's 3072 B of levels into a ring, the residual
+//                   stage of the group (luma of two macroblocks / chroma of four per pass), tap rows of the Intra4x4
+//                   blocks, then chroma prediction of each macroblock. It has no luma dependency on other macroblocks
+//                   and runs ahead of the pixels.
+//       pixel warp  waits for the bottom line of the row above (64-bit payload|tag words, relaxed loads), predicts + adds
+//                   the residual + clips (two samples per VIADDMNMX) into a shared-memory pixel tile, stores 128-bit
+//                   rows, publishes its own bottom line. Prediction is a gather from the tile: no shuffles, per-lane
+//                   sample addresses come from host-built tap tables.
 //   recon_residual_add_kernel  dequant + transform + add to a supplied prediction picture.
 // No tensor cores: the H.264 transforms are shift/add butterflies with exact integer rounding.
 //
@@ -30,49 +30,51 @@
 
 namespace dryv {
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 4;  // residual-only kernel and level expansion
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 
 constexpr int kLumaStride = kLumaTileStride;  // pixel (x, y) at (y + 1) * 48 + 16 + x, x in -4..31 (row -1), y in -1..15
 constexpr int kLumaTileBytes = 17 * kLumaStride;
 constexpr int kChromaStride = 24;        // pixel (x, y) at (y + 1) * 24 + 8 + x, x in -4..15 (row -1), y in -1..7
 constexpr int kChromaTileBytes = 9 * kChromaStride;
-constexpr int kScratchBytes = 1152;      // 8x8 coefficient slab (4 * 144 B) aliased with the transpose buffer (4 * 72 words)
 
-// wavefront kernel: a "row team" = one CTA of two warps walking one macroblock row.
-// The front warp hands each macroblock to the pixel warp through a ring of kSlots slots.
-// Ring depth, measured (64 / 16 x 1080p, ms per step): 2 slots 0.900 / 0.504, 3: 0.917 / 0.504, 4: 0.903 / 0.498,
-// 5: 0.924 / 0.505, 6 (9 teams per SM: one named barrier per slot) 0.926 / 0.500, 8 (7 teams) 0.979 / 0.477. Flat: the
-// depth of the ring is not what lets the classes overlap. Again at eight teams per SM with three batches in flight
-// (64 x 1080p, one batch at a time / overlapped): 3 slots 0.879 / 0.738, 4: 0.866 / 0.725, 5: 0.873 / 0.741, 6: 0.884 / 0.752.
-#ifndef DRYV_SLOTS
-#define DRYV_SLOTS 4
+// wavefront kernel: a "row team" = one CTA of two warps walking one macroblock row, a group of kGroupMbs macroblocks at
+// a time. The front warp hands each group to the pixel warp through a ring of kGroupSlots group slots.
+#ifndef DRYV_GROUP_SLOTS
+#define DRYV_GROUP_SLOTS 2
 #endif
-constexpr int kSlots = DRYV_SLOTS;
+constexpr int kGroupSlots = DRYV_GROUP_SLOTS;
+constexpr int kLvStages = 2;  // level ring: the bulk copy of group g + 1 runs under the residual stage of group g
 constexpr int kTeamThreads = 64;
-struct Slot {
-  alignas(16) int16_t res[256];  // luma residual [16][16]
-  uint32_t modes_lo, modes_hi;   // resolved Intra4x4/8x8 modes in schedule order (resolve_modes_kernel)
+struct MbSlot {
+  alignas(16) uint16_t res[kResLumaTile];  // luma residual fields (residual_stage.cuh)
   alignas(16) uint8_t rows[32];  // Intra4x4: tap rows, half-warp A's steps 0..9 then half-warp B's steps 2..7; rest 0
-  int32_t frame, row, x;         // row < 0: no more work
-  int32_t mbcls, mode16;         // 0/1/2 = Intra4x4/8x8/16x16; Intra16x16 prediction mode | intra_chroma_pred_mode << 8
-  int32_t pad[1];
+  uint32_t modes_lo, modes_hi;   // resolved Intra4x4/8x8 modes in schedule order (resolve_modes_kernel)
+  int32_t mbcls, mode16;         // 0/1/2 = Intra4x4/8x8/16x16; Intra16x16 prediction mode
 };
-static_assert(sizeof(Slot) % 16 == 0, "slot alignment");
+static_assert(sizeof(MbSlot) % 16 == 0, "slot alignment");
+struct GroupSlot {
+  MbSlot mb[kGroupMbs];
+  int32_t frame, row, x0, n;     // row < 0: no more work
+};
 struct TeamSmem {
-  DeviceTables tab;
-  Slot slot[kSlots];
-  alignas(16) int16_t coef[4][DRYV_COEFFS_PER_MB];  // level ring filled by cp.async (front warp)
-  alignas(16) int16_t cres[128];                    // chroma residual [2][8][8] of the front warp's current MB
-  alignas(16) uint8_t luma[kLumaTileBytes];         // luma pixel tile (pixel warp)
-  alignas(16) uint8_t chroma[2 * kChromaTileBytes]; // chroma pixel tiles (front warp)
-  alignas(16) uint8_t lcol[16];                     // right-most luma column of the previous MB, contiguous
-  alignas(16) uint8_t ccol[16];                     // right-most Cb | Cr columns of the previous MB
-  alignas(16) uint8_t e8[32];                       // filtered edge vector p' of the current Intra8x8 block
-  alignas(16) uint8_t scratch[kScratchBytes];
-  alignas(8) unsigned long long full[kSlots];       // mbarriers: slot filled by the front warp
-  uint32_t pace;                                    // holds its own address: pacing chain of the poll loops
+  alignas(16) unsigned char tab[kTeamTableBytes];           // DeviceTables without t4
+  GroupSlot grp[kGroupSlots];
+  alignas(16) int16_t lv[kLvStages][kGroupMbs * DRYV_COEFFS_PER_MB];  // level ring (bulk-copy destinations)
+  // chroma residual fields of the front warp's current group; the 8x8 passes, which run before the chroma pass writes
+  // them, transpose through the same bytes
+  alignas(16) uint16_t cres[kGroupMbs][kResChromaMb];
+  alignas(16) uint32_t hdr[kGroupMbs];                      // class | qp << 8 | chroma mode << 16 | mb_type << 24
+  alignas(16) uint8_t luma[kLumaTileBytes];                 // luma pixel tile (pixel warp)
+  alignas(16) uint8_t chroma[2 * kChromaTileBytes];         // chroma pixel tiles (front warp)
+  alignas(16) uint8_t lcol[16];                             // right-most luma column of the previous MB, contiguous
+  alignas(16) uint8_t ccol[16];                             // right-most Cb | Cr columns of the previous MB
+  alignas(16) uint8_t e8[32];                               // filtered edge vector p' of the current Intra8x8 block
+  alignas(8) unsigned long long full[kGroupSlots];          // mbarriers: group slot filled by the front warp
+  alignas(8) unsigned long long lvfull[kLvStages];          // mbarriers: level stage landed
+  uint32_t pace;                                            // holds its own address: pacing chain of the poll loops
 };
+static_assert(sizeof(uint16_t) * kGroupMbs * kResChromaMb >= sizeof(int) * kScratchWords, "scratch aliases the chroma tiles");
 
 enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
 
@@ -121,215 +123,16 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned 
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ int ld_relaxed_gpu_s32(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
   int d;
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
-// two residuals -> one s16x2 word, saturating: the final sample is clip(pred + r, 0, 255) with pred in 0..255,
-// so any r beyond +-255 already pins the result and saturating at +-32767 keeps every input exact
-__device__ __forceinline__ uint32_t pack2(int lo, int hi) {
-  uint32_t d;
-  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
-  return d;
-}
-__device__ __forceinline__ int16_t sat16(int v) { return (int16_t)min(max(v, -32768), 32767); }
+__device__ __forceinline__ int clip255(int v) { return vimin_relu_s32(v, 255); }
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
   return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
 }
-__device__ __forceinline__ int lo16(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
-__device__ __forceinline__ int hi16(uint32_t w) { return ((int)w) >> 16; }
-
-// 4-point inverse core transform, transform.rs:159-181
-__device__ __forceinline__ void idct4(int& a, int& b, int& c, int& d) {
-  int e0 = a + c, e1 = a - c, e2 = (b >> 1) - d, e3 = b + (d >> 1);
-  a = e0 + e3;
-  b = e1 + e2;
-  c = e1 - e2;
-  d = e0 - e3;
-}
-// Per-lane constants that do not change over the kernel.
-struct LaneConst {
-  int res_off;      // int16 offset of this lane's 4x4 block inside the luma (lanes 0..15) / chroma (16..23) residual tile
-  int res_stride;   // 16 (luma) or 8 (chroma)
-  // Intra16x16 luma-DC Hadamard: partner lanes / signs of the four butterfly stages + final routing
-  uint32_t dc_partners;  // 5 x 5 bits: stage0..3 partner lane, then routing source lane
-  uint32_t dc_signs;     // bit 2s: own sign negative, bit 2s+1: other sign negative
-  uint32_t zz8_lo, zz8_hi;  // zig-zag indices of row (lane & 7) of an 8x8 block, one byte per column
-};
-
-__device__ __forceinline__ LaneConst make_lane_const(int lane, const DeviceTables& tab) {
-  LaneConst lc;
-  // 4x4 block position (spec block order, pred4x4.rs:14-17)
-  if (lane < 16) {
-    int bx = ((lane >> 2) & 1) * 8 + (lane & 1) * 4;
-    int by = (lane >> 3) * 8 + ((lane >> 1) & 1) * 4;
-    lc.res_off = by * 16 + bx;
-    lc.res_stride = 16;
-  } else {
-    int b = lane & 3, pl = (lane >> 2) & 1;
-    lc.res_off = pl * 64 + (b >> 1) * 32 + (b & 1) * 4;
-    lc.res_stride = 8;
-  }
-  // luma DC: lane L (< 16) holds c[i][j] with (i, j) = zig-zag position of L.
-  const int zi[16] = {0, 0, 1, 2, 1, 0, 0, 1, 2, 3, 3, 2, 1, 2, 3, 3};
-  const int zj[16] = {0, 1, 0, 0, 1, 2, 3, 2, 1, 0, 1, 2, 3, 3, 2, 3};
-  const int inv[4][4] = {{0, 1, 5, 6}, {2, 4, 7, 12}, {3, 8, 11, 13}, {9, 10, 14, 15}};
-  int L = lane & 15;
-  int i = zi[L], j = zj[L];
-  uint32_t partners = 0, signs = 0;
-  // stage 0: j ^ 1 ; stage 1: j ^ 2 ; stage 2: i ^ 1 ; stage 3: i ^ 2
-  int p0 = inv[i][j ^ 1], p1 = inv[i][j ^ 2], p2 = inv[i ^ 1][j], p3 = inv[i ^ 2][j];
-  partners = (uint32_t)p0 | ((uint32_t)p1 << 5) | ((uint32_t)p2 << 10) | ((uint32_t)p3 << 15);
-  // stage "first" (pairs 0-1, 2-3): even index: own + other ; odd index: other - own
-  // stage "second" (pairs 0-2, 1-3): idx0: own+other, idx2: other-own, idx1: own-other, idx3: own+other
-  if (j & 1) signs |= 1u << 0;       // stage0 own negative
-  if (j == 2) signs |= 1u << 2;      // stage1 own negative
-  if (j == 1) signs |= 1u << 3;      // stage1 other negative
-  if (i & 1) signs |= 1u << 4;       // stage2 own negative
-  if (i == 2) signs |= 1u << 6;      // stage3 own negative
-  if (i == 1) signs |= 1u << 7;      // stage3 other negative
-  // after the four stages the lane at (i, j) holds f[s(i)][s(j)], s = swap(1, 2).
-  // block b (= lane) wants dcY[by][bx] (pred16x16.rs:27-31) -> source lane inv[s(by)][s(bx)].
-  {
-    int gx = ((L >> 2) & 1) * 2 + (L & 1), gy = (L >> 3) * 2 + ((L >> 1) & 1);
-    const int s[4] = {0, 2, 1, 3};
-    partners |= (uint32_t)inv[s[gy]][s[gx]] << 20;
-  }
-  lc.dc_partners = partners;
-  lc.dc_signs = signs;
-  int r = lane & 7;
-  uint32_t lo = 0, hi = 0;
-  for (int c = 0; c < 4; c++) lo |= (uint32_t)tab.zz8inv[r][c] << (8 * c);
-  for (int c = 0; c < 4; c++) hi |= (uint32_t)tab.zz8inv[r][4 + c] << (8 * c);
-  lc.zz8_lo = lo;
-  lc.zz8_hi = hi;
-  return lc;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Residual stage: levels (registers c0, c1 of lanes 0..23) -> int16 residual tile.
-//   mbcls: 0 Intra4x4, 1 Intra8x8, 2 Intra16x16.  qp: QP'Y of the MB.
-// ------------------------------------------------------------------------------------------------
-//   res_luma: int16 [16][16]; res_chroma: int16 [2][8][8]; scratch: kScratchBytes, 16-byte aligned.
-__device__ __forceinline__ void residual_stage(const DeviceTables& tab, uint8_t* scratch, int16_t* res_luma,
-                                               int16_t* res_chroma, const LaneConst& lc, int lane, uint4 c0, uint4 c1,
-                                               int mbcls, int qp, int cb_off, int cr_off) {
-  // ---- Intra8x8 luma: 8 lanes per block -----------------------------------------------------
-  if (mbcls == 1) {
-    if (lane < 16) {
-      uint8_t* dst = scratch + (lane >> 2) * 144 + (lane & 3) * 32;
-      *reinterpret_cast<uint4*>(dst) = c0;
-      *reinterpret_cast<uint4*>(dst + 16) = c1;
-    }
-    __syncwarp();
-    const int blk = lane >> 3, i = lane & 7;
-    const uint8_t* slab = scratch + blk * 144;
-    const int qpm = qp % 6, qpd = qp / 6;
-    const uint4 lsv = *reinterpret_cast<const uint4*>(&tab.ls8[qpm][i * 8]);
-    const uint32_t lsw[4] = {lsv.x, lsv.y, lsv.z, lsv.w};
-    int d[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      uint32_t zw = j < 4 ? lc.zz8_lo : lc.zz8_hi;
-      int k = (zw >> (8 * (j & 3))) & 0xff;
-      int c = *reinterpret_cast<const int16_t*>(slab + 2 * k);
-      int ls = (j & 1) ? (int)(lsw[j >> 1] >> 16) : (int)(lsw[j >> 1] & 0xffffu);
-      // pred8x8.rs:71-80
-      d[j] = qp >= 36 ? ((c * ls) << (qpd - 6)) : ((c * ls + (1 << (5 - qpd))) >> (6 - qpd));
-    }
-    if (i == 0) d[0] += 32;  // folds the final (m + 32) >> 6 rounding: d00 reaches every output with weight 1
-    idct8(d);
-    __syncwarp();
-    int* tb = reinterpret_cast<int*>(scratch) + blk * 72;
-    *reinterpret_cast<int4*>(tb + i * 8) = make_int4(d[0], d[1], d[2], d[3]);
-    *reinterpret_cast<int4*>(tb + i * 8 + 4) = make_int4(d[4], d[5], d[6], d[7]);
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 8; r++) d[r] = tb[r * 8 + i];
-    idct8(d);
-    int16_t* rl = res_luma + ((blk >> 1) * 8) * 16 + (blk & 1) * 8 + i;
-#pragma unroll
-    for (int r = 0; r < 8; r++) rl[r * 16] = sat16(d[r] >> 6);
-  }
-
-  // ---- 4x4 path: one block per lane (luma lanes 0..15 unless Intra8x8, chroma lanes 16..23) --
-  const bool is_chroma_lane = lane >= 16;
-  int qpl = qp;
-  if (is_chroma_lane) {
-    int q = qp + (lane < 20 ? cb_off : cr_off);
-    q = min(max(q, 0), 51);
-    qpl = tab.qpc[q];  // transform.rs:194-216
-  }
-  int v[16];
-  v[0] = lo16(c0.x); v[1] = hi16(c0.x); v[2] = lo16(c0.y); v[3] = hi16(c0.y);
-  v[4] = lo16(c0.z); v[5] = hi16(c0.z); v[6] = lo16(c0.w); v[7] = hi16(c0.w);
-  v[8] = lo16(c1.x); v[9] = hi16(c1.x); v[10] = lo16(c1.y); v[11] = hi16(c1.y);
-  v[12] = lo16(c1.z); v[13] = hi16(c1.z); v[14] = lo16(c1.w); v[15] = hi16(c1.w);
-
-  const int qpm = qpl % 6, qpd = qpl / 6;
-  const int ls00 = tab.t4[qpm][0];  // LevelScale4x4[qP%6][0][0] (rows 0..5 of t4 carry no pre-shift)
-
-  // chroma DC, trans_chroma.rs:389-415: f = H c H over the 4 lanes of a plane, then ((f*LS) << (qP/6)) >> 5
-  int dcv;
-  {
-    int o = __shfl_xor_sync(0xffffffffu, v[0], 1);
-    int t = (lane & 1) ? o - v[0] : v[0] + o;
-    o = __shfl_xor_sync(0xffffffffu, t, 2);
-    t = (lane & 2) ? o - t : t + o;
-    dcv = ((t * ls00) << qpd) >> 5;
-  }
-  // Intra16x16 luma DC, pred16x16.rs:428-482 (warp-uniform branch)
-  if (mbcls == 2) {
-    int t = v[0];
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      int o = __shfl_sync(0xffffffffu, t, (lc.dc_partners >> (5 * s)) & 31);
-      int so = (lc.dc_signs >> (2 * s)) & 1, sp = (lc.dc_signs >> (2 * s + 1)) & 1;
-      t = (so ? -t : t) + (sp ? -o : o);
-    }
-    // here qpl == qp for the luma lanes
-    int dq = qp >= 36 ? ((t * ls00) << (qpd - 6)) : ((t * ls00 + (1 << (5 - qpd))) >> (6 - qpd));
-    int routed = __shfl_sync(0xffffffffu, dq, (lc.dc_partners >> 20) & 31);
-    if (!is_chroma_lane) dcv = routed;
-  }
-  const bool dc_pass = is_chroma_lane || mbcls == 2;  // transform.rs:145-146
-
-  if (lane < 24 && (mbcls != 1 || is_chroma_lane)) {
-    const int4* tp = reinterpret_cast<const int4*>(&tab.t4[qpl][0]);
-    int4 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
-    const int tt[16] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z, t3.w};
-    const int shr = max(4 - qpd, 0);
-    const int rnd = qpd < 4 ? (1 << (3 - qpd)) : 0;
-    // transform.rs:143-155; t4 carries LevelScale << max(qP/6-4, 0), so one form covers both branches
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = (v[k] * tt[k] + rnd) >> shr;
-    if (dc_pass) v[0] = dcv;
-    v[0] += 32;  // folds (h + 32) >> 6: d00 reaches every output sample with weight 1 and no shift
-    // zig-zag: (i, j) <- k   row0: 0 1 5 6 | row1: 2 4 7 12 | row2: 3 8 11 13 | row3: 9 10 14 15
-    idct4(v[0], v[1], v[5], v[6]);
-    idct4(v[2], v[4], v[7], v[12]);
-    idct4(v[3], v[8], v[11], v[13]);
-    idct4(v[9], v[10], v[14], v[15]);
-    idct4(v[0], v[2], v[3], v[9]);
-    idct4(v[1], v[4], v[8], v[10]);
-    idct4(v[5], v[7], v[11], v[14]);
-    idct4(v[6], v[12], v[13], v[15]);
-    int16_t* r = (is_chroma_lane ? res_chroma : res_luma) + lc.res_off;
-    const int st = lc.res_stride;
-    *reinterpret_cast<uint2*>(r) = make_uint2(pack2(v[0] >> 6, v[1] >> 6), pack2(v[5] >> 6, v[6] >> 6));
-    *reinterpret_cast<uint2*>(r + st) = make_uint2(pack2(v[2] >> 6, v[4] >> 6), pack2(v[7] >> 6, v[12] >> 6));
-    *reinterpret_cast<uint2*>(r + 2 * st) = make_uint2(pack2(v[3] >> 6, v[8] >> 6), pack2(v[11] >> 6, v[13] >> 6));
-    *reinterpret_cast<uint2*>(r + 3 * st) = make_uint2(pack2(v[9] >> 6, v[10] >> 6), pack2(v[14] >> 6, v[15] >> 6));
-  }
-  __syncwarp();
-}
+__device__ __forceinline__ uint32_t splat4(int v) { return (uint32_t)v * 0x01010101u; }
 
 // ------------------------------------------------------------------------------------------------
 // Prediction stage (pixel warp). Every neighbour sample is read from the shared-memory pixel tiles:
@@ -364,7 +167,7 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
   const int half = lane >> 4, p = lane & 15, px = p & 3, py = p >> 2;
   pl.half = half;
   pl.i4_pix = py * kLumaStride + px;
-  pl.i4_res2 = 2 * (py * 16 + px);
+  pl.i4_res2 = 2 * (py * kResLumaStride + px);
   pl.i4_tab = p * 16;
   // edge sample `lane` of an 8x8 block: 0..15 top, 16..23 left, 24 corner (pred8x8.rs:166-200)
   int s, pv, nx;
@@ -388,7 +191,7 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
   pl.e8_p = pv;
   pl.e8_n = nx;
   pl.i8_pix = (lane >> 2) * kLumaStride + (lane & 3) * 2;
-  pl.i8_res2 = 2 * ((lane >> 2) * 16 + (lane & 3) * 2);
+  pl.i8_res2 = 2 * ((lane >> 2) * kResLumaStride + (lane & 3) * 2);
   pl.i8_tab = lane * 8;
   return pl;
 }
@@ -405,15 +208,15 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
 struct I4Regs {
   uint4 tap;      // three sample offsets (biased), kind
   uint32_t org;   // tile offset of the block origin
-  int r;          // residual
+  int r;          // residual field (r + 512)
 };
 __device__ __forceinline__ void i4_fetch(I4Regs& q, const I4Step* e, const uint8_t* tap4, int row, const uint8_t* resp) {
   q.tap = *reinterpret_cast<const uint4*>(tap4 + row * kTap4Row);
   const uint2 st = *reinterpret_cast<const uint2*>(e);
   q.org = st.x;
-  q.r = *reinterpret_cast<const int16_t*>(resp + st.y);
+  q.r = *reinterpret_cast<const uint16_t*>(resp + st.y);
 }
-__device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const int16_t* res_luma,
+__device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const uint16_t* res_luma,
                                              const PixLane& pl, const uint8_t* rows) {
   const I4Step* st = &tab.i4tab[0][pl.half];
   const uint8_t* tap4 = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0]) + pl.i4_tab;
@@ -428,7 +231,7 @@ __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* l
     const uint8_t* ob = ltb + cur.org;
     const int e0 = ob[cur.tap.x], e1 = ob[cur.tap.y], e2 = ob[cur.tap.z];
     int kind = (int)cur.tap.w;
-    const int r = cur.r;
+    const int r = cur.r - kResBias;
     uint8_t* dst = lt + cur.org + pl.i4_pix;
     i4_fetch(cur, st + 2 * (s + 1), tap4, rows[s + 1], resp);  // step 10 = step 9 again (table and Slot::rows padding)
     int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
@@ -460,7 +263,7 @@ __device__ __forceinline__ int i4_tap_row(const DeviceTables& tab, int k, uint32
 // each (pred8x8.rs:222-288, with the x = 0 overwrite of quirk Q2) into e8[]. Phase 2: two pixels per lane
 // gathered from e8[].
 __device__ __forceinline__ void predict_i8x8(const DeviceTables& tab, uint8_t* lt, uint8_t* e8,
-                                             const int16_t* res_luma, const PixLane& pl, int lane, uint32_t modes_lo,
+                                             const uint16_t* res_luma, const PixLane& pl, int lane, uint32_t modes_lo,
                                              uint32_t modes_hi, bool A, bool B, bool C, bool D) {
   const uint8_t* resp8 = reinterpret_cast<const uint8_t*>(res_luma) + pl.i8_res2;
   constexpr int t7 = -kLumaStride + 7;
@@ -491,7 +294,7 @@ __device__ __forceinline__ void predict_i8x8(const DeviceTables& tab, uint8_t* l
     e8[lane] = (uint8_t)((pv + 2 * raw + nv + 2) >> 2);
     const uint8_t* tp = &tab.tap8[0][0][0] + mode * kTap8Row + pl.i8_tab;
     const uint32_t i0 = tp[0], i1 = tp[1], i2 = tp[2], i3 = tp[3], i4 = tp[4], i5 = tp[5];
-    const uint32_t rw = *reinterpret_cast<const uint32_t*>(resp8 + 2 * (((blk >> 1) * 8) * 16 + (blk & 1) * 8));
+    const uint32_t rw = *reinterpret_cast<const uint32_t*>(resp8 + 2 * (((blk >> 1) * 8) * kResLumaStride + (blk & 1) * 8));
     __syncwarp();
     int pr0, pr1;
     if (mode == 2) {  // DC, pred8x8.rs:326-425 (warp-uniform): sums of the filtered top 0..7 and left 0..7
@@ -499,37 +302,34 @@ __device__ __forceinline__ void predict_i8x8(const DeviceTables& tab, uint8_t* l
       const int sT = dp4a_us(ew[1], 0x01010101, dp4a_us(ew[0], 0x01010101, 0));
       const int sL = dp4a_us(ew[5], 0x01010101, dp4a_us(ew[4], 0x01010101, 0));
       pr0 = (aT && aL) ? ((sT + sL + 8) >> 4) : (aL ? ((sL + 4) >> 3) : (aT ? ((sT + 4) >> 3) : 128));
+      pr0 -= kResBias;
       pr1 = pr0;
     } else {
-      pr0 = ((int)e8[i0] + 2 * (int)e8[i1] + (int)e8[i2] + 2) >> 2;
-      pr1 = ((int)e8[i3] + 2 * (int)e8[i4] + (int)e8[i5] + 2) >> 2;
+      // the - 512 that cancels the bias of the residual field rides on the rounding constant (2 - 4 * 512)
+      pr0 = ((int)e8[i0] + 2 * (int)e8[i1] + (int)e8[i2] + 2 - 4 * kResBias) >> 2;
+      pr1 = ((int)e8[i3] + 2 * (int)e8[i4] + (int)e8[i5] + 2 - 4 * kResBias) >> 2;
     }
-    if (!((legal_mask(aT, aL, aTL) >> mode) & 1u)) pr0 = pr1 = 0;
-    const int o0 = clip255(pr0 + lo16(rw)), o1 = clip255(pr1 + hi16(rw));
-    *reinterpret_cast<uint16_t*>(&lt[o8 + pl.i8_pix]) = (uint16_t)(o0 | (o1 << 8));
+    if (!((legal_mask(aT, aL, aTL) >> mode) & 1u)) pr0 = pr1 = -kResBias;
+    const uint32_t o = viaddmin_relu_s16x2(rw, prmt((uint32_t)pr0, (uint32_t)pr1, 0x5410u), 0x00ff00ffu);
+    *reinterpret_cast<uint16_t*>(&lt[o8 + pl.i8_pix]) = (uint16_t)prmt(o, 0u, 0x4420u);
     __syncwarp();
   }
 }
 
 // ---- Intra16x16 luma, pred16x16.rs:79-425 + pred16x16.rs:64-75. Lane = (row, half): 8 pixels ----------
 //   lcol: the left neighbour column as 16 contiguous bytes.
-__device__ __forceinline__ void predict_i16x16(uint8_t* lt, const uint8_t* lcol, const int16_t* res_luma, int lane,
+__device__ __forceinline__ void predict_i16x16(uint8_t* lt, const uint8_t* lcol, const uint16_t* res_luma, int lane,
                                                int mode, bool availA, bool availB) {
   const int row = lane >> 1, h = lane & 1;
   const uint4 tv = *reinterpret_cast<const uint4*>(&lt[luma_at(0, -1)]);
-  const uint4 rv = *reinterpret_cast<const uint4*>(&res_luma[row * 16 + 8 * h]);
-  int pr[8];
+  const uint2* rp = reinterpret_cast<const uint2*>(&res_luma[row * kResLumaStride + 8 * h]);
+  const uint2 r0 = rp[0], r1 = rp[1];
+  uint32_t p0, p1;  // prediction, four samples per word
   if (mode == 0) {  // vertical
-    const uint32_t t0 = h ? tv.z : tv.x, t1 = h ? tv.w : tv.y;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      pr[k] = availB ? (int)((t0 >> (8 * k)) & 0xff) : 0;
-      pr[4 + k] = availB ? (int)((t1 >> (8 * k)) & 0xff) : 0;
-    }
+    p0 = availB ? (h ? tv.z : tv.x) : 0u;
+    p1 = availB ? (h ? tv.w : tv.y) : 0u;
   } else if (mode == 1) {  // horizontal
-    const int left = lcol[row];
-#pragma unroll
-    for (int k = 0; k < 8; k++) pr[k] = availA ? left : 0;
+    p0 = p1 = availA ? splat4(lcol[row]) : 0u;
   } else {
     const uint4 lv = *reinterpret_cast<const uint4*>(lcol);
     if (mode == 2) {  // DC
@@ -540,8 +340,7 @@ __device__ __forceinline__ void predict_i16x16(uint8_t* lt, const uint8_t* lcol,
       else if (availA) dc = (sl + 8) >> 4;
       else if (availB) dc = (st + 8) >> 4;
       else dc = 128;
-#pragma unroll
-      for (int k = 0; k < 8; k++) pr[k] = dc;
+      p0 = p1 = splat4(dc);
     } else {  // plane (needs A and B; the corner is read unchecked like pred16x16.rs:404, quirk Q5)
       const int corner = lt[luma_at(-1, -1)];
       // H = sum_{x'=0..7} (x'+1) * (p[8+x',-1] - p[6-x',-1]),  p[-1,-1] = corner ; V likewise over the left column
@@ -552,30 +351,29 @@ __device__ __forceinline__ void predict_i16x16(uint8_t* lt, const uint8_t* lcol,
       const int cc = (5 * V + 32) >> 6;
       const bool ok = availA && availB;
       const int base = a + bb * (8 * h - 7) + cc * (row - 7) + 16;
+      int pr[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) pr[k] = ok ? clip255((base + bb * k) >> 5) : 0;
+      p0 = pack4(pr[0], pr[1], pr[2], pr[3]);
+      p1 = pack4(pr[4], pr[5], pr[6], pr[7]);
     }
   }
-  const int o0 = clip255(pr[0] + lo16(rv.x)), o1 = clip255(pr[1] + hi16(rv.x));
-  const int o2 = clip255(pr[2] + lo16(rv.y)), o3 = clip255(pr[3] + hi16(rv.y));
-  const int o4 = clip255(pr[4] + lo16(rv.z)), o5 = clip255(pr[5] + hi16(rv.z));
-  const int o6 = clip255(pr[6] + lo16(rv.w)), o7 = clip255(pr[7] + hi16(rv.w));
   // rows 0..15 / columns 0..15 are written, row -1 and the left column vector are read: no hazard
-  *reinterpret_cast<uint2*>(&lt[luma_at(8 * h, row)]) = make_uint2(pack4(o0, o1, o2, o3), pack4(o4, o5, o6, o7));
+  *reinterpret_cast<uint2*>(&lt[luma_at(8 * h, row)]) = make_uint2(add_clip4(r0.x, r0.y, p0), add_clip4(r1.x, r1.y, p1));
   __syncwarp();
 }
 
 // ---- Chroma Cb + Cr, trans_chroma.rs:96-366 + trans_chroma.rs:81-92. Lane = (plane, row, half): 4 px ---
 //   ct: two chroma tiles of kChromaTileBytes each; ccol: left neighbour columns, 8 bytes per plane;
-//   res_chroma: int16 [2][8][8]
-__device__ __forceinline__ void predict_chroma(uint8_t* ct, const uint8_t* ccol, const int16_t* res_chroma, int lane,
+//   res_chroma: the macroblock's chroma residual tile (residual_stage.cuh)
+__device__ __forceinline__ void predict_chroma(uint8_t* ct, const uint8_t* ccol, const uint16_t* res_chroma, int lane,
                                                int mode, bool availA, bool availB, bool availD) {
   const int pl = lane >> 4, row = (lane >> 1) & 7, h = lane & 1;
   uint8_t* tile = ct + pl * kChromaTileBytes;
   const uint8_t* cv = ccol + pl * 8;
   const uint32_t tw = *reinterpret_cast<const uint32_t*>(&tile[chroma_at(4 * h, -1)]);
-  const uint2 rv = *reinterpret_cast<const uint2*>(&res_chroma[pl * 64 + row * 8 + 4 * h]);
-  int pr[4];
+  const uint2 rv = *reinterpret_cast<const uint2*>(&res_chroma[pl * kResChromaPlane + row * 8 + 4 * h]);
+  uint32_t p;  // prediction, four samples
   if (mode == 0) {
     // DC per 4x4 chroma block with the reference's ">= 0" / "> 0" tests (quirk Q3)
     const int by4 = row >> 2;
@@ -601,15 +399,11 @@ __device__ __forceinline__ void predict_chroma(uint8_t* ct, const uint8_t* ccol,
       else if (t3_gt) val = (sumT + 2) >> 2;
       else val = 128;
     }
-#pragma unroll
-    for (int k = 0; k < 4; k++) pr[k] = val;
+    p = splat4(val);
   } else if (mode == 1) {
-    const int left = cv[row];
-#pragma unroll
-    for (int k = 0; k < 4; k++) pr[k] = availA ? left : 0;
+    p = availA ? splat4(cv[row]) : 0u;
   } else if (mode == 2) {
-#pragma unroll
-    for (int k = 0; k < 4; k++) pr[k] = availB ? (int)((tw >> (8 * k)) & 0xff) : 0;
+    p = availB ? tw : 0u;
   } else {  // plane, trans_chroma.rs:319-364 (needs top, left and the corner)
     const int corner = tile[chroma_at(-1, -1)];
     const uint2 tv = *reinterpret_cast<const uint2*>(&tile[chroma_at(0, -1)]);
@@ -621,12 +415,12 @@ __device__ __forceinline__ void predict_chroma(uint8_t* ct, const uint8_t* ccol,
     const int cc = (34 * V + 32) >> 6;
     const bool ok = availA && availB && availD;
     const int base = a + bb * (4 * h - 3) + cc * (row - 3) + 16;
+    int pr[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) pr[k] = ok ? clip255((base + bb * k) >> 5) : 0;
+    p = pack4(pr[0], pr[1], pr[2], pr[3]);
   }
-  const int o0 = clip255(pr[0] + lo16(rv.x)), o1 = clip255(pr[1] + hi16(rv.x));
-  const int o2 = clip255(pr[2] + lo16(rv.y)), o3 = clip255(pr[3] + hi16(rv.y));
-  *reinterpret_cast<uint32_t*>(&tile[chroma_at(4 * h, row)]) = pack4(o0, o1, o2, o3);
+  *reinterpret_cast<uint32_t*>(&tile[chroma_at(4 * h, row)]) = add_clip4(rv.x, rv.y, p);
   __syncwarp();
 }
 

@@ -22,6 +22,7 @@ namespace dryv {
 //   tap8: indices into the filtered edge vector p' of an 8x8 block: 0..15 top, 16..23 left, 24 corner.
 enum { E4_LEFT = 8, E4_CORNER = 12, E8_LEFT = 16, E8_CORNER = 24 };
 constexpr int kLumaTileStride = 48;
+constexpr int kResLumaStride = 20;  // 16-bit fields per row of a luma residual tile (16 used; see residual_stage.cuh)
 constexpr int kTap4Bias = 256;
 
 // Intra4x4 schedule: ten dependency steps, blocks (spec 4x4 block order) of half-warp A / B per step.
@@ -33,7 +34,7 @@ constexpr int kI4BlkB[10] = {-1, -1, 4, 5, 6, 7, 12, 13, -1, -1};
 // luma tile (columns 16.. of rows 0..15 are padding), so the step needs no "active" predicate.
 struct I4Step {
   uint32_t org;     // tile offset of the block origin
-  uint32_t res2;    // byte offset of the block's residual inside the 16x16 int16 residual tile
+  uint32_t res2;    // byte offset of the block's first residual field inside the luma residual tile
 };
 constexpr uint32_t kI4DummyOrg = (4 + 1) * kLumaTileStride + 16 + 20;  // pixel (20, 4): rows 4..7, columns 20..23
 // Rows of DeviceTables::tap4. A row is chosen per block by the front warp from the block's mode and its

@@ -259,7 +259,7 @@ constexpr int kScratchWords = 4 * 72;    // 8x8 transposes: four blocks of 8 row
 // with one 4x4 block per lane: a luma row stride of 40 bytes puts the four block rows of a macroblock 32 bytes apart
 // modulo 128, a chroma plane stride of 144 bytes and a macroblock stride that is 32 modulo 128 (kResChromaMb) do the
 // same for the eight chroma blocks of two macroblocks: every store instruction is free of bank conflicts.
-constexpr int kResLumaStride = 20;                   // fields per luma row (16 used)
+// kResLumaStride = 20 fields per luma row (16 used): recon_tables.h
 constexpr int kResLumaTile = 16 * kResLumaStride;    // fields per macroblock
 constexpr int kResChromaPlane = 72;                  // fields per chroma plane (8 rows of 8, + 8)
 constexpr int kResChromaMb = 2 * kResChromaPlane;    // fields per macroblock: 288 bytes

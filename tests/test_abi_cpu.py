@@ -184,7 +184,7 @@ def test_intra4x4_schedule_respects_decode_order(recon_lib):
                 assert e.org == (4 + 1) * TILE_STRIDE + 16 + 20 and e.res2 == 0
                 continue
             gx, gy = pos(b)
-            assert e.org == (4 * gy + 1) * TILE_STRIDE + 16 + 4 * gx and e.res2 == 2 * (4 * gy * 16 + 4 * gx)
+            assert e.org == (4 * gy + 1) * TILE_STRIDE + 16 + 4 * gx and e.res2 == 2 * (4 * gy * 20 + 4 * gx)
             for av in range(16):
                 A, B, Cc, D = bool(av & 1), bool(av & 2), bool(av & 4), bool(av & 8)
                 aT, aL = gy > 0 or B, gx > 0 or A

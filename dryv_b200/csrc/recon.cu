@@ -116,31 +116,28 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
 //            re-issuing hundreds of times per macroblock in this kernel (sleepers are woken far earlier than
 //            their time-out). Ids are compile-time constants: the SM has 64 barriers, a CTA that indexes them
 //            with a register is charged all 16 and caps residency at 4 teams per SM.
-__device__ __forceinline__ void bar_sync_empty(unsigned si) {
-  switch (si) {
-    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-    case 3: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-    case 4: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
-    case 5: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
-    case 6: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
-    default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
+#define DRYV_BAR_CASES(OP)                                         \
+  switch (si) {                                                    \
+    case 0: asm volatile(OP " 1, 64;" ::: "memory"); break;        \
+    case 1: asm volatile(OP " 2, 64;" ::: "memory"); break;        \
+    case 2: asm volatile(OP " 3, 64;" ::: "memory"); break;        \
+    case 3: asm volatile(OP " 4, 64;" ::: "memory"); break;        \
+    case 4: asm volatile(OP " 5, 64;" ::: "memory"); break;        \
+    case 5: asm volatile(OP " 6, 64;" ::: "memory"); break;        \
+    case 6: asm volatile(OP " 7, 64;" ::: "memory"); break;        \
+    case 7: asm volatile(OP " 8, 64;" ::: "memory"); break;        \
+    case 8: asm volatile(OP " 9, 64;" ::: "memory"); break;        \
+    case 9: asm volatile(OP " 10, 64;" ::: "memory"); break;       \
+    case 10: asm volatile(OP " 11, 64;" ::: "memory"); break;      \
+    case 11: asm volatile(OP " 12, 64;" ::: "memory"); break;      \
+    case 12: asm volatile(OP " 13, 64;" ::: "memory"); break;      \
+    case 13: asm volatile(OP " 14, 64;" ::: "memory"); break;      \
+    default: asm volatile(OP " 15, 64;" ::: "memory"); break;      \
   }
-}
-__device__ __forceinline__ void bar_arrive_empty(unsigned si) {
-  switch (si) {
-    case 0: asm volatile("bar.arrive 1, 64;" ::: "memory"); break;
-    case 1: asm volatile("bar.arrive 2, 64;" ::: "memory"); break;
-    case 2: asm volatile("bar.arrive 3, 64;" ::: "memory"); break;
-    case 3: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
-    case 4: asm volatile("bar.arrive 5, 64;" ::: "memory"); break;
-    case 5: asm volatile("bar.arrive 6, 64;" ::: "memory"); break;
-    case 6: asm volatile("bar.arrive 7, 64;" ::: "memory"); break;
-    default: asm volatile("bar.arrive 8, 64;" ::: "memory"); break;
-  }
-}
-static_assert(kGroupSlots >= 2 && kGroupSlots <= 8, "named-barrier ids above cover up to eight group slots");
+__device__ __forceinline__ void bar_sync_empty(unsigned si) { DRYV_BAR_CASES("bar.sync") }
+__device__ __forceinline__ void bar_arrive_empty(unsigned si) { DRYV_BAR_CASES("bar.arrive") }
+#undef DRYV_BAR_CASES
+static_assert(kGroupSlots >= 2 && kGroupSlots * kTeamsPerCta <= 15, "named-barrier ids 1..15: one per team and group slot");
 
 // Long waits (the front warp runs kSlots macroblocks ahead and then blocks on the pixel warp for a whole
 // macroblock time): the hinted try_wait above is woken by every mbarrier event of the SM and re-issues ~100
@@ -180,7 +177,7 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned long long* b, uint32_
 #define DRYV_POLL_PACE 0
 #endif
 #ifndef DRYV_POLL_UNROLL
-#define DRYV_POLL_UNROLL 8
+#define DRYV_POLL_UNROLL 1
 #endif
 // Measured (64 x 1080p): rolling the poll loop (DRYV_POLL_UNROLL 1) changes nothing; making wait_line_words a real
 // function (__noinline__, -280 static instructions) costs 11 % (0.90 -> 1.00 ms): the call sits on the critical path.
@@ -400,21 +397,24 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
 #define DRYV_START_LAG 2
 #endif
 constexpr int kStartLag = DRYV_START_LAG;
-// Teams per SM = the register budget handed to ptxas (and 27 KB of shared memory per team).
-#ifndef DRYV_TEAMS_PER_SM
-#define DRYV_TEAMS_PER_SM 8
+// CTAs per SM = the register budget handed to ptxas; shared memory: 11 KB of tables per CTA + 14 KB per team.
+#ifndef DRYV_CTAS_PER_SM
+#define DRYV_CTAS_PER_SM 8
 #endif
-__global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefront_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefront_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TeamSmem& ts = *reinterpret_cast<TeamSmem*>(smem_raw);
+  WaveCtaSmem& cs = *reinterpret_cast<WaveCtaSmem*>(smem_raw);
+  const unsigned team = threadIdx.x / kTeamThreads;
+  TeamSmem& ts = cs.team[team];
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.tables);
-    uint4* dst = reinterpret_cast<uint4*>(ts.tab);
-    for (int i = threadIdx.x; i < (int)(kTeamTableBytes / 16); i += kTeamThreads) dst[i] = src[i];
+    uint4* dst = reinterpret_cast<uint4*>(cs.tab);
+    for (int i = threadIdx.x; i < (int)(kTeamTableBytes / 16); i += kWaveThreads) dst[i] = src[i];
     // tap-row bytes 16..31 of every slot stay zero: the look-ahead of the Intra4x4 loop reads up to byte 18
-    for (int i = threadIdx.x; i < kGroupSlots * kGroupMbs * 4; i += kTeamThreads)
+    const int tt = threadIdx.x % kTeamThreads;
+    for (int i = tt; i < kGroupSlots * kGroupMbs * 4; i += kTeamThreads)
       reinterpret_cast<uint32_t*>(ts.grp[i / (kGroupMbs * 4)].mb[(i / 4) % kGroupMbs].rows + 16)[i % 4] = 0u;
-    if (threadIdx.x == 0) {
+    if (tt == 0) {
       for (int i = 0; i < kGroupSlots; i++) mbar_init(&ts.full[i], 1);
       for (int i = 0; i < kLvStages; i++) mbar_init(&ts.lvfull[i], 1);
       ts.pace = smem_u32(&ts.pace);  // a word that holds its own shared-memory address (see wait_line_words)
@@ -423,8 +423,9 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
   __syncthreads();
   uint32_t pace_addr = smem_u32(&ts.pace);
   const int lane = threadIdx.x & 31;
-  const bool is_front = threadIdx.x < 32;
-  const DeviceTables& tab = *reinterpret_cast<const DeviceTables*>(ts.tab);  // everything but t4
+  const bool is_front = ((threadIdx.x >> 5) & 1) == 0;  // even warps: the front and the pixel warps of an SM sit on different schedulers
+  const DeviceTables& tab = *reinterpret_cast<const DeviceTables*>(cs.tab);  // everything but t4
+  const unsigned bar0 = team * kGroupSlots;  // the team's named barriers
   const int W = a.W, H = a.H;
   const size_t n_mb = (size_t)W * H;
   const int strideY = W * 16;
@@ -526,12 +527,14 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         // ---- group slot: wait until the pixel warp has released its previous use ----
         const unsigned gs = gn % kGroupSlots, use = gn / kGroupSlots;
         GroupSlot& G = ts.grp[gs];
-        if (use > 0) bar_sync_empty(gs);
+        if (use > 0) bar_sync_empty(bar0 + gs);
         CLK_MARK(1);  // wait for a free slot
         mbar_wait(&ts.lvfull[stage], (lvw >> 1) & 1u);
+#ifndef DRYV_EXP_NO_RESID  // (experiment: how fast is each role with the other one's code out of the instruction cache)
         residual_group(tab, a.tables, lc, lane, ts.hdr, m4, m8, ts.lv[stage], n, reinterpret_cast<int*>(&ts.cres[0][0]),
                        G.mb[0].res, (int)(sizeof(MbSlot) / sizeof(uint16_t)), &ts.cres[0][0], kResChromaMb, a.cb_off,
                        a.cr_off);
+#endif
         lvw++;
         CLK_MARK(2);  // residual stage
         // ---- mode records of the Intra4x4 / Intra8x8 macroblocks (fetched a group ago): the pre-pass may still be
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
     // no more rows: tell the pixel warp
     {
       const unsigned gs = gn % kGroupSlots, use = gn / kGroupSlots;
-      if (use > 0) bar_sync_empty(gs);
+      if (use > 0) bar_sync_empty(bar0 + gs);
       if (lane == 0) ts.grp[gs].row = -1;
       __syncwarp();
       if (lane == 0) mbar_arrive(&ts.full[gs]);
@@ -705,10 +708,18 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         CLK_MARK(2);  // wait for the luma line of the row above
         TRACE_MARK(1);
 
+#ifdef DRYV_EXP_NO_PRED
+        if (mbcls == 7) {
+#else
         if (mbcls == 0) {
-          predict_i4x4(tab, ts.luma, slot.res, pl, slot.rows + 8 * pl.half);
+#endif
+          predict_i4x4(tab, ts.luma, slot.res, pl, slot.rows);
           CLK_MARK(3);
+#ifdef DRYV_EXP_NO_PRED
+        } else if (mbcls == 8) {
+#else
         } else if (mbcls == 1) {
+#endif
           predict_i8x8(tab, ts.luma, ts.e8, slot.res, pl, lane, slot.modes_lo, slot.modes_hi, availA, availB, availC, availD);
           CLK_MARK(4);
         } else {
@@ -750,7 +761,7 @@ __global__ void __launch_bounds__(kTeamThreads, DRYV_TEAMS_PER_SM) recon_wavefro
         TRACE_MARK(3);
         CLK_MARK(7);  // stores + publish + carry
       }
-      bar_arrive_empty(gs);
+      bar_arrive_empty(bar0 + gs);
       gn++;
     }
     CLK_FLUSH(8);
@@ -1282,15 +1293,15 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   const int mode_threads = (((int)pp->pic_height_in_mbs + 31) / 32) * 32;  // one warp per band of 32 MB rows
   dryv::resolve_modes_kernel<<<n_frames, mode_threads, 0, s>>>(a);
   CU(cudaGetLastError());
-  size_t want = rows;  // one row team (CTA) per macroblock row at most
+  size_t want = (rows + dryv::kTeamsPerCta - 1) / dryv::kTeamsPerCta;  // one row team per macroblock row at most
   size_t cap = (size_t)ctx->sm_count * ctx->wave_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
   // The wavefront kernel is a programmatic dependent of the pre-pass: it starts once every pre-pass CTA is
   // resident and consumes mode records as they appear (tagged words, no grid-wide wait).
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(dryv::kTeamThreads);
-  cfg.dynamicSmemBytes = sizeof(dryv::TeamSmem);
+  cfg.blockDim = dim3(dryv::kWaveThreads);
+  cfg.dynamicSmemBytes = sizeof(dryv::WaveCtaSmem);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1481,9 +1492,9 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
   ok = ok && cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
        cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(dryv::TeamSmem)) == cudaSuccess;
+                            (int)sizeof(dryv::WaveCtaSmem)) == cudaSuccess;
   ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wave_ctas_per_sm, dryv::recon_wavefront_kernel,
-                                                           dryv::kTeamThreads, sizeof(dryv::TeamSmem)) == cudaSuccess &&
+                                                           dryv::kWaveThreads, sizeof(dryv::WaveCtaSmem)) == cudaSuccess &&
        cudaFuncSetAttribute(dryv::recon_residual_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(dryv::ResidCtaSmem)) == cudaSuccess &&
        cudaFuncSetAttribute(dryv::recon_residual_add_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,

@@ -58,7 +58,6 @@ struct GroupSlot {
   int32_t frame, row, x0, n;     // row < 0: no more work
 };
 struct TeamSmem {
-  alignas(16) unsigned char tab[kTeamTableBytes];           // DeviceTables without t4
   GroupSlot grp[kGroupSlots];
   alignas(16) int16_t lv[kLvStages][kGroupMbs * DRYV_COEFFS_PER_MB];  // level ring (bulk-copy destinations)
   // chroma residual fields of the front warp's current group; the 8x8 passes, which run before the chroma pass writes
@@ -75,6 +74,17 @@ struct TeamSmem {
   uint32_t pace;                                            // holds its own address: pacing chain of the poll loops
 };
 static_assert(sizeof(uint16_t) * kGroupMbs * kResChromaMb >= sizeof(int) * kScratchWords, "scratch aliases the chroma tiles");
+// A CTA holds several row teams that share one copy of the tables: shared memory, not registers, is what limits the
+// number of teams per SM, and every team in flight hides latency for the others (each team is a serial chain).
+#ifndef DRYV_TEAMS_PER_CTA
+#define DRYV_TEAMS_PER_CTA 1
+#endif
+constexpr int kTeamsPerCta = DRYV_TEAMS_PER_CTA;
+constexpr int kWaveThreads = kTeamThreads * kTeamsPerCta;
+struct WaveCtaSmem {
+  alignas(16) unsigned char tab[kTeamTableBytes];           // DeviceTables without t4
+  TeamSmem team[kTeamsPerCta];
+};
 
 enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
 
@@ -197,14 +207,20 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
 }
 
 // ---- Intra4x4 luma, pred4x4.rs:10-360 + transform.rs:98-110 -------------------------------------------
-// Ten dependency steps, two blocks per step where the decode-order availability rules allow it
-// (kI4BlkA / kI4BlkB); one pixel per lane, 16 lanes per block. A rolled loop: the kernel is instruction-fetch
-// bound when a dozen teams share an SM (an unrolled version with immediates was measured: faster on Intra4x4-only
-// pictures, slower on the mix), so code size matters more than the handful of instructions an unrolled
-// version saves. Everything that depends on the mode or on availability was folded into the tap row chosen by the front
-// warp (i4_tap_row), the schedule entries and tap records are 32-bit fields used as loaded, and a half-warp without a
-// block in a step works on a dummy block in the tile's padding: a step is loads, three adds and a clamp.
-//   rows: this half-warp's ten tap-row bytes (Slot::rows + 0 or 8)
+// Ten dependency steps, two blocks per step where the decode-order availability rules allow it (kI4BlkA / kI4BlkB:
+// half-warp B's block always sits 8 px right / 4 px up of half-warp A's); one pixel per lane, 16 lanes per block.
+// Everything that depends on the mode or on availability was folded into the tap row chosen by the front warp
+// (i4_tap_row), so a step is: tap record (one 128-bit load), three sample loads, three adds, a shift, the residual and a
+// clamp. The ten steps are unrolled with the block positions as immediates (about half the instructions of a rolled
+// loop that reads them from a table); the DC flavours, a quarter of the blocks, share one out-of-line function.
+//   rows: the slot's tap-row bytes (MbSlot::rows)
+#ifndef DRYV_I4_ROLLED
+#define DRYV_I4_ROLLED 1
+#endif
+#ifndef DRYV_I4_DC_INLINE
+#define DRYV_I4_DC_INLINE 0
+#endif
+#if DRYV_I4_ROLLED
 struct I4Regs {
   uint4 tap;      // three sample offsets (biased), kind
   uint32_t org;   // tile offset of the block origin
@@ -217,7 +233,8 @@ __device__ __forceinline__ void i4_fetch(I4Regs& q, const I4Step* e, const uint8
   q.r = *reinterpret_cast<const uint16_t*>(resp + st.y);
 }
 __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const uint16_t* res_luma,
-                                             const PixLane& pl, const uint8_t* rows) {
+                                             const PixLane& pl, const uint8_t* rows0) {
+  const uint8_t* rows = rows0 + 8 * pl.half;
   const I4Step* st = &tab.i4tab[0][pl.half];
   const uint8_t* tap4 = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0]) + pl.i4_tab;
   const uint8_t* resp = reinterpret_cast<const uint8_t*>(res_luma) + pl.i4_res2;
@@ -247,6 +264,90 @@ __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* l
     __syncwarp();
   }
 }
+
+#else
+#if DRYV_I4_DC_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+int i4_dc_pred(const uint8_t* eb, int kind) {  // pred4x4.rs:116-167; eb = block origin in the tile
+  const int sT = dp4a_us(*reinterpret_cast<const uint32_t*>(eb - kLumaStride), 0x01010101, 0);
+  const int sL = eb[-1] + eb[kLumaStride - 1] + eb[2 * kLumaStride - 1] + eb[3 * kLumaStride - 1];
+  return kind == kI4KindDc ? ((sT + sL + 4) >> 3)
+                           : (kind == kI4KindDcTop ? ((sT + 2) >> 2) : (kind == kI4KindDcLeft ? ((sL + 2) >> 2) : 128));
+}
+struct I4Tap {
+  uint4 t;  // three sample offsets (biased by kTap4Bias, relative to the block origin), kind
+  int r;    // residual field (r + 512)
+};
+__host__ __device__ constexpr int i4_org(int blk) { return luma_at(((blk >> 2) & 1) * 8 + (blk & 1) * 4, (blk >> 3) * 8 + ((blk >> 1) & 1) * 4); }
+__host__ __device__ constexpr int i4_res2(int blk) {
+  return 2 * (((blk >> 3) * 8 + ((blk >> 1) & 1) * 4) * kResLumaStride + ((blk >> 2) & 1) * 8 + (blk & 1) * 4);
+}
+constexpr int kI4HalfTile = 8 - 4 * kLumaStride;          // half-warp B's block relative to A's, tile bytes
+constexpr int kI4HalfRes2 = 2 * (8 - 4 * kResLumaStride);  // ... residual bytes
+template <int S>
+__device__ __forceinline__ I4Tap i4_fetch(const uint8_t* tapl, uint2 rb, uint32_t rb2, const uint8_t* resl) {
+  // tap row of step S = byte S of the half-warp's row bytes; times kTap4Row (256): one PRMT puts it into byte 1
+  const uint32_t w = S < 4 ? rb.x : (S < 8 ? rb.y : rb2);
+  const uint32_t rowoff = prmt(w, 0u, 0x4404u | ((uint32_t)(S < 8 ? (S & 3) : S - 8) << 4));
+  I4Tap q;
+  q.t = *reinterpret_cast<const uint4*>(tapl + rowoff);
+  q.r = *reinterpret_cast<const uint16_t*>(resl + i4_res2(kI4BlkA[S]));
+  return q;
+}
+//   ltl: sample gather base of the half-warp (tile - kTap4Bias + half-warp displacement); dstl: block origin base
+template <int S>
+__device__ __forceinline__ void i4_step(const I4Tap& q, const uint8_t* ltl, uint8_t* dstl, int i4_pix, bool has_blk) {
+  constexpr int org = i4_org(kI4BlkA[S]);
+  if (has_blk) {
+    const int e0 = ltl[q.t.x + org], e1 = ltl[q.t.y + org], e2 = ltl[q.t.z + org];
+    int kind = (int)q.t.w;
+    int pred = (e0 + 2 * e1 + e2 + 2) >> 2;
+    if (kind >= kI4KindDc) {
+      pred = i4_dc_pred(dstl + org, kind);
+      kind = 1;
+    }
+    dstl[org + i4_pix] = (uint8_t)clip255(pred * kind + q.r - kResBias);
+  }
+}
+static_assert(kTap4Row == 256, "i4_fetch multiplies the row index by placing it in byte 1");
+__device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* lt, const uint16_t* res_luma,
+                                             const PixLane& pl, const uint8_t* rows) {
+  const bool isA = pl.half == 0;
+  const int hoff = isA ? 0 : kI4HalfTile;
+  const uint8_t* tapl = reinterpret_cast<const uint8_t*>(&tab.tap4[0][0][0]) + pl.i4_tab;
+  const uint8_t* resl = reinterpret_cast<const uint8_t*>(res_luma) + pl.i4_res2 + (isA ? 0 : kI4HalfRes2);
+  const uint8_t* ltl = lt - kTap4Bias + hoff;
+  uint8_t* dstl = lt + hoff;
+  // the half-warp's ten row bytes: A rows[0..9], B rows[8..17] (B's steps 2..7 are bytes 10..15, 16.. stay zero)
+  const uint2 rb = *reinterpret_cast<const uint2*>(rows + 8 * pl.half);
+  const uint32_t rb2 = *reinterpret_cast<const uint16_t*>(rows + 8 * pl.half + 8);
+  // software pipeline: the table look-ups of step s+1 (which do not depend on any pixel) are issued before the warp
+  // barrier that closes step s, so a step's dependent chain is pixel load -> three adds -> clamp -> store
+#define DRYV_I4_STEP(S, HASB)                                                  \
+  {                                                                            \
+    const I4Tap nx = i4_fetch<((S) < 9 ? (S) + 1 : 9)>(tapl, rb, rb2, resl);   \
+    i4_step<(S)>(cur, ltl, dstl, pl.i4_pix, (HASB) || isA);                    \
+    __syncwarp();                                                              \
+    cur = nx;                                                                  \
+  }
+  I4Tap cur = i4_fetch<0>(tapl, rb, rb2, resl);
+  DRYV_I4_STEP(0, false)
+  DRYV_I4_STEP(1, false)
+  DRYV_I4_STEP(2, true)
+  DRYV_I4_STEP(3, true)
+  DRYV_I4_STEP(4, true)
+  DRYV_I4_STEP(5, true)
+  DRYV_I4_STEP(6, true)
+  DRYV_I4_STEP(7, true)
+  DRYV_I4_STEP(8, false)
+  DRYV_I4_STEP(9, false)
+#undef DRYV_I4_STEP
+}
+
+#endif
 
 // Front-warp side of predict_i4x4: lane k < 16 turns the mode of the block behind Slot::rows[k] into its tap
 // row. modes_lo / modes_hi: see kModeWords; av = A | B<<1 | C<<2 | D<<3.

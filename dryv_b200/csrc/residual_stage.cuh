@@ -173,16 +173,15 @@ DRYV_HD void cols4x4_packed(const int f[4][4], uint32_t U, uint32_t out[8]) {
   }
 }
 
-// The same on 32-bit scalars, for blocks the guard rejects (any int32-representable input). rb = the bias of f, e as above.
-DRYV_HD void cols4x4_wide(const int f[4][4], int rb, int e, uint32_t out[8]) {
+// The same on 32-bit scalars (any int32-representable input); f unbiased.
+DRYV_HD void cols4x4_wide(const int f[4][4], uint32_t out[8]) {
 #pragma unroll
   for (int jp = 0; jp < 2; jp++) {
     int r[2][4];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       const int j = 2 * jp + q;
-      row4((f[0][j] - rb) << e, (f[1][j] - rb) << e, (f[2][j] - rb) << e, (f[3][j] - rb) << e, r[q][0], r[q][1], r[q][2],
-           r[q][3]);
+      row4(f[0][j], f[1][j], f[2][j], f[3][j], r[q][0], r[q][1], r[q][2], r[q][3]);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -197,7 +196,9 @@ DRYV_HD void cols4x4_wide(const int f[4][4], int rb, int e, uint32_t out[8]) {
 // multiples of 4 when e > 0, and the DC, which may be anything, meets no shift on its way — dropping its low e bits
 // cannot change floor((h + 32) / 64)).
 //   dc_pass: the DC comes from the Intra16x16 / chroma DC transform (already dequantised, transform.rs:145-146).
-DRYV_HD void block4x4_bytes(const uint32_t cw[8], const uint32_t bs[8], int e, bool dc_pass, int dcv, uint32_t out[8]) {
+// Returns false when a row-pass output lies outside [-8192, 8192): `out` is then meaningless and the block has to go
+// through block4x4_wide (no conforming stream produces such a block).
+DRYV_HD bool block4x4_fast(const uint32_t cw[8], const uint32_t bs[8], int e, bool dc_pass, int dcv, uint32_t out[8]) {
   const int rb = kRowBias >> e, rb0 = rb + (32 >> e);
   int d[16], f[4][4];
 #pragma unroll
@@ -208,23 +209,24 @@ DRYV_HD void block4x4_bytes(const uint32_t cw[8], const uint32_t bs[8], int e, b
   }
   if (dc_pass) d[0] = ((dcv + 32) >> e) + rb;
   const uint32_t g = rows4x4(d, f);
-  if (g & ~((16384u >> e) - 1u)) cols4x4_wide(f, rb, e, out);
-  else cols4x4_packed(f, 1u << e, out);
+  cols4x4_packed(f, 1u << e, out);
+  return (g & ~((16384u >> e) - 1u)) == 0;
 }
 
-// General dequantisation, transform.rs:143-155: tt = t4[qP] (LevelScale << max(qP/6 - 4, 0)), shr = max(4 - qP/6, 0)
-DRYV_HD void block4x4_general(const uint32_t cw[8], const int tt[16], int shr, bool dc_pass, int dcv, uint32_t out[8]) {
+// The whole block in 32-bit arithmetic with the general dequantisation, transform.rs:143-155: tt = t4[qP]
+// (LevelScale << max(qP/6 - 4, 0)), shr = max(4 - qP/6, 0). Any qP, any scaling list, any level whose products fit int32.
+DRYV_HD void block4x4_wide(const uint32_t cw[8], const int tt[16], int shr, bool dc_pass, int dcv, uint32_t out[8]) {
   const int rnd = shr > 0 ? (1 << (shr - 1)) : 0;
   int d[16], f[4][4];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
     const int v = (k & 1) ? ((int)cw[k >> 1] >> 16) : (int)(int16_t)(cw[k >> 1] & 0xffffu);
-    d[k] = ((v * tt[k] + rnd) >> shr) + ((k == 0) ? kRowBias + 32 : ((k == 2 || k == 3 || k == 9) ? kRowBias : 0));
+    d[k] = (v * tt[k] + rnd) >> shr;
   }
-  if (dc_pass) d[0] = dcv + kRowBias + 32;
-  const uint32_t g = rows4x4(d, f);
-  if (g & 0xffffc000u) cols4x4_wide(f, kRowBias, 0, out);
-  else cols4x4_packed(f, 1u, out);
+  if (dc_pass) d[0] = dcv;
+  d[0] += 32;
+  rows4x4(d, f);
+  cols4x4_wide(f, out);
 }
 
 // 8-point inverse transform, pred8x8.rs:85-112
@@ -317,31 +319,49 @@ __device__ __forceinline__ ResLane make_res_lane(int lane, const DeviceTables& t
   return lc;
 }
 
-// One pass of 4x4 blocks, one per lane.
-//   c0, c1   the lane's 16 levels;  qpl its qP (QP'Y or QPc);  dc_pass / dcv: see block4x4
-//   dst      the block's first residual field, `stride` fields per sample row (16 luma, 8 chroma); null: lane idle
+// The rare lanes of a pass: blocks outside the packed range and qP without a byte-scale form. A real function, so that it
+// exists once and stays out of the instruction stream of the passes (the kernels are sensitive to code size); everything
+// is recomputed from the levels, so nothing but registers crosses the call.
+__device__ __noinline__ void pass4x4_wide(const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl, bool dc_pass, int dcv,
+                                          uint16_t* dst, int stride) {
+  if (!dst) return;
+  const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const int4* tp = reinterpret_cast<const int4*>(&gtab->t4[qpl][0]);
+  const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
+  const int tt[16] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z, t3.w};
+  const int qpd = qpl / 6;
+  uint32_t out[8];
+  block4x4_wide(cw, tt, qpd < 4 ? 4 - qpd : 0, dc_pass, dcv, out);
+#pragma unroll
+  for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(dst + i * stride) = make_uint2(out[2 * i], out[2 * i + 1]);
+}
+
+// One pass of 4x4 blocks, one per lane. One copy in each kernel (luma and chroma passes call it).
+//   c0, c1   the lane's 16 levels;  qpl its qP (QP'Y or QPc);  dc_pass / dcv: see block4x4_fast
+//   dst      the block's first residual field, `stride` fields per sample row (20 luma, 8 chroma); null: lane idle
 //   tab: the shared-memory copy (residual part), gtab: the whole table in global memory (t4, for qP without a byte form)
-__device__ __forceinline__ void pass4x4(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
-                                        bool dc_pass, int dcv, uint16_t* dst, int stride) {
+#ifndef DRYV_PASS4_INLINE
+#define DRYV_PASS4_INLINE 0
+#endif
+#if DRYV_PASS4_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void pass4x4(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
+                                     bool dc_pass, int dcv, uint16_t* dst, int stride) {
   const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
   uint32_t out[8];
   const int e = tab.t4b_e[qpl];
-  if (__all_sync(0xffffffffu, e != 0xff)) {
-    const uint4* bp = reinterpret_cast<const uint4*>(&tab.t4b[qpl][0]);
-    const uint4 b0 = bp[0], b1 = bp[1];
-    const uint32_t bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    block4x4_bytes(cw, bs, e, dc_pass, dcv, out);
-  } else {
-    const int4* tp = reinterpret_cast<const int4*>(&gtab->t4[qpl][0]);
-    const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
-    const int tt[16] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z, t3.w};
-    const int qpd = qpl / 6;
-    block4x4_general(cw, tt, qpd < 4 ? 4 - qpd : 0, dc_pass, dcv, out);
-  }
-  if (dst) {
+  const uint4* bp = reinterpret_cast<const uint4*>(&tab.t4b[qpl][0]);
+  const uint4 b0 = bp[0], b1 = bp[1];
+  const uint32_t bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const bool ok = block4x4_fast(cw, bs, e & 7, dc_pass, dcv, out) && e != 0xff;
+  if (dst && ok) {
 #pragma unroll
     for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(dst + i * stride) = make_uint2(out[2 * i], out[2 * i + 1]);
   }
+  if (__any_sync(0xffffffffu, dst && !ok)) pass4x4_wide(gtab, c0, c1, qpl, dc_pass, dcv, ok ? nullptr : dst, stride);
 }
 
 // Intra16x16 luma DC (pred16x16.rs:428-482) for the 16 lanes of a half-warp: v0 = level 0 of the lane's block.

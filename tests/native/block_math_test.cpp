@@ -81,23 +81,19 @@ int main() {
           uint32_t cw[8], out[8];
           for (int w = 0; w < 8; w++) cw[w] = (uint32_t)(uint16_t)lv[2 * w] | ((uint32_t)(uint16_t)lv[2 * w + 1] << 16);
           const int e = tab.t4b_e[qpl];
-          const bool fast = e != 0xff;
+          const bool has = e != 0xff;
           const int qpd = qpl / 6;
           int tt[16];
           for (int k = 0; k < 16; k++) tt[k] = tab.t4[qpl][k];
-          if (fast) block4x4_bytes(cw, tab.t4b[qpl], e, mode >= 1, dcv, out);
-          else block4x4_general(cw, tt, qpd < 4 ? 4 - qpd : 0, mode >= 1, dcv, out);
-          n_fast_deq += fast;
-          if (fast) {  // statistics: how often the guard fires on the byte-scale path
-            const int rb = kRowBias >> e;
-            int d[16], f[4][4];
-            for (int w = 0; w < 8; w++) {
-              d[2 * w] = dp2a_lo_su(cw[w], tab.t4b[qpl][w], w == 0 ? rb + (32 >> e) : (w == 1 ? rb : 0));
-              d[2 * w + 1] = dp2a_hi_su(cw[w], tab.t4b[qpl][w], (w == 1 || w == 4) ? rb : 0);
-            }
-            if (mode >= 1) d[0] = ((dcv + 32) >> e) + rb;
-            n_wide += (rows4x4(d, f) & ~((16384u >> e) - 1u)) != 0;
-          }
+          // what pass4x4 does: the packed path where the tables allow it and the guard accepts the block, else 32-bit
+          bool fast = false;
+          if (has) fast = block4x4_fast(cw, tab.t4b[qpl], e, mode >= 1, dcv, out);
+          n_fast_deq += has;
+          n_wide += has && !fast;
+          uint32_t wide[8];
+          block4x4_wide(cw, tt, qpd < 4 ? 4 - qpd : 0, mode >= 1, dcv, wide);
+          if (!fast) memcpy(out, wide, sizeof out);
+          else if (memcmp(out, wide, sizeof out) != 0) { printf("packed and 32-bit paths differ: lists %d qp %d mode %d trial %d\n", lists, qp, mode, trial); return 1; }
           n_blocks++;
           for (int i = 0; i < 4; i++)
             for (int j = 0; j < 4; j++) {

@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         CLK_MARK(1);  // wait for a free slot
         mbar_wait(&ts.lvfull[stage], (lvw >> 1) & 1u);
 #ifndef DRYV_EXP_NO_RESID  // (experiment: how fast is each role with the other one's code out of the instruction cache)
-        residual_group(tab, a.tables, lc, lane, ts.hdr, m4, m8, ts.lv[stage], n, reinterpret_cast<int*>(&ts.cres[0][0]),
+        residual_group<false>(tab, a.tables, lc, lane, ts.hdr, m4, m8, ts.lv[stage], n, reinterpret_cast<int*>(&ts.cres[0][0]),
                        G.mb[0].res, (int)(sizeof(MbSlot) / sizeof(uint16_t)), &ts.cres[0][0], kResChromaMb, a.cb_off,
                        a.cr_off);
 #endif
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residua
       pc[m] = __ldg(reinterpret_cast<const uint32_t*>(a.pred_in + co + 8 * mm));
     }
     mbar_wait(&ws.full[st], (it >> 1) & 1);
-    residual_group(tab, a.tables, lc, lane, ws.hdr, m4, m8, ws.lv[st], n, reinterpret_cast<int*>(&ws.res_chroma[0][0]),
+    residual_group<true>(tab, a.tables, lc, lane, ws.hdr, m4, m8, ws.lv[st], n, reinterpret_cast<int*>(&ws.res_chroma[0][0]),
                    &ws.res_luma[0][0], kResLumaTile, &ws.res_chroma[0][0], kResChromaMb, a.cb_off, a.cr_off);
 #pragma unroll
     for (int m = 0; m < kGroupMbs; m++) {

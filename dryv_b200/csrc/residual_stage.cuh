@@ -340,16 +340,8 @@ __device__ __noinline__ void pass4x4_wide(const DeviceTables* gtab, uint4 c0, ui
 //   c0, c1   the lane's 16 levels;  qpl its qP (QP'Y or QPc);  dc_pass / dcv: see block4x4_fast
 //   dst      the block's first residual field, `stride` fields per sample row (20 luma, 8 chroma); null: lane idle
 //   tab: the shared-memory copy (residual part), gtab: the whole table in global memory (t4, for qP without a byte form)
-#ifndef DRYV_PASS4_INLINE
-#define DRYV_PASS4_INLINE 0
-#endif
-#if DRYV_PASS4_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-void pass4x4(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
-                                     bool dc_pass, int dcv, uint16_t* dst, int stride) {
+__device__ __forceinline__ void pass4x4_body(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
+                                             bool dc_pass, int dcv, uint16_t* dst, int stride) {
   const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
   uint32_t out[8];
   const int e = tab.t4b_e[qpl];
@@ -362,6 +354,19 @@ void pass4x4(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 
     for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(dst + i * stride) = make_uint2(out[2 * i], out[2 * i + 1]);
   }
   if (__any_sync(0xffffffffu, dst && !ok)) pass4x4_wide(gtab, c0, c1, qpl, dc_pass, dcv, ok ? nullptr : dst, stride);
+}
+// The wavefront kernel calls the pass (one copy for the luma and the chroma passes: the kernel sits at the capacity of the
+// instruction cache, profiles/r02_ifetch.txt); the residual-only kernel inlines it (a call drains the scoreboard, which
+// would expose the latency of the prediction loads issued ahead of the passes).
+__device__ __noinline__ void pass4x4_call(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
+                                          bool dc_pass, int dcv, uint16_t* dst, int stride) {
+  pass4x4_body(tab, gtab, c0, c1, qpl, dc_pass, dcv, dst, stride);
+}
+template <bool INLINE>
+__device__ __forceinline__ void pass4x4(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
+                                        bool dc_pass, int dcv, uint16_t* dst, int stride) {
+  if (INLINE) pass4x4_body(tab, gtab, c0, c1, qpl, dc_pass, dcv, dst, stride);
+  else pass4x4_call(tab, gtab, c0, c1, qpl, dc_pass, dcv, dst, stride);
 }
 
 // Intra16x16 luma DC (pred16x16.rs:428-482) for the 16 lanes of a half-warp: v0 = level 0 of the lane's block.
@@ -434,6 +439,7 @@ __device__ __forceinline__ void pass8x8(const DeviceTables& tab, const ResLane& 
 //   lv        the group's levels as they lie in HBM (384 int16 per macroblock), in shared memory
 //   n_mb      macroblocks in the group (1..4)
 //   luma / chroma + m * stride: macroblock m's luma and chroma residual tiles (kResLumaTile / kResChromaMb fields)
+template <bool INLINE_PASS>
 __device__ __forceinline__ void residual_group(const DeviceTables& tab, const DeviceTables* gtab, const ResLane& lc, int lane, const uint32_t* hdr,
                                                uint32_t m4, uint32_t m8, const int16_t* lv, int n_mb, int* scratch,
                                                uint16_t* luma, int luma_mb_stride, uint16_t* chroma,
@@ -453,7 +459,7 @@ __device__ __forceinline__ void residual_group(const DeviceTables& tab, const De
       const uint4 c0 = src[0], c1 = src[1];
       int dcv = 0;
       if (__any_sync(0xffffffffu, active && i16)) dcv = luma_dc16(tab, lc, lane, (int)(int16_t)(c0.x & 0xffffu), qp);
-      pass4x4(tab, gtab, c0, c1, qp, i16, dcv, active ? luma + mm * luma_mb_stride + lc.res_off_luma : nullptr, kResLumaStride);
+      pass4x4<INLINE_PASS>(tab, gtab, c0, c1, qp, i16, dcv, active ? luma + mm * luma_mb_stride + lc.res_off_luma : nullptr, kResLumaStride);
     }
   }
   // ---- luma, 8x8 transform: one macroblock per pass ----
@@ -473,7 +479,7 @@ __device__ __forceinline__ void residual_group(const DeviceTables& tab, const De
     const uint4* src = reinterpret_cast<const uint4*>(lv + mm * DRYV_COEFFS_PER_MB + 256 + (lane & 7) * 16);
     const uint4 c0 = src[0], c1 = src[1];
     const int dcv = chroma_dc(tab, lane, (int)(int16_t)(c0.x & 0xffffu), qpc);
-    pass4x4(tab, gtab, c0, c1, qpc, true, dcv, active ? chroma + mm * chroma_mb_stride + lc.res_off_chroma : nullptr, 8);
+    pass4x4<INLINE_PASS>(tab, gtab, c0, c1, qpc, true, dcv, active ? chroma + mm * chroma_mb_stride + lc.res_off_chroma : nullptr, 8);
   }
   __syncwarp();
 }

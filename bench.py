@@ -32,9 +32,29 @@ METRIC = "idr_reconstruct_mpixels_per_s"
 UNIT = "Mpixels/s"
 BYTES_PER_MB_FULL = 1172   # 768 levels + 20 syntax + 384 pixels out (SURVEY.md §8d / BASELINE.md §3)
 BYTES_PER_MB_RESID = 1540  # 768 + 4 + 384 prediction in + 384 out
-# DRAM bytes of one recon_wavefront_kernel launch on the default workload, from the committed ncu capture
-# (profiles/r01_v16_wavefront_summary.txt: 424.45 MB read + 215.19 MB written)
-TRAFFIC_BYTES_PER_LAUNCH = 639_644_416
+# ncu counters of one recon_wavefront_kernel launch on the default workload (64 x 1080p), read from the newest committed
+# capture summary (profiles/rNN_wavefront_counters.json: dram bytes, warp instructions); None when there is none
+def profile_counters():
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(_ROOT, "profiles", "r*_wavefront_counters.json"))):
+        try:
+            with open(p) as f:
+                best = dict(json.load(f), source=os.path.relpath(p, _ROOT))
+        except Exception:
+            pass
+    return best
+
+
+def issue_peak():
+    """Measured issue rate of a balanced ALU + FMA-pipe integer stream (tools/micro/int_issue.cu, committed output):
+    T warp-instructions/s for the whole chip, the roof the kernels' instruction counts are read against."""
+    try:
+        with open(os.path.join(_ROOT, "profiles", "r02_int_issue.txt")) as f:
+            vals = [float(l.split("=>")[1].split("T")[0]) for l in f if l.startswith("mix IADD+IMAD")]
+        return max(vals), "profiles/r02_int_issue.txt (mix IADD+IMAD)"
+    except Exception:
+        return None, None
 # independent batches kept in flight by the device-resident timed region: consecutive steps rotate over this many CUDA
 # streams and output buffers (the library's four wavefront control blocks allow up to four)
 N_FLIGHT = 3
@@ -53,7 +73,10 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the residual-only (configs[1]) side measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (configs[1], [3], [4], export, deblock)")
+    ap.add_argument("--config4-frames", type=int, default=256, help="BASELINE configs[3]: 2160p pictures in total, over all GPUs")
+    ap.add_argument("--config5-streams", type=int, default=32, help="BASELINE configs[4]: independent 1080p streams (QP 10..45)")
+    ap.add_argument("--config5-frames", type=int, default=8, help="IDR pictures per stream")
     return ap.parse_args()
 
 
@@ -188,6 +211,148 @@ def run_reference(args):
     return 0
 
 
+
+def _device_soa_of(pp, seeds, dev, qps=None, chunk=32):
+    """Generate pictures seeded `seeds` (one synth call each, so the seeds need not be consecutive) straight into
+    device-resident SoA buffers, `chunk` pictures of host memory at a time. Returns (DeviceSoa, first SyntaxBatch picture,
+    last SyntaxBatch picture) - the two host copies are kept for the parity check."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from dryv_b200 import recon, synth
+    from dryv_b200.abi import FIELDS, SyntaxBatch
+    n = len(seeds)
+    tens = None
+    first = last = None
+    pool = ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1))
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        hb = SyntaxBatch.empty(pp, c1 - c0)
+        jobs = [pool.submit(synth.generate, pp, 1, seeds[i], qp_base=(qps[i] if qps else 26), threads=1,
+                            out=hb.frames(i - c0, i - c0 + 1)) for i in range(c0, c1)]
+        for j in jobs:
+            j.result()
+        if tens is None:
+            tens = {f: torch.empty((n * pp.n_mb,) + getattr(hb, f).shape[1:], dtype=torch.from_numpy(getattr(hb, f)).dtype,
+                                   device=dev) for f in FIELDS}
+        for f in FIELDS:
+            tens[f][c0 * pp.n_mb:c1 * pp.n_mb].copy_(torch.from_numpy(getattr(hb, f)))
+        if c0 == 0:
+            first = hb.frames(0, 1).copy()
+        if c1 == n:
+            last = hb.frames(c1 - c0 - 1, c1 - c0).copy()
+    pool.shutdown()
+    d = object.__new__(recon.DeviceSoa)
+    d.pp, d.n_frames, d.tensors = pp, n, tens
+    return d, first, last
+
+
+def run_config4(args, ctx, dev, rank, world, barrier, streams):
+    """BASELINE configs[3]: 2160p intra reconstruct, `--config4-frames` (256) IDR pictures in total, picture f on GPU
+    f mod N (seed 4000 + f): strong scaling, no collective. Returns this rank's (ms per pass, pictures, parity)."""
+    import torch
+    import oracle
+    from dryv_b200.abi import PicParams
+    pp = PicParams.make(240, 135)
+    mine = list(range(rank, args.config4_frames, world))
+    if not mine:
+        return 0.0, 0, True
+    dsoa, first, last = _device_soa_of(pp, [4000 + f for f in mine], dev, chunk=16)
+    d_out = torch.zeros((len(mine), pp.frame_bytes), dtype=torch.uint8, device=dev)
+    sub = 32   # pictures per launch; launches rotate over the streams so that consecutive ones overlap
+
+    def one_pass():
+        for i, lo in enumerate(range(0, len(mine), sub)):
+            hi = min(len(mine), lo + sub)
+            ctx.reconstruct_device(dsoa.frames(lo, hi), d_out[lo:hi], streams[i % len(streams)].cuda_stream)
+
+    one_pass()
+    ctx.wait()
+    reps = max(2, min(args.steps, 5))
+    e0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    barrier()
+    e0.record(streams[0])
+    for s_ in streams[1:]:
+        s_.wait_event(e0)
+    for _ in range(reps):
+        one_pass()
+    for e, s_ in zip(ends, streams):
+        e.record(s_)
+    barrier()
+    ctx.wait()
+    ms = max(e0.elapsed_time(e) for e in ends) / reps
+    ok = bool(np.array_equal(d_out[0].cpu().numpy(), oracle.reconstruct(first)[0])) and \
+        bool(np.array_equal(d_out[len(mine) - 1].cpu().numpy(), oracle.reconstruct(last)[0]))
+    return ms, len(mine), ok
+
+
+def config5_qp(s, n_streams):
+    return 10 + (35 * s) // max(1, n_streams - 1)
+
+
+def run_config5(args, ctx, dev, rank, world, barrier, streams):
+    """BASELINE configs[4]: `--config5-streams` (32) independent 1080p IDR streams with QP 10..45 (dense -> sparse levels),
+    stream s on GPU s mod N, `--config5-frames` pictures each (seed 5000 + 64 s + k); every stream is reconstructed as a
+    batch of its own, launches of different streams overlap. Returns (ms per pass over this rank's streams, pictures,
+    parity, {qp: isolated ms of that stream's batch} for QP 10 / 26-ish / 45 when the rank owns them)."""
+    import torch
+    import oracle
+    from dryv_b200.abi import PicParams
+    pp = PicParams.make(120, 68)
+    ns, k = args.config5_streams, args.config5_frames
+    mine = list(range(rank, ns, world))
+    if not mine:
+        return 0.0, 0, True, {}
+    seeds, qps = [], []
+    for s_ in mine:
+        for j in range(k):
+            seeds.append(5000 + 64 * s_ + j)
+            qps.append(config5_qp(s_, ns))
+    dsoa, first, last = _device_soa_of(pp, seeds, dev, qps=qps, chunk=64)
+    d_out = torch.zeros((len(seeds), pp.frame_bytes), dtype=torch.uint8, device=dev)
+
+    def launch(i, stream):
+        ctx.reconstruct_device(dsoa.frames(i * k, (i + 1) * k), d_out[i * k:(i + 1) * k], stream.cuda_stream)
+
+    def one_pass():
+        for i in range(len(mine)):
+            launch(i, streams[i % len(streams)])
+
+    one_pass()
+    ctx.wait()
+    reps = max(2, min(args.steps, 5))
+    e0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    barrier()
+    e0.record(streams[0])
+    for s_ in streams[1:]:
+        s_.wait_event(e0)
+    for _ in range(reps):
+        one_pass()
+    for e, s_ in zip(ends, streams):
+        e.record(s_)
+    barrier()
+    ctx.wait()
+    ms = max(e0.elapsed_time(e) for e in ends) / reps
+    ok = bool(np.array_equal(d_out[0].cpu().numpy(), oracle.reconstruct(first)[0])) and \
+        bool(np.array_equal(d_out[len(seeds) - 1].cpu().numpy(), oracle.reconstruct(last)[0]))
+    per_qp = {}
+    want = {config5_qp(0, ns), config5_qp(ns - 1, ns), min((config5_qp(s_, ns) for s_ in range(ns)), key=lambda q: abs(q - 26))}
+    for i, s_ in enumerate(mine):
+        q = config5_qp(s_, ns)
+        if q in want and q not in per_qp:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            a0.record(streams[0])
+            for _ in range(5):
+                launch(i, streams[0])
+            a1.record(streams[0])
+            torch.cuda.synchronize(dev)
+            ctx.wait()
+            per_qp[q] = a0.elapsed_time(a1) / 5
+    return ms, len(seeds), ok, per_qp
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -312,13 +477,64 @@ def main():
         e2e_ms, e2e_single_ms = timed(lambda o: ctx.submit_compact(hbatch, levels, o))
         e2e_out0 = outs[(args.steps - 1) & 1][0].copy()
         e2e_dense_ms, e2e_dense_single_ms = timed(lambda o: ctx.submit(hbatch, o))
+
+        def copy_floor(h2d_bytes, d2h_bytes):
+            """The same bytes as one e2e step, copied by plain cudaMemcpyAsync in both directions at once (pinned host
+            memory, two streams, all ranks together): what the link alone allows, measured in this run."""
+            src_pin = recon.PinnedArray(h2d_bytes, np.uint8)
+            src = torch.from_numpy(src_pin.array)
+            dst_h = torch.from_numpy(hout.array.reshape(-1))[:d2h_bytes]
+            d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+            d_src = d_out.reshape(-1)[:d2h_bytes]
+            sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            f0, fa, fb = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            reps = max(3, min(args.steps, 10))
+            barrier()
+            f0.record(sa)
+            sb.wait_event(f0)
+            for _ in range(reps):
+                with torch.cuda.stream(sa):
+                    d_in.copy_(src, non_blocking=True)
+                with torch.cuda.stream(sb):
+                    dst_h.copy_(d_src, non_blocking=True)
+            fa.record(sa)
+            fb.record(sb)
+            barrier()
+            return max(f0.elapsed_time(fa), f0.elapsed_time(fb)) / reps
+
+        floor_ms = copy_floor(int(levels.nbytes + (hbatch.input_bytes - hbatch.coeff.nbytes)), int(hout.array.nbytes))
+        floor_dense_ms = copy_floor(int(hbatch.input_bytes), int(hout.array.nbytes))
     clocks = sampler.stop()
 
+    # parity on every rank, outside the timed region: the rank's first and last picture against the oracle, and the
+    # output buffers of the batches in flight against each other; AND-reduced over the ranks
+    import oracle
+    last_buf = d_outs[(args.steps - 1) % N_FLIGHT]
+    got0, got_last = last_buf[0].cpu().numpy(), last_buf[n_frames - 1].cpu().numpy()
+    ref0 = oracle.reconstruct(hbatch.frames(0, 1))[0]
+    ref_last = oracle.reconstruct(hbatch.frames(n_frames - 1, n_frames))[0]
+    parity = bool(np.array_equal(got0, ref0)) and bool(np.array_equal(got_last, ref_last)) and \
+        all(bool(torch.equal(d_outs[0], o)) for o in d_outs[1:])
+
+    # BASELINE configs[3] and configs[4] (all ranks take part; rank 0 reports)
+    c4 = c5 = None
+    if not args.no_extra:
+        c4 = run_config4(args, ctx, dev, rank, world, barrier, streams)
+        c5 = run_config5(args, ctx, dev, rank, world, barrier, streams)
+
     t = torch.tensor([ms_total, e2e_ms if e2e_ms is not None else 0.0, wave_ms_avg,
-                      e2e_dense_ms if e2e_dense_ms is not None else 0.0], dtype=torch.float64, device=dev)
+                      e2e_dense_ms if e2e_dense_ms is not None else 0.0,
+                      c4[0] if c4 else 0.0, c5[0] if c5 else 0.0,
+                      floor_ms if e2e_ms is not None else 0.0, floor_dense_ms if e2e_ms is not None else 0.0],
+                     dtype=torch.float64, device=dev)
+    flags = torch.tensor([1 if parity else 0, 1 if (c4 is None or c4[2]) else 0, 1 if (c5 is None or c5[2]) else 0],
+                         dtype=torch.int32, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     ms_total, e2e_ms_max, wave_ms_avg, e2e_dense_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    c4_ms, c5_ms, floor_ms_max, floor_dense_ms_max = float(t[4]), float(t[5]), float(t[6]), float(t[7])
+    parity_all, c4_ok, c5_ok = bool(flags[0]), bool(flags[1]), bool(flags[2])
     ms_per_step = ms_total / args.steps
     total_px = world * n_frames * pp.luma_pixels
     value = total_px / (ms_per_step * 1e-3) / 1e6
@@ -328,12 +544,6 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # parity spot check outside the timed region: first picture against the oracle
-    import oracle
-    got0 = d_outs[(args.steps - 1) % N_FLIGHT][0].cpu().numpy()
-    ref0 = oracle.reconstruct(hbatch.frames(0, 1))[0]
-    parity = bool(np.array_equal(got0, ref0)) and all(bool(torch.equal(d_outs[0], o)) for o in d_outs[1:])
-
     peak, peak_src = measured_peak_gbs()
     n_mb_step = n_frames * pp.n_mb
     # a step = ticket memset + resolve_modes_kernel (prediction-mode pre-pass) + recon_wavefront_kernel. The wavefront
@@ -342,6 +552,8 @@ def main():
     # duration of a launch that has the GPU to itself, quoted against the wavefront kernel's algorithmic bytes as well
     kernel_s = wave_ms_avg * 1e-3
     achieved = n_mb_step * BYTES_PER_MB_FULL / kernel_s / 1e9
+    counters = profile_counters()
+    default_workload = (n_frames, args.width_mbs, args.height_mbs, args.qp) == (64, 120, 68, 26)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -354,10 +566,11 @@ def main():
                           "value": n_frames * pp.luma_pixels / (ms_serial_step * 1e-3) / 1e6,
                           "note": "rank 0, one batch at a time on one stream (no overlap between consecutive batches)"},
         "parity_vs_oracle_first_picture": parity,
+        "parity_all_ranks_first_and_last_picture": parity_all,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": TRAFFIC_BYTES_PER_LAUNCH if (n_frames, args.width_mbs, args.height_mbs) == (64, 120, 68) else None,
+                     "traffic": (counters or {}).get("dram_bytes") if default_workload else None,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch "
-                                       "(profiles/r01_v16_wavefront_summary.txt); algorithmic bytes per launch = "
+                                       f"({(counters or {}).get('source')}); algorithmic bytes per launch = "
                                        f"{n_mb_step * BYTES_PER_MB_FULL}",
                      "peak_source": peak_src, "kernel": "dryv::recon_wavefront_kernel",
                      "kernel_ms": wave_ms_avg, "kernel_share_of_step": wave_ms_avg / ms_per_step,
@@ -379,12 +592,48 @@ def main():
                 "back-to-back batches on separate streams hide); the period is the serial instruction stream of a row team's "
                 "slower warp (DESIGN.md §5), ~25x what the HBM roofline would allow",
     }
+    # The kernel is bound by instruction issue, not by HBM: its warp-instruction count (ncu) against the measured issue
+    # rate of a balanced integer stream (tools/micro/int_issue.cu)
+    ipeak, ipeak_src = issue_peak()
+    if default_workload and counters and counters.get("warp_instructions") and ipeak:
+        wi = float(counters["warp_instructions"])
+        line["roofline_alu"] = {
+            "bound": "issue", "warp_instructions_per_launch": wi, "warp_instructions_per_mb": wi / n_mb_step,
+            "achieved": wi / kernel_s / 1e12, "peak": ipeak, "unit": "T warp-instr/s", "frac": wi / kernel_s / 1e12 / ipeak,
+            "frac_isolated": wi / (wave_ms_isolated * 1e-3) / 1e12 / ipeak,
+            "counter_source": counters.get("source"), "peak_source": ipeak_src,
+            "warp_instructions_per_mb_at_hbm_target": ipeak * 1e12 / (0.6 * peak * 1e9 / BYTES_PER_MB_FULL),
+            "note": "what the instruction stream would have to shrink to for the 60 % HBM target at a 100 % issue rate"}
+    if c4 is not None:
+        pp4_px = 240 * 135 * 256
+        line["config4_2160p"] = {
+            "workload": f"3840x2160 full intra reconstruct, {args.config4_frames} IDR pictures in total, picture f on GPU f mod N "
+                        "(seed 4000 + f), 32 pictures per launch (BASELINE.json configs[3])",
+            "scaling": "strong", "n_gpus": world, "pictures_total": args.config4_frames, "ms_per_pass": c4_ms,
+            "value": args.config4_frames * pp4_px / (c4_ms * 1e-3) / 1e6 if c4_ms > 0 else None, "unit": UNIT,
+            "per_gpu_value": args.config4_frames * pp4_px / (c4_ms * 1e-3) / 1e6 / world if c4_ms > 0 else None,
+            "roofline_frac_per_gpu": (args.config4_frames * 240 * 135 * BYTES_PER_MB_FULL / world / (c4_ms * 1e-3) / 1e9 / peak) if c4_ms > 0 else None,
+            "parity_all_ranks_first_and_last_picture": c4_ok}
+    if c5 is not None:
+        ns5, k5 = args.config5_streams, args.config5_frames
+        px5 = ns5 * k5 * 120 * 68 * 256
+        line["config5_qp_sweep"] = {
+            "workload": f"{ns5} independent 1920x1088 IDR streams, QP {config5_qp(0, ns5)}..{config5_qp(ns5 - 1, ns5)} (dense -> "
+                        f"sparse levels), stream s on GPU s mod N, {k5} pictures per stream (seed 5000 + 64 s + k), one launch per "
+                        "stream, launches of different streams overlap (BASELINE.json configs[4])",
+            "n_gpus": world, "ms_per_pass": c5_ms, "value": px5 / (c5_ms * 1e-3) / 1e6 if c5_ms > 0 else None, "unit": UNIT,
+            "rank0_isolated_stream": {f"qp{q}": {"ms_per_batch": ms_, "value": k5 * 120 * 68 * 256 / (ms_ * 1e-3) / 1e6}
+                                      for q, ms_ in sorted(c5[3].items())},
+            "parity_all_ranks_first_and_last_picture": c5_ok}
     if e2e_ms is not None:
         syntax_bytes = int(hbatch.input_bytes - hbatch.coeff.nbytes)
         line["e2e"] = {"value": total_px / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": int(levels.nbytes + syntax_bytes),
                        "d2h_bytes_per_step": int(hout.array.nbytes), "ms_per_step": e2e_ms_max,
                        "single_step_ms": e2e_single_ms,
+                       "pcie_floor_ms": floor_ms_max, "fraction_of_pcie_floor": floor_ms_max / e2e_ms_max,
+                       "pcie_floor_how": "the step's H2D and D2H bytes moved by plain cudaMemcpyAsync on two streams at once, "
+                                         "pinned host memory, all ranks together, same run (max over ranks)",
                        "levels_wire_format": "compact (per MB: coded-slot mask, 16-bit significance masks, non-zero "
                                              "levels as int8/int16; include/dryv_recon.h dryv_mb_levels_compact)",
                        "parity_vs_oracle_first_picture": bool(np.array_equal(e2e_out0, ref0)),
@@ -396,6 +645,7 @@ def main():
                              "h2d_bytes_per_step": int(hbatch.input_bytes),
                              "d2h_bytes_per_step": int(hout.array.nbytes), "ms_per_step": e2e_dense_ms_max,
                              "single_step_ms": e2e_dense_single_ms,
+                             "pcie_floor_ms": floor_dense_ms_max, "fraction_of_pcie_floor": floor_dense_ms_max / e2e_dense_ms_max,
                              "how": "same with dryv_recon_submit (dense int16 levels)"}
 
     if not args.no_extra:

@@ -132,6 +132,9 @@ class SyntaxBatch:
         n = self.pp.n_mb
         return SyntaxBatch(self.pp, hi - lo, *[a[lo * n:hi * n] for a in self.arrays()])
 
+    def copy(self) -> "SyntaxBatch":
+        return SyntaxBatch(self.pp, self.n_frames, *[a.copy() for a in self.arrays()])
+
     @property
     def input_bytes(self) -> int:
         return sum(a.nbytes for a in self.arrays())

@@ -28,6 +28,8 @@ EXPORTS = [
     "dryv_recon_wavefront_times", "dryv_recon_pack_levels", "dryv_recon_unpack_levels", "dryv_recon_submit_compact",
     "dryv_recon_expand_levels_device", "dryv_recon_wait_oldest", "dryv_recon_surface_bytes", "dryv_recon_export_device",
     "dryv_recon_set_surface", "dryv_recon_deblock_device",
+    "dryv_recon_multi_create", "dryv_recon_multi_destroy", "dryv_recon_multi_device_count", "dryv_recon_multi_last_error",
+    "dryv_recon_multi_reconstruct", "dryv_recon_multi_reconstruct_compact",
 ]
 HOST_EXPORTS = ["dryv_cabac_scan", "dryv_cabac_parse", "dryv_cabac_parse_range", "dryv_cabac_parse_compact",
                 "dryv_cabac_surface"]  # include/dryv_cabac_host.h
@@ -38,7 +40,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp", "levels_pack.cpp", "cabac_host.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp", "levels_pack.cpp", "cabac_host.cpp", "multi.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "residual_stage.cuh", "deblock_kernel.cuh", "recon_tables.h", "cabac_tables.inc", "levels_record.h")] + [
         os.path.join(_HERE, "..", "include", "dryv_recon.h"), os.path.join(_HERE, "..", "include", "dryv_cabac_host.h")]
     if not force and os.path.exists(LIB_PATH) and all(
@@ -128,6 +130,18 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_set_surface.restype = C.c_int
     lib.dryv_cabac_surface.argtypes = [vp, sz, C.POINTER(Surface)]
     lib.dryv_cabac_surface.restype = C.c_int
+    lib.dryv_recon_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.dryv_recon_multi_create.restype = C.c_int
+    lib.dryv_recon_multi_destroy.argtypes = [vp]
+    lib.dryv_recon_multi_destroy.restype = None
+    lib.dryv_recon_multi_device_count.argtypes = [vp]
+    lib.dryv_recon_multi_device_count.restype = C.c_int
+    lib.dryv_recon_multi_last_error.argtypes = [vp]
+    lib.dryv_recon_multi_last_error.restype = C.c_char_p
+    lib.dryv_recon_multi_reconstruct.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, vp]
+    lib.dryv_recon_multi_reconstruct.restype = C.c_int
+    lib.dryv_recon_multi_reconstruct_compact.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), C.POINTER(LevelsCompact), u32, vp]
+    lib.dryv_recon_multi_reconstruct_compact.restype = C.c_int
     _lib = lib
     return lib
 
@@ -376,6 +390,58 @@ class ReconContext:
         if got < 0:
             raise ReconError(got, "dryv_recon_wavefront_times")
         return [float(buf[i]) for i in range(got)]
+
+
+class MultiDeviceContext:
+    """dryv_recon_multi: one dryv_recon_ctx and one host thread per device inside this process; pictures are dealt in
+    contiguous blocks (shard.frames_for_rank) and land in disjoint slices of one output array. `devices`: list of CUDA
+    device indices (None: every visible device); an index may repeat (each entry gets its own context)."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if devices is None:
+            rc = self.lib.dryv_recon_multi_create(None, 0, C.byref(h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.dryv_recon_multi_create(arr, len(devices), C.byref(h))
+        if rc != OK:
+            raise ReconError(rc, "dryv_recon_multi_create failed (no usable sm_100 GPU / bad device list; no CPU fallback)")
+        self.h = h
+
+    @property
+    def n_devices(self) -> int:
+        return int(self.lib.dryv_recon_multi_device_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.dryv_recon_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != OK:
+            raise ReconError(rc, (self.lib.dryv_recon_multi_last_error(self.h) or b"").decode())
+
+    def reconstruct(self, batch: SyntaxBatch, out: np.ndarray | None = None, levels: "CompactLevels | None" = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((batch.n_frames, batch.pp.frame_bytes), np.uint8)
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= batch.n_frames * batch.pp.frame_bytes
+        soa = batch.as_soa()
+        if levels is None:
+            self._check(self.lib.dryv_recon_multi_reconstruct(self.h, C.byref(batch.pp), C.byref(soa), batch.n_frames,
+                                                              out.ctypes.data))
+        else:
+            soa.coeff = None
+            lv = levels.as_struct()
+            self._check(self.lib.dryv_recon_multi_reconstruct_compact(self.h, C.byref(batch.pp), C.byref(soa), C.byref(lv),
+                                                                      batch.n_frames, out.ctypes.data))
+        return out
 
 
 def write_yuv_file(frame: np.ndarray, path: str):

@@ -268,6 +268,27 @@ uint64_t dryv_recon_launch_count(dryv_recon_ctx* ctx);
  * quoted on this kernel alone. */
 int dryv_recon_wavefront_times(dryv_recon_ctx* ctx, float* out_ms, int cap);
 
+/* ---- several GPUs in one process --------------------------------------------------------------
+ * Independent IDR pictures never reference each other on this path (the reference starts every picture from zeroed
+ * planes: Frame::new, src/video/frame/mod.rs:29-46; one Frame per sample, src/video/decoder.rs:124), so several GPUs are
+ * used by dealing pictures to them: one dryv_recon_ctx and one host thread per device, device d of N reconstructs the
+ * d-th contiguous block of pictures (the first n_frames % N blocks hold one picture more) and writes it into its slice
+ * of the caller's buffer. No data is exchanged between devices: no collective, no NCCL.
+ * `devices` lists the CUDA devices to use (a device may be named more than once: each entry gets a context of its own);
+ * NULL = devices 0 .. n_devices-1, and every visible device when n_devices <= 0. */
+typedef struct dryv_recon_multi dryv_recon_multi;
+int dryv_recon_multi_create(const int* devices, int n_devices, dryv_recon_multi** out);
+void dryv_recon_multi_destroy(dryv_recon_multi* m);
+int dryv_recon_multi_device_count(const dryv_recon_multi* m);
+const char* dryv_recon_multi_last_error(dryv_recon_multi* m);
+/* dryv_recon_submit + dryv_recon_wait (dryv_recon_submit_compact + dryv_recon_wait) of every device's share, concurrently;
+ * HOST pointers, blocking, the result is byte-identical to a single device's. Returns the first device's error code
+ * that is not DRYV_OK (dryv_recon_multi_last_error names the device). */
+int dryv_recon_multi_reconstruct(dryv_recon_multi* m, const dryv_pic_params* pp, const dryv_mb_soa* soa, uint32_t n_frames,
+                                 uint8_t* out_yuv);
+int dryv_recon_multi_reconstruct_compact(dryv_recon_multi* m, const dryv_pic_params* pp, const dryv_mb_soa* soa,
+                                         const dryv_mb_levels_compact* levels, uint32_t n_frames, uint8_t* out_yuv);
+
 #ifdef __cplusplus
 }
 #endif

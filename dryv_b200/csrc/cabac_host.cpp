@@ -45,6 +45,10 @@ struct Bits {
   uint32_t ue() {
     int z = 0;
     while (!bit() && !bad && z < 32) z++;
+    if (z >= 32) {  // not a valid Exp-Golomb code of this syntax (and 1u << 32 is undefined)
+      bad = true;
+      return 0;
+    }
     return z == 0 ? 0 : ((1u << z) - 1 + u(z));
   }
   int32_t se() {
@@ -229,15 +233,66 @@ int collect_nals(const uint8_t* d, size_t len, std::vector<Nal>& out) {
   return DRYV_OK;
 }
 
+// Scaling matrix of an SPS / PPS as the reference builds it (ScalingLists::new, src/video/atom/avcc/sps.rs:207-248):
+// a list that is not present, or that signals useDefaultScalingMatrixFlag, becomes the Default table of its kind
+// directly (the reference has no fall-back rule A / B: SURVEY.md quirk Q6). Values in zig-zag order.
+struct Matrix {
+  bool present = false;
+  int n8 = 0;  // 8x8 lists parsed: 2 (4:2:0), or 0 for a PPS with transform_8x8_mode_flag = 0
+  uint8_t l4[6][16];
+  uint8_t l8[6][64];
+};
+const uint8_t kDefault4Intra[16] = {6, 13, 13, 20, 20, 20, 28, 28, 28, 28, 32, 32, 32, 37, 37, 42};
+const uint8_t kDefault4Inter[16] = {10, 14, 14, 20, 20, 20, 24, 24, 24, 24, 27, 27, 27, 30, 30, 34};
+const uint8_t kDefault8Intra[64] = {6,  10, 10, 13, 11, 13, 16, 16, 16, 16, 18, 18, 18, 18, 18, 23, 23, 23, 23, 23, 23, 25,
+                                    25, 25, 25, 25, 25, 25, 27, 27, 27, 27, 27, 27, 27, 27, 29, 29, 29, 29, 29, 29, 29, 31,
+                                    31, 31, 31, 31, 31, 33, 33, 33, 33, 33, 36, 36, 36, 36, 38, 38, 38, 40, 40, 42};
+const uint8_t kDefault8Inter[64] = {9,  13, 13, 15, 13, 15, 17, 17, 17, 17, 19, 19, 19, 19, 19, 21, 21, 21, 21, 21, 21, 22,
+                                    22, 22, 22, 22, 22, 22, 24, 24, 24, 24, 24, 24, 24, 24, 25, 25, 25, 25, 25, 25, 25, 27,
+                                    27, 27, 27, 27, 27, 28, 28, 28, 28, 28, 30, 30, 30, 30, 32, 32, 32, 33, 33, 35};
+// scaling_list(), sps.rs:179-198 (7.3.2.1.1.1); returns useDefaultScalingMatrixFlag
+bool parse_scaling_list(Bits& b, uint8_t* out, int size) {
+  bool use_default = false;
+  int last = 8, next = 8;
+  for (int j = 0; j < size; j++) {
+    if (next != 0) {
+      const int delta = b.se();
+      next = (last + delta + 256) % 256;
+      if (next < 0) next += 256;  // malformed delta
+      use_default = j == 0 && next == 0;
+    }
+    out[j] = (uint8_t)(next == 0 ? last : next);
+    last = out[j];
+  }
+  return use_default;
+}
+void parse_matrix(Bits& b, int n_lists, Matrix& m) {
+  m.present = true;
+  m.n8 = n_lists - 6;
+  for (int i = 0; i < n_lists && !b.bad; i++) {
+    const bool intra = i < 6 ? i < 3 : ((i - 6) & 1) == 0;
+    uint8_t* dst = i < 6 ? m.l4[i] : m.l8[i - 6];
+    const int size = i < 6 ? 16 : 64;
+    const uint8_t* def = i < 6 ? (intra ? kDefault4Intra : kDefault4Inter) : (intra ? kDefault8Intra : kDefault8Inter);
+    bool use_default = true;
+    if (b.u(1)) use_default = parse_scaling_list(b, dst, size);  // scaling_list_present_flag
+    if (use_default) memcpy(dst, def, (size_t)size);
+  }
+}
+
 struct Sps {
   bool ok = false;
+  int id = 0;
   int w_mbs = 0, h_mbs = 0, log2_max_frame_num = 4, poc_type = 0, log2_max_poc_lsb = 4, delta_pic_order_always_zero = 0;
   uint32_t crop_l = 0, crop_r = 0, crop_t = 0, crop_b = 0;  // frame_crop_*_offset, in units of two luma samples (4:2:0 frames)
+  Matrix matrix;  // seq_scaling_matrix
 };
 struct Pps {
   bool ok = false;
+  int id = 0, sps_id = 0;
   int bottom_field_pic_order = 0, pic_init_qp = 26, cb_off = 0, cr_off = 0, deblocking_control = 0, redundant_pic_cnt = 0,
       transform_8x8_mode = 0;
+  Matrix matrix;  // pic_scaling_matrix
 };
 
 int parse_sps(const Nal& nal, Sps& s) {
@@ -245,13 +300,14 @@ int parse_sps(const Nal& nal, Sps& s) {
   const int profile = (int)b.u(8);
   b.u(8);
   b.u(8);
-  b.ue();
+  s.id = (int)b.ue();
+  if (s.id > 31) return DRYV_ERR_ARG;
   if (profile == 100 || profile == 110 || profile == 122 || profile == 244 || profile == 44 || profile == 83 || profile == 86 ||
       profile == 118 || profile == 128 || profile == 138 || profile == 139 || profile == 134 || profile == 135) {
     if (b.ue() != 1) return DRYV_ERR_UNSUPPORTED;                  // chroma_format_idc: 4:2:0 only
     if (b.ue() != 0 || b.ue() != 0) return DRYV_ERR_UNSUPPORTED;   // 8-bit only
     b.u(1);                                                        // qpprime_y_zero_transform_bypass_flag
-    if (b.u(1)) return DRYV_ERR_UNSUPPORTED;                       // seq_scaling_matrix_present_flag
+    if (b.u(1)) parse_matrix(b, 8, s.matrix);                      // seq_scaling_matrix_present_flag, sps.rs:89-93
   }
   s.log2_max_frame_num = (int)b.ue() + 4;
   s.poc_type = (int)b.ue();
@@ -284,8 +340,9 @@ int parse_sps(const Nal& nal, Sps& s) {
 
 int parse_pps(const Nal& nal, Pps& p) {
   Bits b(nal.rbsp.data(), nal.rbsp.size());
-  b.ue();
-  b.ue();
+  p.id = (int)b.ue();
+  p.sps_id = (int)b.ue();
+  if (p.id > 255 || p.sps_id > 31) return DRYV_ERR_ARG;
   if (!b.u(1)) return DRYV_ERR_UNSUPPORTED;  // entropy_coding_mode_flag: CABAC only (the reference has no CAVLC)
   p.bottom_field_pic_order = (int)b.u(1);
   if (b.ue() != 0) return DRYV_ERR_UNSUPPORTED;  // slice groups
@@ -300,9 +357,9 @@ int parse_pps(const Nal& nal, Pps& p) {
   b.u(1);  // constrained_intra_pred_flag: irrelevant inside an I picture
   p.redundant_pic_cnt = (int)b.u(1);
   p.transform_8x8_mode = 0;
-  if (b.more_rbsp_data()) {
+  if (b.more_rbsp_data()) {  // ExtraRbspData, pps.rs:68-88
     p.transform_8x8_mode = (int)b.u(1);
-    if (b.u(1)) return DRYV_ERR_UNSUPPORTED;  // pic_scaling_matrix_present_flag
+    if (b.u(1)) parse_matrix(b, 6 + 2 * p.transform_8x8_mode, p.matrix);  // pic_scaling_matrix_present_flag
     p.cr_off = b.se();
   }
   if (b.bad) return DRYV_ERR_ARG;
@@ -609,22 +666,72 @@ struct SliceParser {
   int transform8 = 0;
 };
 
-struct Stream {
+// One IDR picture with the parameter sets in force when its slice arrived (copies: a set re-sent later does not reach back)
+struct Picture {
+  const Nal* nal;
   Sps sps;
   Pps pps;
-  std::vector<const Nal*> idr;
+};
+struct Stream {
+  std::vector<Picture> pic;
 };
 
+// Parameter sets are kept by id and activated through the slice header's pic_parameter_set_id -> seq_parameter_set_id
+// (7.4.1.2.1), also when they arrive between pictures. (The reference reads the sets of the avcC box only and decodes the
+// first sample only, src/video/decoder.rs:86-150: for that picture this is the same thing.) Every picture of a stream
+// must have the geometry of the first.
 int analyse(const std::vector<Nal>& nals, Stream& st) {
+  std::vector<Sps> sps(32);
+  std::vector<Pps> pps(256);
   for (const Nal& nal : nals) {
-    int rc = DRYV_OK;
-    if (nal.type == 7 && st.idr.empty()) rc = parse_sps(nal, st.sps);
-    else if (nal.type == 8 && st.idr.empty()) rc = parse_pps(nal, st.pps);
-    else if (nal.type == 5) st.idr.push_back(&nal);
-    else if (nal.type == 1) return DRYV_ERR_UNSUPPORTED;  // non-IDR pictures: the path reconstructs IDR pictures only
-    if (rc != DRYV_OK) return rc;
+    if (nal.type == 7) {
+      Sps s;
+      const int rc = parse_sps(nal, s);
+      if (rc != DRYV_OK) return rc;
+      sps[(size_t)s.id] = s;
+    } else if (nal.type == 8) {
+      Pps p;
+      const int rc = parse_pps(nal, p);
+      if (rc != DRYV_OK) return rc;
+      pps[(size_t)p.id] = p;
+    } else if (nal.type == 5) {
+      Bits b(nal.rbsp.data(), nal.rbsp.size());
+      b.ue();  // first_mb_in_slice
+      b.ue();  // slice_type
+      const uint32_t pid = b.ue();
+      if (b.bad || pid > 255 || !pps[pid].ok || !sps[(size_t)pps[pid].sps_id].ok) return DRYV_ERR_ARG;
+      Picture pc{&nal, sps[(size_t)pps[pid].sps_id], pps[pid]};
+      if (!st.pic.empty() && (pc.sps.w_mbs != st.pic[0].sps.w_mbs || pc.sps.h_mbs != st.pic[0].sps.h_mbs))
+        return DRYV_ERR_UNSUPPORTED;  // a batch has one geometry
+      st.pic.push_back(pc);
+    } else if (nal.type == 1) {
+      return DRYV_ERR_UNSUPPORTED;  // non-IDR pictures: the path reconstructs IDR pictures only
+    }
   }
-  if (!st.sps.ok || !st.pps.ok || st.idr.empty()) return DRYV_ERR_ARG;
+  if (st.pic.empty()) return DRYV_ERR_ARG;
+  return DRYV_OK;
+}
+
+// dryv_pic_params of one picture. Scaling lists as the reference picks them (SliceHeader::scaling_lists,
+// src/video/slice/header.rs:317-332): the SPS matrix if the SPS has one, else the PPS matrix, else Flat_16; the kernels
+// take list 0 of each size (Intra Y: Frame::scaling idx 0 for luma, and dryv dequantises chroma with the luma list, quirk
+// Q1). A PPS matrix without 8x8 lists (transform_8x8_mode_flag = 0) makes the reference index an empty list
+// (frame/transform.rs:48): unsupported.
+int picture_params(const Picture& pc, dryv_pic_params* pp) {
+  memset(pp, 0, sizeof *pp);
+  pp->pic_width_in_mbs = (uint16_t)pc.sps.w_mbs;
+  pp->pic_height_in_mbs = (uint16_t)pc.sps.h_mbs;
+  pp->chroma_qp_index_offset = (int8_t)pc.pps.cb_off;
+  pp->second_chroma_qp_index_offset = (int8_t)pc.pps.cr_off;
+  const Matrix* m = pc.sps.matrix.present ? &pc.sps.matrix : (pc.pps.matrix.present ? &pc.pps.matrix : nullptr);
+  if (!m) {
+    memset(pp->scaling_list4x4, 16, sizeof pp->scaling_list4x4);  // Flat_4x4_16 / Flat_8x8_16
+    memset(pp->scaling_list8x8, 16, sizeof pp->scaling_list8x8);
+    return DRYV_OK;
+  }
+  if (m->n8 < 1) return DRYV_ERR_UNSUPPORTED;
+  memcpy(pp->scaling_list4x4, m->l4[0], 16);
+  memcpy(pp->scaling_list8x8, m->l8[0], 64);
   return DRYV_OK;
 }
 
@@ -634,15 +741,17 @@ struct CompactPicture {
   std::vector<uint32_t> size;
 };
 
-// `coeff` (dense, 384 int16 per macroblock) or `compact` (records, include/dryv_recon.h) receives the levels
-int parse_picture(const Stream& st, const Nal& nal, uint8_t* mb_type, uint8_t* t8x8, uint8_t* chroma_mode, uint8_t* qp,
-                  uint8_t* pred_syntax, int16_t* coeff, CompactPicture* compact = nullptr) {
-  Bits b(nal.rbsp.data(), nal.rbsp.size());
-  // slice_header (7.3.3), IDR picture
+struct SliceInfo {
+  int slice_qp = 26, disable_deblocking_filter_idc = 0, alpha_div2 = 0, beta_div2 = 0, pps_id = 0;
+};
+
+// slice_header (7.3.3) of an IDR picture; leaves `b` at the first byte of slice_data
+int parse_slice_header(const Picture& st, Bits& b, SliceInfo& si) {
+  const Nal& nal = *st.nal;
   if (b.ue() != 0) return DRYV_ERR_UNSUPPORTED;  // first_mb_in_slice: one slice per picture
   const uint32_t slice_type = b.ue();
   if (slice_type != 2 && slice_type != 7) return DRYV_ERR_UNSUPPORTED;
-  b.ue();                             // pic_parameter_set_id
+  si.pps_id = (int)b.ue();            // pic_parameter_set_id (resolved by analyse)
   b.u(st.sps.log2_max_frame_num);     // frame_num
   b.ue();                             // idr_pic_id
   if (st.sps.poc_type == 0) {
@@ -654,15 +763,32 @@ int parse_picture(const Stream& st, const Nal& nal, uint8_t* mb_type, uint8_t* t
   }
   if (st.pps.redundant_pic_cnt) b.ue();
   if (nal.ref_idc != 0) b.u(2);       // dec_ref_pic_marking of an IDR picture
-  const int slice_qp = st.pps.pic_init_qp + b.se();
+  si.slice_qp = st.pps.pic_init_qp + b.se();
   if (st.pps.deblocking_control) {
-    if (b.ue() != 1) {                // dryv has no deblocking filter: such a stream would not reconstruct to what it codes
-      b.se();
-      b.se();
+    // dryv has no deblocking filter (README.md:15; the fields are parsed in slice/header.rs:609-640 and ignored): a stream
+    // that asks for it reconstructs to the unfiltered pictures. dryv_cabac_slice_info reports what the stream asked for.
+    si.disable_deblocking_filter_idc = (int)b.ue();
+    if (si.disable_deblocking_filter_idc != 1) {
+      si.alpha_div2 = b.se();
+      si.beta_div2 = b.se();
     }
   }
   while (b.pos & 7) b.bit();          // cabac_alignment_one_bit
-  if (b.bad || slice_qp < 0 || slice_qp > 51) return DRYV_ERR_ARG;
+  if (b.bad || si.slice_qp < 0 || si.slice_qp > 51 || si.disable_deblocking_filter_idc > 2 || si.alpha_div2 < -6 ||
+      si.alpha_div2 > 6 || si.beta_div2 < -6 || si.beta_div2 > 6)
+    return DRYV_ERR_ARG;
+  return DRYV_OK;
+}
+
+// `coeff` (dense, 384 int16 per macroblock) or `compact` (records, include/dryv_recon.h) receives the levels
+int parse_picture(const Picture& st, uint8_t* mb_type, uint8_t* t8x8, uint8_t* chroma_mode, uint8_t* qp,
+                  uint8_t* pred_syntax, int16_t* coeff, CompactPicture* compact = nullptr) {
+  const Nal& nal = *st.nal;
+  Bits b(nal.rbsp.data(), nal.rbsp.size());
+  SliceInfo si;
+  const int hrc = parse_slice_header(st, b, si);
+  if (hrc != DRYV_OK) return hrc;
+  const int slice_qp = si.slice_qp;
   SliceParser sp;
   sp.W = st.sps.w_mbs;
   sp.H = st.sps.h_mbs;
@@ -708,14 +834,46 @@ int dryv_cabac_scan(const uint8_t* annexb, size_t len, dryv_pic_params* pp, uint
   Stream st;
   rc = analyse(nals, st);
   if (rc != DRYV_OK) return rc;
-  memset(pp, 0, sizeof *pp);
-  pp->pic_width_in_mbs = (uint16_t)st.sps.w_mbs;
-  pp->pic_height_in_mbs = (uint16_t)st.sps.h_mbs;
-  pp->chroma_qp_index_offset = (int8_t)st.pps.cb_off;
-  pp->second_chroma_qp_index_offset = (int8_t)st.pps.cr_off;
-  memset(pp->scaling_list4x4, 16, sizeof pp->scaling_list4x4);  // Flat_4x4_16 / Flat_8x8_16 (slice/header.rs:317-332)
-  memset(pp->scaling_list8x8, 16, sizeof pp->scaling_list8x8);
-  *n_pictures = (uint32_t)st.idr.size();
+  rc = picture_params(st.pic[0], pp);
+  if (rc != DRYV_OK) return rc;
+  *n_pictures = (uint32_t)st.pic.size();
+  return DRYV_OK;
+}
+
+int dryv_cabac_picture_params(const uint8_t* annexb, size_t len, uint32_t picture, dryv_pic_params* pp) {
+  if (!annexb || !pp || len < 8) return DRYV_ERR_ARG;
+  std::vector<Nal> nals;
+  int rc = collect_nals(annexb, len, nals);
+  if (rc != DRYV_OK) return rc;
+  Stream st;
+  rc = analyse(nals, st);
+  if (rc != DRYV_OK) return rc;
+  if (picture >= st.pic.size()) return DRYV_ERR_ARG;
+  return picture_params(st.pic[picture], pp);
+}
+
+int dryv_cabac_slice_info(const uint8_t* annexb, size_t len, uint32_t picture, dryv_slice_info* out) {
+  if (!annexb || !out || len < 8) return DRYV_ERR_ARG;
+  std::vector<Nal> nals;
+  int rc = collect_nals(annexb, len, nals);
+  if (rc != DRYV_OK) return rc;
+  Stream st;
+  rc = analyse(nals, st);
+  if (rc != DRYV_OK) return rc;
+  if (picture >= st.pic.size()) return DRYV_ERR_ARG;
+  const Picture& pc = st.pic[picture];
+  Bits b(pc.nal->rbsp.data(), pc.nal->rbsp.size());
+  SliceInfo si;
+  rc = parse_slice_header(pc, b, si);
+  if (rc != DRYV_OK) return rc;
+  memset(out, 0, sizeof *out);
+  out->pic_parameter_set_id = (uint8_t)si.pps_id;
+  out->seq_parameter_set_id = (uint8_t)pc.sps.id;
+  out->slice_qp = (uint8_t)si.slice_qp;
+  out->disable_deblocking_filter_idc = (uint8_t)si.disable_deblocking_filter_idc;
+  out->slice_alpha_c0_offset_div2 = (int8_t)si.alpha_div2;
+  out->slice_beta_offset_div2 = (int8_t)si.beta_div2;
+  out->scaling_matrix_source = pc.sps.matrix.present ? 1 : (pc.pps.matrix.present ? 2 : 0);
   return DRYV_OK;
 }
 
@@ -727,8 +885,9 @@ int dryv_cabac_surface(const uint8_t* annexb, size_t len, dryv_surface* out) {
   Stream st;
   rc = analyse(nals, st);
   if (rc != DRYV_OK) return rc;
-  const uint64_t W = 16ull * (uint64_t)st.sps.w_mbs, H = 16ull * (uint64_t)st.sps.h_mbs;
-  const uint64_t l = 2ull * st.sps.crop_l, r = 2ull * st.sps.crop_r, t = 2ull * st.sps.crop_t, b = 2ull * st.sps.crop_b;
+  const Sps& sps = st.pic[0].sps;
+  const uint64_t W = 16ull * (uint64_t)sps.w_mbs, H = 16ull * (uint64_t)sps.h_mbs;
+  const uint64_t l = 2ull * sps.crop_l, r = 2ull * sps.crop_r, t = 2ull * sps.crop_t, b = 2ull * sps.crop_b;
   if (l + r >= W || t + b >= H) return DRYV_ERR_ARG;
   out->format = DRYV_SURFACE_I420;
   out->crop_left = (uint32_t)l;
@@ -757,9 +916,9 @@ int dryv_cabac_parse_range(const uint8_t* annexb, size_t len, const dryv_pic_par
   Stream st;
   rc = analyse(nals, st);
   if (rc != DRYV_OK) return rc;
-  if (st.sps.w_mbs != pp->pic_width_in_mbs || st.sps.h_mbs != pp->pic_height_in_mbs) return DRYV_ERR_ARG;
-  if ((uint64_t)first_picture + n_pictures > st.idr.size() || (must_be_all && st.idr.size() != n_pictures)) return DRYV_ERR_ARG;
-  const size_t n_mb = (size_t)st.sps.w_mbs * st.sps.h_mbs;
+  if (st.pic[0].sps.w_mbs != pp->pic_width_in_mbs || st.pic[0].sps.h_mbs != pp->pic_height_in_mbs) return DRYV_ERR_ARG;
+  if ((uint64_t)first_picture + n_pictures > st.pic.size() || (must_be_all && st.pic.size() != n_pictures)) return DRYV_ERR_ARG;
+  const size_t n_mb = (size_t)st.pic[0].sps.w_mbs * st.pic[0].sps.h_mbs;
   std::atomic<uint32_t> next(0);
   std::atomic<int> status(DRYV_OK);
   auto work = [&]() {
@@ -767,7 +926,7 @@ int dryv_cabac_parse_range(const uint8_t* annexb, size_t len, const dryv_pic_par
       const uint32_t f = next.fetch_add(1);
       if (f >= n_pictures) break;
       const size_t o = (size_t)f * n_mb;
-      const int r = parse_picture(st, *st.idr[first_picture + f], mb_type + o, transform_size_8x8_flag + o, intra_chroma_pred_mode + o, qp + o,
+      const int r = parse_picture(st.pic[first_picture + f], mb_type + o, transform_size_8x8_flag + o, intra_chroma_pred_mode + o, qp + o,
                                   pred_syntax + o * 16, coeff + o * DRYV_COEFFS_PER_MB);
       if (r != DRYV_OK) {
         int expect = DRYV_OK;
@@ -799,9 +958,9 @@ int dryv_cabac_parse_compact(const uint8_t* annexb, size_t len, const dryv_pic_p
   Stream st;
   rc = analyse(nals, st);
   if (rc != DRYV_OK) return rc;
-  if (st.sps.w_mbs != pp->pic_width_in_mbs || st.sps.h_mbs != pp->pic_height_in_mbs) return DRYV_ERR_ARG;
-  if ((uint64_t)first_picture + n_pictures > st.idr.size()) return DRYV_ERR_ARG;
-  const size_t n_mb = (size_t)st.sps.w_mbs * st.sps.h_mbs;
+  if (st.pic[0].sps.w_mbs != pp->pic_width_in_mbs || st.pic[0].sps.h_mbs != pp->pic_height_in_mbs) return DRYV_ERR_ARG;
+  if ((uint64_t)first_picture + n_pictures > st.pic.size()) return DRYV_ERR_ARG;
+  const size_t n_mb = (size_t)st.pic[0].sps.w_mbs * st.pic[0].sps.h_mbs;
   std::vector<CompactPicture> pics(n_pictures);
   std::atomic<uint32_t> next(0);
   std::atomic<int> status(DRYV_OK);
@@ -810,7 +969,7 @@ int dryv_cabac_parse_compact(const uint8_t* annexb, size_t len, const dryv_pic_p
       const uint32_t f = next.fetch_add(1);
       if (f >= n_pictures) break;
       const size_t o = (size_t)f * n_mb;
-      const int r = parse_picture(st, *st.idr[first_picture + f], mb_type + o, transform_size_8x8_flag + o,
+      const int r = parse_picture(st.pic[first_picture + f], mb_type + o, transform_size_8x8_flag + o,
                                   intra_chroma_pred_mode + o, qp + o, pred_syntax + o * 16, nullptr, &pics[f]);
       if (r != DRYV_OK) {
         int expect = DRYV_OK;

@@ -1888,6 +1888,10 @@ int dryv_recon_expand_levels_device(dryv_recon_ctx* ctx, const dryv_mb_levels_co
   CU(cudaMemcpyAsync(&o_last, d_levels->offset + n_mbs, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (o_last < o_first) return fail(ctx, DRYV_ERR_ARG, "compact level stream: offsets not monotone");
+  // the kernel reads record headers as 32-bit words: a misaligned first record or stream pointer would fault (a sticky
+  // CUDA error) instead of being reported like every other malformed stream
+  if ((o_first & 3u) || (reinterpret_cast<uintptr_t>(d_levels->stream) & 3u))
+    return fail(ctx, DRYV_ERR_ARG, "compact level stream: stream pointer and first offset must be 4-byte aligned");
   int rc = launch_expand(ctx, d_levels->offset, d_levels->stream + o_first, o_first, o_last - o_first, n_mbs, d_coeff, s);
   if (rc != DRYV_OK) return rc;
   if (cuda_stream) {

@@ -26,6 +26,36 @@ def scan(stream: bytes):
     return pp, int(n.value)
 
 
+def picture_params(stream: bytes, picture: int) -> PicParams:
+    """dryv_cabac_picture_params: the parameters (geometry, chroma QP offsets, the scaling lists the reference would pick)
+    of picture `picture`; pictures of one stream may name different parameter sets."""
+    lib = load_library()
+    buf = np.frombuffer(stream, np.uint8)
+    pp = PicParams()
+    rc = lib.dryv_cabac_picture_params(buf.ctypes.data, buf.size, picture, C.byref(pp))
+    if rc != OK:
+        raise ReconError(rc, "dryv_cabac_picture_params")
+    return pp
+
+
+class SliceInfo(C.Structure):
+    """include/dryv_cabac_host.h dryv_slice_info"""
+    _fields_ = [("pic_parameter_set_id", C.c_uint8), ("seq_parameter_set_id", C.c_uint8), ("slice_qp", C.c_uint8),
+                ("disable_deblocking_filter_idc", C.c_uint8), ("slice_alpha_c0_offset_div2", C.c_int8),
+                ("slice_beta_offset_div2", C.c_int8), ("scaling_matrix_source", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+def slice_info(stream: bytes, picture: int) -> SliceInfo:
+    """dryv_cabac_slice_info: what picture `picture`'s slice header asks for (deblocking filter, parameter sets)."""
+    lib = load_library()
+    buf = np.frombuffer(stream, np.uint8)
+    si = SliceInfo()
+    rc = lib.dryv_cabac_slice_info(buf.ctypes.data, buf.size, picture, C.byref(si))
+    if rc != OK:
+        raise ReconError(rc, "dryv_cabac_slice_info")
+    return si
+
+
 def surface(stream: bytes) -> Surface:
     """The display rectangle the stream's SPS asks for (frame_crop_*_offset) as an I420 Surface; the whole coded picture
     when the SPS does not crop."""

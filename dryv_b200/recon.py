@@ -32,7 +32,7 @@ EXPORTS = [
     "dryv_recon_multi_reconstruct", "dryv_recon_multi_reconstruct_compact",
 ]
 HOST_EXPORTS = ["dryv_cabac_scan", "dryv_cabac_parse", "dryv_cabac_parse_range", "dryv_cabac_parse_compact",
-                "dryv_cabac_surface"]  # include/dryv_cabac_host.h
+                "dryv_cabac_surface", "dryv_cabac_picture_params", "dryv_cabac_slice_info"]  # include/dryv_cabac_host.h
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -130,6 +130,10 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_set_surface.restype = C.c_int
     lib.dryv_cabac_surface.argtypes = [vp, sz, C.POINTER(Surface)]
     lib.dryv_cabac_surface.restype = C.c_int
+    lib.dryv_cabac_picture_params.argtypes = [vp, sz, u32, C.POINTER(PicParams)]
+    lib.dryv_cabac_picture_params.restype = C.c_int
+    lib.dryv_cabac_slice_info.argtypes = [vp, sz, u32, vp]
+    lib.dryv_cabac_slice_info.restype = C.c_int
     lib.dryv_recon_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     lib.dryv_recon_multi_create.restype = C.c_int
     lib.dryv_recon_multi_destroy.argtypes = [vp]

@@ -23,8 +23,11 @@
  * first sample only (src/video/decoder.rs:88), every IDR picture of the track is parsed.
  *
  * Supported, like the reference's reconstruction: 8-bit 4:2:0, frame macroblocks, CABAC, one slice per picture
- * (first_mb_in_slice == 0), I slices with I_NxN (4x4 / 8x8 transform) and I_16x16 macroblocks, no scaling matrices.
- * Anything else (I_PCM, inter slices, CAVLC, slice groups, scaling lists, ...) returns DRYV_ERR_UNSUPPORTED.
+ * (first_mb_in_slice == 0), I slices with I_NxN (4x4 / 8x8 transform) and I_16x16 macroblocks, SPS / PPS scaling
+ * matrices with the reference's own selection and fall-back (atom/avcc/sps.rs:207-248, slice/header.rs:317-332:
+ * SURVEY.md quirk Q6). Parameter sets are kept by id and activated through the slice header, also between pictures;
+ * every picture of a stream must have the geometry of the first.
+ * Anything else (I_PCM, inter slices, CAVLC, slice groups, ...) returns DRYV_ERR_UNSUPPORTED.
  */
 #ifndef DRYV_CABAC_HOST_H
 #define DRYV_CABAC_HOST_H
@@ -35,9 +38,29 @@
 extern "C" {
 #endif
 
-/* Walks the NAL units, parses the (last) SPS and PPS before the first IDR slice into `pp`, and counts the IDR
- * pictures. Returns DRYV_OK, DRYV_ERR_ARG (no SPS/PPS/IDR, truncated data) or DRYV_ERR_UNSUPPORTED. */
+/* Walks the NAL units, fills `pp` with the parameters of the FIRST IDR picture (geometry, chroma QP offsets, the
+ * scaling lists the reference would use for it) and counts the IDR pictures. Returns DRYV_OK, DRYV_ERR_ARG (no
+ * SPS/PPS/IDR, truncated data) or DRYV_ERR_UNSUPPORTED. */
 int dryv_cabac_scan(const uint8_t* annexb, size_t len, dryv_pic_params* pp, uint32_t* n_pictures);
+
+/* The same parameters for picture `picture` (0-based): pictures of one stream may name different picture parameter sets
+ * (chroma QP offsets, scaling matrix), and a dryv_recon_submit batch shares one dryv_pic_params, so a host groups the
+ * pictures by equal parameters. */
+int dryv_cabac_picture_params(const uint8_t* annexb, size_t len, uint32_t picture, dryv_pic_params* pp);
+
+/* What the slice header of picture `picture` says about things this path does not do itself. The reference has no
+ * deblocking filter (README.md:15; the fields are parsed in slice/header.rs:609-640 and ignored): a consumer that wants
+ * what a conformant decoder outputs calls dryv_recon_deblock_device with these offsets when
+ * disable_deblocking_filter_idc != 1 (idc 2, "not across slice edges", equals 0 for one slice per picture). */
+typedef struct dryv_slice_info {
+  uint8_t pic_parameter_set_id, seq_parameter_set_id;
+  uint8_t slice_qp;                       /* SliceQPY */
+  uint8_t disable_deblocking_filter_idc;  /* 0 when the PPS has no deblocking_filter_control_present_flag */
+  int8_t slice_alpha_c0_offset_div2, slice_beta_offset_div2;
+  uint8_t scaling_matrix_source;          /* 0 flat, 1 SPS matrix, 2 PPS matrix (slice/header.rs:317-332) */
+  uint8_t reserved;
+} dryv_slice_info;
+int dryv_cabac_slice_info(const uint8_t* annexb, size_t len, uint32_t picture, dryv_slice_info* out);
 
 /* The display rectangle the stream's SPS asks for (frame_cropping_flag and frame_crop_*_offset, 7.4.2.1.1; the fields the
  * reference parses in atom/avcc/sps.rs:252-267 and never applies), as a DRYV_SURFACE_I420 surface for

@@ -79,18 +79,41 @@ def nal_unit(ref_idc, nal_type, rbsp: bytes) -> bytes:
     return bytes(out)
 
 
-def sps_rbsp(w_mbs, h_mbs, crop=None):
-    """crop: None or (left, right, top, bottom) frame_crop_*_offset values (units of two luma samples for 4:2:0 frames)."""
+def write_scaling_matrix(w, matrix, n_lists):
+    """7.3.2.1.1.1 scaling_list() for lists 0..n_lists-1 (0..5: 4x4, 6..: 8x8). `matrix`: {list index: values in zig-zag
+    order (16 or 64 of them, 1..255) | "default" (the list is present and signals useDefaultScalingMatrixFlag)};
+    lists that are not named are written as absent (scaling_list_present_flag = 0)."""
+    for i in range(n_lists):
+        v = matrix.get(i)
+        w.u(1, 0 if v is None else 1)
+        if v is None:
+            continue
+        if isinstance(v, str):
+            w.se(-8)          # delta_scale: nextScale = 0 at j = 0 -> useDefaultScalingMatrixFlag
+            continue
+        assert len(v) == (16 if i < 6 else 64) and all(1 <= x <= 255 for x in v)
+        last = 8
+        for x in v:
+            d = (x - last + 128) % 256 - 128
+            w.se(d)
+            last = x
+
+
+def sps_rbsp(w_mbs, h_mbs, crop=None, matrix=None, sps_id=0):
+    """crop: None or (left, right, top, bottom) frame_crop_*_offset values (units of two luma samples for 4:2:0 frames).
+    matrix: None or the seq_scaling_matrix (see write_scaling_matrix; 8 lists)."""
     w = BitWriter()
     w.u(8, 100)   # profile_idc: High
     w.u(8, 0)     # constraint flags + reserved
     w.u(8, 51)    # level_idc
-    w.ue(0)       # seq_parameter_set_id
+    w.ue(sps_id)  # seq_parameter_set_id
     w.ue(1)       # chroma_format_idc 4:2:0
     w.ue(0)       # bit_depth_luma_minus8
     w.ue(0)       # bit_depth_chroma_minus8
     w.u(1, 0)     # qpprime_y_zero_transform_bypass_flag
-    w.u(1, 0)     # seq_scaling_matrix_present_flag
+    w.u(1, 0 if matrix is None else 1)     # seq_scaling_matrix_present_flag
+    if matrix is not None:
+        write_scaling_matrix(w, matrix, 8)
     w.ue(0)       # log2_max_frame_num_minus4
     w.ue(2)       # pic_order_cnt_type
     w.ue(1)       # max_num_ref_frames
@@ -108,10 +131,10 @@ def sps_rbsp(w_mbs, h_mbs, crop=None):
     return w.tobytes()
 
 
-def pps_rbsp(cb_off, cr_off):
+def pps_rbsp(cb_off, cr_off, matrix=None, pps_id=0, sps_id=0, pic_init_qp=26):
     w = BitWriter()
-    w.ue(0)       # pic_parameter_set_id
-    w.ue(0)       # seq_parameter_set_id
+    w.ue(pps_id)  # pic_parameter_set_id
+    w.ue(sps_id)  # seq_parameter_set_id
     w.u(1, 1)     # entropy_coding_mode_flag: CABAC
     w.u(1, 0)     # bottom_field_pic_order_in_frame_present_flag
     w.ue(0)       # num_slice_groups_minus1
@@ -119,14 +142,16 @@ def pps_rbsp(cb_off, cr_off):
     w.ue(0)       # num_ref_idx_l1_default_active_minus1
     w.u(1, 0)     # weighted_pred_flag
     w.u(2, 0)     # weighted_bipred_idc
-    w.se(0)       # pic_init_qp_minus26
+    w.se(pic_init_qp - 26)   # pic_init_qp_minus26
     w.se(0)       # pic_init_qs_minus26
     w.se(cb_off)  # chroma_qp_index_offset
     w.u(1, 1)     # deblocking_filter_control_present_flag
     w.u(1, 0)     # constrained_intra_pred_flag
     w.u(1, 0)     # redundant_pic_cnt_present_flag
     w.u(1, 1)     # transform_8x8_mode_flag
-    w.u(1, 0)     # pic_scaling_matrix_present_flag
+    w.u(1, 0 if matrix is None else 1)     # pic_scaling_matrix_present_flag
+    if matrix is not None:
+        write_scaling_matrix(w, matrix, 8)   # 6 + 2 * transform_8x8_mode_flag lists (4:2:0)
     w.se(cr_off)  # second_chroma_qp_index_offset
     w.trailing()
     return w.tobytes()
@@ -475,7 +500,7 @@ class SliceWriter:
         return self.bits
 
 
-def encode_picture(batch, frame, cbps, idr_pic_id=0, deblock=None) -> bytes:
+def encode_picture(batch, frame, cbps, idr_pic_id=0, deblock=None, pps_id=0, pic_init_qp=26) -> bytes:
     """One IDR access unit (slice NAL only) of picture `frame`. deblock: None (filter disabled, what dryv decodes) or
     (slice_alpha_c0_offset_div2, slice_beta_offset_div2) for a stream that asks for the in-loop filter."""
     base = frame * batch.pp.n_mb
@@ -483,12 +508,12 @@ def encode_picture(batch, frame, cbps, idr_pic_id=0, deblock=None) -> bytes:
     w = BitWriter()
     w.ue(0)                 # first_mb_in_slice
     w.ue(7)                 # slice_type: I (all slices of the picture)
-    w.ue(0)                 # pic_parameter_set_id
+    w.ue(pps_id)            # pic_parameter_set_id
     w.u(4, 0)               # frame_num
     w.ue(idr_pic_id)        # idr_pic_id
     w.u(1, 0)               # no_output_of_prior_pics_flag
     w.u(1, 0)               # long_term_reference_flag
-    w.se(slice_qp - 26)     # slice_qp_delta
+    w.se(slice_qp - pic_init_qp)     # slice_qp_delta
     if deblock is None:
         w.ue(1)             # disable_deblocking_filter_idc: no deblocking (dryv has none)
     else:
@@ -504,14 +529,23 @@ def encode_picture(batch, frame, cbps, idr_pic_id=0, deblock=None) -> bytes:
     return nal_unit(3, 5, w.tobytes())
 
 
-def encode_stream(batch, crop=None, deblock=None) -> bytes:
+def encode_stream(batch, crop=None, deblock=None, sps_matrix=None, pps_matrix=None, extra_pps=None) -> bytes:
     """Annex-B stream: SPS, PPS, then one IDR picture per frame of `batch` (canonicalises `batch` in place). `crop`: the
-    SPS frame_crop_{left,right,top,bottom}_offset values, or None for no cropping."""
+    SPS frame_crop_{left,right,top,bottom}_offset values, or None for no cropping. `sps_matrix` / `pps_matrix`: scaling
+    matrices (write_scaling_matrix); the levels of `batch` are written as they are, so the caller generates them against
+    the lists the decoder will end up with. `extra_pps`: None or (pic_init_qp, which) - a second PPS (id 1, that
+    pic_init_qp, same offsets) is written as well and the pictures f with which(f) true name it."""
     pp = batch.pp
-    assert all(v == 16 for v in pp.scaling_list4x4) and all(v == 16 for v in pp.scaling_list8x8), "flat lists only"
+    if sps_matrix is None and pps_matrix is None:
+        assert all(v == 16 for v in pp.scaling_list4x4) and all(v == 16 for v in pp.scaling_list8x8), "flat lists only"
     cbps = canonicalise(batch)
-    out = nal_unit(3, 7, sps_rbsp(pp.pic_width_in_mbs, pp.pic_height_in_mbs, crop))
-    out += nal_unit(3, 8, pps_rbsp(int(pp.chroma_qp_index_offset), int(pp.second_chroma_qp_index_offset)))
+    cb, cr = int(pp.chroma_qp_index_offset), int(pp.second_chroma_qp_index_offset)
+    out = nal_unit(3, 7, sps_rbsp(pp.pic_width_in_mbs, pp.pic_height_in_mbs, crop, sps_matrix))
+    out += nal_unit(3, 8, pps_rbsp(cb, cr, pps_matrix))
+    if extra_pps:
+        out += nal_unit(3, 8, pps_rbsp(cb, cr, pps_matrix, pps_id=1, pic_init_qp=extra_pps[0]))
     for f in range(batch.n_frames):
-        out += encode_picture(batch, f, cbps, idr_pic_id=f & 1, deblock=deblock)
+        second = bool(extra_pps and extra_pps[1](f))
+        out += encode_picture(batch, f, cbps, idr_pic_id=f & 1, deblock=deblock, pps_id=1 if second else 0,
+                              pic_init_qp=extra_pps[0] if second else 26)
     return out

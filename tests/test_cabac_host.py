@@ -247,3 +247,116 @@ def test_corrupted_mp4_files_never_crash(recon_lib):
         assert rc in (recon.OK, recon.ERR_ARG, recon.ERR_UNSUPPORTED)
         seen.add(rc)
     assert recon.ERR_ARG in seen
+
+
+# ---- scaling matrices and parameter sets by id -----------------------------------------------------
+DEFAULT_4X4_INTRA = [6, 13, 13, 20, 20, 20, 28, 28, 28, 28, 32, 32, 32, 37, 37, 42]   # Table 7-3 / atom/avcc/sps.rs:161-163
+DEFAULT_8X8_INTRA = [6, 10, 10, 13, 11, 13, 16, 16, 16, 16, 18, 18, 18, 18, 18, 23, 23, 23, 23, 23, 23, 25, 25, 25, 25, 25,
+                     25, 25, 27, 27, 27, 27, 27, 27, 27, 27, 29, 29, 29, 29, 29, 29, 29, 31, 31, 31, 31, 31, 31, 33, 33, 33,
+                     33, 33, 36, 36, 36, 36, 38, 38, 38, 40, 40, 42]
+
+
+def _lists(seed):
+    rng = np.random.default_rng(seed)
+    return [int(v) for v in rng.integers(4, 60, 16)], [int(v) for v in rng.integers(4, 60, 64)]
+
+
+@pytest.mark.parametrize("case", ["sps_explicit", "sps_absent_lists", "sps_default_flag", "pps_only", "sps_wins", "wraparound"])
+def test_scaling_matrix_selection_follows_the_reference(recon_lib, case):
+    """SliceHeader::scaling_lists (slice/header.rs:317-332) + ScalingLists::new (atom/avcc/sps.rs:207-248): the SPS matrix
+    if there is one, else the PPS matrix, else flat; a list that is absent or flags useDefault becomes the Default table."""
+    l4, l8 = _lists(1)
+    m4, m8 = _lists(2)
+    pp = PicParams.make(3, 2)
+    b = synth.generate(pp, 1, 31, zero_residual=True)
+    kw, want4, want8, src = {}, None, None, 0
+    if case == "sps_explicit":
+        kw = dict(sps_matrix={0: l4, 6: l8, 3: m4})
+        want4, want8, src = l4, l8, 1
+    elif case == "sps_absent_lists":   # a matrix with only an inter list: list 0 and list 6 fall to the Default tables
+        kw = dict(sps_matrix={4: m4})
+        want4, want8, src = DEFAULT_4X4_INTRA, DEFAULT_8X8_INTRA, 1
+    elif case == "sps_default_flag":
+        kw = dict(sps_matrix={0: "default", 6: "default"})
+        want4, want8, src = DEFAULT_4X4_INTRA, DEFAULT_8X8_INTRA, 1
+    elif case == "pps_only":
+        kw = dict(pps_matrix={0: l4, 6: l8})
+        want4, want8, src = l4, l8, 2
+    elif case == "sps_wins":
+        kw = dict(sps_matrix={0: l4, 6: l8}, pps_matrix={0: m4, 6: m8})
+        want4, want8, src = l4, l8, 1
+    else:                              # delta_scale wraps modulo 256 (7.3.2.1.1.1)
+        w4 = [250, 3, 250, 3] * 4
+        kw = dict(sps_matrix={0: w4, 6: l8})
+        want4, want8, src = w4, l8, 1
+    data = stream.encode_stream(b, **kw)
+    got, n = host.scan(data)
+    assert n == 1 and list(got.scaling_list4x4) == want4 and list(got.scaling_list8x8) == want8
+    assert host.slice_info(data, 0).scaling_matrix_source == src
+    assert_same_syntax(host.parse(data), b)
+
+
+def _matrix_stream(seed):
+    l4, l8 = _lists(seed)
+    pp = PicParams.make(6, 4, 0, 0, l4, l8)
+    # stress_pct = 0: the stress macroblocks' levels, quantised against small weights, leave the 16-bit coefficient range
+    # a conforming stream keeps to (8.5.12.1 note), and libavcodec stores coefficients in int16
+    b = synth.generate(pp, 2, 41 + seed, standard_only=True, stress_pct=0)
+    return pp, b, stream.encode_stream(b, sps_matrix={0: l4, 6: l8}), l4, l8
+
+
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_scaling_matrix_stream_reconstructs_like_libavcodec(recon_lib, seed):
+    """A stream whose SPS carries Intra-Y lists only (all three macroblock classes): bytes -> parse (lists from the SPS)
+    -> oracle must give a conformant decoder's luma."""
+    from avc import decode
+    if not decode.available():
+        pytest.skip("cv2 with the FFmpeg backend is not available")
+    pp, b, data, l4, l8 = _matrix_stream(seed)
+    got_pp, n = host.scan(data)
+    assert list(got_pp.scaling_list4x4) == l4 and list(got_pp.scaling_list8x8) == l8
+    parsed = host.parse(data)
+    parsed.pp = got_pp
+    assert np.array_equal(luma_of(oracle.reconstruct(parsed), pp), decode.decode_luma(data, 2, 96, 64))
+
+
+@pytest.mark.gpu
+def test_scaling_matrix_stream_bytes_to_cuda_equals_libavcodec(recon_lib):
+    from avc import decode
+    pp, b, data, l4, l8 = _matrix_stream(8)
+    parsed = host.parse(data)
+    parsed.pp = host.scan(data)[0]
+    ctx = recon.ReconContext(0)
+    got = ctx.reconstruct(parsed)
+    ctx.close()
+    assert np.array_equal(got, oracle.reconstruct(parsed))
+    if decode.available():
+        assert np.array_equal(luma_of(got, pp), decode.decode_luma(data, 2, 96, 64))
+
+
+def test_parameter_sets_are_activated_by_id_per_picture(recon_lib):
+    """Two PPS with different pic_init_qp; pictures alternate between them: every slice's QP comes from the PPS it names
+    (7.4.1.2.1), also for a set that arrives after other pictures."""
+    pp = PicParams.make(4, 3, 1, -2)
+    b = synth.generate(pp, 4, 51, qp_base=30, qp_jitter=3)
+    data = stream.encode_stream(b, extra_pps=(35, lambda f: f % 2 == 1))
+    assert_same_syntax(host.parse(data), b)
+    assert [host.slice_info(data, f).pic_parameter_set_id for f in range(4)] == [0, 1, 0, 1]
+    for f in range(4):
+        assert host.slice_info(data, f).slice_qp == int(b.qp[f * pp.n_mb])
+        got = host.picture_params(data, f)
+        assert (got.chroma_qp_index_offset, got.second_chroma_qp_index_offset) == (1, -2)
+    # a slice that names a PPS the stream never sent
+    bad = stream.nal_unit(3, 7, stream.sps_rbsp(4, 3)) + stream.encode_picture(b, 0, stream.canonicalise(b), pps_id=3)
+    with pytest.raises(recon.ReconError) as e:
+        host.scan(bad)
+    assert e.value.code == recon.ERR_ARG
+
+
+def test_slice_info_reports_the_deblocking_request(recon_lib):
+    pp = PicParams.make(3, 2)
+    b = synth.generate(pp, 1, 61)
+    si = host.slice_info(stream.encode_stream(b), 0)
+    assert si.disable_deblocking_filter_idc == 1
+    si = host.slice_info(stream.encode_stream(b, deblock=(2, -3)), 0)
+    assert (si.disable_deblocking_filter_idc, si.slice_alpha_c0_offset_div2, si.slice_beta_offset_div2) == (0, 2, -3)

@@ -180,6 +180,19 @@ def test_malformed_stream_is_reported_not_read_out_of_bounds(gpu_ctx):
     gpu_ctx.expand_levels_device(d_off, d_str, 4, d_coeff)
     gpu_ctx.wait()
     assert np.array_equal(d_coeff.cpu().numpy(), c)
+    # a misaligned stream pointer / first offset is an argument error, not a misaligned-address fault
+    d_pad = torch.zeros(lv.stream.size + 8, dtype=torch.uint8, device="cuda")
+    d_pad[2:2 + lv.stream.size] = d_str
+    with pytest.raises(recon.ReconError) as e:
+        gpu_ctx.expand_levels_device(d_off, d_pad[2:], 4, d_coeff)
+    assert e.value.code == recon.ERR_ARG
+    off2 = lv.offset.copy() + 2
+    with pytest.raises(recon.ReconError) as e:
+        gpu_ctx.expand_levels_device(torch.from_numpy(off2.view(np.int32)).cuda(), d_pad, 4, d_coeff)
+    assert e.value.code == recon.ERR_ARG
+    gpu_ctx.expand_levels_device(d_off, d_str, 4, d_coeff)   # and the context is still fine
+    gpu_ctx.wait()
+    assert np.array_equal(d_coeff.cpu().numpy(), c)
 
 
 @pytest.mark.gpu

@@ -85,8 +85,8 @@ typedef struct dryv_pic_params {
  *               Arithmetic range: the kernels compute in int32 where the reference computes in isize. Every level a
  *               conforming stream can carry is exact (8.5.12.1: dequantised coefficients and transform intermediates fit
  *               16 + bit-depth bits); results are identical to the reference's for any input with
- *               |level| * LevelScale(qP, i, j) << max(qP/6 - 4, 0) below 2^26 (flat lists: every int16 level up to qP 51;
- *               tested at +-2047 and +-32767). Beyond that (large levels against large custom scaling-list entries at
+ *               |level| * LevelScale(qP, i, j) << max(qP/6 - 4, 0) below 2^26 (flat lists: every int16 level up to qP 41,
+ *               |level| < 9000 at qP 51; tested at +-2047). Beyond that (large levels against large custom scaling-list entries at
  *               high qP) int32 wraps where isize does not and the output is unspecified.
  * Reconstruction never reads coded_block_pattern: absent blocks are all-zero arrays (cabac/mod.rs:669-673).
  */

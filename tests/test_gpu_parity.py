@@ -33,7 +33,9 @@ def check(ctx, batch, host=True, device=True):
         assert np.array_equal(ref, got), "device path: " + first_difference(batch.pp, ref, got)
 
 
-# ---- golden fixtures (no oracle involved) ---------------------------------------------------------------
+# ---- oracle snapshots (tests/golden/*.npz are written by make_golden.py FROM THE ORACLE: they hold the CUDA path to the
+# oracle's past output without executing it, they are not independent evidence; the libavcodec-derived fixtures are in
+# tests/golden/avc/, the dryv pinning kit in tests/golden/pin/) ------------------------------------------------------
 @pytest.mark.parametrize("name", golden_cases())
 def test_golden(gpu_ctx, name):
     b, expected = load_golden(name)

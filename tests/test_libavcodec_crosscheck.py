@@ -113,6 +113,41 @@ def test_fixture_still_decodes_to_the_same_luma():
     assert np.array_equal(decode.decode_luma(data, b.n_frames, luma.shape[2], luma.shape[1]), luma)
 
 
+# ---- per-class fixtures: libavcodec's luma AND BGR pictures (chroma) of Intra4x4-only / Intra8x8-only / Intra16x16-only streams
+# with chroma QP offsets, decoded in the build container (tests/golden/avc/make_avc_golden.py); the reference follows the
+# H.264 text on every sample of these pictures (no Intra8x8 in column 0, no chroma sample equal to 0)
+CLASS_FIXTURE = os.path.join(os.path.dirname(FIXTURE), "classes.npz")
+
+
+def load_class_fixture(name):
+    z = np.load(CLASS_FIXTURE)
+    pp = PicParams.make(int(z["w_mbs"]), int(z["h_mbs"]), int(z["cb_off"]), int(z["cr_off"]))
+    b = SyntaxBatch(pp, int(z["n_frames"]), *[np.ascontiguousarray(z[name + "_" + f]) for f in FIELDS])
+    return b, z[name + "_stream"].tobytes(), z[name + "_luma"], z[name + "_bgr"]
+
+
+def check_against_class_fixture(frames, b, luma, bgr):
+    pp = b.pp
+    assert np.array_equal(luma_of(frames, pp), luma)
+    if decode.available():   # the chroma planes, through the same swscale conversion libavcodec's pictures went through
+        assert np.array_equal(decode.bgr_of_pictures(frames, pp.pic_width_in_mbs * 16, pp.pic_height_in_mbs * 16), bgr)
+
+
+@pytest.mark.parametrize("name", ["i4x4", "i8x8", "i16x16"])
+def test_oracle_equals_libavcodec_class_fixture(name):
+    b, data, luma, bgr = load_class_fixture(name)
+    assert stream.encode_stream(b) == data
+    check_against_class_fixture(oracle.reconstruct(b), b, luma, bgr)
+    assert np.array_equal(spec_model.reconstruct(b, quirks=False), oracle.reconstruct(b))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["i4x4", "i8x8", "i16x16"])
+def test_cuda_path_equals_libavcodec_class_fixture(gpu_ctx, name):
+    b, _, luma, bgr = load_class_fixture(name)
+    check_against_class_fixture(gpu_ctx.reconstruct(b), b, luma, bgr)
+
+
 @pytest.mark.gpu
 def test_cuda_path_equals_libavcodec_fixture(gpu_ctx):
     b, _, luma = load_fixture()

@@ -3,8 +3,8 @@
 TEST TOOLING ONLY. It exists so that the CPU oracle can be cross-checked against an
 independent, conformant decoder (libavcodec through cv2, tests/test_libavcodec_crosscheck.py): the reference ships no
 test vectors and cannot be built here, and no H.264 encoder or sample stream exists in the image. Written from the
-text of ITU-T H.264 (7.3 syntax, 9.3 CABAC); the constant tables of 9.3 are loaded from tests/golden/cabac_tables.json
-(see tests/golden/make_cabac_tables.py). The inverse of what the reference parses in src/video/cabac/mod.rs:89-675,
+text of ITU-T H.264 (7.3 syntax, 9.3 CABAC); the constant tables of 9.3 are loaded from dryv_b200/csrc/cabac_tables.json, the product's own copy
+(see tools/make_cabac_tables.py). The inverse of what the reference parses in src/video/cabac/mod.rs:89-675,
 src/video/slice/header.rs:145-315, src/video/atom/avcc/{sps,pps}.rs.
 
 One IDR picture per access unit, one slice per picture, 8-bit 4:2:0, frame macroblocks, flat scaling lists,
@@ -17,7 +17,7 @@ import os
 
 import numpy as np
 
-_T = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "golden", "cabac_tables.json")))
+_T = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "dryv_b200", "csrc", "cabac_tables.json")))
 CTX_INIT_I = _T["ctx_init_i"]
 RANGE_LPS = _T["range_tab_lps"]
 TRANS_LPS = _T["trans_idx_lps"]

@@ -1,10 +1,10 @@
 """Extracts the H.264 CABAC constant tables (ITU-T H.264 Tables 9-12..9-33 context initialisation for I slices,
 Table 9-44 rangeTabLPS, Table 9-45 transIdxLPS/MPS, Table 9-43 8x8 ctxIdxInc maps) as plain numbers from the
 reference's Rust source, where they appear as literal arrays (src/video/cabac/table.rs:4-1172,
-src/video/cabac/consts.rs:135-213, :402-466), into tests/golden/cabac_tables.json. They are standard constants, not
+src/video/cabac/consts.rs:135-213, :402-466), into dryv_b200/csrc/cabac_tables.json. They are standard constants, not
 code; the stream writer in tests/avc/ (test tooling for the libavcodec cross-check of the oracle) loads the JSON.
 
-    python tests/golden/make_cabac_tables.py        # needs /root/reference, run in the build container only
+    python tools/make_cabac_tables.py        # needs /root/reference, run in the build container only
 """
 import json
 import os
@@ -55,6 +55,6 @@ out = {
     "sig8x8_frame": tab8[0::3],
     "last8x8": tab8[2::3],
 }
-with open(os.path.join(HERE, "cabac_tables.json"), "w") as f:
+with open(os.path.join(HERE, "..", "dryv_b200", "csrc", "cabac_tables.json"), "w") as f:
     json.dump(out, f, separators=(",", ":"))
 print("ctx", len(ctx_init_i), "first", ctx_init_i[:4], "range[0]", out["range_tab_lps"][0], "sig8", out["sig8x8_frame"][:8], "last8", out["last8x8"][:8])

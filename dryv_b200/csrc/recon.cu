@@ -1050,58 +1050,68 @@ template <> struct ExportVec<4> { typedef uint32_t type; };
 template <> struct ExportVec<2> { typedef uint16_t type; };
 template <> struct ExportVec<1> { typedef uint8_t type; };
 
-struct ExportArgs {
-  const uint8_t* src;   // first wanted sample of picture 0's plane (crop offset applied)
-  const uint8_t* src2;  // interleave only: the Cr plane, same position
-  uint8_t* dst;         // picture 0's destination plane
-  size_t src_frame_stride, dst_frame_stride;
-  uint32_t src_row_stride;  // bytes between rows of the coded plane
-  uint32_t row_bytes;       // bytes per destination row
-  uint32_t rows;            // rows per picture
-  unsigned long long total; // n_frames * rows * (row_bytes / V)
+// The whole surface in ONE launch (the three launches of the per-plane kernels left a fifth of the step to launch gaps):
+// every thread moves V output bytes of one of the planes; a picture's threads are laid out luma | chroma, so a thread
+// finds its plane by comparing its index inside the picture with the plane sizes. NV12: the chroma part interleaves
+// V/2 Cb and V/2 Cr bytes with prmt.
+struct ExportAllArgs {
+  const uint8_t* src_y;   // first wanted luma sample of picture 0 (crop applied)
+  const uint8_t* src_cb;  // ... Cb sample; Cr lies cr_delta bytes behind it
+  uint8_t* dst;           // picture 0's surface
+  size_t src_frame_stride, dst_frame_stride, cr_delta;
+  uint32_t src_stride_y, src_stride_c;  // bytes between rows of the coded planes
+  uint32_t w, h;                        // the rectangle, luma samples
+  uint32_t vec_y, vec_c;                // vectors per picture: luma; one chroma plane (I420) / the interleaved plane (NV12)
+  uint32_t nv12;
+  unsigned long long total;             // n_frames * (vec_y + (nv12 ? 1 : 2) * vec_c)
 };
 
 template <int V>
-__global__ void __launch_bounds__(256) export_rows_kernel(const ExportArgs a) {
+__global__ void __launch_bounds__(256) export_all_kernel(const ExportAllArgs a) {
   typedef typename ExportVec<V>::type T;
   const unsigned long long idx = (unsigned long long)blockIdx.x * 256u + threadIdx.x;
   if (idx >= a.total) return;
-  const uint32_t per_row = a.row_bytes / V;
-  const uint32_t c = (uint32_t)(idx % per_row);
-  const unsigned long long rr = idx / per_row;
-  const uint32_t row = (uint32_t)(rr % a.rows);
-  const size_t f = (size_t)(rr / a.rows);
-  const T v = __ldcs(reinterpret_cast<const T*>(a.src + f * a.src_frame_stride + (size_t)row * a.src_row_stride) + c);
-  __stcs(reinterpret_cast<T*>(a.dst + f * a.dst_frame_stride + (size_t)row * a.row_bytes) + c, v);
-}
-
-// NV12 chroma rows: V output bytes = V/2 Cb samples and V/2 Cr samples, interleaved
-template <int V>
-__global__ void __launch_bounds__(256) export_interleave_kernel(const ExportArgs a) {
-  typedef typename ExportVec<V>::type T;
-  typedef typename ExportVec<V / 2>::type H;
-  const unsigned long long idx = (unsigned long long)blockIdx.x * 256u + threadIdx.x;
-  if (idx >= a.total) return;
-  const uint32_t per_row = a.row_bytes / V;
-  const uint32_t c = (uint32_t)(idx % per_row);
-  const unsigned long long rr = idx / per_row;
-  const uint32_t row = (uint32_t)(rr % a.rows);
-  const size_t f = (size_t)(rr / a.rows);
-  const size_t so = f * a.src_frame_stride + (size_t)row * a.src_row_stride;
-  const H cb = __ldcs(reinterpret_cast<const H*>(a.src + so) + c);
-  const H cr = __ldcs(reinterpret_cast<const H*>(a.src2 + so) + c);
-  T out;
-  if constexpr (V == 16) {
-    out = make_uint4(__byte_perm(cb.x, cr.x, 0x5140), __byte_perm(cb.x, cr.x, 0x7362), __byte_perm(cb.y, cr.y, 0x5140),
-                     __byte_perm(cb.y, cr.y, 0x7362));
-  } else if constexpr (V == 8) {
-    out = make_uint2(__byte_perm(cb, cr, 0x5140), __byte_perm(cb, cr, 0x7362));
-  } else if constexpr (V == 4) {
-    out = __byte_perm((uint32_t)cb, (uint32_t)cr, 0x5140);
-  } else {
-    out = (uint16_t)((uint32_t)cb | ((uint32_t)cr << 8));
+  const uint32_t per_frame = a.vec_y + (a.nv12 ? 1u : 2u) * a.vec_c;
+  const size_t f = (size_t)(idx / per_frame);
+  uint32_t r = (uint32_t)(idx - (unsigned long long)f * per_frame);
+  const uint8_t* sp = a.src_y + f * a.src_frame_stride;
+  uint8_t* dp = a.dst + f * a.dst_frame_stride;
+  if (r < a.vec_y) {
+    const uint32_t per_row = a.w / V, row = r / per_row, c = r - row * per_row;
+    __stcs(reinterpret_cast<T*>(dp + (size_t)row * a.w) + c, __ldcs(reinterpret_cast<const T*>(sp + (size_t)row * a.src_stride_y) + c));
+    return;
   }
-  __stcs(reinterpret_cast<T*>(a.dst + f * a.dst_frame_stride + (size_t)row * a.row_bytes) + c, out);
+  r -= a.vec_y;
+  dp += (size_t)a.w * a.h;
+  sp = a.src_cb + f * a.src_frame_stride;
+  if (!a.nv12) {
+    if (r >= a.vec_c) {  // Cr
+      r -= a.vec_c;
+      sp += a.cr_delta;
+      dp += (size_t)(a.w / 2) * (a.h / 2);
+    }
+    const uint32_t per_row = (a.w / 2) / V, row = r / per_row, c = r - row * per_row;
+    __stcs(reinterpret_cast<T*>(dp + (size_t)row * (a.w / 2)) + c,
+           __ldcs(reinterpret_cast<const T*>(sp + (size_t)row * a.src_stride_c) + c));
+  } else if constexpr (V >= 2) {
+    typedef typename ExportVec<V / 2>::type H;
+    const uint32_t per_row = a.w / V, row = r / per_row, c = r - row * per_row;
+    const size_t so = (size_t)row * a.src_stride_c;
+    const H cb = __ldcs(reinterpret_cast<const H*>(sp + so) + c);
+    const H cr = __ldcs(reinterpret_cast<const H*>(sp + a.cr_delta + so) + c);
+    T out;
+    if constexpr (V == 16) {
+      out = make_uint4(__byte_perm(cb.x, cr.x, 0x5140), __byte_perm(cb.x, cr.x, 0x7362), __byte_perm(cb.y, cr.y, 0x5140),
+                       __byte_perm(cb.y, cr.y, 0x7362));
+    } else if constexpr (V == 8) {
+      out = make_uint2(__byte_perm(cb, cr, 0x5140), __byte_perm(cb, cr, 0x7362));
+    } else if constexpr (V == 4) {
+      out = __byte_perm((uint32_t)cb, (uint32_t)cr, 0x5140);
+    } else {
+      out = (uint16_t)((uint32_t)cb | ((uint32_t)cr << 8));
+    }
+    __stcs(reinterpret_cast<T*>(dp + (size_t)row * a.w) + c, out);
+  }
 }
 
 }  // namespace dryv
@@ -1350,35 +1360,7 @@ int common_vector(std::initializer_list<unsigned long long> q, int cap, int floo
   return v;
 }
 
-int launch_rows(dryv_recon_ctx* ctx, int v, dryv::ExportArgs a, unsigned long long vectors, cudaStream_t st) {
-  a.total = vectors;
-  if (vectors == 0) return DRYV_OK;
-  const unsigned blocks = (unsigned)((vectors + 255) / 256);
-  switch (v) {
-    case 16: dryv::export_rows_kernel<16><<<blocks, 256, 0, st>>>(a); break;
-    case 8: dryv::export_rows_kernel<8><<<blocks, 256, 0, st>>>(a); break;
-    case 4: dryv::export_rows_kernel<4><<<blocks, 256, 0, st>>>(a); break;
-    case 2: dryv::export_rows_kernel<2><<<blocks, 256, 0, st>>>(a); break;
-    default: dryv::export_rows_kernel<1><<<blocks, 256, 0, st>>>(a); break;
-  }
-  CU(cudaGetLastError());
-  return DRYV_OK;
-}
-int launch_interleave(dryv_recon_ctx* ctx, int v, dryv::ExportArgs a, unsigned long long vectors, cudaStream_t st) {
-  a.total = vectors;
-  if (vectors == 0) return DRYV_OK;
-  const unsigned blocks = (unsigned)((vectors + 255) / 256);
-  switch (v) {
-    case 16: dryv::export_interleave_kernel<16><<<blocks, 256, 0, st>>>(a); break;
-    case 8: dryv::export_interleave_kernel<8><<<blocks, 256, 0, st>>>(a); break;
-    case 4: dryv::export_interleave_kernel<4><<<blocks, 256, 0, st>>>(a); break;
-    default: dryv::export_interleave_kernel<2><<<blocks, 256, 0, st>>>(a); break;
-  }
-  CU(cudaGetLastError());
-  return DRYV_OK;
-}
-
-// enqueue the surface export of n_frames coded pictures (d_yuv, `pp` geometry) into d_out on stream st
+// enqueue the surface export of n_frames coded pictures (d_yuv, `pp` geometry) into d_out on stream st: one launch
 int launch_export(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const uint8_t* d_yuv, uint32_t n_frames,
                   const dryv_surface* s, uint8_t* d_out, cudaStream_t st) {
   const size_t W = 16u * (size_t)pp->pic_width_in_mbs, H = 16u * (size_t)pp->pic_height_in_mbs;
@@ -1388,48 +1370,39 @@ int launch_export(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const uint8_t*
   const size_t w = s->width, h = s->height, cl = s->crop_left, ct = s->crop_top;
   const unsigned long long pa = (unsigned long long)reinterpret_cast<uintptr_t>(d_yuv),
                            pb = (unsigned long long)reinterpret_cast<uintptr_t>(d_out);
-  dryv::ExportArgs a;
+  const bool nv12 = s->format == DRYV_SURFACE_NV12;
+  // one vector width for every plane: it has to divide the luma quantities and, per chroma plane, half of them
+  // (NV12: V output bytes = V/2 source bytes of each plane). W / 2: the coded chroma row stride is 8 * pic_width_in_mbs,
+  // so with an odd macroblock count rows alternate between 16- and 8-byte alignment.
+  const int v = nv12 ? common_vector({pa, pb, cl, w, w * h, dst_frame}, 16, 2)
+                     : common_vector({pa, pb, cl / 2, w / 2, W / 2, w * h, w * h / 4, dst_frame}, 16, 1);
+  dryv::ExportAllArgs a;
   memset(&a, 0, sizeof a);
+  a.src_y = d_yuv + ct * W + cl;
+  a.src_cb = d_yuv + W * H + (ct / 2) * (W / 2) + cl / 2;
+  a.cr_delta = (W / 2) * (H / 2);
+  a.dst = d_out;
   a.src_frame_stride = src_frame;
   a.dst_frame_stride = dst_frame;
-  // luma
-  {
-    const int v = common_vector({pa, pb, cl, w, dst_frame}, 16, 1);
-    a.src = d_yuv + ct * W + cl;
-    a.dst = d_out;
-    a.src_row_stride = (uint32_t)W;
-    a.row_bytes = (uint32_t)w;
-    a.rows = (uint32_t)h;
-    int rc = launch_rows(ctx, v, a, (unsigned long long)n_frames * h * (w / v), st);
-    if (rc != DRYV_OK) return rc;
-    ctx->launches++;
+  a.src_stride_y = (uint32_t)W;
+  a.src_stride_c = (uint32_t)(W / 2);
+  a.w = (uint32_t)w;
+  a.h = (uint32_t)h;
+  a.nv12 = nv12 ? 1u : 0u;
+  a.vec_y = (uint32_t)(h * (w / v));
+  a.vec_c = (uint32_t)(nv12 ? (h / 2) * (w / v) : (h / 2) * (w / 2 / v));
+  a.total = (unsigned long long)n_frames * (a.vec_y + (nv12 ? 1u : 2u) * a.vec_c);
+  if (a.total == 0) return DRYV_OK;
+  const unsigned blocks = (unsigned)((a.total + 255) / 256);
+  switch (v) {
+    case 16: dryv::export_all_kernel<16><<<blocks, 256, 0, st>>>(a); break;
+    case 8: dryv::export_all_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    case 4: dryv::export_all_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    case 2: dryv::export_all_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+    default: dryv::export_all_kernel<1><<<blocks, 256, 0, st>>>(a); break;
   }
-  const uint8_t* cb = d_yuv + W * H + (ct / 2) * (W / 2) + cl / 2;
-  const uint8_t* cr = cb + (W / 2) * (H / 2);
-  a.src_row_stride = (uint32_t)(W / 2);
-  a.rows = (uint32_t)(h / 2);
-  if (s->format == DRYV_SURFACE_NV12) {
-    const int v = common_vector({pa, pb, cl, w, w * h, dst_frame}, 16, 2);  // V/2 source bytes per plane: cl/2 % (V/2) == 0
-    a.src = cb;
-    a.src2 = cr;
-    a.dst = d_out + w * h;
-    a.row_bytes = (uint32_t)w;
-    int rc = launch_interleave(ctx, v, a, (unsigned long long)n_frames * (h / 2) * (w / v), st);
-    if (rc != DRYV_OK) return rc;
-    ctx->launches++;
-  } else {
-    // W / 2: the coded chroma row stride is 8 * pic_width_in_mbs, so with an odd macroblock count rows alternate between
-    // 16- and 8-byte alignment
-    const int v = common_vector({pa, pb, cl / 2, w / 2, W / 2, w * h, w * h / 4, dst_frame}, 16, 1);
-    a.row_bytes = (uint32_t)(w / 2);
-    for (int pl = 0; pl < 2; pl++) {
-      a.src = pl ? cr : cb;
-      a.dst = d_out + w * h + (size_t)pl * (w / 2) * (h / 2);
-      int rc = launch_rows(ctx, v, a, (unsigned long long)n_frames * (h / 2) * (w / 2 / v), st);
-      if (rc != DRYV_OK) return rc;
-      ctx->launches++;
-    }
-  }
+  CU(cudaGetLastError());
+  ctx->launches++;
   return DRYV_OK;
 }
 

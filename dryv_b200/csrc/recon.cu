@@ -780,13 +780,11 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
 // ------------------------------------------------------------------------------------------------
 struct ResidWarpSmem {
   alignas(16) int16_t lv[2][kGroupMbs * DRYV_COEFFS_PER_MB];  // level ring (bulk-copy destinations)
-  alignas(16) uint16_t res_luma[kGroupMbs][kResLumaTile];     // residual fields
-  // chroma residual fields; the 8x8 passes, which run before the chroma pass writes them, transpose through the same bytes
-  alignas(16) uint16_t res_chroma[kGroupMbs][kResChromaMb];
+  alignas(16) uint16_t res_luma[kResLumaTile];                // residual fields of an Intra8x8 macroblock
+  alignas(16) int scratch[kScratchWords];                     // 8x8 transposes
   alignas(16) uint32_t hdr[kGroupMbs];                        // class | qp << 8
   alignas(8) unsigned long long full[2];                      // mbarriers of the level ring
 };
-static_assert(sizeof(uint16_t) * kGroupMbs * kResChromaMb >= sizeof(int) * kScratchWords, "scratch aliases the chroma tiles");
 struct ResidCtaSmem {
   alignas(16) unsigned char tab[kResidTableBytes];  // the residual part of DeviceTables
   ResidWarpSmem warp[kWarpsPerCta];
@@ -892,32 +890,88 @@ __global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residua
       m4 = ((1u << n) - 1u) & ~m8;
       __syncwarp();
     }
-    // the prediction samples of the whole group, issued before the transforms so that their latency is covered
+    // Blocks with the 4x4 transform stay in registers from the levels to the stored samples: the lane that transforms a
+    // block also adds its prediction and stores it (four 4-byte rows; the two macroblocks of a luma pass are neighbours,
+    // so every 32-byte sector is still fully used). The prediction words of all passes are loaded here, before the
+    // transforms, so that their latency is covered. Only Intra8x8 luma goes through a residual tile in shared memory.
     const size_t fo = (size_t)cur.frame * n_mb * 384;
-    const size_t lo = fo + (size_t)(16u * cur.row) * strideY + 16u * cur.x0() + lane_lo;
-    const size_t co = fo + (size_t)(8u * cur.row) * strideC + 8u * cur.x0() + lane_co;
-    uint2 pl[kGroupMbs];
-    uint32_t pc[kGroupMbs];
+    const uint8_t* const pin = a.pred_in + fo;
+    uint8_t* const pout = a.out + fo;
+    const size_t ybase = (size_t)(16u * cur.row) * strideY + 16u * cur.x0();               // luma of macroblock 0 of the group
+    const size_t cbase = (size_t)n_mb * 256 + (size_t)(8u * cur.row) * strideC + 8u * cur.x0();  // Cb of macroblock 0
+    const uint32_t list = tab.setbits4[m4];
+    const int n4 = __popc(m4);
+    size_t lo[2];        // this lane's block in luma pass 0 / 1: byte offset of its first row
+    uint32_t pl[2][4];   // its prediction rows
+    bool la[2];
 #pragma unroll
-    for (int m = 0; m < kGroupMbs; m++) {
-      const int mm = m < n ? m : 0;
-      pl[m] = __ldg(reinterpret_cast<const uint2*>(a.pred_in + lo + 16 * mm));
-      pc[m] = __ldg(reinterpret_cast<const uint32_t*>(a.pred_in + co + 8 * mm));
+    for (int p = 0; p < 2; p++) {
+      const uint32_t m = (list >> (4 * (2 * p + (lane >> 4)))) & 15u;
+      la[p] = 2 * p < n4 && m < (uint32_t)kGroupMbs;
+      const int b4 = lane & 15;
+      lo[p] = ybase + 16u * (la[p] ? m : 0u) + (size_t)((b4 >> 3) * 8 + ((b4 >> 1) & 1) * 4) * strideY + ((b4 >> 2) & 1) * 8 + (b4 & 1) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; i++) pl[p][i] = la[p] ? __ldg(reinterpret_cast<const uint32_t*>(pin + lo[p] + (size_t)i * strideY)) : 0u;
     }
-    mbar_wait(&ws.full[st], (it >> 1) & 1);
-    residual_group<true>(tab, a.tables, lc, lane, ws.hdr, m4, m8, ws.lv[st], n, reinterpret_cast<int*>(&ws.res_chroma[0][0]),
-                   &ws.res_luma[0][0], kResLumaTile, &ws.res_chroma[0][0], kResChromaMb, a.cb_off, a.cr_off);
+    // chroma pass: lane = (macroblock lane >> 3, plane (lane >> 2) & 1, block lane & 3)
+    const bool ca = (lane >> 3) < n;
+    const size_t co = cbase + 8u * (ca ? (uint32_t)(lane >> 3) : 0u) + (size_t)((lane >> 2) & 1) * n_mb * 64 +
+                      (size_t)(((lane >> 1) & 1) * 4) * strideC + (lane & 1) * 4;
+    uint32_t pc[4];
 #pragma unroll
-    for (int m = 0; m < kGroupMbs; m++) {
-      if (m < n) {
-        const uint2* rp = reinterpret_cast<const uint2*>(&ws.res_luma[m][(lane >> 1) * kResLumaStride + 8 * (lane & 1)]);
-        const uint2 r0 = rp[0], r1 = rp[1];
-        __stcs(reinterpret_cast<uint2*>(a.out + lo + 16 * m),
-               make_uint2(add_clip4(r0.x, r0.y, pl[m].x), add_clip4(r1.x, r1.y, pl[m].y)));
-        const uint2 rc = *reinterpret_cast<const uint2*>(
-            &ws.res_chroma[m][(lane >> 4) * kResChromaPlane + ((lane >> 1) & 7) * 8 + 4 * (lane & 1)]);
-        __stcs(reinterpret_cast<uint32_t*>(a.out + co + 8 * m), add_clip4(rc.x, rc.y, pc[m]));
+    for (int i = 0; i < 4; i++) pc[i] = ca ? __ldg(reinterpret_cast<const uint32_t*>(pin + co + (size_t)i * strideC)) : 0u;
+    mbar_wait(&ws.full[st], (it >> 1) & 1);
+    const int16_t* const lv = ws.lv[st];
+    // ---- luma, 4x4 transform: two macroblocks per pass ----
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      if (2 * p < n4) {
+        const uint32_t m = (list >> (4 * (2 * p + (lane >> 4)))) & 15u;
+        const uint32_t mm = la[p] ? m : 0u;
+        const uint32_t h = ws.hdr[mm];
+        const int qp = (int)((h >> 8) & 0xffu);
+        const bool i16 = (h & 0xffu) == 2u;
+        const uint4* src = reinterpret_cast<const uint4*>(lv + mm * DRYV_COEFFS_PER_MB + (lane & 15) * 16);
+        const uint4 c0 = src[0], c1 = src[1];
+        int dcv = 0;
+        if (__any_sync(0xffffffffu, la[p] && i16)) dcv = luma_dc16(tab, lc, lane, (int)(int16_t)(c0.x & 0xffffu), qp);
+        uint32_t out[8];
+        pass4x4_regs(tab, a.tables, c0, c1, qp, i16, dcv, la[p], out);
+        if (la[p]) {
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            __stcs(reinterpret_cast<uint32_t*>(pout + lo[p] + (size_t)i * strideY), add_clip4(out[2 * i], out[2 * i + 1], pl[p][i]));
+        }
       }
+    }
+    // ---- chroma: the 8 blocks of each of the four macroblocks in one pass ----
+    {
+      const int mm = ca ? (lane >> 3) : 0;
+      int q = (int)((ws.hdr[mm] >> 8) & 0xffu) + ((lane & 4) ? a.cr_off : a.cb_off);
+      q = min(max(q, 0), 51);
+      const int qpc = tab.qpc[q];  // transform.rs:194-216
+      const uint4* src = reinterpret_cast<const uint4*>(lv + mm * DRYV_COEFFS_PER_MB + 256 + (lane & 7) * 16);
+      const uint4 c0 = src[0], c1 = src[1];
+      const int dcv = chroma_dc(tab, lane, (int)(int16_t)(c0.x & 0xffffu), qpc);
+      uint32_t out[8];
+      pass4x4_regs(tab, a.tables, c0, c1, qpc, true, dcv, ca, out);
+      if (ca) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          __stcs(reinterpret_cast<uint32_t*>(pout + co + (size_t)i * strideC), add_clip4(out[2 * i], out[2 * i + 1], pc[i]));
+      }
+    }
+    // ---- luma, 8x8 transform: one macroblock per pass, through the residual tile; lane = (row r, half h): 8 samples ----
+    for (uint32_t left = m8; left;) {
+      const int m = __ffs(left) - 1;
+      left &= left - 1;
+      const size_t o = ybase + 16u * (uint32_t)m + (size_t)(lane >> 1) * strideY + 8 * (lane & 1);
+      const uint2 pv = __ldg(reinterpret_cast<const uint2*>(pin + o));
+      pass8x8(tab, lc, lane, lv + m * DRYV_COEFFS_PER_MB, ws.scratch, (int)((ws.hdr[m] >> 8) & 0xffu), ws.res_luma);
+      const uint2* rp = reinterpret_cast<const uint2*>(&ws.res_luma[(lane >> 1) * kResLumaStride + 8 * (lane & 1)]);
+      const uint2 r0 = rp[0], r1 = rp[1];
+      __stcs(reinterpret_cast<uint2*>(pout + o), make_uint2(add_clip4(r0.x, r0.y, pv.x), add_clip4(r1.x, r1.y, pv.y)));
+      __syncwarp();
     }
     __syncwarp();
     cur = nxt;

@@ -322,9 +322,10 @@ __device__ __forceinline__ ResLane make_res_lane(int lane, const DeviceTables& t
 // The rare lanes of a pass: blocks outside the packed range and qP without a byte-scale form. A real function, so that it
 // exists once and stays out of the instruction stream of the passes (the kernels are sensitive to code size); everything
 // is recomputed from the levels, so nothing but registers crosses the call.
-__device__ __noinline__ void pass4x4_wide(const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl, bool dc_pass, int dcv,
-                                          uint16_t* dst, int stride) {
-  if (!dst) return;
+struct Out8 {
+  uint4 a, b;
+};
+__device__ __noinline__ Out8 pass4x4_wide(const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl, bool dc_pass, int dcv) {
   const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
   const int4* tp = reinterpret_cast<const int4*>(&gtab->t4[qpl][0]);
   const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
@@ -332,28 +333,43 @@ __device__ __noinline__ void pass4x4_wide(const DeviceTables* gtab, uint4 c0, ui
   const int qpd = qpl / 6;
   uint32_t out[8];
   block4x4_wide(cw, tt, qpd < 4 ? 4 - qpd : 0, dc_pass, dcv, out);
-#pragma unroll
-  for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(dst + i * stride) = make_uint2(out[2 * i], out[2 * i + 1]);
+  Out8 r;
+  r.a = make_uint4(out[0], out[1], out[2], out[3]);
+  r.b = make_uint4(out[4], out[5], out[6], out[7]);
+  return r;
 }
 
-// One pass of 4x4 blocks, one per lane. One copy in each kernel (luma and chroma passes call it).
-//   c0, c1   the lane's 16 levels;  qpl its qP (QP'Y or QPc);  dc_pass / dcv: see block4x4_fast
-//   dst      the block's first residual field, `stride` fields per sample row (20 luma, 8 chroma); null: lane idle
+// One pass of 4x4 blocks, one per lane, result in registers: out[2 * i + jp] = samples (2 jp, 2 jp + 1) of row i of the
+// lane's block as biased residual fields.
+//   c0, c1   the lane's 16 levels;  qpl its qP (QP'Y or QPc);  dc_pass / dcv: see block4x4_fast;  active: the lane has a block
 //   tab: the shared-memory copy (residual part), gtab: the whole table in global memory (t4, for qP without a byte form)
-__device__ __forceinline__ void pass4x4_body(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
-                                             bool dc_pass, int dcv, uint16_t* dst, int stride) {
+__device__ __forceinline__ void pass4x4_regs(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
+                                             bool dc_pass, int dcv, bool active, uint32_t out[8]) {
   const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-  uint32_t out[8];
   const int e = tab.t4b_e[qpl];
   const uint4* bp = reinterpret_cast<const uint4*>(&tab.t4b[qpl][0]);
   const uint4 b0 = bp[0], b1 = bp[1];
   const uint32_t bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   const bool ok = block4x4_fast(cw, bs, e & 7, dc_pass, dcv, out) && e != 0xff;
-  if (dst && ok) {
+  if (__any_sync(0xffffffffu, active && !ok)) {
+    const Out8 w = pass4x4_wide(gtab, c0, c1, qpl, dc_pass, dcv);
+    if (!ok) {
+      out[0] = w.a.x; out[1] = w.a.y; out[2] = w.a.z; out[3] = w.a.w;
+      out[4] = w.b.x; out[5] = w.b.y; out[6] = w.b.z; out[7] = w.b.w;
+    }
+  }
+}
+
+// The same with the result stored to a residual tile in shared memory.
+//   dst      the block's first residual field, `stride` fields per sample row (20 luma, 8 chroma); null: lane idle
+__device__ __forceinline__ void pass4x4_body(const DeviceTables& tab, const DeviceTables* gtab, uint4 c0, uint4 c1, int qpl,
+                                             bool dc_pass, int dcv, uint16_t* dst, int stride) {
+  uint32_t out[8];
+  pass4x4_regs(tab, gtab, c0, c1, qpl, dc_pass, dcv, dst != nullptr, out);
+  if (dst) {
 #pragma unroll
     for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(dst + i * stride) = make_uint2(out[2 * i], out[2 * i + 1]);
   }
-  if (__any_sync(0xffffffffu, dst && !ok)) pass4x4_wide(gtab, c0, c1, qpl, dc_pass, dcv, ok ? nullptr : dst, stride);
 }
 // The wavefront kernel calls the pass (one copy for the luma and the chroma passes: the kernel sits at the capacity of the
 // instruction cache, profiles/r02_ifetch.txt); the residual-only kernel inlines it (a call drains the scoreboard, which

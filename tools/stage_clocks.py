@@ -16,7 +16,7 @@ frames = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 so = os.path.join(recon.CSRC, "libdryv_recon_clocks.so")
 subprocess.check_call(["/usr/local/cuda/bin/nvcc"] + recon.NVCC_FLAGS + ["-DDRYV_STAGE_CLOCKS",
                       os.path.join(recon.CSRC, "recon.cu"), os.path.join(recon.CSRC, "recon_tables.cpp"),
-                      os.path.join(recon.CSRC, "levels_pack.cpp"), os.path.join(recon.CSRC, "cabac_host.cpp"), "-o", so])
+                      os.path.join(recon.CSRC, "levels_pack.cpp"), os.path.join(recon.CSRC, "cabac_host.cpp"), os.path.join(recon.CSRC, "multi.cpp"), "-o", so])
 recon.LIB_PATH = so
 ctx = recon.ReconContext(0)
 pp = PicParams.make(120, 68)

@@ -92,6 +92,17 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                "l"(gmem_src), "r"(bytes), "r"(b)
                : "memory");
 }
+// Ampere-style alternative for the level fetch (development knob DRYV_LEVEL_CPASYNC): every lane copies 16 bytes per
+// instruction, completion through cp.async groups
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#ifndef DRYV_LEVEL_CPASYNC
+#define DRYV_LEVEL_CPASYNC 0
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
   const uint32_t addr = smem_u32(b);
   asm volatile(
@@ -481,13 +492,33 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
       uint8_t* c_st = a.out + (size_t)frame * n_mb * 384 + n_mb * 256 + (size_t)((lane >> 3) & 1) * n_mb * 64 +
                       (size_t)(8 * row + (lane & 7)) * strideC;
       unsigned long long lvc = 0;
+#ifndef DRYV_CHROMA_LAG
+#define DRYV_CHROMA_LAG 0
+#endif
+      if (DRYV_CHROMA_LAG > 0 && availB) {
+        // Chroma start lag (development knob): the chroma walks of neighbouring rows run in lock-step (each macroblock waits
+        // for the line the row above publishes a moment earlier); starting a row only when the row above is this many
+        // macroblocks into its chroma walk gives the waits some slack to fall into.
+        const unsigned long long* far = c_above + (size_t)min(DRYV_CHROMA_LAG, W - 1) * kLineWords;
+        unsigned long long vf = 0;
+        if (c_lane) vf = ld_relaxed_gpu_u64(far);
+        wait_line_words(far, vf, c_lane, tag, true, a.status, dead, pace_addr);
+      }
       if (availB && c_lane) lvc = ld_relaxed_gpu_u64(c_above);
 
       const int16_t* const lv_row = a.coeff + mb_row0 * DRYV_COEFFS_PER_MB;
       auto fetch = [&](int g, unsigned k) {  // levels of group g of this row -> stage k & 1
         const int nn = min(kGroupMbs, W - g * kGroupMbs);
-        bulk_load(ts.lv[k & 1], lv_row + (size_t)g * (kGroupMbs * DRYV_COEFFS_PER_MB), (uint32_t)nn * (DRYV_COEFFS_PER_MB * 2),
-                  &ts.lvfull[k & 1]);
+#if DRYV_LEVEL_CPASYNC
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(lv_row + (size_t)g * (kGroupMbs * DRYV_COEFFS_PER_MB));
+        uint8_t* dst = reinterpret_cast<uint8_t*>(ts.lv[k & 1]);
+        for (int o = lane * 16; o < nn * (DRYV_COEFFS_PER_MB * 2); o += 512) cp_async_16(dst + o, src + o);
+        cp_async_commit();
+#else
+        if (lane == 0)
+          bulk_load(ts.lv[k & 1], lv_row + (size_t)g * (kGroupMbs * DRYV_COEFFS_PER_MB), (uint32_t)nn * (DRYV_COEFFS_PER_MB * 2),
+                    &ts.lvfull[k & 1]);
+#endif
       };
       auto load_hdr = [&](int g) -> uint32_t {
         const int x = g * kGroupMbs + (lane & 3);
@@ -497,14 +528,18 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         const int x = g * kGroupMbs + m_mb;
         return (m_lane && x < W) ? ld_relaxed_gpu_u64(a.modes + (mb_row0 + x) * kModeWords + (lane & 1)) : 0ull;
       };
-      if (lane == 0) fetch(0, lvw);
+      fetch(0, lvw);
       uint32_t hv = load_hdr(0);
       unsigned long long mv = load_modes(0);
 
       for (int g = 0; g < gpr; g++) {
         const int x0 = g * kGroupMbs, n = min(kGroupMbs, W - x0);
         const int stage = (int)(lvw & 1u);
-        if (g + 1 < gpr && lane == 0) fetch(g + 1, lvw + 1);  // the other stage held group g - 1: consumed
+#ifndef DRYV_FETCH_LATE
+#define DRYV_FETCH_LATE 1
+#endif
+        if (!DRYV_FETCH_LATE && g + 1 < gpr) fetch(g + 1, lvw + 1);  // the other stage held group g - 1: consumed
+        CLK_MARK(6);  // level fetch issued
         // ---- headers of the group ----
         uint32_t v = hv;
         const unsigned long long mvc = mv;
@@ -512,6 +547,7 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
           hv = load_hdr(g + 1);
           mv = load_modes(g + 1);
         }
+        CLK_MARK(7);  // loads of the next group's headers / mode records issued
         if (v > hdr_lim) {  // I_PCM / inter / out-of-range syntax: flagged, never decoded
           unsupported = true;
           v = (lane >> 2) == 2 ? (v & 3u) : hdr_lim;
@@ -534,7 +570,13 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         GroupSlot& G = ts.grp[gs];
         if (use > 0) bar_sync_empty(bar0 + gs);
         CLK_MARK(1);  // wait for a free slot
+#if DRYV_LEVEL_CPASYNC
+        if (g + 1 < gpr) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncwarp();
+#else
         mbar_wait(&ts.lvfull[stage], (lvw >> 1) & 1u);
+#endif
 #ifndef DRYV_EXP_NO_RESID  // (experiment: how fast is each role with the other one's code out of the instruction cache)
         residual_group<false>(tab, a.tables, lc, lane, ts.hdr, m4, m8, ts.lv[stage], n, reinterpret_cast<int*>(&ts.cres[0][0]),
                        G.mb[0].res, (int)(sizeof(MbSlot) / sizeof(uint16_t)), &ts.cres[0][0], kResChromaMb, a.cb_off,
@@ -579,6 +621,10 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         __syncwarp();
         if (lane == 0) mbar_arrive(&ts.full[gs]);
         gn++;
+        // The next group's levels: issuing the bulk copy costs the issuing warp ~1200 cycles (stage clocks), so it is issued
+        // here, in front of the chroma walk, whose waits for the row above absorb it; the copy still has the whole chroma
+        // phase of this group to land. (lvw already counts this group: the next fetch is number lvw, its stage the other one.)
+        if (DRYV_FETCH_LATE && g + 1 < gpr) fetch(g + 1, lvw);
         CLK_MARK(4);  // hand-off
 
         // ---- chroma of the group's macroblocks: prediction needs line x of the row above (no top-right), so the chroma
@@ -623,7 +669,6 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
           CLK_MARK(5);  // chroma prediction + store + carry
         }
       }
-      CLK_MARK(7);  // row change
     }
     CLK_FLUSH(0);
     // no more rows: tell the pixel warp

@@ -41,8 +41,8 @@ nmb = frames * pp.n_mb
 cls = np.where(b.mb_type != 0, 2, b.transform_size_8x8_flag)
 n4, n8, n16 = [(cls == k).sum() for k in (0, 1, 2)]
 print(f"frames {frames}, {nmb} MBs ({n4} I4x4, {n8} I8x8, {n16} I16x16)")
-fn = ["level fetch + header", "wait free slot (bar.sync, deferred)", "residual", "wait chroma line (above)",
-      "mode record + tap rows + hand-off", "chroma pred + store + carry", "-", "row change"]
+fn = ["headers (shuffles, masks)", "wait free slot (bar.sync, deferred)", "wait levels + residual", "wait chroma line (above)",
+      "mode record + tap rows + hand-off", "chroma pred + store + carry", "issue level fetch (bulk copy)", "issue next headers/modes loads"]
 ln = ["wait filled slot", "row start", "wait luma line (above)", "I4x4 pred (per I4x4 MB)", "I8x8 pred (per I8x8 MB)",
       "I16x16 pred (per I16 MB)", "-", "publish + store + carry"]
 tot_f = sum(clk[:8]) / nmb

@@ -721,17 +721,22 @@ def main():
 
         # side measurement, SURVEY.md §8(f) next-4: the optional in-loop deblocking post-pass over the batch's pictures, in
         # place (not part of dryv parity: the reference has no filter). Parity of the kernel: tests/test_deblock_oracle.py.
+        # Every timed launch filters a FRESH copy of the reconstruction (filtering the same buffer again and again would time
+        # ever smoother pictures, on which the filter switches itself off); the copy is outside the event pair.
         d_db = d_outs[0].clone()
-        for _ in range(2):
-            ctx.deblock_device(dsoa, d_db, 0, 0, sptr)
-        torch.cuda.synchronize(dev)
-        a0.record(stream)
-        for _ in range(args.steps):
-            ctx.deblock_device(dsoa, d_db, 0, 0, sptr)
-        a1.record(stream)
-        torch.cuda.synchronize(dev)
+        dts = []
+        with torch.cuda.stream(stream):
+            for i in range(2 + args.steps):
+                d_db.copy_(d_outs[0])
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record(stream)
+                ctx.deblock_device(dsoa, d_db, 0, 0, sptr)
+                b1.record(stream)
+                torch.cuda.synchronize(dev)
+                if i >= 2:
+                    dts.append(b0.elapsed_time(b1))
         ctx.wait()
-        dms = a0.elapsed_time(a1) / args.steps
+        dms = sum(dts) / len(dts)
         dbytes = n_mb_step * (384 + 384 + 2)   # every sample read and written once, qp + transform flag per macroblock
         line["deblock"] = {"workload": f"H.264 8.7 deblocking of the {n_frames} reconstructed pictures, in place "
                                        "(dryv_recon_deblock_device; intra: bS 4 / 3 on every edge)",

@@ -6,20 +6,31 @@
 // The standard filters macroblocks in raster order, vertical edges then horizontal edges, each macroblock reading and
 // changing up to three samples of its left and upper neighbours. That makes macroblock (x, y) depend on (x-1, y), (x, y-1)
 // and (x+1, y-1) — the same x + 2y wavefront as intra prediction. One warp walks one macroblock row (rows dealt by an atomic
-// ticket in row-major order over the pictures, so a row only ever waits on a lower ticket); a per-row progress counter in
-// global memory says how many macroblocks of the row are finished. Inside a macroblock: lanes 0..15 take the sixteen luma
-// lines, lanes 16..31 the eight lines of Cb and of Cr; the macroblock and its margins sit in a shared-memory tile.
+// ticket in row-major order over the pictures, so a row only ever waits on a lower ticket). Data flow of a row:
+//   * its own macroblocks come from global memory exactly as the reconstruction left them, one macroblock ahead of use;
+//   * the right four columns of a macroblock stay in the shared-memory tile as the left margin of the next one;
+//   * the bottom four luma rows and two chroma rows of a macroblock go DOWN to the next row as 24 tagged 64-bit words
+//     (payload | launch tag << 32), published once the macroblock on the right has filtered its left edge — the words
+//     carry the samples themselves, so there is no counter, no fence and no second read of global memory;
+//   * the lower row writes the upper macroblock's last three luma rows / last chroma row after filtering across the edge;
+//     the upper row never writes them (the last picture row writes its own), so every byte has one writer per phase and
+//     the two writes a row makes to the same word (macroblock, then its right columns one macroblock later) come from the
+//     same thread in program order.
+// Inside a macroblock: lanes 0..15 take the sixteen luma lines, lanes 16..31 the eight lines of Cb and of Cr.
 #pragma once
 #include <stdint.h>
 
 namespace dryv {
 
+constexpr int kDbLineWords = 24;  // 4 luma rows x 4 words, then Cb and Cr: 2 rows x 2 words each
+
 struct DeblockArgs {
   uint8_t* yuv;             // pictures, in place
   const uint8_t* qp;        // per macroblock
   const uint8_t* t8x8;      // per macroblock
-  int* progress;            // [n_frames * H] finished macroblocks per row, zeroed before the launch
+  unsigned long long* line; // [n_frames * H * W][kDbLineWords] tagged bottom rows handed to the row below
   unsigned int* ticket;     // row ticket, zeroed before the launch
+  uint32_t tag;             // this launch's tag (never 0; the buffer starts zeroed)
   int* status;              // sticky STATUS_*
   int W, H, n_frames;
   int cb_off, cr_off;       // chroma_qp_index_offset, second_chroma_qp_index_offset
@@ -96,7 +107,10 @@ constexpr int kDbWarps = 4;          // rows (warps) per CTA
 struct DeblockTile {
   alignas(16) uint8_t luma[20 * kDbLumaStride];
   alignas(16) uint8_t chroma[2][12 * kDbChromaStride];
+  uint32_t pend[kDbLineWords];  // bottom rows of the previous macroblock, waiting for this one's left-edge filter
 };
+
+__device__ __forceinline__ uint32_t& db_word(uint8_t* p) { return *reinterpret_cast<uint32_t*>(p); }
 
 __global__ void __launch_bounds__(32 * kDbWarps, 8) deblock_wavefront_kernel(const DeblockArgs a) {
   __shared__ DeblockTile tiles[kDbWarps];
@@ -107,6 +121,12 @@ __global__ void __launch_bounds__(32 * kDbWarps, 8) deblock_wavefront_kernel(con
   const size_t lw = 16 * (size_t)W, cw = 8 * (size_t)W;
   const size_t luma_bytes = lw * 16 * H, frame_bytes = luma_bytes * 3 / 2;
   const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
+  const unsigned long long tag64 = (unsigned long long)a.tag << 32;
+  // lane roles: luma line `lane` (lanes 0..15); chroma plane cpl, line cln (lanes 16..31)
+  const bool is_luma = lane < 16;
+  const int cpl = (lane >> 3) & 1, cln = lane & 7;
+  // line-word roles (lanes 0..23): luma row lane>>2 word lane&3; chroma plane wpl row wr word wh
+  const int wk = lane - 16, wpl = (wk >> 2) & 1, wr = (wk >> 1) & 1, wh = wk & 1;
   for (;;) {
     if (lane == 0) s_row[wid] = atomicAdd(a.ticket, 1u);
     __syncwarp();
@@ -114,80 +134,100 @@ __global__ void __launch_bounds__(32 * kDbWarps, 8) deblock_wavefront_kernel(con
     __syncwarp();
     if (row >= total_rows) return;
     const int f = (int)(row / (unsigned)H), my = (int)(row % (unsigned)H);
+    const bool last_row = my == H - 1;
     uint8_t* Y = a.yuv + (size_t)f * frame_bytes;
-    uint8_t* C[2] = {Y + luma_bytes, Y + luma_bytes + luma_bytes / 4};
-    const uint8_t* qp_row = a.qp + ((size_t)f * H + my) * W;
-    const uint8_t* t8_row = a.t8x8 + ((size_t)f * H + my) * W;
-    const volatile int* above = my > 0 ? a.progress + row - 1 : nullptr;
+    uint8_t* Cp = Y + luma_bytes + (cpl ? luma_bytes / 4 : 0);
+    uint8_t* own = is_luma ? Y + (size_t)(16 * my + lane) * lw : Cp + (size_t)(8 * my + cln) * cw;  // this lane's line
+    uint8_t* own_tile = is_luma ? t.luma + (4 + lane) * kDbLumaStride : t.chroma[cpl] + (4 + cln) * kDbChromaStride;
+    const bool own_stored = last_row || (is_luma ? lane < 13 : cln < 7);
+    const uint8_t* qp_row = a.qp + (size_t)row * W;
+    const uint8_t* t8_row = a.t8x8 + (size_t)row * W;
+    unsigned long long* line_mine = a.line + (size_t)row * W * kDbLineWords + lane;
+    const unsigned long long* line_above = line_mine - (size_t)W * kDbLineWords;
+    // where this lane's line word lives in the tile: top margin (read side) and bottom rows (write side)
+    uint8_t* top_dst = is_luma ? t.luma + (lane >> 2) * kDbLumaStride + 4 + 4 * (lane & 3)
+                               : t.chroma[wpl] + (2 + wr) * kDbChromaStride + 4 + 4 * wh;
+    uint8_t* bot_src = is_luma ? t.luma + (16 + (lane >> 2)) * kDbLumaStride + 4 + 4 * (lane & 3)
+                               : t.chroma[wpl] + (10 + wr) * kDbChromaStride + 4 + 4 * wh;
+    // the same rows' left-margin word: the previous macroblock's last word after this macroblock's left-edge filter
+    uint8_t* bot_left = is_luma ? t.luma + (16 + (lane >> 2)) * kDbLumaStride : t.chroma[wpl] + (10 + wr) * kDbChromaStride;
+    const bool patched = is_luma ? (lane & 3) == 3 : wh == 1;
     bool dead = false;
+    uint4 cy = make_uint4(0, 0, 0, 0);
+    int nq = 0, nt8 = 0, nqup = -1;
+    unsigned long long tv = 0;
+    auto fetch = [&](int mx) {  // macroblock mx of this row: samples, QPs, and a first look at the words from above
+      if (is_luma) cy = __ldcg(reinterpret_cast<const uint4*>(own + 16 * mx));
+      else {
+        const uint2 c = __ldcg(reinterpret_cast<const uint2*>(own + 8 * mx));
+        cy.x = c.x;
+        cy.y = c.y;
+      }
+      nq = qp_row[mx];
+      nt8 = t8_row[mx];
+      if (my > 0) {
+        nqup = qp_row[mx - W];
+        if (lane < kDbLineWords) tv = ld_relaxed_gpu_u64(line_above + (size_t)mx * kDbLineWords);
+      }
+    };
+    fetch(0);
+    int q_left = -1;
     for (int mx = 0; mx < W; mx++) {
-      // the row above must have finished the upper-right neighbour (its left edge changes samples this macroblock reads)
-      if (above) {
-        const int need = min(mx + 2, W);
-        if (lane == 0 && !dead) {
-          unsigned spins = 0;
-          while (*above < need) {
-            if (++spins > (1u << 24) || ((spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(a.status) == STATUS_WATCHDOG)) {
-              atomicExch(a.status, STATUS_WATCHDOG);
-              dead = true;
-              break;
-            }
+      const int q = nq, q_up = nqup, step = nt8 ? 8 : 4;
+      // ---- this macroblock into the tile; the words from above into the top margin
+      db_word(own_tile + 4) = cy.x;
+      db_word(own_tile + 8) = cy.y;
+      if (is_luma) {
+        db_word(own_tile + 12) = cy.z;
+        db_word(own_tile + 16) = cy.w;
+      }
+      if (my > 0 && lane < kDbLineWords) {
+        const unsigned long long* p = line_above + (size_t)mx * kDbLineWords;
+        unsigned spins = 0;
+        while ((uint32_t)(tv >> 32) != a.tag) {
+          if (++spins > (1u << 22) || ((spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(a.status) == STATUS_WATCHDOG)) {
+            atomicExch(a.status, STATUS_WATCHDOG);
+            dead = true;
+            break;
           }
+          tv = ld_relaxed_gpu_u64(p);
         }
-        dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
-        __threadfence();
+        db_word(top_dst) = (uint32_t)tv;
       }
-      const int q = qp_row[mx];
-      const int q_left = mx > 0 ? qp_row[mx - 1] : -1;
-      const int q_up = my > 0 ? qp_row[mx - W] : -1;
-      const int step = t8_row[mx] ? 8 : 4;
-      // ---- load the macroblock with a 4-sample (chroma: 2 of 4) margin on the left and on top; L2 loads: the margins were
-      // written by other SMs
-      // (32-bit words of luma, 16-bit words of chroma: the margins start 4 / 2 samples left of the macroblock)
-      for (int i = lane; i < 20 * 5; i += 32) {
-        const int r = i / 5, wc = i % 5;
-        const int gy = 16 * my + r - 4, gx = 16 * mx + 4 * wc - 4;
-        *reinterpret_cast<uint32_t*>(t.luma + r * kDbLumaStride + 4 * wc) =
-            (gy >= 0 && gx >= 0) ? __ldcg(reinterpret_cast<const uint32_t*>(Y + (size_t)gy * lw + gx)) : 0u;
-      }
-      for (int i = lane; i < 2 * 10 * 5; i += 32) {
-        const int pl = i / 50, r = (i % 50) / 5, hc = i % 5;
-        const int gy = 8 * my + r - 2, gx = 8 * mx + 2 * hc - 2;
-        *reinterpret_cast<uint16_t*>(t.chroma[pl] + (r + 2) * kDbChromaStride + 2 * hc + 2) =
-            (gy >= 0 && gx >= 0) ? __ldcg(reinterpret_cast<const uint16_t*>(C[pl] + (size_t)gy * cw + gx)) : (uint16_t)0;
-      }
+      if (mx + 1 < W) fetch(mx + 1);
       __syncwarp();
       // ---- vertical edges, left to right: lane = line
-      if (lane < 16) {
-        uint8_t* line = t.luma + (4 + lane) * kDbLumaStride + 4;
+      if (is_luma) {
+        uint8_t* ln = own_tile + 4;
         for (int e = 0; e < 16; e += step) {
           if (e == 0 && q_left < 0) continue;
-          deblock_line(line + e, 1, e == 0, false, e == 0 ? (q + q_left + 1) >> 1 : q, a.off_a, a.off_b);
+          deblock_line(ln + e, 1, e == 0, false, e == 0 ? (q + q_left + 1) >> 1 : q, a.off_a, a.off_b);
         }
       } else {
-        const int pl = (lane - 16) >> 3, ln = lane & 7;
-        const int off = pl ? a.cr_off : a.cb_off;
+        const int off = cpl ? a.cr_off : a.cb_off;
         const int qc = kDbQpc[db_clip(q + off, 0, 51)];
-        uint8_t* line = t.chroma[pl] + (4 + ln) * kDbChromaStride + 4;
+        uint8_t* ln = own_tile + 4;
         for (int e = 0; e < 8; e += 4) {
           if (e == 0 && q_left < 0) continue;
           const int qa = e == 0 ? (qc + kDbQpc[db_clip(q_left + off, 0, 51)] + 1) >> 1 : qc;
-          deblock_line(line + e, 1, e == 0, true, qa, a.off_a, a.off_b);
+          deblock_line(ln + e, 1, e == 0, true, qa, a.off_a, a.off_b);
         }
       }
       __syncwarp();
+      // ---- the previous macroblock is finished down to its last rows: hand those to the row below
+      if (mx > 0 && !last_row && lane < kDbLineWords)
+        st_relaxed_gpu_u64(line_mine + (size_t)(mx - 1) * kDbLineWords, tag64 | (patched ? db_word(bot_left) : t.pend[lane]));
       // ---- horizontal edges, top to bottom: lane = column
-      if (lane < 16) {
+      if (is_luma) {
         uint8_t* col = t.luma + 4 * kDbLumaStride + 4 + lane;
         for (int e = 0; e < 16; e += step) {
           if (e == 0 && q_up < 0) continue;
           deblock_line(col + e * kDbLumaStride, kDbLumaStride, e == 0, false, e == 0 ? (q + q_up + 1) >> 1 : q, a.off_a, a.off_b);
         }
       } else {
-        const int pl = (lane - 16) >> 3, cn = lane & 7;
-        const int off = pl ? a.cr_off : a.cb_off;
+        const int off = cpl ? a.cr_off : a.cb_off;
         const int qc = kDbQpc[db_clip(q + off, 0, 51)];
-        uint8_t* col = t.chroma[pl] + 4 * kDbChromaStride + 4 + cn;
+        uint8_t* col = t.chroma[cpl] + 4 * kDbChromaStride + 4 + cln;
         for (int e = 0; e < 8; e += 4) {
           if (e == 0 && q_up < 0) continue;
           const int qa = e == 0 ? (qc + kDbQpc[db_clip(q_up + off, 0, 51)] + 1) >> 1 : qc;
@@ -195,37 +235,34 @@ __global__ void __launch_bounds__(32 * kDbWarps, 8) deblock_wavefront_kernel(con
         }
       }
       __syncwarp();
-      // ---- write back what may have changed: the macroblock, three columns of the left neighbour (this macroblock's rows),
-      // three rows of the upper neighbour (this macroblock's columns); chroma: one column / one row
-      // (whole words: the outermost margin sample of a word is written back unchanged, and nobody else touches it before
-      // this macroblock is published)
-      for (int i = lane; i < 16 * 5; i += 32) {
-        const int r = i / 5, wc = i % 5;
-        if (wc == 0 && mx == 0) continue;
-        *reinterpret_cast<uint32_t*>(Y + (size_t)(16 * my + r) * lw + 16 * mx + 4 * wc - 4) =
-            *reinterpret_cast<const uint32_t*>(t.luma + (4 + r) * kDbLumaStride + 4 * wc);
+      // ---- stores: this lane's line of the macroblock (not the rows the next picture row still filters), the left
+      // neighbour's last word of the same line, and the upper neighbour's last rows
+      if (own_stored) {
+        if (is_luma)
+          *reinterpret_cast<uint4*>(own + 16 * mx) =
+              make_uint4(db_word(own_tile + 4), db_word(own_tile + 8), db_word(own_tile + 12), db_word(own_tile + 16));
+        else
+          *reinterpret_cast<uint2*>(own + 8 * mx) = make_uint2(db_word(own_tile + 4), db_word(own_tile + 8));
+        if (mx > 0) db_word(own + (is_luma ? 16 : 8) * mx - 4) = db_word(own_tile);
       }
-      if (my > 0 && lane < 12) {
-        const int r = lane / 4 - 3, wc = lane % 4;
-        *reinterpret_cast<uint32_t*>(Y + (size_t)(16 * my + r) * lw + 16 * mx + 4 * wc) =
-            *reinterpret_cast<const uint32_t*>(t.luma + (4 + r) * kDbLumaStride + 4 + 4 * wc);
+      if (my > 0 && lane < 16) {
+        if (lane < 12)
+          db_word(Y + (size_t)(16 * my - 3 + (lane >> 2)) * lw + 16 * mx + 4 * (lane & 3)) =
+              db_word(t.luma + (1 + (lane >> 2)) * kDbLumaStride + 4 + 4 * (lane & 3));
+        else {
+          const int pl = (lane >> 1) & 1, h = lane & 1;
+          db_word(Y + luma_bytes + (pl ? luma_bytes / 4 : 0) + (size_t)(8 * my - 1) * cw + 8 * mx + 4 * h) =
+              db_word(t.chroma[pl] + 3 * kDbChromaStride + 4 + 4 * h);
+        }
       }
-      for (int i = lane; i < 2 * 8 * 5; i += 32) {
-        const int pl = i / 40, r = (i % 40) / 5, hc = i % 5;
-        if (hc == 0 && mx == 0) continue;
-        *reinterpret_cast<uint16_t*>(C[pl] + (size_t)(8 * my + r) * cw + 8 * mx + 2 * hc - 2) =
-            *reinterpret_cast<const uint16_t*>(t.chroma[pl] + (4 + r) * kDbChromaStride + 2 + 2 * hc);
-      }
-      if (my > 0 && lane < 8) {
-        const int pl = lane >> 2, hc = lane & 3;
-        *reinterpret_cast<uint16_t*>(C[pl] + (size_t)(8 * my - 1) * cw + 8 * mx + 2 * hc) =
-            *reinterpret_cast<const uint16_t*>(t.chroma[pl] + 3 * kDbChromaStride + 4 + 2 * hc);
-      }
-      // ---- publish: every lane's stores are visible before the counter moves
-      __threadfence();
+      // ---- keep the last rows for the hand-off, and the right columns as the next macroblock's left margin
+      if (lane < kDbLineWords) t.pend[lane] = db_word(bot_src);
+      db_word(own_tile) = db_word(own_tile + (is_luma ? 16 : 8));
+      q_left = q;
       __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile int*>(a.progress + row) = mx + 1;
     }
+    if (!last_row && lane < kDbLineWords) st_relaxed_gpu_u64(line_mine + (size_t)(W - 1) * kDbLineWords, tag64 | t.pend[lane]);
+    if (__any_sync(0xffffffffu, dead)) return;
   }
 }
 

@@ -1282,9 +1282,11 @@ struct dryv_recon_ctx {
   bool surface_set = false;
   uint8_t* d_exp[kStages] = {};
   size_t exp_cap = 0;
-  // deblocking post-pass: per-row progress counters + row ticket; one launch of it at a time (guarded by db_done)
-  int* d_db_progress = nullptr;
-  size_t db_rows_cap = 0;
+  // deblocking post-pass: row ticket + the tagged words rows hand down; one launch of it at a time (guarded by db_done)
+  unsigned int* d_db_ticket = nullptr;
+  unsigned long long* d_db_line = nullptr;
+  size_t db_line_cap = 0;  // macroblocks
+  uint32_t db_tag = 0;
   cudaEvent_t db_done = nullptr;
   bool db_used = false;
   cudaStream_t pending_user = nullptr;
@@ -1615,7 +1617,8 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
     if (ctx->ctl[i].done) cudaEventDestroy(ctx->ctl[i].done);
   }
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
-  if (ctx->d_db_progress) cudaFree(ctx->d_db_progress);
+  if (ctx->d_db_ticket) cudaFree(ctx->d_db_ticket);
+  if (ctx->d_db_line) cudaFree(ctx->d_db_line);
   if (ctx->db_done) cudaEventDestroy(ctx->db_done);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -1875,43 +1878,62 @@ int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
                               int slice_alpha_c0_offset_div2, int slice_beta_offset_div2, uint8_t* d_yuv, void* cuda_stream) {
   if (!ctx) return DRYV_ERR_ARG;
   if (!pp_ok(pp) || !d_soa || !d_soa->qp || !d_soa->transform_size_8x8_flag || !d_yuv || n_frames == 0 ||
-      (reinterpret_cast<uintptr_t>(d_yuv) & 3u) || slice_alpha_c0_offset_div2 < -6 || slice_alpha_c0_offset_div2 > 6 ||
+      (reinterpret_cast<uintptr_t>(d_yuv) & 15u) || slice_alpha_c0_offset_div2 < -6 || slice_alpha_c0_offset_div2 > 6 ||
       slice_beta_offset_div2 < -6 || slice_beta_offset_div2 > 6)
     return fail(ctx, DRYV_ERR_ARG, "bad argument");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute[0];
-  const size_t rows = (size_t)n_frames * pp->pic_height_in_mbs;
-  if (rows + 1 > ctx->db_rows_cap) {  // [0]: the row ticket, [1 + r]: progress of row r
-    CU(cudaDeviceSynchronize());
-    if (ctx->d_db_progress) cudaFree(ctx->d_db_progress);
-    ctx->d_db_progress = nullptr;
-    ctx->db_rows_cap = 0;
-    CU(cudaMalloc(&ctx->d_db_progress, (rows + 1) * sizeof(int)));
-    ctx->db_rows_cap = rows + 1;
+  // the hand-off buffer takes 192 bytes per macroblock: long batches go through it in chunks of pictures
+  const size_t mbs_per_frame = (size_t)pp->pic_width_in_mbs * pp->pic_height_in_mbs;
+  const size_t frame_bytes = mbs_per_frame * 384;
+  constexpr size_t kDbMaxMbs = (size_t)512 << 20 >> 7;  // ~768 MB of words at most
+  const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_frames, kDbMaxMbs / mbs_per_frame));
+  if (!ctx->d_db_ticket) {
+    CU(cudaMalloc(&ctx->d_db_ticket, sizeof(unsigned int)));
   }
-  if (ctx->db_used) CU(cudaStreamWaitEvent(st, ctx->db_done, 0));  // the counters serve one launch at a time
-  CU(cudaMemsetAsync(ctx->d_db_progress, 0, (rows + 1) * sizeof(int), st));
-  dryv::DeblockArgs a;
-  memset(&a, 0, sizeof a);
-  a.yuv = d_yuv;
-  a.qp = d_soa->qp;
-  a.t8x8 = d_soa->transform_size_8x8_flag;
-  a.ticket = reinterpret_cast<unsigned int*>(ctx->d_db_progress);
-  a.progress = ctx->d_db_progress + 1;
-  a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
-  a.W = pp->pic_width_in_mbs;
-  a.H = pp->pic_height_in_mbs;
-  a.n_frames = (int)n_frames;
-  a.cb_off = pp->chroma_qp_index_offset;
-  a.cr_off = pp->second_chroma_qp_index_offset;
-  a.off_a = 2 * slice_alpha_c0_offset_div2;
-  a.off_b = 2 * slice_beta_offset_div2;
-  const size_t want = (rows + dryv::kDbWarps - 1) / dryv::kDbWarps, cap = (size_t)ctx->sm_count * 8;
-  dryv::deblock_wavefront_kernel<<<(unsigned)(want < cap ? want : cap), 32 * dryv::kDbWarps, 0, st>>>(a);
-  CU(cudaGetLastError());
+  if (chunk * mbs_per_frame > ctx->db_line_cap) {
+    CU(cudaDeviceSynchronize());
+    if (ctx->d_db_line) cudaFree(ctx->d_db_line);
+    ctx->d_db_line = nullptr;
+    ctx->db_line_cap = 0;
+    const size_t bytes = chunk * mbs_per_frame * dryv::kDbLineWords * sizeof(unsigned long long);
+    CU(cudaMalloc(&ctx->d_db_line, bytes));
+    CU(cudaMemset(ctx->d_db_line, 0, bytes));
+    ctx->db_line_cap = chunk * mbs_per_frame;
+    ctx->db_tag = 0;
+  }
+  if (ctx->db_used) CU(cudaStreamWaitEvent(st, ctx->db_done, 0));  // ticket and words serve one launch at a time
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += chunk) {
+    const uint32_t nf = std::min(chunk, n_frames - f0);
+    const size_t rows = (size_t)nf * pp->pic_height_in_mbs;
+    if (++ctx->db_tag == 0) {  // tag wrap: stale words could match again
+      CU(cudaMemsetAsync(ctx->d_db_line, 0, ctx->db_line_cap * dryv::kDbLineWords * sizeof(unsigned long long), st));
+      ctx->db_tag = 1;
+    }
+    CU(cudaMemsetAsync(ctx->d_db_ticket, 0, sizeof(unsigned int), st));
+    dryv::DeblockArgs a;
+    memset(&a, 0, sizeof a);
+    a.yuv = d_yuv + (size_t)f0 * frame_bytes;
+    a.qp = d_soa->qp + (size_t)f0 * mbs_per_frame;
+    a.t8x8 = d_soa->transform_size_8x8_flag + (size_t)f0 * mbs_per_frame;
+    a.line = ctx->d_db_line;
+    a.ticket = ctx->d_db_ticket;
+    a.tag = ctx->db_tag;
+    a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
+    a.W = pp->pic_width_in_mbs;
+    a.H = pp->pic_height_in_mbs;
+    a.n_frames = (int)nf;
+    a.cb_off = pp->chroma_qp_index_offset;
+    a.cr_off = pp->second_chroma_qp_index_offset;
+    a.off_a = 2 * slice_alpha_c0_offset_div2;
+    a.off_b = 2 * slice_beta_offset_div2;
+    const size_t want = (rows + dryv::kDbWarps - 1) / dryv::kDbWarps, cap = (size_t)ctx->sm_count * 8;
+    dryv::deblock_wavefront_kernel<<<(unsigned)(want < cap ? want : cap), 32 * dryv::kDbWarps, 0, st>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches++;
+  }
   CU(cudaEventRecord(ctx->db_done, st));
   ctx->db_used = true;
-  ctx->launches++;
   if (cuda_stream) {
     ctx->pending_user = st;
     ctx->pending_user_valid = true;

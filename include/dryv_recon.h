@@ -244,7 +244,7 @@ int dryv_recon_set_surface(dryv_recon_ctx* ctx, const dryv_surface* s);
  * The reference has no in-loop filter (README.md:15; it parses disable_deblocking_filter_idc and the two offsets in
  * slice/header.rs:609-640 and ignores them), so its output — and everything above in this header — is the unfiltered
  * reconstruction. For streams that ask for the filter this applies H.264 8.7 to n_frames reconstructed intra pictures IN
- * PLACE (device memory, 4-byte aligned, the dryv_recon_reconstruct_device layout): bS 4 on macroblock edges, 3 on transform edges, every
+ * PLACE (device memory, 16-byte aligned, the dryv_recon_reconstruct_device layout): bS 4 on macroblock edges, 3 on transform edges, every
  * edge filtered (disable_deblocking_filter_idc 0; with one slice per picture 2 is the same). d_soa: the batch's device
  * syntax buffers, of which qp and transform_size_8x8_flag are read. The offsets are the slice header's
  * slice_alpha_c0_offset_div2 / slice_beta_offset_div2 (-6..6). Asynchronous on `cuda_stream` (0: the context's own);

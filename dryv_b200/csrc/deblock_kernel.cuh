@@ -16,9 +16,16 @@
 //     the upper row never writes them (the last picture row writes its own), so every byte has one writer per phase and
 //     the two writes a row makes to the same word (macroblock, then its right columns one macroblock later) come from the
 //     same thread in program order.
-// Inside a macroblock: lanes 0..15 take the sixteen luma lines, lanes 16..31 the eight lines of Cb and of Cr.
+// A warp walks the same macroblock row of TWO pictures, one per half-warp (the pictures are independent, the control flow
+// is identical): the kernel is bound by instruction issue, and the packed filters of deblock_packed.cuh need only sixteen
+// lanes per macroblock — eight for luma, four for Cb, four for Cr, two lines (vertical edges) or two columns (horizontal
+// edges) per lane in the two 16-bit fields of a register. Per macroblock: the two lines of a lane are unpacked from the
+// row words (PRMT), the four vertical edges filtered in registers, the lines written to the shared-memory tile; then every
+// lane reads its two columns of the tile (rows -4..15), filters the four horizontal edges and writes them back.
 #pragma once
 #include <stdint.h>
+
+#include "deblock_packed.cuh"
 
 namespace dryv {
 
@@ -37,231 +44,257 @@ struct DeblockArgs {
   int off_a, off_b;         // FilterOffsetA / FilterOffsetB (2 * slice_*_offset_div2)
 };
 
-__constant__ uint8_t kDbAlpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13,
-                                     15, 17, 20, 22, 25, 28, 32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144,
-                                     162, 182, 203, 226, 255, 255};
-__constant__ uint8_t kDbBeta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4,
-                                    6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16,
-                                    17, 17, 18, 18};
-__constant__ uint8_t kDbTc0[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1,
-                                   1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 23, 25};  // bS = 3
-__constant__ uint8_t kDbQpc[52] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25,
-                                   26, 27, 28, 29, 29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38,
-                                   39, 39, 39, 39};
-
 __device__ __forceinline__ int db_clip(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-// one line of samples across one edge, 8.7.2.3 / 8.7.2.4: s points at q0, `step` is the distance between samples across the edge
-__device__ __forceinline__ void deblock_line(uint8_t* s, int step, bool strong, bool chroma, int qp_av, int off_a, int off_b) {
-  const int ia = db_clip(qp_av + off_a, 0, 51), ib = db_clip(qp_av + off_b, 0, 51);
-  const int alpha = kDbAlpha[ia], beta = kDbBeta[ib];
-  const int p0 = s[-step], p1 = s[-2 * step], q0 = s[0], q1 = s[step];
-  if (!(abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta)) return;
-  if (chroma) {
-    if (strong) {
-      s[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-      s[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-    } else {
-      const int tc = kDbTc0[ia] + 1;
-      const int d = db_clip((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-      s[-step] = (uint8_t)db_clip(p0 + d, 0, 255);
-      s[0] = (uint8_t)db_clip(q0 - d, 0, 255);
-    }
-    return;
-  }
-  const int p2 = s[-3 * step], q2 = s[2 * step];
-  const bool ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
-  if (strong) {
-    const bool small = abs(p0 - q0) < ((alpha >> 2) + 2);
-    if (ap && small) {
-      const int p3 = s[-4 * step];
-      s[-step] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-      s[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
-      s[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-    } else {
-      s[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-    }
-    if (aq && small) {
-      const int q3 = s[3 * step];
-      s[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-      s[step] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
-      s[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
-    } else {
-      s[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-    }
-  } else {
-    const int tc0 = kDbTc0[ia];
-    const int tc = tc0 + (ap ? 1 : 0) + (aq ? 1 : 0);
-    const int d = db_clip((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-    s[-step] = (uint8_t)db_clip(p0 + d, 0, 255);
-    s[0] = (uint8_t)db_clip(q0 - d, 0, 255);
-    if (ap) s[-2 * step] = (uint8_t)(p1 + db_clip((p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1, -tc0, tc0));
-    if (aq) s[step] = (uint8_t)(q1 + db_clip((q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1, -tc0, tc0));
-  }
-}
+__constant__ uint8_t kDbAlpha[52] = DRYV_DB_ALPHA;
+__constant__ uint8_t kDbBeta[52] = DRYV_DB_BETA;
+__constant__ uint8_t kDbTc0[52] = DRYV_DB_TC0_BS3;
+__constant__ uint8_t kDbQpc[52] = DRYV_DB_QPC;
 
-constexpr int kDbLumaStride = 20;    // 4 margin + 16
-constexpr int kDbChromaStride = 12;  // 4 margin (2 used) + 8
-constexpr int kDbWarps = 4;          // rows (warps) per CTA
+constexpr int kDbWarps = 4;  // warps per CTA
 
-struct DeblockTile {
-  alignas(16) uint8_t luma[20 * kDbLumaStride];
-  alignas(16) uint8_t chroma[2][12 * kDbChromaStride];
-  uint32_t pend[kDbLineWords];  // bottom rows of the previous macroblock, waiting for this one's left-edge filter
+// edge constants by table index, and the QP each lane kind filters with (luma: QPY; Cb / Cr: QPC of QPY + the offset)
+struct DbTables {
+  uint4 a[52];     // by indexA: ka, ks, tcb (luma), lo1 — see EdgeConst
+  uint32_t b[52];  // by indexB: kb
+  uint8_t qmap[3][52];
 };
+
+// one picture's macroblock and its margins: every row 16 bytes apart, rows -4..-1 are the upper neighbour's last rows
+struct DbHalf {
+  alignas(16) uint8_t luma[20 * 16];
+  alignas(16) uint8_t chroma[2][12 * 16];  // 8 bytes of a row used; rows -4, -3 unused
+  uint32_t patch[8];                       // the left neighbour's last word of its bottom rows after this macroblock's left edge
+  uint32_t pad[24];                        // the two halves of a warp 64 bytes apart modulo 128: their accesses share no bank
+};
+static_assert(sizeof(DbHalf) % 128 == 64, "half tiles must not alias in the banks");
 
 __device__ __forceinline__ uint32_t& db_word(uint8_t* p) { return *reinterpret_cast<uint32_t*>(p); }
 
-__global__ void __launch_bounds__(32 * kDbWarps, 8) deblock_wavefront_kernel(const DeblockArgs a) {
-  __shared__ DeblockTile tiles[kDbWarps];
+// two row words (4 samples of line A, of line B) -> four packed registers
+__device__ __forceinline__ void db_unpack4(uint32_t wa, uint32_t wb, uint32_t* r) {
+  const uint32_t lo = prmt(wa, wb, 0x6240), hi = prmt(wa, wb, 0x7351);
+  r[0] = prmt(lo, 0, 0x4140);
+  r[1] = prmt(hi, 0, 0x4140);
+  r[2] = prmt(lo, 0, 0x4342);
+  r[3] = prmt(hi, 0, 0x4342);
+}
+__device__ __forceinline__ void db_pack4(const uint32_t* r, uint32_t& wa, uint32_t& wb) {
+  const uint32_t x01 = prmt(r[0], r[1], 0x6420), x23 = prmt(r[2], r[3], 0x6420);
+  wa = prmt(x01, x23, 0x6420);
+  wb = prmt(x01, x23, 0x7531);
+}
+
+__device__ __forceinline__ EdgeConst db_edge_const(const DbTables& tb, int qp_av, int off_a, int off_b, uint32_t chroma_inc) {
+  const int ia = db_clip(qp_av + off_a, 0, 51), ib = db_clip(qp_av + off_b, 0, 51);
+  const uint4 a = tb.a[ia];
+  EdgeConst k;
+  k.ka = a.x;
+  k.ks = a.y;
+  k.tcb = a.z + chroma_inc;
+  k.lo1 = a.w;
+  k.kb = tb.b[ib];
+  return k;
+}
+
+// the four edges of one direction over the twenty packed registers of a lane (r[4e - 4 .. 4e + 3] around edge e)
+__device__ __forceinline__ void db_filter_edges(uint32_t* r, const EdgeConst& k_mb, const EdgeConst& k_in, uint32_t off0,
+                                                uint32_t off_odd, uint32_t off_hi, uint32_t chroma) {
+  filter_edge_strong(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], k_mb, off0, chroma);
+  filter_edge_normal(r[5], r[6], r[7], r[8], r[9], r[10], k_in, off_odd, chroma);
+  filter_edge_normal(r[9], r[10], r[11], r[12], r[13], r[14], k_in, off_hi, chroma);
+  filter_edge_normal(r[13], r[14], r[15], r[16], r[17], r[18], k_in, off_odd | off_hi, chroma);
+}
+
+__global__ void __launch_bounds__(32 * kDbWarps, 4) deblock_wavefront_kernel(const DeblockArgs a) {
+  __shared__ DbTables tb;
+  __shared__ DbHalf tiles[kDbWarps][2];
   __shared__ unsigned int s_row[kDbWarps];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  DeblockTile& t = tiles[wid];
+  for (int i = threadIdx.x; i < 52; i += blockDim.x) {
+    const EdgeConst k = make_edge_const(kDbAlpha[i], kDbBeta[i], kDbTc0[i], false);
+    tb.a[i] = make_uint4(k.ka, k.ks, k.tcb, k.lo1);
+    tb.b[i] = k.kb;
+    tb.qmap[0][i] = (uint8_t)i;
+    tb.qmap[1][i] = kDbQpc[db_clip(i + a.cb_off, 0, 51)];
+    tb.qmap[2][i] = kDbQpc[db_clip(i + a.cr_off, 0, 51)];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+  DbHalf& t = tiles[wid][half];
   const int W = a.W, H = a.H;
   const size_t lw = 16 * (size_t)W, cw = 8 * (size_t)W;
   const size_t luma_bytes = lw * 16 * H, frame_bytes = luma_bytes * 3 / 2;
-  const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
+  const unsigned total_rows = (unsigned)((a.n_frames + 1) / 2) * (unsigned)H;
   const unsigned long long tag64 = (unsigned long long)a.tag << 32;
-  // lane roles: luma line `lane` (lanes 0..15); chroma plane cpl, line cln (lanes 16..31)
-  const bool is_luma = lane < 16;
-  const int cpl = (lane >> 3) & 1, cln = lane & 7;
-  // line-word roles (lanes 0..23): luma row lane>>2 word lane&3; chroma plane wpl row wr word wh
-  const int wk = lane - 16, wpl = (wk >> 2) & 1, wr = (wk >> 1) & 1, wh = wk & 1;
+  // ---- lane roles inside the half-warp
+  const bool is_luma = hl < 8;
+  const int cpl = (hl >> 2) & 1, cj = hl & 3;  // chroma lanes: plane, line / column pair
+  const uint32_t chroma_mask = is_luma ? 0u : 0xffffffffu;
+  const uint8_t* qmap = tb.qmap[is_luma ? 0 : 1 + cpl];
+  // vertical edges: lines la and la + lstep of the macroblock (tile rows 4 + la, 4 + la + lstep)
+  const int la = is_luma ? hl : cj, lstep = is_luma ? 8 : 4;
+  uint8_t* const plane_tile = is_luma ? t.luma : t.chroma[cpl];
+  uint8_t* const v_rowA = plane_tile + (4 + la) * 16;
+  uint8_t* const v_rowB = v_rowA + lstep * 16;
+  // horizontal edges: two columns of the tile
+  uint8_t* const h_col = is_luma ? t.luma + 2 * hl : t.chroma[cpl] + 2 * cj;
+  // hand-off words: luma word hl; lanes 0..7 also chroma word hl (plane hl >> 2, row (hl >> 1) & 1, word hl & 1)
+  uint8_t* const cw_tile = t.chroma[(hl >> 2) & 1] + ((hl >> 1) & 1) * 16 + 4 * (hl & 1);
   for (;;) {
     if (lane == 0) s_row[wid] = atomicAdd(a.ticket, 1u);
     __syncwarp();
     const unsigned row = s_row[wid];
     __syncwarp();
     if (row >= total_rows) return;
-    const int f = (int)(row / (unsigned)H), my = (int)(row % (unsigned)H);
+    const int f = 2 * (int)(row / (unsigned)H) + half, my = (int)(row % (unsigned)H);
+    const bool active = f < a.n_frames;
     const bool last_row = my == H - 1;
-    uint8_t* Y = a.yuv + (size_t)f * frame_bytes;
-    uint8_t* Cp = Y + luma_bytes + (cpl ? luma_bytes / 4 : 0);
-    uint8_t* own = is_luma ? Y + (size_t)(16 * my + lane) * lw : Cp + (size_t)(8 * my + cln) * cw;  // this lane's line
-    uint8_t* own_tile = is_luma ? t.luma + (4 + lane) * kDbLumaStride : t.chroma[cpl] + (4 + cln) * kDbChromaStride;
-    const bool own_stored = last_row || (is_luma ? lane < 13 : cln < 7);
-    const uint8_t* qp_row = a.qp + (size_t)row * W;
-    const uint8_t* t8_row = a.t8x8 + (size_t)row * W;
-    unsigned long long* line_mine = a.line + (size_t)row * W * kDbLineWords + lane;
-    const unsigned long long* line_above = line_mine - (size_t)W * kDbLineWords;
-    // where this lane's line word lives in the tile: top margin (read side) and bottom rows (write side)
-    uint8_t* top_dst = is_luma ? t.luma + (lane >> 2) * kDbLumaStride + 4 + 4 * (lane & 3)
-                               : t.chroma[wpl] + (2 + wr) * kDbChromaStride + 4 + 4 * wh;
-    uint8_t* bot_src = is_luma ? t.luma + (16 + (lane >> 2)) * kDbLumaStride + 4 + 4 * (lane & 3)
-                               : t.chroma[wpl] + (10 + wr) * kDbChromaStride + 4 + 4 * wh;
-    // the same rows' left-margin word: the previous macroblock's last word after this macroblock's left-edge filter
-    uint8_t* bot_left = is_luma ? t.luma + (16 + (lane >> 2)) * kDbLumaStride : t.chroma[wpl] + (10 + wr) * kDbChromaStride;
-    const bool patched = is_luma ? (lane & 3) == 3 : wh == 1;
+    const size_t frow = (size_t)(active ? f : 0) * H + my;  // this half's macroblock row among all rows
+    uint8_t* const Y = a.yuv + (size_t)(active ? f : 0) * frame_bytes;
+    uint8_t* const plane = is_luma ? Y : Y + luma_bytes + (cpl ? luma_bytes / 4 : 0);
+    const size_t pitch = is_luma ? lw : cw;
+    const int mbw = is_luma ? 16 : 8;  // bytes of a macroblock's line in this lane's plane
+    uint8_t* const gA = plane + (size_t)(mbw * my + la) * pitch;
+    uint8_t* const gB = gA + (size_t)lstep * pitch;
+    const bool storeA = active, storeB = active && (last_row || la + lstep < mbw - 3 + (is_luma ? 0 : 2));
+    const bool store_top = active && my > 0 && (is_luma ? hl < 3 : cj == 0);
+    uint8_t* const g_top = is_luma ? Y + (size_t)(16 * my - 3 + hl) * lw : plane + (size_t)(8 * my - 1) * cw;
+    const uint8_t* const top_tile = is_luma ? t.luma + (1 + hl) * 16 : t.chroma[cpl] + 3 * 16;
+    const uint8_t* const qp_row = a.qp + frow * W;
+    const uint8_t* const t8_row = a.t8x8 + frow * W;
+    unsigned long long* const line_mine = a.line + frow * W * kDbLineWords;
+    const unsigned long long* const line_above = line_mine - (size_t)W * kDbLineWords;
+    const bool poll0 = active && my > 0, poll1 = poll0 && hl < 8;
+    const bool pub0 = active && !last_row, pub1 = pub0 && hl < 8;
     bool dead = false;
-    uint4 cy = make_uint4(0, 0, 0, 0);
-    int nq = 0, nt8 = 0, nqup = -1;
-    unsigned long long tv = 0;
+    uint4 cyA = make_uint4(0, 0, 0, 0), cyB = cyA;
+    int nq = 0, nt8 = 0, nqup = 0;
+    unsigned long long ftv0 = 0, ftv1 = 0;
+    uint32_t pend0 = 0, pend1 = 0;
     auto fetch = [&](int mx) {  // macroblock mx of this row: samples, QPs, and a first look at the words from above
-      if (is_luma) cy = __ldcg(reinterpret_cast<const uint4*>(own + 16 * mx));
-      else {
-        const uint2 c = __ldcg(reinterpret_cast<const uint2*>(own + 8 * mx));
-        cy.x = c.x;
-        cy.y = c.y;
+      if (active) {
+        if (is_luma) {
+          cyA = __ldcg(reinterpret_cast<const uint4*>(gA + 16 * mx));
+          cyB = __ldcg(reinterpret_cast<const uint4*>(gB + 16 * mx));
+        } else {
+          const uint2 c0 = __ldcg(reinterpret_cast<const uint2*>(gA + 8 * mx));
+          const uint2 c1 = __ldcg(reinterpret_cast<const uint2*>(gB + 8 * mx));
+          cyA.x = c0.x;
+          cyA.y = c0.y;
+          cyB.x = c1.x;
+          cyB.y = c1.y;
+        }
+        nq = qp_row[mx];
+        nt8 = t8_row[mx];
+        if (my > 0) nqup = qp_row[mx - W];
       }
-      nq = qp_row[mx];
-      nt8 = t8_row[mx];
-      if (my > 0) {
-        nqup = qp_row[mx - W];
-        if (lane < kDbLineWords) tv = ld_relaxed_gpu_u64(line_above + (size_t)mx * kDbLineWords);
-      }
+      if (poll0) ftv0 = ld_relaxed_gpu_u64(line_above + (size_t)mx * kDbLineWords + hl);
+      if (poll1) ftv1 = ld_relaxed_gpu_u64(line_above + (size_t)mx * kDbLineWords + 16 + hl);
     };
     fetch(0);
-    int q_left = -1;
+    int q_left = 0;
     for (int mx = 0; mx < W; mx++) {
-      const int q = nq, q_up = nqup, step = nt8 ? 8 : 4;
-      // ---- this macroblock into the tile; the words from above into the top margin
-      db_word(own_tile + 4) = cy.x;
-      db_word(own_tile + 8) = cy.y;
+      const int q = nq, q_up = nqup;
+      unsigned long long tv0 = ftv0, tv1 = ftv1;  // the first look at this macroblock's words; fetch() moves on to the next
+      const uint32_t off_odd = (is_luma && nt8) ? 0xffffffffu : 0u;  // luma edges 4 and 12 of an 8x8-transform macroblock
+      const uint32_t off_hi = is_luma ? 0u : 0xffffffffu;            // chroma has no edges 8 and 12
+      // ---- the lane's edge constants: inner edges, left edge, top edge
+      const int qe = qmap[q], qel = qmap[q_left], qeu = qmap[q_up];
+      const uint32_t cinc = chroma_mask & 0x00010001u;
+      const EdgeConst k_in = db_edge_const(tb, qe, a.off_a, a.off_b, cinc);
+      const EdgeConst k_left = db_edge_const(tb, (qe + qel + 1) >> 1, a.off_a, a.off_b, cinc);
+      const EdgeConst k_top = db_edge_const(tb, (qe + qeu + 1) >> 1, a.off_a, a.off_b, cinc);
+      uint32_t r[20];
+      // ---- vertical edges: the left margin is what the previous macroblock left in the tile's last word
+      db_unpack4(db_word(v_rowA + mbw - 4), db_word(v_rowB + mbw - 4), r);
+      db_unpack4(cyA.x, cyB.x, r + 4);
+      db_unpack4(cyA.y, cyB.y, r + 8);
       if (is_luma) {
-        db_word(own_tile + 12) = cy.z;
-        db_word(own_tile + 16) = cy.w;
+        db_unpack4(cyA.z, cyB.z, r + 12);
+        db_unpack4(cyA.w, cyB.w, r + 16);
+      } else {
+#pragma unroll
+        for (int i = 12; i < 20; i++) r[i] = 0;
       }
-      if (my > 0 && lane < kDbLineWords) {
-        const unsigned long long* p = line_above + (size_t)mx * kDbLineWords;
+      if (mx + 1 < W) fetch(mx + 1);
+      db_filter_edges(r, k_left, k_in, mx == 0 ? 0xffffffffu : 0u, off_odd, off_hi, chroma_mask);
+      {
+        uint32_t mA, mB, a0, b0, a1, b1;
+        db_pack4(r, mA, mB);
+        db_pack4(r + 4, a0, b0);
+        db_pack4(r + 8, a1, b1);
+        if (is_luma) {
+          uint32_t a2, b2, a3, b3;
+          db_pack4(r + 12, a2, b2);
+          db_pack4(r + 16, a3, b3);
+          *reinterpret_cast<uint4*>(v_rowA) = make_uint4(a0, a1, a2, a3);
+          *reinterpret_cast<uint4*>(v_rowB) = make_uint4(b0, b1, b2, b3);
+          if (hl >= 4) t.patch[hl - 4] = mB;
+        } else {
+          *reinterpret_cast<uint2*>(v_rowA) = make_uint2(a0, a1);
+          *reinterpret_cast<uint2*>(v_rowB) = make_uint2(b0, b1);
+          if (cj >= 2) t.patch[4 + 2 * cpl + (cj - 2)] = mB;
+        }
+        // the left neighbour's last word of these two lines is final now (its bottom rows go to the row below instead)
+        if (mx > 0) {
+          if (storeA) db_word(gA + mbw * mx - 4) = mA;
+          if (storeB) db_word(gB + mbw * mx - 4) = mB;
+        }
+      }
+      // ---- the words from above into the top margin
+      if (poll0) {
+        const unsigned long long* p = line_above + (size_t)mx * kDbLineWords + hl;
         unsigned spins = 0;
-        while ((uint32_t)(tv >> 32) != a.tag) {
+        while ((uint32_t)(tv0 >> 32) != a.tag || (poll1 && (uint32_t)(tv1 >> 32) != a.tag)) {
           if (++spins > (1u << 22) || ((spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(a.status) == STATUS_WATCHDOG)) {
             atomicExch(a.status, STATUS_WATCHDOG);
             dead = true;
             break;
           }
-          tv = ld_relaxed_gpu_u64(p);
+          tv0 = ld_relaxed_gpu_u64(p);
+          if (poll1) tv1 = ld_relaxed_gpu_u64(p + 16);
         }
-        db_word(top_dst) = (uint32_t)tv;
-      }
-      if (mx + 1 < W) fetch(mx + 1);
-      __syncwarp();
-      // ---- vertical edges, left to right: lane = line
-      if (is_luma) {
-        uint8_t* ln = own_tile + 4;
-        for (int e = 0; e < 16; e += step) {
-          if (e == 0 && q_left < 0) continue;
-          deblock_line(ln + e, 1, e == 0, false, e == 0 ? (q + q_left + 1) >> 1 : q, a.off_a, a.off_b);
-        }
-      } else {
-        const int off = cpl ? a.cr_off : a.cb_off;
-        const int qc = kDbQpc[db_clip(q + off, 0, 51)];
-        uint8_t* ln = own_tile + 4;
-        for (int e = 0; e < 8; e += 4) {
-          if (e == 0 && q_left < 0) continue;
-          const int qa = e == 0 ? (qc + kDbQpc[db_clip(q_left + off, 0, 51)] + 1) >> 1 : qc;
-          deblock_line(ln + e, 1, e == 0, true, qa, a.off_a, a.off_b);
-        }
+        db_word(t.luma + 4 * hl) = (uint32_t)tv0;
+        if (poll1) db_word(cw_tile + 2 * 16) = (uint32_t)tv1;
       }
       __syncwarp();
       // ---- the previous macroblock is finished down to its last rows: hand those to the row below
-      if (mx > 0 && !last_row && lane < kDbLineWords)
-        st_relaxed_gpu_u64(line_mine + (size_t)(mx - 1) * kDbLineWords, tag64 | (patched ? db_word(bot_left) : t.pend[lane]));
-      // ---- horizontal edges, top to bottom: lane = column
-      if (is_luma) {
-        uint8_t* col = t.luma + 4 * kDbLumaStride + 4 + lane;
-        for (int e = 0; e < 16; e += step) {
-          if (e == 0 && q_up < 0) continue;
-          deblock_line(col + e * kDbLumaStride, kDbLumaStride, e == 0, false, e == 0 ? (q + q_up + 1) >> 1 : q, a.off_a, a.off_b);
-        }
-      } else {
-        const int off = cpl ? a.cr_off : a.cb_off;
-        const int qc = kDbQpc[db_clip(q + off, 0, 51)];
-        uint8_t* col = t.chroma[cpl] + 4 * kDbChromaStride + 4 + cln;
-        for (int e = 0; e < 8; e += 4) {
-          if (e == 0 && q_up < 0) continue;
-          const int qa = e == 0 ? (qc + kDbQpc[db_clip(q_up + off, 0, 51)] + 1) >> 1 : qc;
-          deblock_line(col + e * kDbChromaStride, kDbChromaStride, e == 0, true, qa, a.off_a, a.off_b);
-        }
+      if (mx > 0) {
+        if (pub0)
+          st_relaxed_gpu_u64(line_mine + (size_t)(mx - 1) * kDbLineWords + hl, tag64 | ((hl & 3) == 3 ? t.patch[hl >> 2] : pend0));
+        if (pub1)
+          st_relaxed_gpu_u64(line_mine + (size_t)(mx - 1) * kDbLineWords + 16 + hl,
+                             tag64 | ((hl & 1) ? t.patch[4 + (hl >> 1)] : pend1));
       }
+      // ---- horizontal edges: two columns per lane, rows -4..15 (chroma: -4..7)
+#pragma unroll
+      for (int i = 0; i < 20; i++) {
+        if (i < 12 || is_luma) r[i] = prmt(*reinterpret_cast<const uint16_t*>(h_col + i * 16), 0, 0x4140);
+        else r[i] = 0;
+      }
+      db_filter_edges(r, k_top, k_in, my == 0 ? 0xffffffffu : 0u, off_odd, off_hi, chroma_mask);
+#pragma unroll
+      for (int i = 1; i < 18; i++)
+        if (i < 12 || is_luma) *reinterpret_cast<uint16_t*>(h_col + i * 16) = (uint16_t)prmt(r[i], 0, 0x4420);
       __syncwarp();
-      // ---- stores: this lane's line of the macroblock (not the rows the next picture row still filters), the left
-      // neighbour's last word of the same line, and the upper neighbour's last rows
-      if (own_stored) {
-        if (is_luma)
-          *reinterpret_cast<uint4*>(own + 16 * mx) =
-              make_uint4(db_word(own_tile + 4), db_word(own_tile + 8), db_word(own_tile + 12), db_word(own_tile + 16));
-        else
-          *reinterpret_cast<uint2*>(own + 8 * mx) = make_uint2(db_word(own_tile + 4), db_word(own_tile + 8));
-        if (mx > 0) db_word(own + (is_luma ? 16 : 8) * mx - 4) = db_word(own_tile);
+      // ---- stores: the lane's two lines of the macroblock (not the rows the next picture row still filters) and the
+      // upper neighbour's last rows; the last rows of this macroblock wait in registers for the hand-off
+      if (is_luma) {
+        if (storeA) *reinterpret_cast<uint4*>(gA + 16 * mx) = *reinterpret_cast<const uint4*>(v_rowA);
+        if (storeB) *reinterpret_cast<uint4*>(gB + 16 * mx) = *reinterpret_cast<const uint4*>(v_rowB);
+        if (store_top) *reinterpret_cast<uint4*>(g_top + 16 * mx) = *reinterpret_cast<const uint4*>(top_tile);
+      } else {
+        if (storeA) *reinterpret_cast<uint2*>(gA + 8 * mx) = *reinterpret_cast<const uint2*>(v_rowA);
+        if (storeB) *reinterpret_cast<uint2*>(gB + 8 * mx) = *reinterpret_cast<const uint2*>(v_rowB);
+        if (store_top) *reinterpret_cast<uint2*>(g_top + 8 * mx) = *reinterpret_cast<const uint2*>(top_tile);
       }
-      if (my > 0 && lane < 16) {
-        if (lane < 12)
-          db_word(Y + (size_t)(16 * my - 3 + (lane >> 2)) * lw + 16 * mx + 4 * (lane & 3)) =
-              db_word(t.luma + (1 + (lane >> 2)) * kDbLumaStride + 4 + 4 * (lane & 3));
-        else {
-          const int pl = (lane >> 1) & 1, h = lane & 1;
-          db_word(Y + luma_bytes + (pl ? luma_bytes / 4 : 0) + (size_t)(8 * my - 1) * cw + 8 * mx + 4 * h) =
-              db_word(t.chroma[pl] + 3 * kDbChromaStride + 4 + 4 * h);
-        }
-      }
-      // ---- keep the last rows for the hand-off, and the right columns as the next macroblock's left margin
-      if (lane < kDbLineWords) t.pend[lane] = db_word(bot_src);
-      db_word(own_tile) = db_word(own_tile + (is_luma ? 16 : 8));
+      pend0 = db_word(t.luma + 16 * 16 + 4 * hl);
+      pend1 = db_word(cw_tile + 10 * 16);
       q_left = q;
       __syncwarp();
     }
-    if (!last_row && lane < kDbLineWords) st_relaxed_gpu_u64(line_mine + (size_t)(W - 1) * kDbLineWords, tag64 | t.pend[lane]);
+    if (pub0) st_relaxed_gpu_u64(line_mine + (size_t)(W - 1) * kDbLineWords + hl, tag64 | pend0);
+    if (pub1) st_relaxed_gpu_u64(line_mine + (size_t)(W - 1) * kDbLineWords + 16 + hl, tag64 | pend1);
     if (__any_sync(0xffffffffu, dead)) return;
   }
 }

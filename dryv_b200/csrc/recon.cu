@@ -1905,7 +1905,7 @@ int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
   if (ctx->db_used) CU(cudaStreamWaitEvent(st, ctx->db_done, 0));  // ticket and words serve one launch at a time
   for (uint32_t f0 = 0; f0 < n_frames; f0 += chunk) {
     const uint32_t nf = std::min(chunk, n_frames - f0);
-    const size_t rows = (size_t)nf * pp->pic_height_in_mbs;
+    const size_t rows = (size_t)((nf + 1) / 2) * pp->pic_height_in_mbs;  // a warp walks the same row of two pictures
     if (++ctx->db_tag == 0) {  // tag wrap: stale words could match again
       CU(cudaMemsetAsync(ctx->d_db_line, 0, ctx->db_line_cap * dryv::kDbLineWords * sizeof(unsigned long long), st));
       ctx->db_tag = 1;
@@ -1927,7 +1927,7 @@ int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
     a.cr_off = pp->second_chroma_qp_index_offset;
     a.off_a = 2 * slice_alpha_c0_offset_div2;
     a.off_b = 2 * slice_beta_offset_div2;
-    const size_t want = (rows + dryv::kDbWarps - 1) / dryv::kDbWarps, cap = (size_t)ctx->sm_count * 8;
+    const size_t want = (rows + dryv::kDbWarps - 1) / dryv::kDbWarps, cap = (size_t)ctx->sm_count * 4;
     dryv::deblock_wavefront_kernel<<<(unsigned)(want < cap ? want : cap), 32 * dryv::kDbWarps, 0, st>>>(a);
     CU(cudaGetLastError());
     ctx->launches++;

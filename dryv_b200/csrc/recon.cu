@@ -1287,6 +1287,9 @@ struct dryv_recon_ctx {
   unsigned long long* d_db_line = nullptr;
   size_t db_line_cap = 0;  // macroblocks
   uint32_t db_tag = 0;
+  // dryv_recon_set_deblock: the host submit paths run the post-pass behind the reconstruction of every slot
+  bool deblock_on = false;
+  int db_alpha_div2 = 0, db_beta_div2 = 0;
   cudaEvent_t db_done = nullptr;
   bool db_used = false;
   cudaStream_t pending_user = nullptr;
@@ -1685,6 +1688,63 @@ int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* p
 // Shared pipeline of the two host-buffer entry points. Chunks of pictures travel through kStages staging slots on
 // three kinds of streams: H2D copies, kernels (two compute streams, one wavefront control block each, so the latency
 // bound kernels of neighbouring chunks overlap) and D2H copies.
+// the deblocking post-pass over n_frames pictures at d_yuv on stream st (arguments checked by the callers)
+static int launch_deblock(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa, uint32_t n_frames,
+                          int slice_alpha_c0_offset_div2, int slice_beta_offset_div2, uint8_t* d_yuv, cudaStream_t st) {
+  // the hand-off buffer takes 192 bytes per macroblock: long batches go through it in chunks of pictures
+  const size_t mbs_per_frame = (size_t)pp->pic_width_in_mbs * pp->pic_height_in_mbs;
+  const size_t frame_bytes = mbs_per_frame * 384;
+  constexpr size_t kDbMaxMbs = (size_t)512 << 20 >> 7;  // ~768 MB of words at most
+  const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_frames, kDbMaxMbs / mbs_per_frame));
+  if (!ctx->d_db_ticket) {
+    CU(cudaMalloc(&ctx->d_db_ticket, sizeof(unsigned int)));
+  }
+  if (chunk * mbs_per_frame > ctx->db_line_cap) {
+    CU(cudaDeviceSynchronize());
+    if (ctx->d_db_line) cudaFree(ctx->d_db_line);
+    ctx->d_db_line = nullptr;
+    ctx->db_line_cap = 0;
+    const size_t bytes = chunk * mbs_per_frame * dryv::kDbLineWords * sizeof(unsigned long long);
+    CU(cudaMalloc(&ctx->d_db_line, bytes));
+    CU(cudaMemset(ctx->d_db_line, 0, bytes));
+    ctx->db_line_cap = chunk * mbs_per_frame;
+    ctx->db_tag = 0;
+  }
+  if (ctx->db_used) CU(cudaStreamWaitEvent(st, ctx->db_done, 0));  // ticket and words serve one launch at a time
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += chunk) {
+    const uint32_t nf = std::min(chunk, n_frames - f0);
+    const size_t rows = (size_t)((nf + 1) / 2) * pp->pic_height_in_mbs;  // a warp walks the same row of two pictures
+    if (++ctx->db_tag == 0) {  // tag wrap: stale words could match again
+      CU(cudaMemsetAsync(ctx->d_db_line, 0, ctx->db_line_cap * dryv::kDbLineWords * sizeof(unsigned long long), st));
+      ctx->db_tag = 1;
+    }
+    CU(cudaMemsetAsync(ctx->d_db_ticket, 0, sizeof(unsigned int), st));
+    dryv::DeblockArgs a;
+    memset(&a, 0, sizeof a);
+    a.yuv = d_yuv + (size_t)f0 * frame_bytes;
+    a.qp = d_soa->qp + (size_t)f0 * mbs_per_frame;
+    a.t8x8 = d_soa->transform_size_8x8_flag + (size_t)f0 * mbs_per_frame;
+    a.line = ctx->d_db_line;
+    a.ticket = ctx->d_db_ticket;
+    a.tag = ctx->db_tag;
+    a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
+    a.W = pp->pic_width_in_mbs;
+    a.H = pp->pic_height_in_mbs;
+    a.n_frames = (int)nf;
+    a.cb_off = pp->chroma_qp_index_offset;
+    a.cr_off = pp->second_chroma_qp_index_offset;
+    a.off_a = 2 * slice_alpha_c0_offset_div2;
+    a.off_b = 2 * slice_beta_offset_div2;
+    const size_t want = (rows + dryv::kDbWarps - 1) / dryv::kDbWarps, cap = (size_t)ctx->sm_count * 4;
+    dryv::deblock_wavefront_kernel<<<(unsigned)(want < cap ? want : cap), 32 * dryv::kDbWarps, 0, st>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(ctx->db_done, st));
+  ctx->db_used = true;
+  return DRYV_OK;
+}
+
 static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* soa,
                        const dryv_mb_levels_compact* lv, uint32_t n_frames, uint8_t* out_yuv) {
   constexpr int kStages = dryv_recon_ctx::kStages;
@@ -1836,6 +1896,10 @@ static int submit_impl(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dry
     }
     rc = launch_wavefront(ctx, pp, &d, nf, ctx->d_out[slot], sc);
     if (rc != DRYV_OK) return rc;
+    if (ctx->deblock_on) {
+      rc = launch_deblock(ctx, pp, &d, nf, ctx->db_alpha_div2, ctx->db_beta_div2, ctx->d_out[slot], sc);
+      if (rc != DRYV_OK) return rc;
+    }
     if (exporting) {
       rc = launch_export(ctx, pp, ctx->d_out[slot], nf, &surf, ctx->d_exp[slot], sc);
       if (rc != DRYV_OK) return rc;
@@ -1883,61 +1947,23 @@ int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
     return fail(ctx, DRYV_ERR_ARG, "bad argument");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->s_compute[0];
-  // the hand-off buffer takes 192 bytes per macroblock: long batches go through it in chunks of pictures
-  const size_t mbs_per_frame = (size_t)pp->pic_width_in_mbs * pp->pic_height_in_mbs;
-  const size_t frame_bytes = mbs_per_frame * 384;
-  constexpr size_t kDbMaxMbs = (size_t)512 << 20 >> 7;  // ~768 MB of words at most
-  const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_frames, kDbMaxMbs / mbs_per_frame));
-  if (!ctx->d_db_ticket) {
-    CU(cudaMalloc(&ctx->d_db_ticket, sizeof(unsigned int)));
-  }
-  if (chunk * mbs_per_frame > ctx->db_line_cap) {
-    CU(cudaDeviceSynchronize());
-    if (ctx->d_db_line) cudaFree(ctx->d_db_line);
-    ctx->d_db_line = nullptr;
-    ctx->db_line_cap = 0;
-    const size_t bytes = chunk * mbs_per_frame * dryv::kDbLineWords * sizeof(unsigned long long);
-    CU(cudaMalloc(&ctx->d_db_line, bytes));
-    CU(cudaMemset(ctx->d_db_line, 0, bytes));
-    ctx->db_line_cap = chunk * mbs_per_frame;
-    ctx->db_tag = 0;
-  }
-  if (ctx->db_used) CU(cudaStreamWaitEvent(st, ctx->db_done, 0));  // ticket and words serve one launch at a time
-  for (uint32_t f0 = 0; f0 < n_frames; f0 += chunk) {
-    const uint32_t nf = std::min(chunk, n_frames - f0);
-    const size_t rows = (size_t)((nf + 1) / 2) * pp->pic_height_in_mbs;  // a warp walks the same row of two pictures
-    if (++ctx->db_tag == 0) {  // tag wrap: stale words could match again
-      CU(cudaMemsetAsync(ctx->d_db_line, 0, ctx->db_line_cap * dryv::kDbLineWords * sizeof(unsigned long long), st));
-      ctx->db_tag = 1;
-    }
-    CU(cudaMemsetAsync(ctx->d_db_ticket, 0, sizeof(unsigned int), st));
-    dryv::DeblockArgs a;
-    memset(&a, 0, sizeof a);
-    a.yuv = d_yuv + (size_t)f0 * frame_bytes;
-    a.qp = d_soa->qp + (size_t)f0 * mbs_per_frame;
-    a.t8x8 = d_soa->transform_size_8x8_flag + (size_t)f0 * mbs_per_frame;
-    a.line = ctx->d_db_line;
-    a.ticket = ctx->d_db_ticket;
-    a.tag = ctx->db_tag;
-    a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
-    a.W = pp->pic_width_in_mbs;
-    a.H = pp->pic_height_in_mbs;
-    a.n_frames = (int)nf;
-    a.cb_off = pp->chroma_qp_index_offset;
-    a.cr_off = pp->second_chroma_qp_index_offset;
-    a.off_a = 2 * slice_alpha_c0_offset_div2;
-    a.off_b = 2 * slice_beta_offset_div2;
-    const size_t want = (rows + dryv::kDbWarps - 1) / dryv::kDbWarps, cap = (size_t)ctx->sm_count * 4;
-    dryv::deblock_wavefront_kernel<<<(unsigned)(want < cap ? want : cap), 32 * dryv::kDbWarps, 0, st>>>(a);
-    CU(cudaGetLastError());
-    ctx->launches++;
-  }
-  CU(cudaEventRecord(ctx->db_done, st));
-  ctx->db_used = true;
+  const int rc = launch_deblock(ctx, pp, d_soa, n_frames, slice_alpha_c0_offset_div2, slice_beta_offset_div2, d_yuv, st);
+  if (rc != DRYV_OK) return rc;
   if (cuda_stream) {
     ctx->pending_user = st;
     ctx->pending_user_valid = true;
   }
+  return DRYV_OK;
+}
+
+int dryv_recon_set_deblock(dryv_recon_ctx* ctx, int enable, int slice_alpha_c0_offset_div2, int slice_beta_offset_div2) {
+  if (!ctx) return DRYV_ERR_ARG;
+  if (enable && (slice_alpha_c0_offset_div2 < -6 || slice_alpha_c0_offset_div2 > 6 || slice_beta_offset_div2 < -6 ||
+                 slice_beta_offset_div2 > 6))
+    return fail(ctx, DRYV_ERR_ARG, "filter offsets outside -6..6");
+  ctx->deblock_on = enable != 0;
+  ctx->db_alpha_div2 = slice_alpha_c0_offset_div2;
+  ctx->db_beta_div2 = slice_beta_offset_div2;
   return DRYV_OK;
 }
 

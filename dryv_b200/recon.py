@@ -27,7 +27,7 @@ EXPORTS = [
     "dryv_recon_write_yuv_file", "dryv_recon_launch_count", "dryv_recon_last_submit_ms", "dryv_recon_device_tables",
     "dryv_recon_wavefront_times", "dryv_recon_pack_levels", "dryv_recon_unpack_levels", "dryv_recon_submit_compact",
     "dryv_recon_expand_levels_device", "dryv_recon_wait_oldest", "dryv_recon_surface_bytes", "dryv_recon_export_device",
-    "dryv_recon_set_surface", "dryv_recon_deblock_device",
+    "dryv_recon_set_surface", "dryv_recon_deblock_device", "dryv_recon_set_deblock",
     "dryv_recon_multi_create", "dryv_recon_multi_destroy", "dryv_recon_multi_device_count", "dryv_recon_multi_last_error",
     "dryv_recon_multi_reconstruct", "dryv_recon_multi_reconstruct_compact",
 ]
@@ -41,7 +41,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in ("recon.cu", "recon_tables.cpp", "levels_pack.cpp", "cabac_host.cpp", "multi.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "residual_stage.cuh", "deblock_kernel.cuh", "recon_tables.h", "cabac_tables.inc", "levels_record.h")] + [
+    deps = srcs + [os.path.join(CSRC, f) for f in ("recon_kernels.cuh", "residual_stage.cuh", "deblock_kernel.cuh", "deblock_packed.cuh", "recon_tables.h", "cabac_tables.inc", "levels_record.h")] + [
         os.path.join(_HERE, "..", "include", "dryv_recon.h"), os.path.join(_HERE, "..", "include", "dryv_cabac_host.h")]
     if not force and os.path.exists(LIB_PATH) and all(
             os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
@@ -122,6 +122,8 @@ def load_library() -> C.CDLL:
     lib.dryv_recon_expand_levels_device.argtypes = [vp, C.POINTER(LevelsCompact), sz, vp, vp]
     lib.dryv_recon_deblock_device.argtypes = [vp, C.POINTER(PicParams), C.POINTER(MbSoa), u32, C.c_int, C.c_int, vp, vp]
     lib.dryv_recon_deblock_device.restype = C.c_int
+    lib.dryv_recon_set_deblock.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.dryv_recon_set_deblock.restype = C.c_int
     lib.dryv_recon_surface_bytes.argtypes = [C.POINTER(Surface)]
     lib.dryv_recon_surface_bytes.restype = sz
     lib.dryv_recon_export_device.argtypes = [vp, C.POINTER(PicParams), vp, u32, C.POINTER(Surface), vp, vp]
@@ -305,6 +307,11 @@ class ReconContext:
     def _out_bytes(self, pp: PicParams) -> int:
         sf = getattr(self, "_surface", None)
         return sf.nbytes if sf is not None else pp.frame_bytes
+
+    def set_deblock(self, enable: bool, alpha_div2: int = 0, beta_div2: int = 0):
+        """dryv_recon_set_deblock: the host submit paths (reconstruct, reconstruct_compact) filter every picture behind the
+        reconstruction — off by default, the reference has no filter."""
+        self._check(self.lib.dryv_recon_set_deblock(self.h, 1 if enable else 0, alpha_div2, beta_div2))
 
     def deblock_device(self, dsoa: "DeviceSoa", d_yuv, alpha_div2: int = 0, beta_div2: int = 0, stream_ptr: int = 0):
         """dryv_recon_deblock_device: the optional H.264 in-loop filter over reconstructed pictures, in place (not dryv parity)."""

@@ -252,6 +252,12 @@ int dryv_recon_set_surface(dryv_recon_ctx* ctx, const dryv_surface* s);
 int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_mb_soa* d_soa, uint32_t n_frames,
                               int slice_alpha_c0_offset_div2, int slice_beta_offset_div2, uint8_t* d_yuv, void* cuda_stream);
 
+/* The same post-pass as a mode of the host submit paths: with enable != 0 every dryv_recon_reconstruct /
+ * dryv_recon_reconstruct_compact filters the pictures of a slot behind their reconstruction, before the surface export
+ * and the copy back (the dryv_recon_multi_* forms own their contexts and always reconstruct unfiltered). Off by default and
+ * off on the dryv-parity path — the reference decodes every stream unfiltered. DRYV_ERR_ARG for offsets outside -6..6. */
+int dryv_recon_set_deblock(dryv_recon_ctx* ctx, int enable, int slice_alpha_c0_offset_div2, int slice_beta_offset_div2);
+
 /* Frame::write_to_yuv_file (frame/mod.rs:48-70): writes one reconstructed picture (host memory, the
  * layout above) to `path`, creating the parent directory of "temp/yuv_frame"-style paths if needed. */
 int dryv_recon_write_yuv_file(const uint8_t* frame_yuv, size_t bytes, const char* path);

@@ -96,6 +96,29 @@ def test_deblock_kernel_matches_oracle(case):
 
 
 @pytest.mark.gpu
+def test_deblock_as_a_mode_of_the_host_submit_path(monkeypatch):
+    """dryv_recon_set_deblock: reconstruct() from host buffers returns filtered pictures, slot by slot (three pipeline
+    stages of an odd number of pictures each), and unfiltered ones again once the mode is off."""
+    from dryv_b200 import recon
+    monkeypatch.setenv("DRYV_CHUNK_MB", "1")
+    pp = PicParams.make(6, 5, 2, -1)
+    n = 101
+    b = synth.generate(pp, n, 9177, qp_base=33)
+    frames = oracle.reconstruct(b)
+    want = np.stack([dbl.deblock(frames[f], 6, 5, b.qp[f * pp.n_mb:(f + 1) * pp.n_mb],
+                                 b.transform_size_8x8_flag[f * pp.n_mb:(f + 1) * pp.n_mb], 2, -1, 2, -3) for f in range(n)])
+    ctx = recon.ReconContext(0)
+    ctx.set_deblock(True, 2, -3)
+    assert np.array_equal(ctx.reconstruct(b), want)
+    assert np.array_equal(ctx.reconstruct(b), want)
+    ctx.set_deblock(False)
+    assert np.array_equal(ctx.reconstruct(b), frames)
+    with pytest.raises(Exception):
+        ctx.set_deblock(True, 7, 0)
+    ctx.close()
+
+
+@pytest.mark.gpu
 def test_deblock_kernel_on_a_batch_larger_than_the_resident_rows():
     """More macroblock rows than the launch has warps: rows are dealt by ticket, later rows start as earlier ones finish.
     Checked by a property the domain offers: every picture of a batch of identical pictures comes out identical to the

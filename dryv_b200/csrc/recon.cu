@@ -1292,8 +1292,13 @@ struct dryv_recon_ctx {
   int db_alpha_div2 = 0, db_beta_div2 = 0;
   cudaEvent_t db_done = nullptr;
   bool db_used = false;
-  cudaStream_t pending_user = nullptr;
-  bool pending_user_valid = false;
+  // launches on caller streams: one completion event per distinct stream, re-recorded by every launch on it, so that
+  // dryv_recon_wait and a table re-upload cover all of them (an event outlives its stream)
+  struct UserStream {
+    cudaStream_t stream;
+    cudaEvent_t done;
+  };
+  std::vector<UserStream> user_streams;
   uint64_t launches = 0;
   // development aid (DRYV_SUBMIT_TRACE=1): per-chunk stage completion events of the last submit, printed by wait
   std::vector<cudaEvent_t> trace_ev;
@@ -1320,12 +1325,38 @@ bool pp_ok(const dryv_pic_params* pp) {
          pp->second_chroma_qp_index_offset <= 12;
 }
 
+// a launch went to the caller's stream `st`: remember to wait for it
+int note_user_stream(dryv_recon_ctx* ctx, cudaStream_t st) {
+  for (auto& u : ctx->user_streams)
+    if (u.stream == st) {
+      CU(cudaEventRecord(u.done, st));
+      return DRYV_OK;
+    }
+  if (ctx->user_streams.size() >= 64) {  // a caller that keeps creating streams: retire the oldest entry
+    CU(cudaEventSynchronize(ctx->user_streams.front().done));
+    cudaEventDestroy(ctx->user_streams.front().done);
+    ctx->user_streams.erase(ctx->user_streams.begin());
+  }
+  dryv_recon_ctx::UserStream u{st, nullptr};
+  CU(cudaEventCreateWithFlags(&u.done, cudaEventDisableTiming));
+  CU(cudaEventRecord(u.done, st));
+  ctx->user_streams.push_back(u);
+  return DRYV_OK;
+}
+int sync_user_streams(dryv_recon_ctx* ctx) {
+  for (auto& u : ctx->user_streams) CU(cudaEventSynchronize(u.done));
+  return DRYV_OK;
+}
+
 int ensure_tables(dryv_recon_ctx* ctx, const dryv_pic_params* pp, cudaStream_t s) {
   if (ctx->tables_valid && memcmp(&ctx->tables_pp, pp, sizeof *pp) == 0) return DRYV_OK;
   // the pinned host copy may still be in flight from a previous upload on another stream
   CU(cudaStreamSynchronize(ctx->s_compute[0]));
   CU(cudaStreamSynchronize(ctx->s_compute[1]));
-  if (ctx->pending_user_valid) CU(cudaStreamSynchronize(ctx->pending_user));
+  {
+    const int rc = sync_user_streams(ctx);  // kernels on caller streams may still read the tables
+    if (rc != DRYV_OK) return rc;
+  }
   dryv::build_device_tables(*pp, ctx->h_tables);
   CU(cudaMemcpyAsync(ctx->d_tables, ctx->h_tables, sizeof(DeviceTables), cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));
@@ -1623,6 +1654,7 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
   if (ctx->d_db_ticket) cudaFree(ctx->d_db_ticket);
   if (ctx->d_db_line) cudaFree(ctx->d_db_line);
   if (ctx->db_done) cudaEventDestroy(ctx->db_done);
+  for (auto& u : ctx->user_streams) cudaEventDestroy(u.done);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   for (cudaEvent_t e : ctx->trace_ev) cudaEventDestroy(e);
@@ -1651,8 +1683,8 @@ int dryv_recon_reconstruct_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp
   rc = launch_wavefront(ctx, pp, d_soa, n_frames, d_out_yuv, s);
   if (rc != DRYV_OK) return rc;
   if (cuda_stream) {
-    ctx->pending_user = s;
-    ctx->pending_user_valid = true;
+    const int nrc = note_user_stream(ctx, s);
+    if (nrc != DRYV_OK) return nrc;
   }
   return DRYV_OK;
 }
@@ -1679,8 +1711,8 @@ int dryv_recon_residual_add_device(dryv_recon_ctx* ctx, const dryv_pic_params* p
   CU(cudaGetLastError());
   ctx->launches++;
   if (cuda_stream) {
-    ctx->pending_user = s;
-    ctx->pending_user_valid = true;
+    const int nrc = note_user_stream(ctx, s);
+    if (nrc != DRYV_OK) return nrc;
   }
   return DRYV_OK;
 }
@@ -1950,8 +1982,8 @@ int dryv_recon_deblock_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, co
   const int rc = launch_deblock(ctx, pp, d_soa, n_frames, slice_alpha_c0_offset_div2, slice_beta_offset_div2, d_yuv, st);
   if (rc != DRYV_OK) return rc;
   if (cuda_stream) {
-    ctx->pending_user = st;
-    ctx->pending_user_valid = true;
+    const int nrc = note_user_stream(ctx, st);
+    if (nrc != DRYV_OK) return nrc;
   }
   return DRYV_OK;
 }
@@ -1978,8 +2010,8 @@ int dryv_recon_export_device(dryv_recon_ctx* ctx, const dryv_pic_params* pp, con
   int rc = launch_export(ctx, pp, d_yuv, n_frames, s, d_out, st);
   if (rc != DRYV_OK) return rc;
   if (cuda_stream) {
-    ctx->pending_user = st;
-    ctx->pending_user_valid = true;
+    const int nrc = note_user_stream(ctx, st);
+    if (nrc != DRYV_OK) return nrc;
   }
   return DRYV_OK;
 }
@@ -2017,8 +2049,8 @@ int dryv_recon_expand_levels_device(dryv_recon_ctx* ctx, const dryv_mb_levels_co
   int rc = launch_expand(ctx, d_levels->offset, d_levels->stream + o_first, o_first, o_last - o_first, n_mbs, d_coeff, s);
   if (rc != DRYV_OK) return rc;
   if (cuda_stream) {
-    ctx->pending_user = s;
-    ctx->pending_user_valid = true;
+    const int nrc = note_user_stream(ctx, s);
+    if (nrc != DRYV_OK) return nrc;
   }
   return DRYV_OK;
 }
@@ -2049,9 +2081,9 @@ int dryv_recon_wait(dryv_recon_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->s_compute[0]));
   CU(cudaStreamSynchronize(ctx->s_compute[1]));
   CU(cudaStreamSynchronize(ctx->s_d2h));
-  if (ctx->pending_user_valid) {
-    CU(cudaStreamSynchronize(ctx->pending_user));
-    ctx->pending_user_valid = false;
+  {
+    const int rc = sync_user_streams(ctx);
+    if (rc != DRYV_OK) return rc;
   }
   for (int i = 0; i < dryv_recon_ctx::kSets; i++)  // launches on caller streams other than the last one
     if (ctx->ctl[i].used) CU(cudaEventSynchronize(ctx->ctl[i].done));

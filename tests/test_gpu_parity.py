@@ -221,3 +221,40 @@ def test_independent_batches_overlap_on_different_streams(gpu_ctx):
     gpu_ctx.wait()      # waits for every launch of the context, whatever stream it went to
     for k in range(6):
         assert np.array_equal(outs[k].cpu().numpy(), oracle.reconstruct(batches[k], threads=4)), k
+
+
+def test_wait_covers_side_kernels_on_several_caller_streams(gpu_ctx):
+    # residual-add and deblocking launches on two different caller streams, then only dryv_recon_wait — no torch
+    # synchronisation — before the results are read back over a third stream-ordered copy: every launch of the context is
+    # waited for, whatever stream it went to (one completion event per caller stream).
+    import torch
+    from oracle import deblock as dbl
+    pp = PicParams.make(40, 30)
+    b = synth.generate(pp, 6, 6400, qp_base=30)
+    ds = recon.DeviceSoa(b)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    pred = torch.randint(0, 256, (6, pp.frame_bytes), dtype=torch.uint8, generator=g)
+    d_pred = pred.cuda()
+    d_res = torch.zeros_like(d_pred)
+    d_rec = torch.zeros_like(d_pred)
+    gpu_ctx.reconstruct_device(ds, d_rec)
+    gpu_ctx.wait()
+    rec = d_rec.cpu().numpy()
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for rep in range(3):
+        gpu_ctx.residual_add_device(ds, d_pred, d_res, sa.cuda_stream)
+    gpu_ctx.deblock_device(ds, d_rec, 0, 0, sb.cuda_stream)
+    gpu_ctx.wait()
+    h_res = torch.empty_like(d_res, device="cpu").pin_memory()
+    h_db = torch.empty_like(d_rec, device="cpu").pin_memory()
+    sc = torch.cuda.Stream()   # a stream that is ordered behind nothing but the wait above
+    with torch.cuda.stream(sc):
+        h_res.copy_(d_res, non_blocking=True)
+        h_db.copy_(d_rec, non_blocking=True)
+    sc.synchronize()
+    assert np.array_equal(h_res.numpy(), oracle.residual_add(b, pred.numpy()))
+    for f in range(6):
+        sl = slice(f * pp.n_mb, (f + 1) * pp.n_mb)
+        want = dbl.deblock(rec[f], 40, 30, b.qp[sl], b.transform_size_8x8_flag[sl], 0, 0, 0, 0)
+        assert np.array_equal(h_db[f].numpy(), want), f

@@ -496,33 +496,30 @@ struct SliceParser {
     CabacCore eng = c.k;  // registers for the length of the block
     uint8_t* const state = c.state;
     const uint8_t* const next = c.next;
-    uint8_t sig[64];
-    int count = 0, last = n - 1;
+    // positions of the significant coefficients, in coding order (the level loop below walks them backwards)
+    uint8_t pos[64];
+    int count = 0;
+    bool open_end = true;  // no last_significant_coeff_flag seen: the final position is significant by inference
     for (int i = 0; i < n - 1; i++) {
       const int si = cat == 5 ? kSig8x8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
-      const int li = cat == 5 ? kLast8x8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
-      sig[i] = (uint8_t)eng.decision(state, next, kSigBase[cat] + si);
-      if (sig[i]) {
+      pos[count] = (uint8_t)i;
+      if (eng.decision(state, next, kSigBase[cat] + si)) {
         count++;
+        const int li = cat == 5 ? kLast8x8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
         if (eng.decision(state, next, kLastBase[cat] + li)) {
-          last = i;
+          open_end = false;
           break;
         }
       }
     }
-    if (last == n - 1) {
-      sig[n - 1] = 1;  // inferred when no earlier coefficient was flagged last
-      count++;
-    }
-    (void)count;
+    if (open_end) pos[count++] = (uint8_t)(n - 1);
     int eq1 = 0, gt1 = 0;
-    for (int i = last; i >= 0; i--) {
-      if (!sig[i]) continue;
+    const int lim = 4 - (cat == 3 ? 1 : 0);
+    for (int j = count - 1; j >= 0; j--) {
       const int ctx0 = kAbsBase[cat] + (gt1 ? 0 : (1 + eq1 < 4 ? 1 + eq1 : 4));
-      const int lim = 4 - (cat == 3 ? 1 : 0);
-      const int ctxn = kAbsBase[cat] + 5 + (gt1 < lim ? gt1 : lim);
       int a = 0;
       if (eng.decision(state, next, ctx0)) {
+        const int ctxn = kAbsBase[cat] + 5 + (gt1 < lim ? gt1 : lim);
         a = 1;
         while (a < 14 && eng.decision(state, next, ctxn)) a++;
         if (a == 14) {  // 0-th order Exp-Golomb suffix, bypass
@@ -533,11 +530,13 @@ struct SliceParser {
           }
           while (k-- > 0) a += eng.bypass() << k;
         }
+        gt1++;
+      } else {
+        eq1++;
       }
-      const int v = eng.bypass() ? -(a + 1) : (a + 1);
-      out[i] = (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v));
-      if (a == 0) eq1++;
-      else gt1++;
+      const int sign = eng.bypass();
+      const int v = (a + 1 ^ -sign) + sign;  // sign ? -(a + 1) : a + 1
+      out[pos[j]] = (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v));
     }
     c.k = eng;
     return 1;

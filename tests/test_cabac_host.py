@@ -360,3 +360,23 @@ def test_slice_info_reports_the_deblocking_request(recon_lib):
     assert si.disable_deblocking_filter_idc == 1
     si = host.slice_info(stream.encode_stream(b, deblock=(2, -3)), 0)
     assert (si.disable_deblocking_filter_idc, si.slice_alpha_c0_offset_div2, si.slice_beta_offset_div2) == (0, 2, -3)
+
+
+def test_host_parser_survives_corrupted_input_under_sanitizers(tmp_path):
+    """tests/native/cabac_fuzz.cpp: seeded byte flips, truncations, insertions and deletions of a valid Annex-B stream and
+    of two MP4 files through every entry point of include/dryv_cabac_host.h, built with AddressSanitizer + UBSan — the host
+    reads untrusted bytes, so any status is fine and any out-of-bounds access, overflow or crash is not."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cabac_fuzz")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe,
+                           os.path.join(root, "tests/native/cabac_fuzz.cpp"), os.path.join(root, "dryv_b200/csrc/cabac_host.cpp"),
+                           os.path.join(root, "dryv_b200/csrc/levels_pack.cpp"), "-lpthread"])
+    pp = PicParams.make(8, 5, 1, -2)
+    b = synth.generate(pp, 3, 4242, qp_base=27)
+    annexb = tmp_path / "s.264"
+    annexb.write_bytes(stream.encode_stream(b))
+    pin = os.path.join(root, "tests/golden/pin")
+    for path, seed in ((str(annexb), 11), (os.path.join(pin, "matrices_96x64.mp4"), 12), (os.path.join(pin, "i8x8_column0_96x64.mp4"), 13)):
+        out = subprocess.run([exe, path, str(seed), "250"], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and out.stdout.startswith("ok:"), (path, out.stdout[-2000:], out.stderr[-4000:])

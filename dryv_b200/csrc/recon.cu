@@ -397,6 +397,28 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
 // and only checks the tags later: no fences, no flags, and nobody reads the picture back. Luma needs
 // line x+1 of the row above (top-right neighbour: x+2y wavefront); chroma only needs line x.
 // ------------------------------------------------------------------------------------------------
+#if DRYV_CLUSTER > 1
+// Cluster mode: entry `next` of the ring in the CTA below overwrites entry next - kRingEntries; wait until the row below
+// has consumed it (`cons`: this CTA's counter, which the CTA below advances through distributed shared memory).
+__device__ __noinline__ void ring_backpressure(volatile uint32_t* cons, unsigned next, unsigned& known, int lane, int* status,
+                                               bool& dead) {
+  bool trip = false;
+  if (lane == 0 && !dead) {
+    unsigned spins = 0;
+    while (next - (known = *cons) >= (unsigned)kRingEntries) {
+      __nanosleep(100);
+      if (++spins > (1u << 22)) {
+        atomicExch(status, STATUS_WATCHDOG);
+        trip = true;
+        break;
+      }
+    }
+  }
+  known = __shfl_sync(0xffffffffu, known, 0);
+  if (__any_sync(0xffffffffu, trip)) dead = true;
+}
+#endif
+
 // Start lag: how many macroblocks the row above must have finished before a row starts. The x+2y order needs
 // two. Larger values were measured (3, 4, 6, 8): they lengthen the pipeline fill by (lag - 2) macroblock times
 // per row and buy nothing, because per-macroblock cost varies by 3x between Intra16x16 and Intra4x4 and the
@@ -408,6 +430,7 @@ __global__ void __launch_bounds__(kModeThreadsMax) resolve_modes_kernel(const Ke
 #define DRYV_START_LAG 2
 #endif
 constexpr int kStartLag = DRYV_START_LAG;
+static_assert(kCluster == 1 || (kStartLag == 2 && kTeamsPerCta == 1), "cluster mode: one team per CTA, default start lag");
 // CTAs per SM = the register budget handed to ptxas; shared memory: 11 KB of tables per CTA + 14 KB per team.
 #ifndef DRYV_CTAS_PER_SM
 #define DRYV_CTAS_PER_SM 8
@@ -430,8 +453,25 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
       for (int i = 0; i < kLvStages; i++) mbar_init(&ts.lvfull[i], 1);
       ts.pace = smem_u32(&ts.pace);  // a word that holds its own shared-memory address (see wait_line_words)
     }
+#if DRYV_CLUSTER > 1
+    for (int i = tt; i < kRingEntries * kLineWords; i += kTeamThreads) ts.ring[i] = 0ull;  // tag 0: no entry carries it
+    if (tt < kMailSlots) ts.mail[tt] = 0ull;
+    if (tt < 2) ts.cons[tt] = 0u;
+    if (tt < kCluster) ts.ack[tt] = 0u;
+#endif
   }
   __syncthreads();
+#if DRYV_CLUSTER > 1
+  // nobody writes into a neighbour's ring / mailbox before that neighbour has cleared it
+  cluster_sync_all();
+  const unsigned crank = cluster_ctarank();
+  const bool ring_in = crank > 0;                         // the row above is walked by rank - 1 of this cluster
+  const bool ring_out = crank + 1 < (unsigned)kCluster;   // the row below by rank + 1
+  // this lane's word of ring entry 0, here and in the CTA that walks the row below; the counters the row above reads
+  const unsigned long long* const ring_l = &ts.ring[threadIdx.x & 7];
+  unsigned long long* const ringr_l = map_rank(&ts.ring[threadIdx.x & 7], ring_out ? crank + 1 : crank);
+  volatile uint32_t* const cons_up = map_rank(&ts.cons[0], ring_in ? crank - 1 : crank);
+#endif
   uint32_t pace_addr = smem_u32(&ts.pace);
   const int lane = threadIdx.x & 31;
 #ifndef DRYV_ROLE_SWAP
@@ -454,6 +494,7 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
     const uint8_t* const hdr_base = header_base(a, lane >> 2);
     const uint32_t hdr_lim = (lane >> 2) == 0 ? 24u : ((lane >> 2) == 2 ? 3u : ((lane >> 2) == 3 ? 51u : 255u));
     const unsigned total_rows = (unsigned)a.n_frames * (unsigned)H;
+    (void)total_rows;
     const int gpr = (W + kGroupMbs - 1) / kGroupMbs;
     bool unsupported = false;
     unsigned gn = 0;   // groups handed to the pixel warp so far
@@ -478,13 +519,68 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
     const int m_mb = (lane >> 1) & 3;
     bool dead = false;
     CLK_DECL;
+#if DRYV_CLUSTER > 1
+    // A ticket is a band of kCluster consecutive rows of one picture (bands dealt band-major over pictures, so a band
+    // only ever waits on a lower ticket); rank 0 draws it and posts it into the mailboxes of the other ranks.
+    const unsigned bands = (unsigned)(H + kCluster - 1) / (unsigned)kCluster;
+    const unsigned total_tickets = (unsigned)a.n_frames * bands;
+    unsigned kt = 0;                       // tickets taken so far
+    unsigned cin = 0, cout = 0, c_known = 0;  // chroma ring: entries consumed / published / known to be consumed below
+    unsigned long long* const mail_r = map_rank(&ts.mail[0], (lane >= 1 && lane < kCluster) ? (unsigned)lane : crank);
+    volatile uint32_t* const ack_r = map_rank(&ts.ack[crank], 0u);
+#endif
     for (;;) {
       unsigned t = 0;
+#if DRYV_CLUSTER > 1
+      if (crank == 0) {
+        if (kt >= (unsigned)kMailSlots) {  // slot kt & 3 still holds ticket kt - 4 until every rank has taken it
+          bool trip = false;
+          if (lane >= 1 && lane < kCluster) {
+            unsigned spins = 0;
+            while (ts.ack[lane] + (unsigned)kMailSlots - 1u < kt) {
+              __nanosleep(200);
+              if (++spins > (1u << 22)) {
+                atomicExch(a.status, STATUS_WATCHDOG);
+                trip = true;
+                break;
+              }
+            }
+          }
+          if (__any_sync(0xffffffffu, trip)) dead = true;
+        }
+        if (lane == 0) t = atomicAdd(a.ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (lane >= 1 && lane < kCluster) st_relaxed_gpu_u64(mail_r + (kt & (kMailSlots - 1)), ((unsigned long long)(kt + 1u) << 32) | t);
+      } else {
+        if (lane == 0) {
+          const unsigned long long* m = &ts.mail[kt & (kMailSlots - 1)];
+          unsigned long long v = ld_relaxed_gpu_u64(m);
+          unsigned spins = 0;
+          while ((uint32_t)(v >> 32) != kt + 1u) {
+            __nanosleep(200);
+            v = ld_relaxed_gpu_u64(m);
+            if (++spins > (1u << 22)) {
+              atomicExch(a.status, STATUS_WATCHDOG);
+              v = 0xffffffffull;  // no more work
+              break;
+            }
+          }
+          t = (uint32_t)v;
+          st_relaxed_cluster_u32(ack_r, kt + 1u);
+        }
+        t = __shfl_sync(0xffffffffu, t, 0);
+      }
+      kt++;
+      if (dead || t >= total_tickets) break;
+      const int row = (int)(t / (unsigned)a.n_frames) * kCluster + (int)crank, frame = (int)(t % (unsigned)a.n_frames);
+      if (row >= H) continue;  // the last band of a picture may be short
+#else
       if (lane == 0) t = atomicAdd(a.ticket, 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= total_rows) break;
       // tickets are dealt row-major over pictures so that a row only ever waits on a lower ticket
       const int row = (int)(t / (unsigned)a.n_frames), frame = (int)(t % (unsigned)a.n_frames);
+#endif
       const size_t mb_row0 = (size_t)frame * n_mb + (size_t)row * W;
       const bool availB = row > 0, publish = row + 1 < H;
       const unsigned long long* c_above = a.line + (mb_row0 - W) * kLineWords + lane;  // chroma words of line x above
@@ -504,6 +600,15 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         if (c_lane) vf = ld_relaxed_gpu_u64(far);
         wait_line_words(far, vf, c_lane, tag, true, a.status, dead, pace_addr);
       }
+#if DRYV_CLUSTER > 1
+      uint32_t c_tag = tag;
+      if (ring_in) {
+        c_above = ring_l + (size_t)(cin & (kRingEntries - 1)) * kLineWords;
+        c_tag = cin + 1u;
+      }
+#else
+      const uint32_t c_tag = tag;
+#endif
       if (availB && c_lane) lvc = ld_relaxed_gpu_u64(c_above);
 
       const int16_t* const lv_row = a.coeff + mb_row0 * DRYV_COEFFS_PER_MB;
@@ -636,9 +741,21 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
           if (availB) {
             // always the sleeping flavour: the front warp runs ahead of the pixel warp, so this wait is not on the
             // critical path, and a tight poll here would take issue slots from the pixel warps of the SM
-            const uint32_t w = wait_line_words(c_above, lvc, c_lane, tag, DRYV_CHROMA_LONG_WAIT || x == 0, a.status, dead, pace_addr);
+            const uint32_t w = wait_line_words(c_above, lvc, c_lane, c_tag, DRYV_CHROMA_LONG_WAIT || x == 0, a.status, dead, pace_addr);
+#if DRYV_CLUSTER > 1
+            if (ring_in) {  // entry cin consumed: tell the row above, move to the next ring entry
+              cin++;
+              if (lane == 4) st_relaxed_cluster_u32(cons_up + 1, cin);
+            }
+#endif
             if (c_lane) {
               *reinterpret_cast<uint32_t*>(c_fresh) = w;
+#if DRYV_CLUSTER > 1
+              if (ring_in) {
+                c_above = ring_l + (size_t)(cin & (kRingEntries - 1)) * kLineWords;
+                c_tag = cin + 1u;
+              } else
+#endif
               c_above += kLineWords;
               if (x + 1 < W) lvc = ld_relaxed_gpu_u64(c_above);
             }
@@ -646,6 +763,16 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
           }
           CLK_MARK(3);  // wait for the chroma line of the row above
           predict_chroma(ts.chroma, ts.ccol, ts.cres[m], lane, cm, availA, availB, availA && availB);
+#if DRYV_CLUSTER > 1
+          if (publish && ring_out) {
+            // entry cout of the ring of the row below; it overwrites entry cout - kRingEntries, which must have been consumed
+            if (cout - c_known >= (unsigned)kRingEntries) ring_backpressure(&ts.cons[1], cout, c_known, lane, a.status, dead);
+            if (c_lane)
+              st_relaxed_gpu_u64(ringr_l + (size_t)(cout & (kRingEntries - 1)) * kLineWords,
+                                 ((unsigned long long)(cout + 1u) << 32) | *reinterpret_cast<const uint32_t*>(c_pub));
+            cout++;
+          } else
+#endif
           if (publish && c_lane)
             st_relaxed_gpu_u64(c_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(c_pub));
           c_mine += kLineWords;
@@ -699,6 +826,13 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
     uint8_t* st_ptr = nullptr;
     bool availB = false, publish = false;
     unsigned long long lv = 0;  // in-flight fetch of this lane's line word for the current macroblock
+#if DRYV_CLUSTER > 1
+    unsigned lj = 0;                  // luma ring: index of the entry line_above points at (entries below it are consumed)
+    unsigned lout = 0, l_known = 0;   // entries published to the row below / known to be consumed there
+    uint32_t l_tag = tag;
+#else
+    const uint32_t l_tag = tag;
+#endif
     CLK_DECL;
     for (;;) {
       const unsigned gs = gn % kGroupSlots, use = gn / kGroupSlots;
@@ -718,6 +852,12 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
           availB = row > 0;
           publish = row + 1 < H;
           line_above = a.line + (mb_row0 - W) * kLineWords + lane;
+#if DRYV_CLUSTER > 1
+          if (ring_in) {
+            line_above = ring_l + (size_t)(lj & (kRingEntries - 1)) * kLineWords;
+            l_tag = lj + 1u;
+          }
+#endif
           line_mine = a.line + mb_row0 * kLineWords + lane;
           st_ptr = a.out + (size_t)frame * n_mb * 384 + (size_t)(16 * row + (lane & 15)) * strideY;
           if (availB) {
@@ -731,7 +871,7 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
             }
             unsigned long long v0 = 0;
             if (lane < 4) v0 = ld_relaxed_gpu_u64(line_above);
-            const uint32_t w = wait_line_words(line_above, v0, lane < 4, tag, true, a.status, dead, pace_addr);
+            const uint32_t w = wait_line_words(line_above, v0, lane < 4, l_tag, true, a.status, dead, pace_addr);
             if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
             __syncwarp();
             uint32_t sv = 0;
@@ -739,6 +879,15 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
             __syncwarp();
             if (lane < 5) *reinterpret_cast<uint32_t*>(shift_dst) = sv;
             // look one line ahead from here on
+#if DRYV_CLUSTER > 1
+            if (ring_in) {
+              lj++;
+              if (lane == 0) st_relaxed_cluster_u32(cons_up, lj);
+              line_above = ring_l + (size_t)(lj & (kRingEntries - 1)) * kLineWords;
+              l_tag = lj + 1u;
+              if (lane < 4 && W1 > 0) lv = ld_relaxed_gpu_u64(line_above);
+            } else
+#endif
             if (lane < 4) {
               line_above += kLineWords;
               if (W1 > 0) lv = ld_relaxed_gpu_u64(line_above);
@@ -751,8 +900,16 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         const bool availA = x > 0, availC = availB && x < W1, availD = availA && availB;
         // needs line x+1 of the row above (top-right neighbour), if it exists
         if (availC) {
-          const uint32_t w = wait_line_words(line_above, lv, lane < 4, tag, false, a.status, dead, pace_addr);
+          const uint32_t w = wait_line_words(line_above, lv, lane < 4, l_tag, false, a.status, dead, pace_addr);
           if (lane < 4) *reinterpret_cast<uint32_t*>(fresh_dst) = w;
+#if DRYV_CLUSTER > 1
+          if (ring_in) {  // entry lj consumed: tell the row above, move to the next ring entry (fetched after the prediction)
+            lj++;
+            if (lane == 0) st_relaxed_cluster_u32(cons_up, lj);
+            line_above = ring_l + (size_t)(lj & (kRingEntries - 1)) * kLineWords;
+            l_tag = lj + 1u;
+          }
+#endif
         }
         __syncwarp();
         CLK_MARK(2);  // wait for the luma line of the row above
@@ -779,6 +936,21 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         // The row below is waiting for exactly this: publish the bottom line before anything else, and only then
         // fetch the line for the next macroblock (as late as possible: in a tightly coupled wavefront an earlier
         // load would only see that the row above has not got there yet).
+#if DRYV_CLUSTER > 1
+        if (publish && ring_out) {
+          if (lout - l_known >= (unsigned)kRingEntries) ring_backpressure(&ts.cons[0], lout, l_known, lane, a.status, dead);
+          if (lane < 4)
+            st_relaxed_gpu_u64(ringr_l + (size_t)(lout & (kRingEntries - 1)) * kLineWords,
+                               ((unsigned long long)(lout + 1u) << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
+          lout++;
+        } else if (publish && lane < 4) {
+          st_relaxed_gpu_u64(line_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
+        }
+        if (lane < 4 && availB) {
+          if (!ring_in) line_above += kLineWords;  // (the ring pointer moved on when its entry was consumed)
+          if (x + 2 <= W1) lv = ld_relaxed_gpu_u64(line_above);
+        }
+#else
         if (lane < 4) {
           if (publish)
             st_relaxed_gpu_u64(line_mine, ((unsigned long long)tag << 32) | *reinterpret_cast<const uint32_t*>(pub_src));
@@ -787,6 +959,7 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
             if (x + 2 <= W1) lv = ld_relaxed_gpu_u64(line_above);
           }
         }
+#endif
         line_mine += kLineWords;
         TRACE_MARK(2);
 
@@ -816,6 +989,11 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
     }
     CLK_FLUSH(8);
   }
+#if DRYV_CLUSTER > 1
+  // a CTA's shared memory (ring, mailbox, counters) must outlive every remote access to it
+  __syncwarp();
+  cluster_sync_all();
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1230,6 +1408,7 @@ struct dryv_recon_ctx {
   int device = 0;
   int sm_count = 0;
   int wave_ctas_per_sm = 0, resid_ctas_per_sm = 0;
+  int wave_clusters = 0;  // cluster mode: clusters of the wavefront kernel that can be resident at once
   // s_compute[0] doubles as the default stream of the device-pointer entry points; dryv_recon_submit alternates
   // its chunks over both so that the (latency bound) wavefront kernels of neighbouring chunks overlap
   cudaStream_t s_compute[2] = {nullptr, nullptr}, s_h2d = nullptr, s_d2h = nullptr;
@@ -1442,6 +1621,11 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   CU(cudaGetLastError());
   size_t want = (rows + dryv::kTeamsPerCta - 1) / dryv::kTeamsPerCta;  // one row team per macroblock row at most
   size_t cap = (size_t)ctx->sm_count * ctx->wave_ctas_per_sm;
+#if DRYV_CLUSTER > 1
+  // whole clusters only: one per band of kCluster rows at most, and no more than can be resident together
+  want = (size_t)n_frames * ((pp->pic_height_in_mbs + dryv::kCluster - 1) / dryv::kCluster) * dryv::kCluster;
+  cap = (size_t)ctx->wave_clusters * dryv::kCluster;
+#endif
   int grid = (int)(want < cap ? want : cap);
   // The wavefront kernel is a programmatic dependent of the pre-pass: it starts once every pre-pass CTA is
   // resident and consumes mode records as they appear (tagged words, no grid-wide wait).
@@ -1450,11 +1634,18 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   cfg.blockDim = dim3(dryv::kWaveThreads);
   cfg.dynamicSmemBytes = sizeof(dryv::WaveCtaSmem);
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#if DRYV_CLUSTER > 1
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = dryv::kCluster;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.numAttrs = 2;
+#endif
   CU(cudaLaunchKernelEx(&cfg, dryv::recon_wavefront_kernel, a));
   CU(cudaEventRecord(ev[1], s));
   CU(cudaEventRecord(ctx->ctl[set].done, s));
@@ -1611,6 +1802,25 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
                             cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resid_ctas_per_sm, dryv::recon_residual_add_kernel,
                                                      dryv::kThreadsPerCta, sizeof(dryv::ResidCtaSmem)) == cudaSuccess;
+#if DRYV_CLUSTER > 1
+  if (ok) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctx->sm_count * ctx->wave_ctas_per_sm / dryv::kCluster * dryv::kCluster));
+    cfg.blockDim = dim3(dryv::kWaveThreads);
+    cfg.dynamicSmemBytes = sizeof(dryv::WaveCtaSmem);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = dryv::kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ok = cudaOccupancyMaxActiveClusters(&ctx->wave_clusters, dryv::recon_wavefront_kernel, &cfg) == cudaSuccess &&
+         ctx->wave_clusters >= 1;
+    if (getenv("DRYV_VERBOSE")) fprintf(stderr, "dryv: %d clusters of %d row teams resident (%d CTAs per SM by occupancy)\n",
+                                         ctx->wave_clusters, dryv::kCluster, ctx->wave_ctas_per_sm);
+  }
+#endif
   if (!ok || ctx->wave_ctas_per_sm < 1 || ctx->resid_ctas_per_sm < 1) {
     dryv_recon_destroy(ctx);
     return DRYV_ERR_CUDA;

@@ -44,6 +44,17 @@ constexpr int kChromaTileBytes = 9 * kChromaStride;
 #define DRYV_GROUP_SLOTS 2
 #endif
 constexpr int kGroupSlots = DRYV_GROUP_SLOTS;
+#ifndef DRYV_CLUSTER
+#define DRYV_CLUSTER 1
+#endif
+constexpr int kCluster = DRYV_CLUSTER;  // rows per cluster (1: every row team on its own, line hand-off through L2 only)
+#ifndef DRYV_RING
+#define DRYV_RING 16
+#endif
+constexpr int kRingEntries = DRYV_RING;  // line ring of the cluster mode, macroblocks
+constexpr int kMailSlots = 4;
+constexpr int kLineWords = 8;  // words of a macroblock's bottom line, see below
+static_assert((kRingEntries & (kRingEntries - 1)) == 0 && kRingEntries >= 4, "ring size: a power of two");
 constexpr int kLvStages = 2;  // level ring: the bulk copy of group g + 1 runs under the residual stage of group g
 constexpr int kTeamThreads = 64;
 struct MbSlot {
@@ -72,6 +83,14 @@ struct TeamSmem {
   alignas(8) unsigned long long full[kGroupSlots];          // mbarriers: group slot filled by the front warp
   alignas(8) unsigned long long lvfull[kLvStages];          // mbarriers: level stage landed
   uint32_t pace;                                            // holds its own address: pacing chain of the poll loops
+#if DRYV_CLUSTER > 1
+  // Cluster mode (a cluster of DRYV_CLUSTER row teams walks DRYV_CLUSTER consecutive rows of one picture): the bottom
+  // lines of the row above arrive in this ring through distributed shared memory instead of the tagged words in L2.
+  alignas(16) unsigned long long ring[kRingEntries * kLineWords];  // entry s & (kRingEntries - 1): payload | (s + 1) << 32
+  alignas(8) unsigned long long mail[kMailSlots];                  // tickets from rank 0: t | (k + 1) << 32
+  volatile uint32_t cons[2];                                       // entries the row below has consumed: luma, chroma
+  volatile uint32_t ack[DRYV_CLUSTER];                             // rank 0 only: tickets rank r has taken from its mailbox
+#endif
 };
 static_assert(sizeof(uint16_t) * kGroupMbs * kResChromaMb >= sizeof(int) * kScratchWords, "scratch aliases the chroma tiles");
 // A CTA holds several row teams that share one copy of the tables: shared memory, not registers, is what limits the
@@ -91,7 +110,7 @@ enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
 // Bottom line a macroblock hands to the row below: 4 luma words (16 px), 2 Cb, 2 Cr words (8 px each).
 // Every 32-bit payload travels with the launch tag in one 64-bit word, so a single relaxed 64-bit load
 // both fetches the data and proves it is there: no fence, no separate flag, no second round trip.
-constexpr int kLineWords = 8;
+// (kLineWords = 8 is defined above TeamSmem)
 
 // Resolved prediction modes of one macroblock (written by resolve_modes_kernel): one nibble per 4x4 block in the
 // order the Intra4x4 schedule consumes them,
@@ -125,13 +144,39 @@ struct KernelArgs {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
+// In cluster mode a line word lives either in global memory or in the shared memory of a CTA of the cluster (the ring):
+// the accesses are generic there, so that one instruction stream serves both.
+#if DRYV_CLUSTER > 1
+#define DRYV_LINE_SPACE ""
+#else
+#define DRYV_LINE_SPACE ".global"
+#endif
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu" DRYV_LINE_SPACE ".u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu" DRYV_LINE_SPACE ".u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// ---- thread-block cluster helpers (cluster mode) ----
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// generic address of `p` (a generic pointer into this CTA's shared memory) in the CTA with rank `rank` of the cluster
+template <typename T>
+__device__ __forceinline__ T* map_rank(T* p, unsigned rank) {
+  unsigned long long r;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(r) : "l"(reinterpret_cast<unsigned long long>(p)), "r"(rank));
+  return reinterpret_cast<T*>(r);
+}
+__device__ __forceinline__ void st_relaxed_cluster_u32(volatile uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
   int d;

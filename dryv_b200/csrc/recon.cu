@@ -616,13 +616,13 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         const int nn = min(kGroupMbs, W - g * kGroupMbs);
 #if DRYV_LEVEL_CPASYNC
         const uint8_t* src = reinterpret_cast<const uint8_t*>(lv_row + (size_t)g * (kGroupMbs * DRYV_COEFFS_PER_MB));
-        uint8_t* dst = reinterpret_cast<uint8_t*>(ts.lv[k & 1]);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(ts.lv[k % kLvStages]);
         for (int o = lane * 16; o < nn * (DRYV_COEFFS_PER_MB * 2); o += 512) cp_async_16(dst + o, src + o);
         cp_async_commit();
 #else
         if (lane == 0)
-          bulk_load(ts.lv[k & 1], lv_row + (size_t)g * (kGroupMbs * DRYV_COEFFS_PER_MB), (uint32_t)nn * (DRYV_COEFFS_PER_MB * 2),
-                    &ts.lvfull[k & 1]);
+          bulk_load(ts.lv[k % kLvStages], lv_row + (size_t)g * (kGroupMbs * DRYV_COEFFS_PER_MB), (uint32_t)nn * (DRYV_COEFFS_PER_MB * 2),
+                    &ts.lvfull[k % kLvStages]);
 #endif
       };
       auto load_hdr = [&](int g) -> uint32_t {
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
 
       for (int g = 0; g < gpr; g++) {
         const int x0 = g * kGroupMbs, n = min(kGroupMbs, W - x0);
-        const int stage = (int)(lvw & 1u);
+        const int stage = (int)(lvw % kLvStages);
 #ifndef DRYV_FETCH_LATE
 #define DRYV_FETCH_LATE 1
 #endif
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         else cp_async_wait<0>();
         __syncwarp();
 #else
-        mbar_wait(&ts.lvfull[stage], (lvw >> 1) & 1u);
+        mbar_wait(&ts.lvfull[stage], (lvw / kLvStages) & 1u);
 #endif
 #ifndef DRYV_EXP_NO_RESID  // (experiment: how fast is each role with the other one's code out of the instruction cache)
         residual_group<false>(tab, a.tables, lc, lane, ts.hdr, m4, m8, ts.lv[stage], n, reinterpret_cast<int*>(&ts.cres[0][0]),
@@ -1408,6 +1408,7 @@ struct dryv_recon_ctx {
   int device = 0;
   int sm_count = 0;
   int wave_ctas_per_sm = 0, resid_ctas_per_sm = 0;
+  int wave_grid_override = 0;  // DRYV_WAVE_GRID (development): row teams per launch instead of sm_count * teams per SM
   int wave_clusters = 0;  // cluster mode: clusters of the wavefront kernel that can be resident at once
   // s_compute[0] doubles as the default stream of the device-pointer entry points; dryv_recon_submit alternates
   // its chunks over both so that the (latency bound) wavefront kernels of neighbouring chunks overlap
@@ -1627,6 +1628,7 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   cap = (size_t)ctx->wave_clusters * dryv::kCluster;
 #endif
   int grid = (int)(want < cap ? want : cap);
+  if (ctx->wave_grid_override > 0 && (size_t)ctx->wave_grid_override < cap) grid = ctx->wave_grid_override;  // development knob
   // The wavefront kernel is a programmatic dependent of the pre-pass: it starts once every pre-pass CTA is
   // resident and consumes mode records as they appear (tagged words, no grid-wide wait).
   cudaLaunchConfig_t cfg = {};
@@ -1766,6 +1768,7 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->use_pdl = getenv("DRYV_NO_PDL") == nullptr;
+  if (const char* g = getenv("DRYV_WAVE_GRID")) ctx->wave_grid_override = atoi(g);
   bool ok = cudaStreamCreateWithFlags(&ctx->s_compute[0], cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_compute[1], cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&

@@ -55,7 +55,12 @@ constexpr int kRingEntries = DRYV_RING;  // line ring of the cluster mode, macro
 constexpr int kMailSlots = 4;
 constexpr int kLineWords = 8;  // words of a macroblock's bottom line, see below
 static_assert((kRingEntries & (kRingEntries - 1)) == 0 && kRingEntries >= 4, "ring size: a power of two");
-constexpr int kLvStages = 2;  // level ring: the bulk copy of group g + 1 runs under the residual stage of group g
+// level ring: with two stages the bulk copy of group g + 1 may be issued before the residual stage of group g; the kernel
+// issues it after that stage (DRYV_FETCH_LATE), where one stage is enough (the levels of group g have been consumed)
+#ifndef DRYV_LV_STAGES
+#define DRYV_LV_STAGES 2
+#endif
+constexpr int kLvStages = DRYV_LV_STAGES;
 constexpr int kTeamThreads = 64;
 struct MbSlot {
   alignas(16) uint16_t res[kResLumaTile];  // luma residual fields (residual_stage.cuh)

@@ -197,15 +197,21 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned long long* b, uint32_
 #endif
 constexpr int kPollPace = DRYV_POLL_PACE;
 constexpr int kPollUnroll = DRYV_POLL_UNROLL;
+__device__ DRYV_WAIT_INLINE uint32_t wait_line_words_ns(const unsigned long long* p, unsigned long long first, bool mine,
+                                                       uint32_t tag, unsigned ns, int* status, bool& dead, uint32_t& pace_addr);
 __device__ DRYV_WAIT_INLINE uint32_t wait_line_words(const unsigned long long* p, unsigned long long first, bool mine,
                                                     uint32_t tag, bool long_wait, int* status, bool& dead,
                                                     uint32_t& pace_addr) {
+  return wait_line_words_ns(p, first, mine, tag, long_wait ? DRYV_LINE_LONG_NS : DRYV_LINE_SLEEP_NS, status, dead, pace_addr);
+}
+//   ns: sleep between polls (0: spin)
+__device__ DRYV_WAIT_INLINE uint32_t wait_line_words_ns(const unsigned long long* p, unsigned long long first, bool mine,
+                                                       uint32_t tag, unsigned ns, int* status, bool& dead, uint32_t& pace_addr) {
   unsigned long long v = first;
   if (dead || __all_sync(0xffffffffu, !mine || (uint32_t)(v >> 32) == tag)) return (uint32_t)v;
   // Slow path. Only the lanes that own a word poll, each in its own loop (load, compare, branch: three instructions per
   // poll, no vote); the others wait at the __syncwarp below. Every instruction a waiting warp issues is taken from the
   // working warps of its scheduler, so the loop is kept this small and the watchdog counts in steps of eight polls.
-  const unsigned ns = long_wait ? DRYV_LINE_LONG_NS : DRYV_LINE_SLEEP_NS;
   bool tripped = false;
   if (mine) {
     unsigned spins = 0;
@@ -1049,7 +1055,12 @@ struct GroupWalk {
 #ifndef DRYV_RESID_CTAS
 #define DRYV_RESID_CTAS 4
 #endif
-__global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residual_add_kernel(const KernelArgs a) {
+// FIELDS = true (split path, see recon_predict_kernel): nothing is added and no sample is stored; the macroblock's biased
+// residual fields go to KernelArgs::resid instead, kResidMbFields per macroblock in the layout the predictors read from
+// shared memory (luma tile of kResLumaTile fields, then the chroma tile of kResChromaMb fields), so that a row walker
+// fetches them with one bulk copy.
+template <bool FIELDS>
+__device__ __forceinline__ void residual_kernel_body(const KernelArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResidCtaSmem& cs = *reinterpret_cast<ResidCtaSmem*>(smem_raw);
   const int lane = threadIdx.x & 31;
@@ -1136,15 +1147,17 @@ __global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residua
       const int b4 = lane & 15;
       lo[p] = ybase + 16u * (la[p] ? m : 0u) + (size_t)((b4 >> 3) * 8 + ((b4 >> 1) & 1) * 4) * strideY + ((b4 >> 2) & 1) * 8 + (b4 & 1) * 4;
 #pragma unroll
-      for (int i = 0; i < 4; i++) pl[p][i] = la[p] ? __ldg(reinterpret_cast<const uint32_t*>(pin + lo[p] + (size_t)i * strideY)) : 0u;
+      for (int i = 0; i < 4; i++)
+        pl[p][i] = (!FIELDS && la[p]) ? __ldg(reinterpret_cast<const uint32_t*>(pin + lo[p] + (size_t)i * strideY)) : 0u;
     }
+    uint16_t* const fout = FIELDS ? a.resid + (size_t)cur.mb0() * kResidMbFields : nullptr;  // macroblock 0 of the group
     // chroma pass: lane = (macroblock lane >> 3, plane (lane >> 2) & 1, block lane & 3)
     const bool ca = (lane >> 3) < n;
     const size_t co = cbase + 8u * (ca ? (uint32_t)(lane >> 3) : 0u) + (size_t)((lane >> 2) & 1) * n_mb * 64 +
                       (size_t)(((lane >> 1) & 1) * 4) * strideC + (lane & 1) * 4;
     uint32_t pc[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) pc[i] = ca ? __ldg(reinterpret_cast<const uint32_t*>(pin + co + (size_t)i * strideC)) : 0u;
+    for (int i = 0; i < 4; i++) pc[i] = (!FIELDS && ca) ? __ldg(reinterpret_cast<const uint32_t*>(pin + co + (size_t)i * strideC)) : 0u;
     mbar_wait(&ws.full[st], (it >> 1) & 1);
     const int16_t* const lv = ws.lv[st];
     // ---- luma, 4x4 transform: two macroblocks per pass ----
@@ -1162,7 +1175,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residua
         if (__any_sync(0xffffffffu, la[p] && i16)) dcv = luma_dc16(tab, lc, lane, (int)(int16_t)(c0.x & 0xffffu), qp);
         uint32_t out[8];
         pass4x4_regs(tab, a.tables, c0, c1, qp, i16, dcv, la[p], out);
-        if (la[p]) {
+        if (FIELDS) {
+          if (la[p]) {
+            uint16_t* dst = fout + (size_t)mm * kResidMbFields + lc.res_off_luma;
+#pragma unroll
+            for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(dst + i * kResLumaStride) = make_uint2(out[2 * i], out[2 * i + 1]);
+          }
+        } else if (la[p]) {
 #pragma unroll
           for (int i = 0; i < 4; i++)
             __stcs(reinterpret_cast<uint32_t*>(pout + lo[p] + (size_t)i * strideY), add_clip4(out[2 * i], out[2 * i + 1], pl[p][i]));
@@ -1180,7 +1199,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residua
       const int dcv = chroma_dc(tab, lane, (int)(int16_t)(c0.x & 0xffffu), qpc);
       uint32_t out[8];
       pass4x4_regs(tab, a.tables, c0, c1, qpc, true, dcv, ca, out);
-      if (ca) {
+      if (FIELDS) {
+        if (ca) {
+          uint16_t* dst = fout + (size_t)mm * kResidMbFields + kResLumaTile + lc.res_off_chroma;
+#pragma unroll
+          for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(dst + i * 8) = make_uint2(out[2 * i], out[2 * i + 1]);
+        }
+      } else if (ca) {
 #pragma unroll
         for (int i = 0; i < 4; i++)
           __stcs(reinterpret_cast<uint32_t*>(pout + co + (size_t)i * strideC), add_clip4(out[2 * i], out[2 * i + 1], pc[i]));
@@ -1191,11 +1216,19 @@ __global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residua
       const int m = __ffs(left) - 1;
       left &= left - 1;
       const size_t o = ybase + 16u * (uint32_t)m + (size_t)(lane >> 1) * strideY + 8 * (lane & 1);
-      const uint2 pv = __ldg(reinterpret_cast<const uint2*>(pin + o));
+      uint2 pv = make_uint2(0u, 0u);
+      if (!FIELDS) pv = __ldg(reinterpret_cast<const uint2*>(pin + o));
       pass8x8(tab, lc, lane, lv + m * DRYV_COEFFS_PER_MB, ws.scratch, (int)((ws.hdr[m] >> 8) & 0xffu), ws.res_luma);
-      const uint2* rp = reinterpret_cast<const uint2*>(&ws.res_luma[(lane >> 1) * kResLumaStride + 8 * (lane & 1)]);
-      const uint2 r0 = rp[0], r1 = rp[1];
-      __stcs(reinterpret_cast<uint2*>(pout + o), make_uint2(add_clip4(r0.x, r0.y, pv.x), add_clip4(r1.x, r1.y, pv.y)));
+      if (FIELDS) {  // the tile as it lies in shared memory, 16 bytes per lane (kResLumaTile * 2 = 640 bytes)
+        const uint4* src = reinterpret_cast<const uint4*>(ws.res_luma);
+        uint4* dst = reinterpret_cast<uint4*>(fout + (size_t)m * kResidMbFields);
+        dst[lane] = src[lane];
+        if (lane < (int)(kResLumaTile * 2 / 16) - 32) dst[32 + lane] = src[32 + lane];
+      } else {
+        const uint2* rp = reinterpret_cast<const uint2*>(&ws.res_luma[(lane >> 1) * kResLumaStride + 8 * (lane & 1)]);
+        const uint2 r0 = rp[0], r1 = rp[1];
+        __stcs(reinterpret_cast<uint2*>(pout + o), make_uint2(add_clip4(r0.x, r0.y, pv.x), add_clip4(r1.x, r1.y, pv.y)));
+      }
       __syncwarp();
     }
     __syncwarp();
@@ -1203,6 +1236,14 @@ __global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residua
   }
   if (unsupported) atomicCAS(a.status, STATUS_OK, STATUS_UNSUPPORTED);
 }
+__global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residual_add_kernel(const KernelArgs a) {
+  residual_kernel_body<false>(a);
+}
+__global__ void __launch_bounds__(kThreadsPerCta, DRYV_RESID_CTAS) recon_residual_fields_kernel(const KernelArgs a) {
+  residual_kernel_body<true>(a);
+}
+
+#include "split_kernels.cuh"
 
 
 // ------------------------------------------------------------------------------------------------
@@ -1429,6 +1470,10 @@ struct dryv_recon_ctx {
   cudaEvent_t e_wave[kTimedLaunches][2] = {};
   uint64_t wave_launches = 0;
   bool use_pdl = true;  // development switch: DRYV_NO_PDL=1 serialises the pre-pass and the wavefront kernel
+  // DRYV_SPLIT=1: residual-fields kernel + one-warp-per-row predict kernel (split_kernels.cuh) instead of the row teams
+  bool use_split = false;
+  int split_ctas_per_sm = 0;
+  unsigned int* d_ticket_c = nullptr;  // [set] chroma row tickets of the split path
   // tables
   DeviceTables* d_tables = nullptr;
   DeviceTables* h_tables = nullptr;  // pinned
@@ -1443,6 +1488,8 @@ struct dryv_recon_ctx {
     unsigned long long* d_line = nullptr;  // bottom-line hand-off buffer, kLineWords words per macroblock
     unsigned long long* d_modes = nullptr; // resolved prediction modes, kModeWords tagged words per macroblock
     size_t line_cap = 0;                   // in macroblocks
+    uint16_t* d_resid = nullptr;           // split path: kResidMbFields residual fields per macroblock
+    size_t resid_cap = 0;
     cudaEvent_t done = nullptr;            // recorded behind the last launch that used this block
     bool used = false;
   } ctl[kSets];
@@ -1581,6 +1628,8 @@ KernelArgs make_args(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   a.tag = ctx->tag;
   a.ticket = ctx->d_ticket + 2 * set;
   a.status = reinterpret_cast<int*>(ctx->d_ticket + 1);
+  a.ticket_c = ctx->d_ticket_c + set;
+  a.resid = ctx->ctl[set].d_resid;
 #ifdef DRYV_STAGE_CLOCKS
   a.prof = ctx->d_prof;
 #endif
@@ -1613,6 +1662,18 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   if (ctx->ctl[set].used) CU(cudaStreamWaitEvent(s, ctx->ctl[set].done, 0));  // the block's previous launch has finished
   if (++ctx->tag == 0) ctx->tag = 1;  // every launch validates line words with its own tag: no per-launch clearing
   CU(cudaMemsetAsync(ctx->d_ticket + 2 * set, 0, sizeof(unsigned int), s));  // ticket only; status stays sticky until wait
+  if (ctx->use_split) {
+    dryv_recon_ctx::Control& c = ctx->ctl[set];
+    if (mbs > c.resid_cap) {
+      CU(cudaDeviceSynchronize());
+      if (c.d_resid) cudaFree(c.d_resid);
+      c.d_resid = nullptr;
+      c.resid_cap = 0;
+      CU(cudaMalloc(&c.d_resid, mbs * dryv::kResidMbFields * sizeof(uint16_t)));
+      c.resid_cap = mbs;
+    }
+    CU(cudaMemsetAsync(ctx->d_ticket_c + set, 0, sizeof(unsigned int), s));
+  }
   KernelArgs a = make_args(ctx, pp, d_soa, n_frames, d_out, set);
   cudaEvent_t* ev = ctx->e_wave[ctx->wave_launches % dryv_recon_ctx::kTimedLaunches];
   CU(cudaEventRecord(ev[0], s));
@@ -1620,6 +1681,41 @@ int launch_wavefront(dryv_recon_ctx* ctx, const dryv_pic_params* pp, const dryv_
   const int mode_threads = (((int)pp->pic_height_in_mbs + 31) / 32) * 32;  // one warp per band of 32 MB rows
   dryv::resolve_modes_kernel<<<n_frames, mode_threads, 0, s>>>(a);
   CU(cudaGetLastError());
+  if (ctx->use_split) {
+    // residual fields of every macroblock (no dependency on the pre-pass: a programmatic dependent of it, so the two overlap),
+    // then the row walkers, which start once both have finished
+    {
+      const size_t gpr = (pp->pic_width_in_mbs + dryv::kGroupMbs - 1) / dryv::kGroupMbs;
+      const size_t groups = gpr * rows;
+      size_t want = (groups + dryv::kWarpsPerCta - 1) / dryv::kWarpsPerCta;
+      size_t cap = (size_t)ctx->sm_count * ctx->resid_ctas_per_sm;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(want < cap ? want : cap));
+      cfg.blockDim = dim3(dryv::kThreadsPerCta);
+      cfg.dynamicSmemBytes = sizeof(dryv::ResidCtaSmem);
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CU(cudaLaunchKernelEx(&cfg, dryv::recon_residual_fields_kernel, a));
+    }
+    {
+      // one luma walker per macroblock row at most
+      size_t want = (rows + dryv::kSplitLumaWarps - 1) / dryv::kSplitLumaWarps;
+      size_t cap = (size_t)ctx->sm_count * ctx->split_ctas_per_sm;
+      const unsigned grid = (unsigned)(want < cap ? want : cap);
+      dryv::recon_predict_kernel<<<grid, dryv::kSplitThreads, sizeof(dryv::SplitCtaSmem), s>>>(a);
+      CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ev[1], s));
+    CU(cudaEventRecord(ctx->ctl[set].done, s));
+    ctx->ctl[set].used = true;
+    ctx->wave_launches++;
+    ctx->launches += 3;
+    return DRYV_OK;
+  }
   size_t want = (rows + dryv::kTeamsPerCta - 1) / dryv::kTeamsPerCta;  // one row team per macroblock row at most
   size_t cap = (size_t)ctx->sm_count * ctx->wave_ctas_per_sm;
 #if DRYV_CLUSTER > 1
@@ -1769,6 +1865,7 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->use_pdl = getenv("DRYV_NO_PDL") == nullptr;
   if (const char* g = getenv("DRYV_WAVE_GRID")) ctx->wave_grid_override = atoi(g);
+  if (const char* g = getenv("DRYV_SPLIT")) ctx->use_split = atoi(g) != 0;
   bool ok = cudaStreamCreateWithFlags(&ctx->s_compute[0], cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_compute[1], cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1805,6 +1902,18 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
                             cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resid_ctas_per_sm, dryv::recon_residual_add_kernel,
                                                      dryv::kThreadsPerCta, sizeof(dryv::ResidCtaSmem)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_ticket_c, dryv_recon_ctx::kSets * sizeof(unsigned int)) == cudaSuccess &&
+       cudaFuncSetAttribute(dryv::recon_residual_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(dryv::ResidCtaSmem)) == cudaSuccess &&
+       cudaFuncSetAttribute(dryv::recon_residual_fields_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+       cudaFuncSetAttribute(dryv::recon_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(dryv::SplitCtaSmem)) == cudaSuccess &&
+       cudaFuncSetAttribute(dryv::recon_predict_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->split_ctas_per_sm, dryv::recon_predict_kernel,
+                                                     dryv::kSplitThreads, sizeof(dryv::SplitCtaSmem)) == cudaSuccess &&
+       ctx->split_ctas_per_sm >= 1;
 #if DRYV_CLUSTER > 1
   if (ok) {
     cudaLaunchConfig_t cfg = {};
@@ -1864,6 +1973,9 @@ void dryv_recon_destroy(dryv_recon_ctx* ctx) {
     if (ctx->ctl[i].done) cudaEventDestroy(ctx->ctl[i].done);
   }
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->d_ticket_c) cudaFree(ctx->d_ticket_c);
+  for (int i = 0; i < dryv_recon_ctx::kSets; i++)
+    if (ctx->ctl[i].d_resid) cudaFree(ctx->ctl[i].d_resid);
   if (ctx->d_db_ticket) cudaFree(ctx->d_db_ticket);
   if (ctx->d_db_line) cudaFree(ctx->d_db_line);
   if (ctx->db_done) cudaEventDestroy(ctx->db_done);

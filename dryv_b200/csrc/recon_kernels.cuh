@@ -110,6 +110,8 @@ struct WaveCtaSmem {
   TeamSmem team[kTeamsPerCta];
 };
 
+constexpr int kResidMbFields = kResLumaTile + kResChromaMb;  // 464 fields = 928 bytes per macroblock (a multiple of 16)
+static_assert((kResidMbFields * 2) % 16 == 0 && (kResLumaTile * 2) % 16 == 0, "bulk-copy granularity");
 enum { STATUS_OK = 0, STATUS_UNSUPPORTED = 1, STATUS_WATCHDOG = 2 };
 
 // Bottom line a macroblock hands to the row below: 4 luma words (16 px), 2 Cb, 2 Cr words (8 px each).
@@ -134,6 +136,8 @@ struct KernelArgs {
   const int16_t* coeff;
   uint8_t* out;             // n_frames pictures, Y | Cb | Cr each
   const uint8_t* pred_in;   // residual-add kernel only
+  uint16_t* resid;          // split path: [n_mbs][kResidMbFields] biased residual fields (recon_residual_fields_kernel)
+  unsigned int* ticket_c;   // split path: row ticket counter of the chroma walkers
   const DeviceTables* tables;
   unsigned long long* line; // [n_frames * H * W][kLineWords] bottom line of each MB: payload | tag << 32
   unsigned long long* modes; // [n_frames * H * W][kModeWords]: payload | tag << 32

@@ -258,3 +258,25 @@ def test_wait_covers_side_kernels_on_several_caller_streams(gpu_ctx):
         sl = slice(f * pp.n_mb, (f + 1) * pp.n_mb)
         want = dbl.deblock(rec[f], 40, 30, b.qp[sl], b.transform_size_8x8_flag[sl], 0, 0, 0, 0)
         assert np.array_equal(h_db[f].numpy(), want), f
+
+
+# ---- the split formulation (DRYV_SPLIT=1: residual-fields kernel + one-warp-per-row walkers, split_kernels.cuh) --------
+def test_split_path_is_bit_exact(monkeypatch):
+    """Off by default (measured slower, profiles/r02_split_path.txt), but it is the same arithmetic through a second
+    schedule of the same dependencies, so it is held to the same bar: classes, ragged sizes, stress macroblocks, host and
+    device entry points, and the unsupported-syntax status."""
+    monkeypatch.setenv("DRYV_SPLIT", "1")
+    ctx = recon.ReconContext(0)  # the switch is read when the context is created
+    try:
+        for w, h, n, kw in [(1, 1, 2, {}), (2, 1, 2, {}), (1, 9, 2, {}), (17, 5, 3, {}), (40, 23, 3, dict(stress_pct=60)),
+                            (9, 6, 2, dict(pct_i4x4=100, pct_i8x8=0)), (9, 6, 2, dict(pct_i4x4=0, pct_i8x8=100)),
+                            (9, 6, 2, dict(pct_i4x4=0, pct_i8x8=0, qp_base=45)), (120, 68, 6, {})]:
+            check(ctx, synth.generate(PicParams.make(w, h, cb_off=1, cr_off=-2), n, 7000 + 13 * w + h, **kw), host=(w < 100))
+        b = synth.generate(PicParams.make(6, 4), 1, 5)
+        b.mb_type[7] = 25  # I_PCM
+        with pytest.raises(recon.ReconError) as e:
+            ctx.reconstruct(b)
+        assert e.value.code == recon.ERR_UNSUPPORTED
+        check(ctx, synth.generate(PicParams.make(6, 4), 1, 6), device=False)  # the context stays usable
+    finally:
+        ctx.close()

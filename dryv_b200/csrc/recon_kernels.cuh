@@ -275,6 +275,14 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
 #define DRYV_I4_DC_INLINE 0
 #endif
 #if DRYV_I4_ROLLED
+#ifndef DRYV_I4_UNROLL
+#define DRYV_I4_UNROLL 1
+#endif
+// steps per loop iteration (development knob). Measured: 2 makes an Intra4x4-only batch 12 % faster (0.970 -> 0.856 ms,
+// the register moves of the software pipeline go) for 64 more static instructions, and the mixed batch 4 % slower with
+// batches in flight (0.713 -> 0.741; unchanged one batch at a time); 5: Intra4x4-only 0.848, mixed 0.947 — the kernel's hot
+// code sits at the instruction-cache capacity.
+constexpr int kI4Unroll = DRYV_I4_UNROLL;
 struct I4Regs {
   uint4 tap;      // three sample offsets (biased), kind
   uint32_t org;   // tile offset of the block origin
@@ -297,7 +305,7 @@ __device__ __forceinline__ void predict_i4x4(const DeviceTables& tab, uint8_t* l
   // of the pixel loads of step s, so a step's dependent chain is pixel load -> three adds -> clamp -> store
   I4Regs cur;
   i4_fetch(cur, st, tap4, rows[0], resp);
-#pragma unroll 1
+#pragma unroll kI4Unroll
   for (int s = 0; s < 10; s++) {
     const uint8_t* ob = ltb + cur.org;
     const int e0 = ob[cur.tap.x], e1 = ob[cur.tap.y], e2 = ob[cur.tap.z];

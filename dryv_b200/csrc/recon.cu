@@ -1890,8 +1890,10 @@ int dryv_recon_create(int device, dryv_recon_ctx** out) {
     ok = cudaEventCreateWithFlags(&ctx->ctl[i].done, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->db_done, cudaEventDisableTiming) == cudaSuccess;
   // shared memory, not L1, is what the row teams live on: ask for the largest carve-out
+  int wave_carveout = cudaSharedmemCarveoutMaxShared;
+  if (const char* g = getenv("DRYV_WAVE_CARVEOUT")) wave_carveout = atoi(g);  // development: percent of the L1 / shared array
   ok = ok && cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+                                  wave_carveout) == cudaSuccess &&
        cudaFuncSetAttribute(dryv::recon_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(dryv::WaveCtaSmem)) == cudaSuccess;
   ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wave_ctas_per_sm, dryv::recon_wavefront_kernel,

@@ -20,7 +20,7 @@ __device__ __forceinline__ void body(uint32_t (&r)[8], uint32_t k1, uint32_t k2)
 
 // PHASE: 0 = all warps run the body from its start; 1 = warp w starts at quarter (w & 3) of the body
 template <int N, int PHASE>
-__global__ void __launch_bounds__(512) k(uint32_t* out, uint32_t seed, long long* cyc, int iters) {
+__global__ void __launch_bounds__(768) k(uint32_t* out, uint32_t seed, long long* cyc, int iters) {
   uint32_t r[8];
   const uint32_t k1 = seed * 3u + 1u, k2 = seed ^ 0x00ff00ffu;
 #pragma unroll
@@ -89,6 +89,16 @@ int main() {
     run<2048, 1>(w, sms);
     run<4096, 1>(w, sms);
     run<8192, 1>(w, sms);
+  }
+  // where the L1.5 knee is (16 warps per SM out of phase, like eight two-warp row teams; 20 / 24: ten / twelve teams)
+  for (int w = 16; w <= 24; w += 4) {
+    run<1536, 1>(w, sms);
+    run<1792, 1>(w, sms);
+    run<2048, 1>(w, sms);
+    run<2304, 1>(w, sms);
+    run<2560, 1>(w, sms);
+    run<3072, 1>(w, sms);
+    run<3584, 1>(w, sms);
   }
   return 0;
 }

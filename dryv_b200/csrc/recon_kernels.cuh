@@ -281,7 +281,8 @@ __device__ __forceinline__ PixLane make_pix_lane(int lane) {
 // steps per loop iteration (development knob). Measured: 2 makes an Intra4x4-only batch 12 % faster (0.970 -> 0.856 ms,
 // the register moves of the software pipeline go) for 64 more static instructions, and the mixed batch 4 % slower with
 // batches in flight (0.713 -> 0.741; unchanged one batch at a time); 5: Intra4x4-only 0.848, mixed 0.947 — the kernel's hot
-// code sits at the instruction-cache capacity.
+// code sits at the instruction-cache capacity. 2 together with the one-stage level ring (-24 static
+// instructions): mixed batch 0.718 in flight (0.702), 0.779 one at a time (0.803).
 constexpr int kI4Unroll = DRYV_I4_UNROLL;
 struct I4Regs {
   uint4 tap;      // three sample offsets (biased), kind

@@ -436,6 +436,14 @@ __device__ __noinline__ void ring_backpressure(volatile uint32_t* cons, unsigned
 #define DRYV_START_LAG 2
 #endif
 constexpr int kStartLag = DRYV_START_LAG;
+// Who turns an Intra4x4 macroblock's mode record into tap rows: the front warp (two macroblocks per pass) or the pixel warp
+// (development knob). Measured, 64 x 1080p in flight / one at a time: pixel warp 0.718 / 0.827 (default 0.704 / 0.805) although
+// the kernel shrinks by 112 static instructions — the pixel warp's time per macroblock is the hop of the dependency chain;
+// together with DRYV_I4_UNROLL=2 and DRYV_LV_STAGES=1 (3096 instructions): 0.705 / 0.783, one picture 0.342 (0.353),
+// Intra4x4-only batch 0.935 (0.970), 16 pictures in flight 0.270 (0.244): a wash, not adopted.
+#ifndef DRYV_TAPROWS_BY_PIXEL
+#define DRYV_TAPROWS_BY_PIXEL 0
+#endif
 static_assert(kCluster == 1 || (kStartLag == 2 && kTeamsPerCta == 1), "cluster mode: one team per CTA, default start lag");
 // CTAs per SM = the register budget handed to ptxas; shared memory: 11 KB of tables per CTA + 14 KB per team.
 #ifndef DRYV_CTAS_PER_SM
@@ -704,7 +712,7 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
           if (mine) (&G.mb[m_mb].modes_lo)[lane & 1] = w;
           __syncwarp();
           // Intra4x4: per-block tap rows (mode, top-right variant, legality and DC flavour in one byte), two macroblocks per pass
-          if (mI4) {
+          if (!DRYV_TAPROWS_BY_PIXEL && mI4) {
             const uint32_t list = tab.setbits4[mI4];
             const int ni = __popc(mI4);
             for (int p = 0; 2 * p < ni; p++) {
@@ -925,6 +933,13 @@ __global__ void __launch_bounds__(kWaveThreads, DRYV_CTAS_PER_SM) recon_wavefron
         if (mbcls == 7) {
 #else
         if (mbcls == 0) {
+#endif
+#if DRYV_TAPROWS_BY_PIXEL
+          {  // the tap rows of the sixteen blocks: the pixel warp has the time (it waits for the front warp on average)
+            const int av = (availA ? 1 : 0) | (availB ? 2 : 0) | (availC ? 4 : 0) | (availD ? 8 : 0);
+            if (lane < 16) slot.rows[lane] = (uint8_t)i4_tap_row(tab, lane, slot.modes_lo, slot.modes_hi, av);
+            __syncwarp();
+          }
 #endif
           predict_i4x4(tab, ts.luma, slot.res, pl, slot.rows);
           CLK_MARK(3);
